@@ -1,0 +1,268 @@
+"""B200-native fast sparse-grid transform path of AdaM-DG (FP64 CUDA for sm_100a behind a C ABI).
+
+This package is a thin ctypes binding of libamdg_b200.so (include/amdg.h).  There is no CPU fallback: if the
+shared library is missing the import fails, and every compute call needs a CUDA device.  torch is used only
+as plumbing (device buffers, streams, torch.distributed) -- no torch op is on the compute path.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libamdg_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libamdg_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no fallback path.")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+REL_VOL, REL_FLX = 0, 1
+LU_L, LU_U, LU_FULL = 0, 1, 2
+SCHED_LITERAL, SCHED_SHARED = 0, 1
+FLUX_LINEAR, FLUX_BURGERS, FLUX_SIN, FLUX_COS, FLUX_BUCKLEY_X, FLUX_BUCKLEY_Y, FLUX_VLASOV_SMOOTH_E = range(7)
+RK_EULER, RK_RK2SSP, RK_RK2MID, RK_RK3SSP = range(4)
+
+_i, _i64, _d, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+_ip = ctypes.POINTER(ctypes.c_int)
+_lp = ctypes.POINTER(ctypes.c_int64)
+_dp = ctypes.POINTER(ctypes.c_double)
+
+# every symbol include/amdg.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "amdg_version": (ctypes.c_char_p, []),
+    "amdg_last_error": (ctypes.c_char_p, []),
+    "amdg_ctx_create": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(_p)]),
+    "amdg_ctx_destroy": (_i, [_p]),
+    "amdg_ctx_set_stream": (_i, [_p, _p]),
+    "amdg_ctx_sync": (_i, [_p]),
+    "amdg_ctx_set_schedule": (_i, [_p, _i]),
+    "amdg_ctx_set_kernel": (_i, [_p, _i]),
+    "amdg_ctx_launch_count": (_i64, [_p]),
+    "amdg_hash_key": (_i, [_i, _ip, _ip]),
+    "amdg_order_elem": (_i, [_i, _i]),
+    "amdg_sparse_grid": (_i64, [_i, _i, _i, _ip, _ip]),
+    "amdg_grid_set": (_i, [_p, _i64, _ip, _ip]),
+    "amdg_grid_size": (_i64, [_p]),
+    "amdg_grid_keys": (_i, [_p, _ip, _ip]),
+    "amdg_grid_relation": (_i64, [_p, _i, _i, _lp, _ip]),
+    "amdg_grid_fibres": (_i64, [_p, _i, _lp, _ip]),
+    "amdg_op_register": (_i, [_p, _dp, _i, _i, _i, _i, _ip]),
+    "amdg_op_register_hier": (_i, [_p, _ip, _dp, _i, _ip]),
+    "amdg_op_combine": (_i, [_p, _i, _d, _i, _d, _ip]),
+    "amdg_sweep1d": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _i, _d, _i]),
+    "amdg_apply_tensor": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i]),
+    "amdg_hierarchize": (_i, [_p, _i, _p, _p, _i]),
+    "amdg_pointwise": (_i, [_p, _i, _ip, _dp, _p, _p, _p]),
+    "amdg_point_coords": (_i, [_p, _dp, _p]),
+    "amdg_rk_stage": (_i, [_p, _i, _i, _d, _p, _p, _p, _i64]),
+    "amdg_axpby": (_i, [_p, _i64, _d, _p, _d, _p]),
+    "amdg_host_apply_tensor": (_i, [_p, _ip, _ip, _dp, _dp, _i, _d, _i]),
+    "amdg_host_sweep1d": (_i, [_p, _i, _i, _i, _i, _ip, _dp, _dp, _i, _d, _i]),
+    "amdg_host_hierarchize": (_i, [_p, _i, _dp, _dp, _i]),
+    "amdg_host_roundtrip": (_i, [_p, _i, _i, _i, _dp, _dp, _i]),
+    "amdg_dev_alloc": (_i, [_p, _i64, ctypes.POINTER(_p)]),
+    "amdg_dev_free": (_i, [_p, _p]),
+    "amdg_dev_upload": (_i, [_p, _p, _dp, _i64]),
+    "amdg_dev_download": (_i, [_p, _dp, _p, _i64]),
+    "amdg_dev_zero": (_i, [_p, _p, _i64]),
+}
+for _name, (_res, _args) in SYMBOLS.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class AmdgError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc < 0:
+        raise AmdgError("amdg error %d: %s" % (rc, lib.amdg_last_error().decode()))
+    return rc
+
+
+def _ints(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_ip)
+
+
+def _dbls(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _ptr(t):
+    """device pointer of a torch tensor (must be contiguous float64 on the context's device) or a raw int"""
+    if isinstance(t, int):
+        return ctypes.c_void_p(t)
+    assert t.is_cuda and t.is_contiguous() and str(t.dtype) == "torch.float64", "need a contiguous float64 CUDA tensor"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def hash_key(level, suppt):
+    l, lp = _ints(level)
+    j, jp = _ints(suppt)
+    return lib.amdg_hash_key(len(l), lp, jp)
+
+
+def sparse_grid(dim, level_init, sparse=True):
+    """Initial grid of DGSolution (reference source/DGSolution.cpp:10-57), construction order."""
+    n = _check(lib.amdg_sparse_grid(dim, level_init, int(sparse), None, None))
+    lev = np.zeros((n, dim), dtype=np.int32)
+    sup = np.zeros((n, dim), dtype=np.int32)
+    _check(lib.amdg_sparse_grid(dim, level_init, int(sparse), lev.ctypes.data_as(_ip), sup.ctypes.data_as(_ip)))
+    return lev, sup
+
+
+class Context:
+    """One problem configuration on one device (dim, NMAX, Alpert and interpolation degrees)."""
+
+    def __init__(self, dim, nmax, pmax_alpt, pmax_intp, device=0):
+        self.dim, self.nmax, self.a, self.b = dim, nmax, pmax_alpt + 1, pmax_intp + 1
+        self.device = device
+        h = _p()
+        _check(lib.amdg_ctx_create(dim, nmax, pmax_alpt, pmax_intp, device, ctypes.byref(h)))
+        self._h = h
+        self.n_elem = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.amdg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib.amdg_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        _check(lib.amdg_ctx_sync(self._h))
+
+    def set_schedule(self, sched):
+        _check(lib.amdg_ctx_set_schedule(self._h, sched))
+
+    def set_kernel(self, variant):
+        _check(lib.amdg_ctx_set_kernel(self._h, variant))
+
+    @property
+    def launch_count(self):
+        return lib.amdg_ctx_launch_count(self._h)
+
+    # ---- grid
+    def grid_set(self, level, suppt):
+        l, lp = _ints(level)
+        j, jp = _ints(suppt)
+        assert l.shape == j.shape and l.ndim == 2 and l.shape[1] == self.dim
+        _check(lib.amdg_grid_set(self._h, l.shape[0], lp, jp))
+        self.n_elem = l.shape[0]
+
+    def grid_keys(self):
+        hk = np.zeros(self.n_elem, dtype=np.int32)
+        od = np.zeros((self.n_elem, self.dim), dtype=np.int32)
+        _check(lib.amdg_grid_keys(self._h, hk.ctypes.data_as(_ip), od.ctypes.data_as(_ip)))
+        return hk, od
+
+    def grid_relation(self, t, rel):
+        nnz = _check(lib.amdg_grid_relation(self._h, t, rel, None, None))
+        ptr = np.zeros(self.n_elem + 1, dtype=np.int64)
+        idx = np.zeros(max(nnz, 1), dtype=np.int32)
+        _check(lib.amdg_grid_relation(self._h, t, rel, ptr.ctypes.data_as(_lp), idx.ctypes.data_as(_ip)))
+        return ptr, idx[:nnz]
+
+    def grid_fibres(self, t):
+        nf = _check(lib.amdg_grid_fibres(self._h, t, None, None))
+        ptr = np.zeros(nf + 1, dtype=np.int64)
+        el = np.zeros(self.n_elem, dtype=np.int32)
+        _check(lib.amdg_grid_fibres(self._h, t, ptr.ctypes.data_as(_lp), el.ctypes.data_as(_ip)))
+        return ptr, el
+
+    # ---- operators
+    def op_register(self, dense, edge_from, edge_to):
+        m, mp = _dbls(dense)
+        out = _i()
+        _check(lib.amdg_op_register(self._h, mp, m.shape[0], m.shape[1], edge_from, edge_to, ctypes.byref(out)))
+        return out.value
+
+    def op_register_hier(self, anc, wt):
+        a, ap = _ints(anc)
+        w, wp = _dbls(wt)
+        out = _i()
+        _check(lib.amdg_op_register_hier(self._h, ap, wp, w.shape[-1], ctypes.byref(out)))
+        return out.value
+
+    def op_combine(self, op_a, alpha, op_b, beta):
+        out = _i()
+        _check(lib.amdg_op_combine(self._h, op_a, alpha, op_b, beta, ctypes.byref(out)))
+        return out.value
+
+    # ---- device compute (torch tensors are only carriers of device pointers)
+    def sweep1d(self, op, rel, lu, t, sizes_from, src, dst, n_comp=1, coef=1.0, accumulate=False):
+        s, sp = _ints(sizes_from)
+        _check(lib.amdg_sweep1d(self._h, op, rel, lu, t, sp, _ptr(src), _ptr(dst), n_comp, coef, int(accumulate)))
+
+    def apply_tensor(self, ops, rels, src, dst, n_comp=1, coef=1.0, accumulate=False):
+        o, op = _ints(ops)
+        r, rp = _ints(rels)
+        _check(lib.amdg_apply_tensor(self._h, op, rp, _ptr(src), _ptr(dst), n_comp, coef, int(accumulate)))
+
+    def hierarchize(self, hier_op, src, dst, n_comp=1):
+        _check(lib.amdg_hierarchize(self._h, hier_op, _ptr(src), _ptr(dst), n_comp))
+
+    def pointwise(self, flux_ids, params, up, fp, pts=None):
+        f, fp_ = _ints(flux_ids)
+        prm = np.zeros((len(f), 4)) if params is None else np.asarray(params, dtype=np.float64).reshape(len(f), 4)
+        prm, pp = _dbls(prm)
+        _check(lib.amdg_pointwise(self._h, len(f), fp_, pp, _ptr(up), _ptr(fp), _ptr(pts) if pts is not None else None))
+
+    def point_coords(self, pts1d, dev_pts):
+        p, pp = _dbls(pts1d)
+        _check(lib.amdg_point_coords(self._h, pp, _ptr(dev_pts)))
+
+    def rk_stage(self, scheme, stage, dt, u_tn, u, rhs):
+        _check(lib.amdg_rk_stage(self._h, scheme, stage, dt, _ptr(u_tn), _ptr(u), _ptr(rhs), u.numel()))
+
+    def axpby(self, alpha, x, beta, y):
+        _check(lib.amdg_axpby(self._h, y.numel(), alpha, _ptr(x), beta, _ptr(y)))
+
+    # ---- host-buffer entry points (numpy in, numpy out; copies inside)
+    def host_apply_tensor(self, ops, rels, src, edge_to, n_comp=1, coef=1.0, out=None):
+        o, op = _ints(ops)
+        r, rp = _ints(rels)
+        s, sp = _dbls(src)
+        acc = out is not None
+        if out is None:
+            out = np.empty(n_comp * self.n_elem * edge_to ** self.dim)
+        _check(lib.amdg_host_apply_tensor(self._h, op, rp, sp, out.ctypes.data_as(_dp), n_comp, coef, int(acc)))
+        return out
+
+    def host_sweep1d(self, op, rel, lu, t, sizes_from, src, edge_to, n_comp=1, coef=1.0, out=None):
+        z, zp = _ints(sizes_from)
+        s, sp = _dbls(src)
+        acc = out is not None
+        if out is None:
+            blk = int(np.prod(z)) // int(z[t]) * edge_to
+            out = np.empty(n_comp * self.n_elem * blk)
+        _check(lib.amdg_host_sweep1d(self._h, op, rel, lu, t, zp, sp, out.ctypes.data_as(_dp), n_comp, coef, int(acc)))
+        return out
+
+    def host_hierarchize(self, hier_op, src, n_comp=1):
+        s, sp = _dbls(src)
+        out = np.empty_like(s)
+        _check(lib.amdg_host_hierarchize(self._h, hier_op, sp, out.ctypes.data_as(_dp), n_comp))
+        return out
+
+    def host_roundtrip(self, op_fwd, hier_op, op_inv, ucoe, n_comp=1, out=None):
+        s, sp = _dbls(ucoe)
+        if out is None:
+            out = np.empty_like(s)
+        _check(lib.amdg_host_roundtrip(self._h, op_fwd, hier_op, op_inv, sp, out.ctypes.data_as(_dp), n_comp))
+        return out

@@ -1,0 +1,691 @@
+// C ABI (include/amdg.h) over the host tables (grid.hpp) and the sm_100a kernels (kernels.cu).
+// No torch types, no CPU compute path: a context without a device can only build and export tables.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/amdg.h"
+#include "grid.hpp"
+#include "kernels.cuh"
+
+using namespace amdg;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string & msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(AMDG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct Op
+{
+    int kf = 0, kt = 0;
+    bool hier = false;
+    std::vector<double> blocks;     // host copy [n_pairs][kf][kt]
+    double * d_blocks = nullptr;
+};
+
+struct DevDim
+{
+    int * slot_elem = nullptr; int * slot_fbase = nullptr;
+    int64_t * nbr_ptr[2] = { nullptr, nullptr }; int * nbr_split[2] = { nullptr, nullptr }; NbrDev * nbr[2] = { nullptr, nullptr };
+    int64_t * fibre_ptr = nullptr;
+};
+
+struct amdg_ctx
+{
+    int dim = 0, nmax = 0, edge_alpt = 0, edge_intp = 0, device = -1;
+    int sched = AMDG_SCHED_SHARED, kernel_variant = 0;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    Pairs1D pairs;
+    Grid grid; bool have_grid = false;
+    std::vector<DevDim> ddims;
+    int * d_ord1d = nullptr;
+    std::vector<std::unique_ptr<Op>> ops;
+    std::vector<double *> scratch; std::vector<int64_t> scratch_cap;
+    double * h2d = nullptr; int64_t h2d_cap = 0;     // device staging for the host-buffer entry points
+    double * d2h = nullptr; int64_t d2h_cap = 0;
+    int64_t launches = 0;
+};
+
+static int need_device(amdg_ctx * c)
+{
+    if (!c) return fail(AMDG_EINVAL, "null context");
+    if (c->device < 0) return fail(AMDG_ENODEVICE, "context was created without a device: no CPU compute path exists");
+    return AMDG_OK;
+}
+
+static void free_dev_grid(amdg_ctx * c)
+{
+    for (auto & D : c->ddims)
+    {
+        cudaFree(D.slot_elem); cudaFree(D.slot_fbase); cudaFree(D.fibre_ptr);
+        for (int k = 0; k < 2; ++k) { cudaFree(D.nbr_ptr[k]); cudaFree(D.nbr_split[k]); cudaFree(D.nbr[k]); }
+    }
+    c->ddims.clear();
+    cudaFree(c->d_ord1d); c->d_ord1d = nullptr;
+}
+
+template <class T>
+static cudaError_t upload(T ** dptr, const T * h, size_t n, cudaStream_t st)
+{
+    cudaError_t e = cudaMalloc((void **)dptr, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+static int ensure_scratch(amdg_ctx * c, size_t idx, int64_t n)
+{
+    if (c->scratch.size() <= idx) { c->scratch.resize(idx + 1, nullptr); c->scratch_cap.resize(idx + 1, 0); }
+    if (c->scratch_cap[idx] >= n) return AMDG_OK;
+    if (c->scratch[idx]) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch[idx])); c->scratch[idx] = nullptr; c->scratch_cap[idx] = 0; }
+    cudaError_t e = cudaMalloc((void **)&c->scratch[idx], (size_t)n * sizeof(double));
+    if (e != cudaSuccess) return fail(AMDG_ENOMEM, std::string("scratch cudaMalloc: ") + cudaGetErrorString(e));
+    c->scratch_cap[idx] = n;
+    return AMDG_OK;
+}
+
+extern "C" {
+
+const char * amdg_version(void) { return "amdg-b200 0.1 (sm_100a, fp64)"; }
+const char * amdg_last_error(void) { return g_err.c_str(); }
+
+int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device, amdg_ctx ** out)
+{
+    if (!out) return fail(AMDG_EINVAL, "out is null");
+    if (dim < 1 || dim > 8) return fail(AMDG_EINVAL, "dim must be in 1..8");
+    if (nmax < 0 || nmax > 12) return fail(AMDG_EINVAL, "nmax must be in 0..12");
+    if (pmax_alpt < 0 || pmax_alpt > 5 || pmax_intp < 0 || pmax_intp > 5) return fail(AMDG_EINVAL, "pmax must be in 0..5");
+    std::unique_ptr<amdg_ctx> c(new amdg_ctx());
+    c->dim = dim; c->nmax = nmax; c->edge_alpt = pmax_alpt + 1; c->edge_intp = pmax_intp + 1; c->device = device;
+    c->pairs.build(nmax);
+    if (device >= 0)
+    {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) return fail(AMDG_ENODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+        if (device >= count) return fail(AMDG_ENODEVICE, "device ordinal out of range");
+        CU(cudaSetDevice(device));
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    *out = c.release();
+    return AMDG_OK;
+}
+
+int amdg_ctx_destroy(amdg_ctx * c)
+{
+    if (!c) return AMDG_OK;
+    if (c->device >= 0)
+    {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        free_dev_grid(c);
+        for (auto & op : c->ops) cudaFree(op->d_blocks);
+        for (double * p : c->scratch) cudaFree(p);
+        cudaFree(c->h2d); cudaFree(c->d2h);
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+    }
+    delete c;
+    return AMDG_OK;
+}
+
+int amdg_ctx_set_stream(amdg_ctx * c, void * s)
+{
+    int r = need_device(c); if (r) return r;
+    if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = (cudaStream_t)s;
+    return AMDG_OK;
+}
+
+int amdg_ctx_sync(amdg_ctx * c) { int r = need_device(c); if (r) return r; CU(cudaStreamSynchronize(c->stream)); return AMDG_OK; }
+int amdg_ctx_set_schedule(amdg_ctx * c, int s) { if (!c || (s != AMDG_SCHED_LITERAL && s != AMDG_SCHED_SHARED)) return fail(AMDG_EINVAL, "bad schedule"); c->sched = s; return AMDG_OK; }
+int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 2) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
+int64_t amdg_ctx_launch_count(amdg_ctx * c) { return c ? c->launches : -1; }
+
+int amdg_hash_key(int dim, const int * level, const int * suppt) { return hash_key(dim, level, suppt); }
+int amdg_order_elem(int level, int suppt) { return order_elem(level, suppt); }
+
+int64_t amdg_sparse_grid(int dim, int level_init, int sparse, int * level, int * suppt)
+{
+    if (dim < 1 || dim > 8 || level_init < 0) return fail(AMDG_EINVAL, "bad grid parameters");
+    if (!level) return sparse_grid(dim, level_init, sparse != 0, nullptr, nullptr);
+    std::vector<int> l, j;
+    const int64_t n = sparse_grid(dim, level_init, sparse != 0, &l, &j);
+    std::memcpy(level, l.data(), l.size() * sizeof(int)); std::memcpy(suppt, j.data(), j.size() * sizeof(int));
+    return n;
+}
+
+// ---- grid ------------------------------------------------------------------------------------------------------
+int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
+{
+    if (!c || n < 1 || !level || !suppt) return fail(AMDG_EINVAL, "bad arguments to amdg_grid_set");
+    if (n > 0x7fffffff) return fail(AMDG_EINVAL, "too many elements");
+    Grid g;
+    if (g.build(c->dim, c->nmax, n, level, suppt, c->pairs) != 0) return fail(AMDG_EINVAL, "invalid or duplicate element index");
+    c->grid = std::move(g); c->have_grid = true;
+    if (c->device < 0) return AMDG_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    free_dev_grid(c);
+    c->ddims.resize(c->dim);
+    CU(upload(&c->d_ord1d, c->grid.ord1d.data(), c->grid.ord1d.size(), c->stream));
+    for (int t = 0; t < c->dim; ++t)
+    {
+        const DimTables & H = c->grid.dims[t]; DevDim & D = c->ddims[t];
+        std::vector<int> fbase(n);
+        for (int64_t s = 0; s < n; ++s) fbase[s] = (int)H.fibre_ptr[H.slot_fibre[s]];
+        CU(upload(&D.slot_elem, H.slot_elem.data(), (size_t)n, c->stream));
+        CU(upload(&D.slot_fbase, fbase.data(), (size_t)n, c->stream));
+        CU(upload(&D.fibre_ptr, H.fibre_ptr.data(), H.fibre_ptr.size(), c->stream));
+        for (int k = 0; k < 2; ++k)
+        {
+            CU(upload(&D.nbr_ptr[k], H.nbr_ptr[k].data(), H.nbr_ptr[k].size(), c->stream));
+            CU(upload(&D.nbr_split[k], H.nbr_split[k].data(), H.nbr_split[k].size(), c->stream));
+            CU(upload((Nbr **)&D.nbr[k], H.nbr[k].data(), H.nbr[k].size(), c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));   // fbase is a local
+    }
+    return AMDG_OK;
+}
+
+int64_t amdg_grid_size(amdg_ctx * c) { return (c && c->have_grid) ? c->grid.n : -1; }
+
+int amdg_grid_keys(amdg_ctx * c, int * hash, int * ord1d)
+{
+    if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (hash) std::memcpy(hash, c->grid.hash.data(), c->grid.hash.size() * sizeof(int));
+    if (ord1d) std::memcpy(ord1d, c->grid.ord1d.data(), c->grid.ord1d.size() * sizeof(int));
+    return AMDG_OK;
+}
+
+int64_t amdg_grid_relation(amdg_ctx * c, int t, int rel, int64_t * ptr, int * idx)
+{
+    if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (t < 0 || t >= c->dim || rel < 0 || rel > 1) return fail(AMDG_EINVAL, "bad dim/relation");
+    const DimTables & H = c->grid.dims[t];
+    const int64_t nnz = (int64_t)H.nbr[rel].size();
+    if (!idx) return nnz;
+    const int64_t n = c->grid.n;
+    ptr[0] = 0;
+    for (int64_t e = 0; e < n; ++e) { const int64_t s = H.elem_slot[e]; ptr[e + 1] = ptr[e] + (H.nbr_ptr[rel][s + 1] - H.nbr_ptr[rel][s]); }
+    for (int64_t e = 0; e < n; ++e)
+    {
+        const int64_t s = H.elem_slot[e]; const int64_t fb = H.fibre_ptr[H.slot_fibre[s]];
+        int * out = idx + ptr[e]; int64_t k = 0;
+        for (int64_t p = H.nbr_ptr[rel][s]; p < H.nbr_ptr[rel][s + 1]; ++p) out[k++] = H.slot_elem[fb + H.nbr[rel][p].local];
+        std::sort(out, out + k);
+    }
+    return nnz;
+}
+
+int64_t amdg_grid_fibres(amdg_ctx * c, int t, int64_t * ptr, int * elems)
+{
+    if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (t < 0 || t >= c->dim) return fail(AMDG_EINVAL, "bad dim");
+    const DimTables & H = c->grid.dims[t];
+    if (!elems) return H.n_fibre;
+    std::memcpy(ptr, H.fibre_ptr.data(), H.fibre_ptr.size() * sizeof(int64_t));
+    std::memcpy(elems, H.slot_elem.data(), H.slot_elem.size() * sizeof(int));
+    return H.n_fibre;
+}
+
+// ---- operators ---------------------------------------------------------------------------------------------------
+static int push_op(amdg_ctx * c, std::unique_ptr<Op> op, int * out)
+{
+    if (c->device >= 0)
+    {
+        CU(cudaSetDevice(c->device));
+        CU(upload(&op->d_blocks, op->blocks.data(), op->blocks.size(), c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    c->ops.push_back(std::move(op));
+    *out = (int)c->ops.size() - 1;
+    return AMDG_OK;
+}
+
+int amdg_op_register(amdg_ctx * c, const double * dense, int rows, int cols, int kf, int kt, int * out)
+{
+    if (!c || !dense || !out) return fail(AMDG_EINVAL, "null argument");
+    const int T = c->pairs.T;
+    if (rows != T * kf || cols != T * kt) return fail(AMDG_EINVAL, "operator shape must be (2^nmax*edge_from) x (2^nmax*edge_to)");
+    if (!sweep_shape_supported(kf, kt)) return fail(AMDG_EINVAL, "unsupported block edge");
+    std::unique_ptr<Op> op(new Op()); op->kf = kf; op->kt = kt;
+    op->blocks.resize((size_t)c->pairs.n_pairs * kf * kt);
+    for (int p = 0; p < c->pairs.n_pairs; ++p)
+    {
+        const int f = c->pairs.src[p], e = c->pairs.tgt[p];
+        for (int k = 0; k < kf; ++k) for (int q = 0; q < kt; ++q)
+            op->blocks[((size_t)p * kf + k) * kt + q] = dense[(size_t)(f * kf + k) * cols + (e * kt + q)];
+    }
+    return push_op(c, std::move(op), out);
+}
+
+int amdg_op_register_hier(amdg_ctx * c, const int * anc, const double * wt, int p1, int * out)
+{
+    if (!c || !anc || !wt || !out) return fail(AMDG_EINVAL, "null argument");
+    if (!sweep_shape_supported(p1, p1)) return fail(AMDG_EINVAL, "unsupported block edge");
+    const int T = c->pairs.T;
+    std::unique_ptr<Op> op(new Op()); op->kf = p1; op->kt = p1; op->hier = true;
+    op->blocks.assign((size_t)c->pairs.n_pairs * p1 * p1, 0.0);
+    for (int e = 0; e < T; ++e)
+    {
+        const int self = c->pairs.id[(size_t)e * T + e];
+        for (int p = 0; p < p1; ++p) op->blocks[((size_t)self * p1 + p) * p1 + p] = 1.0;   // c_{t+1} = c_t + ...
+        if (e == 0) continue;
+        for (int ic = 0; ic < p1; ++ic)
+        {
+            const int f = anc[((size_t)(e - 1) * p1 + ic) * 2], qf = anc[((size_t)(e - 1) * p1 + ic) * 2 + 1];
+            if (f < 0 || f >= T || qf < 0 || qf >= p1) return fail(AMDG_EINVAL, "hierarchisation stencil out of range");
+            const int pair = c->pairs.id[(size_t)f * T + e];
+            if (pair < 0 || !c->pairs.vol[pair] || level_of_order(f) >= level_of_order(e)) return fail(AMDG_EINVAL, "hierarchisation ancestor is not a coarser overlapping element");
+            for (int p0 = 0; p0 < p1; ++p0) op->blocks[((size_t)pair * p1 + qf) * p1 + p0] += wt[((size_t)(e - 1) * p1 + p0) * p1 + ic];
+        }
+    }
+    return push_op(c, std::move(op), out);
+}
+
+int amdg_op_combine(amdg_ctx * c, int a, double alpha, int b, double beta, int * out)
+{
+    if (!c || !out || a < 0 || b < 0 || a >= (int)c->ops.size() || b >= (int)c->ops.size()) return fail(AMDG_EINVAL, "bad operator handle");
+    const Op & A = *c->ops[a]; const Op & B = *c->ops[b];
+    if (A.kf != B.kf || A.kt != B.kt) return fail(AMDG_EINVAL, "operator shapes differ");
+    std::unique_ptr<Op> op(new Op()); op->kf = A.kf; op->kt = A.kt;
+    op->blocks.resize(A.blocks.size());
+    for (size_t i = 0; i < A.blocks.size(); ++i) op->blocks[i] = alpha * A.blocks[i] + beta * B.blocks[i];
+    return push_op(c, std::move(op), out);
+}
+
+// ---- sweeps ------------------------------------------------------------------------------------------------------
+static int check_op(amdg_ctx * c, int op) { return (op >= 0 && op < (int)c->ops.size()) ? AMDG_OK : fail(AMDG_EINVAL, "bad operator handle"); }
+
+// launch one sweep for a batch of jobs sharing (op, rel, lu, t, inner, outer)
+static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner, const SweepJob * jobs, int n_job, int n_comp)
+{
+    const Op & O = *c->ops[op];
+    const DevDim & D = c->ddims[t];
+    SweepArgs a;
+    a.slot_elem = D.slot_elem; a.slot_fbase = D.slot_fbase; a.nbr_ptr = D.nbr_ptr[rel]; a.nbr_split = D.nbr_split[rel]; a.nbr = D.nbr[rel];
+    a.blocks = O.d_blocks; a.n_elem = c->grid.n; a.inner = inner; a.lu = lu; a.n_comp = n_comp;
+    int done = 0;
+    while (done < n_job)
+    {
+        // group consecutive jobs with equal `outer`
+        int cnt = 1;
+        while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
+        a.n_job = cnt;
+        for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
+        cudaError_t e = launch_sweep_gather(a, O.kf, O.kt, c->stream);
+        if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
+        c->launches++;
+        done += cnt;
+    }
+    return AMDG_OK;
+}
+
+int amdg_sweep1d(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * src, double * dst,
+                 int n_comp, double coef, int accumulate)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if ((r = check_op(c, op))) return r;
+    if (t < 0 || t >= c->dim || rel < 0 || rel > 1 || lu < 0 || lu > 2 || !sizes_from || !src || !dst || n_comp < 1) return fail(AMDG_EINVAL, "bad sweep arguments");
+    const Op & O = *c->ops[op];
+    if (sizes_from[t] != O.kf) return fail(AMDG_EINVAL, "sizes_from[t] does not match the operator's source edge");
+    if (src == dst) return fail(AMDG_EINVAL, "a sweep cannot run in place");
+    int outer = 1, inner = 1;
+    for (int k = 0; k < t; ++k) outer *= sizes_from[k];
+    for (int k = t + 1; k < c->dim; ++k) inner *= sizes_from[k];
+    SweepJob j; j.src = src; j.dst = dst; j.outer = outer; j.accumulate = accumulate; j.coef = coef;
+    CU(cudaSetDevice(c->device));
+    return launch_sweep(c, op, rel, lu, t, inner, &j, 1, n_comp);
+}
+
+static int64_t ipow(int b, int e) { int64_t r = 1; while (e-- > 0) r *= b; return r; }
+
+// the reference's schedule: source/FastMultiplyLU.cpp:614-664 (orderings), :121-142 (chain), :596-612 (sizes)
+static int apply_tensor_literal(amdg_ctx * c, const int * ops, const int * rels, const double * src, double * dst, int n_comp, double coef, int accumulate)
+{
+    const int d = c->dim; const int64_t n = c->grid.n;
+    const int kf = c->ops[ops[0]]->kf, kt = c->ops[ops[0]]->kt;
+    const int64_t cap = n * n_comp * ipow(std::max(kf, kt), d);
+    int r;
+    if ((r = ensure_scratch(c, 0, cap)) || (r = ensure_scratch(c, 1, cap))) return r;
+    const int n_chain = d == 1 ? 1 : (1 << (d - 1));
+    for (int ch = 0; ch < n_chain; ++ch)
+    {
+        // choice of dim k < d-1: bit (d-2-k) of ch (row-major IterativeNestedLoop), 0 = L, 1 = U
+        std::vector<int> order, lus;
+        for (int k = 0; k < d - 1; ++k) if (((ch >> (d - 2 - k)) & 1) == 0) { order.push_back(k); lus.push_back(AMDG_LU_L); }
+        order.push_back(d - 1); lus.push_back(AMDG_LU_FULL);
+        for (int k = 0; k < d - 1; ++k) if (((ch >> (d - 2 - k)) & 1) == 1) { order.push_back(k); lus.push_back(AMDG_LU_U); }
+        std::vector<int> sizes(d, kf);
+        const double * cur = src;
+        for (int step = 0; step < d; ++step)
+        {
+            const int t = order[step];
+            int outer = 1, inner = 1;
+            for (int k = 0; k < t; ++k) outer *= sizes[k];
+            for (int k = t + 1; k < d; ++k) inner *= sizes[k];
+            const bool last = (step == d - 1);
+            SweepJob j;
+            j.src = cur; j.dst = last ? dst : c->scratch[step & 1]; j.outer = outer;
+            j.accumulate = last ? ((ch > 0) || accumulate) : 0;
+            j.coef = (step == 0) ? coef : 1.0;
+            if ((r = launch_sweep(c, ops[t], rels[t], lus[step], t, inner, &j, 1, n_comp))) return r;
+            cur = j.dst; sizes[t] = kt;
+        }
+    }
+    return AMDG_OK;
+}
+
+// Same sum with shared prefixes/suffixes.  With X_S = (prod_{k in S} L_k) x for S subset of {0..d-2},
+//   Y_S = F_{d-1} X_S,   R_{d-1}(S) = Y_S,   R_k(S) = U_k R_{k+1}(S) + R_{k+1}(S + {k})  (S subset of {0..k-1}),
+// the result is R_0({}).  Sweeps: (2^(d-1)-1) L + 2^(d-1) full + (2^(d-1)-1) U instead of d*2^(d-1); all sweeps of
+// one level go out as one batched launch.  Buffers: one per subset S (index = bitmask of S).
+static int apply_tensor_shared(amdg_ctx * c, const int * ops, const int * rels, const double * src, double * dst, int n_comp, double coef, int accumulate)
+{
+    const int d = c->dim; const int64_t n = c->grid.n;
+    if (d == 1) return apply_tensor_literal(c, ops, rels, src, dst, n_comp, coef, accumulate);
+    const int kf = c->ops[ops[0]]->kf, kt = c->ops[ops[0]]->kt;
+    const int nsub = 1 << (d - 1);
+    if (nsub > MAX_JOBS * 4) return fail(AMDG_EINVAL, "dimension too large for the shared schedule");
+    const int64_t cap = n * n_comp * ipow(std::max(kf, kt), d);
+    int r;
+    // X buffers 0..nsub-1 (X_0 = src itself), Y buffers nsub..2*nsub-1
+    for (int s = 1; s < 2 * nsub; ++s) if ((r = ensure_scratch(c, (size_t)s, cap))) return r;
+    auto xbuf = [&](int S) -> const double * { return S == 0 ? src : c->scratch[S]; };
+    auto ybuf = [&](int S) -> double * { return c->scratch[nsub + S]; };
+    auto edge = [&](int S, int k) { return ((S >> k) & 1) ? kt : kf; };   // dims in S already have the target edge
+    std::vector<SweepJob> jobs;
+    // down: L_k applied to every X_S with S subset of {0..k-1}
+    for (int k = 0; k < d - 1; ++k)
+    {
+        jobs.clear();
+        int inner = 1; for (int q = k + 1; q < d; ++q) inner *= kf;
+        for (int S = 0; S < (1 << k); ++S)
+        {
+            int outer = 1; for (int q = 0; q < k; ++q) outer *= edge(S, q);
+            SweepJob j; j.src = xbuf(S); j.dst = c->scratch[S | (1 << k)]; j.outer = outer; j.accumulate = 0; j.coef = 1.0;
+            jobs.push_back(j);
+        }
+        std::stable_sort(jobs.begin(), jobs.end(), [](const SweepJob & a, const SweepJob & b) { return a.outer < b.outer; });
+        if ((r = launch_sweep(c, ops[k], rels[k], AMDG_LU_L, k, inner, jobs.data(), (int)jobs.size(), n_comp))) return r;
+    }
+    // full sweep along d-1 for every S; coef enters here (each chain passes through exactly one full sweep)
+    {
+        jobs.clear();
+        for (int S = 0; S < nsub; ++S)
+        {
+            int outer = 1; for (int q = 0; q < d - 1; ++q) outer *= edge(S, q);
+            SweepJob j; j.src = xbuf(S); j.dst = ybuf(S); j.outer = outer; j.accumulate = 0; j.coef = coef;
+            jobs.push_back(j);
+        }
+        std::stable_sort(jobs.begin(), jobs.end(), [](const SweepJob & a, const SweepJob & b) { return a.outer < b.outer; });
+        if ((r = launch_sweep(c, ops[d - 1], rels[d - 1], AMDG_LU_FULL, d - 1, 1, jobs.data(), (int)jobs.size(), n_comp))) return r;
+    }
+    // up: R_k(S) = U_k R_{k+1}(S) + R_{k+1}(S+{k}); the sum is accumulated into the buffer of S+{k}
+    // (for k = 0 into the caller's dst).  After level k the live buffers are those of S subset of {0..k-1},
+    // stored at index S + {k}... we keep R_{k}(S) in ybuf(S | bit k) to avoid a copy, tracked by `where`.
+    std::vector<int> where(nsub);
+    for (int S = 0; S < nsub; ++S) where[S] = S;      // R_{d-1}(S) lives in ybuf(S)
+    for (int k = d - 2; k >= 0; --k)
+    {
+        jobs.clear();
+        int inner = 1; for (int q = k + 1; q < d; ++q) inner *= kt;
+        std::vector<int> nw(1 << k);
+        for (int S = 0; S < (1 << k); ++S)
+        {
+            int outer = 1; for (int q = 0; q < k; ++q) outer *= edge(S, q);
+            const int lo = where[S], hi = where[S | (1 << k)];
+            SweepJob j; j.src = ybuf(lo); j.outer = outer; j.coef = 1.0;
+            if (k == 0)
+            {
+                // final: dst (+)= U_0 R_1({}) ; then dst += R_1({0})
+                j.dst = dst; j.accumulate = accumulate;
+            }
+            else { j.dst = ybuf(hi); j.accumulate = 1; }
+            nw[S] = hi;
+            jobs.push_back(j);
+        }
+        std::stable_sort(jobs.begin(), jobs.end(), [](const SweepJob & a, const SweepJob & b) { return a.outer < b.outer; });
+        if ((r = launch_sweep(c, ops[k], rels[k], AMDG_LU_U, k, inner, jobs.data(), (int)jobs.size(), n_comp))) return r;
+        for (int S = 0; S < (1 << k); ++S) where[S] = nw[S];
+    }
+    // dst += R_1({0})
+    {
+        const int64_t total = n * n_comp * ipow(kt, d);
+        cudaError_t e = launch_axpby(total, 1.0, ybuf(where[0]), 1.0, dst, c->stream);
+        if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("axpby launch: ") + cudaGetErrorString(e));
+        c->launches++;
+    }
+    return AMDG_OK;
+}
+
+int amdg_apply_tensor(amdg_ctx * c, const int * ops, const int * rels, const double * src, double * dst, int n_comp, double coef, int accumulate)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (!ops || !rels || !src || !dst || n_comp < 1) return fail(AMDG_EINVAL, "bad arguments");
+    for (int t = 0; t < c->dim; ++t)
+    {
+        if ((r = check_op(c, ops[t]))) return r;
+        if (rels[t] < 0 || rels[t] > 1) return fail(AMDG_EINVAL, "bad relation");
+        if (c->ops[ops[t]]->kf != c->ops[ops[0]]->kf || c->ops[ops[t]]->kt != c->ops[ops[0]]->kt) return fail(AMDG_EINVAL, "operators of one tensor product must share block edges");
+    }
+    CU(cudaSetDevice(c->device));
+    if (c->sched == AMDG_SCHED_LITERAL) return apply_tensor_literal(c, ops, rels, src, dst, n_comp, coef, accumulate);
+    return apply_tensor_shared(c, ops, rels, src, dst, n_comp, coef, accumulate);
+}
+
+int amdg_hierarchize(amdg_ctx * c, int hop, const double * src, double * dst, int n_comp)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if ((r = check_op(c, hop))) return r;
+    const Op & O = *c->ops[hop];
+    if (!O.hier) return fail(AMDG_EINVAL, "operator is not a hierarchisation stencil");
+    if (!src || !dst || n_comp < 1) return fail(AMDG_EINVAL, "bad arguments");
+    const int d = c->dim; const int b = O.kf; const int64_t n = c->grid.n;
+    const int64_t cap = n * n_comp * ipow(b, d);
+    if ((r = ensure_scratch(c, 0, cap)) || (r = ensure_scratch(c, 1, cap))) return r;
+    CU(cudaSetDevice(c->device));
+    // pass t reads stage t and writes stage t+1 (source/Interplation.cpp:1260-1400); ancestors are "U" sources
+    const double * cur = src;
+    for (int t = 0; t < d; ++t)
+    {
+        int outer = 1, inner = 1;
+        for (int k = 0; k < t; ++k) outer *= b;
+        for (int k = t + 1; k < d; ++k) inner *= b;
+        SweepJob j; j.src = cur; j.outer = outer; j.accumulate = 0; j.coef = 1.0;
+        const bool last = (t == d - 1);
+        // ping-pong so that the last pass lands in dst even when dst == src
+        j.dst = last ? dst : c->scratch[t & 1];
+        if (last && cur == dst)
+        {
+            j.dst = c->scratch[t & 1];
+            if ((r = launch_sweep(c, hop, AMDG_REL_VOL, AMDG_LU_U, t, inner, &j, 1, n_comp))) return r;
+            CU(cudaMemcpyAsync(dst, j.dst, (size_t)cap * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            return AMDG_OK;
+        }
+        if ((r = launch_sweep(c, hop, AMDG_REL_VOL, AMDG_LU_U, t, inner, &j, 1, n_comp))) return r;
+        cur = j.dst;
+    }
+    return AMDG_OK;
+}
+
+// ---- point-wise, RK ------------------------------------------------------------------------------------------------
+int amdg_pointwise(amdg_ctx * c, int n_flux, const int * flux_id, const double * params, const double * up, double * fp, const double * pts)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (n_flux < 1 || n_flux > 8 || !flux_id || !up || !fp) return fail(AMDG_EINVAL, "bad arguments");
+    PointwiseArgs a; a.up = up; a.fp = fp; a.pts = pts; a.n_points = c->grid.n * ipow(c->edge_intp, c->dim); a.n_flux = n_flux; a.dim = c->dim;
+    for (int i = 0; i < n_flux; ++i)
+    {
+        a.flux_id[i] = flux_id[i];
+        if (flux_id[i] == AMDG_FLUX_VLASOV_SMOOTH_E && !pts) return fail(AMDG_EINVAL, "the Vlasov product needs point coordinates");
+        for (int k = 0; k < 4; ++k) a.params[i][k] = params ? params[i * 4 + k] : 0.0;
+    }
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_pointwise(a, c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("pointwise launch: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+int amdg_point_coords(amdg_ctx * c, const double * host_pts1d, double * dev_pts)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (!host_pts1d || !dev_pts) return fail(AMDG_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    double * d1 = nullptr; const size_t n1 = (size_t)c->pairs.T * c->edge_intp;
+    CU(upload(&d1, host_pts1d, n1, c->stream));
+    cudaError_t e = launch_point_coords(d1, c->d_ord1d, c->grid.n, c->dim, c->edge_intp, dev_pts, c->stream);
+    c->launches++;
+    cudaStreamSynchronize(c->stream); cudaFree(d1);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("point_coords launch: ") + cudaGetErrorString(e));
+    return AMDG_OK;
+}
+
+int amdg_rk_stage(amdg_ctx * c, int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n)
+{
+    int r = need_device(c); if (r) return r;
+    if (!u_tn || !u || !rhs || n < 0) return fail(AMDG_EINVAL, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_rk_stage(scheme, stage, dt, u_tn, u, rhs, n, c->stream);
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? AMDG_EINVAL : AMDG_ECUDA, std::string("rk_stage: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+int amdg_axpby(amdg_ctx * c, int64_t n, double alpha, const double * x, double beta, double * y)
+{
+    int r = need_device(c); if (r) return r;
+    if (!x || !y || n < 0) return fail(AMDG_EINVAL, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_axpby(n, alpha, x, beta, y, c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("axpby: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+// ---- device memory helpers -------------------------------------------------------------------------------------------
+int amdg_dev_alloc(amdg_ctx * c, int64_t n, double ** out)
+{
+    int r = need_device(c); if (r) return r;
+    if (!out || n < 0) return fail(AMDG_EINVAL, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc((void **)out, std::max<int64_t>(n, 1) * sizeof(double));
+    if (e != cudaSuccess) return fail(AMDG_ENOMEM, cudaGetErrorString(e));
+    return AMDG_OK;
+}
+int amdg_dev_free(amdg_ctx * c, double * p) { int r = need_device(c); if (r) return r; CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(p)); return AMDG_OK; }
+int amdg_dev_upload(amdg_ctx * c, double * dst, const double * src, int64_t n)
+{
+    int r = need_device(c); if (r) return r;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMDG_OK;
+}
+int amdg_dev_download(amdg_ctx * c, double * dst, const double * src, int64_t n)
+{
+    int r = need_device(c); if (r) return r;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMDG_OK;
+}
+int amdg_dev_zero(amdg_ctx * c, double * p, int64_t n)
+{
+    int r = need_device(c); if (r) return r;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(p, 0, (size_t)n * sizeof(double), c->stream));
+    return AMDG_OK;
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------------------------------------
+static int ensure_stage(amdg_ctx * c, double ** buf, int64_t * cap, int64_t n)
+{
+    if (*cap >= n) return AMDG_OK;
+    if (*buf) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(*buf)); *buf = nullptr; *cap = 0; }
+    cudaError_t e = cudaMalloc((void **)buf, (size_t)n * sizeof(double));
+    if (e != cudaSuccess) return fail(AMDG_ENOMEM, cudaGetErrorString(e));
+    *cap = n;
+    return AMDG_OK;
+}
+
+int amdg_host_apply_tensor(amdg_ctx * c, const int * ops, const int * rels, const double * hsrc, double * hdst, int n_comp, double coef, int accumulate)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid || !ops || !hsrc || !hdst) return fail(AMDG_EINVAL, "bad arguments");
+    if ((r = check_op(c, ops[0]))) return r;
+    const int64_t nf = c->grid.n * n_comp * ipow(c->ops[ops[0]]->kf, c->dim), nt = c->grid.n * n_comp * ipow(c->ops[ops[0]]->kt, c->dim);
+    CU(cudaSetDevice(c->device));
+    if ((r = ensure_stage(c, &c->h2d, &c->h2d_cap, nf)) || (r = ensure_stage(c, &c->d2h, &c->d2h_cap, nt))) return r;
+    CU(cudaMemcpyAsync(c->h2d, hsrc, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (accumulate) CU(cudaMemcpyAsync(c->d2h, hdst, (size_t)nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((r = amdg_apply_tensor(c, ops, rels, c->h2d, c->d2h, n_comp, coef, accumulate))) return r;
+    CU(cudaMemcpyAsync(hdst, c->d2h, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMDG_OK;
+}
+
+int amdg_host_sweep1d(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * hsrc, double * hdst, int n_comp, double coef, int accumulate)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid || !sizes_from || !hsrc || !hdst) return fail(AMDG_EINVAL, "bad arguments");
+    if ((r = check_op(c, op))) return r;
+    if (t < 0 || t >= c->dim) return fail(AMDG_EINVAL, "bad dim");
+    int64_t bf = 1; for (int k = 0; k < c->dim; ++k) bf *= sizes_from[k];
+    const int64_t bt = bf / sizes_from[t] * c->ops[op]->kt;
+    const int64_t nf = c->grid.n * n_comp * bf, nt = c->grid.n * n_comp * bt;
+    CU(cudaSetDevice(c->device));
+    if ((r = ensure_stage(c, &c->h2d, &c->h2d_cap, nf)) || (r = ensure_stage(c, &c->d2h, &c->d2h_cap, nt))) return r;
+    CU(cudaMemcpyAsync(c->h2d, hsrc, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (accumulate) CU(cudaMemcpyAsync(c->d2h, hdst, (size_t)nt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((r = amdg_sweep1d(c, op, rel, lu, t, sizes_from, c->h2d, c->d2h, n_comp, coef, accumulate))) return r;
+    CU(cudaMemcpyAsync(hdst, c->d2h, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMDG_OK;
+}
+
+int amdg_host_hierarchize(amdg_ctx * c, int hop, const double * hsrc, double * hdst, int n_comp)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid || !hsrc || !hdst) return fail(AMDG_EINVAL, "bad arguments");
+    if ((r = check_op(c, hop))) return r;
+    const int64_t nn = c->grid.n * n_comp * ipow(c->ops[hop]->kf, c->dim);
+    CU(cudaSetDevice(c->device));
+    if ((r = ensure_stage(c, &c->h2d, &c->h2d_cap, nn)) || (r = ensure_stage(c, &c->d2h, &c->d2h_cap, nn))) return r;
+    CU(cudaMemcpyAsync(c->h2d, hsrc, (size_t)nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((r = amdg_hierarchize(c, hop, c->h2d, c->d2h, n_comp))) return r;
+    CU(cudaMemcpyAsync(hdst, c->d2h, (size_t)nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMDG_OK;
+}
+
+int amdg_host_roundtrip(amdg_ctx * c, int op_fwd, int hop, int op_inv, const double * hin, double * hout, int n_comp)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid || !hin || !hout) return fail(AMDG_EINVAL, "bad arguments");
+    if ((r = check_op(c, op_fwd)) || (r = check_op(c, hop)) || (r = check_op(c, op_inv))) return r;
+    const int d = c->dim;
+    const int64_t na = c->grid.n * n_comp * ipow(c->ops[op_fwd]->kf, d), nb = c->grid.n * n_comp * ipow(c->ops[op_fwd]->kt, d);
+    CU(cudaSetDevice(c->device));
+    if ((r = ensure_stage(c, &c->h2d, &c->h2d_cap, std::max(na, nb))) || (r = ensure_stage(c, &c->d2h, &c->d2h_cap, std::max(na, nb)))) return r;
+    std::vector<int> ops(d, op_fwd), rels(d, AMDG_REL_VOL), ops2(d, op_inv);
+    CU(cudaMemcpyAsync(c->h2d, hin, (size_t)na * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((r = amdg_apply_tensor(c, ops.data(), rels.data(), c->h2d, c->d2h, n_comp, 1.0, 0))) return r;       // ucoe_alpt -> up_intp
+    if ((r = amdg_hierarchize(c, hop, c->d2h, c->d2h, n_comp))) return r;                                       // up_intp -> ucoe_intp
+    if ((r = amdg_apply_tensor(c, ops2.data(), rels.data(), c->d2h, c->h2d, n_comp, 1.0, 0))) return r;         // ucoe_intp -> ucoe_alpt
+    CU(cudaMemcpyAsync(hout, c->h2d, (size_t)na * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMDG_OK;
+}
+
+}  // extern "C"

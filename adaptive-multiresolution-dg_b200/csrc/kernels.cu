@@ -1,0 +1,225 @@
+// FP64 CUDA kernels for sm_100a.  See kernels.cuh for the map to the reference functions.
+#include "kernels.cuh"
+#include "../../include/amdg.h"
+
+namespace amdg {
+
+// -------------------------------------------------------------------------------------------------------------
+// K1, gather form.  One thread owns one (target slot, column) and the KT outputs of that column; it walks the
+// target's neighbour list (U sources first, then L sources) and, per source, reads the KF source entries of
+// the same column and the (KF x KT) operator block of the 1D pair.  Reads of a source block are served by
+// L1/L2 (a block is re-read by every related target); the fibre-staged kernel below removes that re-read.
+//   dst[e][o][q][i] = coef * sum_f sum_k src[f][o][k][i] * B[pair(f,e)][k][q]   (+ dst if accumulate)
+// reference loop: source/FastMultiplyLU.cpp:476-506
+// -------------------------------------------------------------------------------------------------------------
+template <int KF, int KT>
+__global__ void __launch_bounds__(128) sweep_gather_kernel(const SweepArgs a)
+{
+    const int jb = blockIdx.y / a.n_comp, comp = blockIdx.y % a.n_comp;
+    const SweepJob J = a.job[jb];
+    const int inner = a.inner;
+    const int W = J.outer * inner;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t slot = g / W;
+    if (slot >= a.n_elem) return;
+    const int c = (int)(g - slot * W);
+    const int o = c / inner, i = c - o * inner;
+    const int64_t s_from = (int64_t)W * KF, s_to = (int64_t)W * KT;
+    const double * __restrict__ src = J.src + (int64_t)comp * a.n_elem * s_from;
+    double * __restrict__ dst = J.dst + (int64_t)comp * a.n_elem * s_to;
+
+    const int e = a.slot_elem[slot];
+    const int fbase = a.slot_fbase[slot];
+    int64_t n0 = a.nbr_ptr[slot], n1 = a.nbr_ptr[slot + 1];
+    const int split = a.nbr_split[slot];
+    if (a.lu == AMDG_LU_U) n1 = n0 + split;
+    else if (a.lu == AMDG_LU_L) n0 = n0 + split;
+
+    double acc[KT];
+#pragma unroll
+    for (int q = 0; q < KT; ++q) acc[q] = 0.0;
+
+    const int64_t col_off = (int64_t)o * KF * inner + i;
+    for (int64_t p = n0; p < n1; ++p)
+    {
+        const NbrDev nb = a.nbr[p];
+        const int f = a.slot_elem[fbase + nb.local];
+        const double * __restrict__ x = src + (int64_t)f * s_from + col_off;
+        const double * __restrict__ B = a.blocks + (int64_t)nb.pair * (KF * KT);
+#pragma unroll
+        for (int k = 0; k < KF; ++k)
+        {
+            const double xv = __ldg(x + (int64_t)k * inner);
+#pragma unroll
+            for (int q = 0; q < KT; ++q) acc[q] = fma(xv, __ldg(B + k * KT + q), acc[q]);
+        }
+    }
+    double * y = dst + (int64_t)e * s_to + (int64_t)o * KT * inner + i;
+#pragma unroll
+    for (int q = 0; q < KT; ++q)
+    {
+        double v = J.coef * acc[q];
+        if (J.accumulate) v += y[(int64_t)q * inner];
+        y[(int64_t)q * inner] = v;
+    }
+}
+
+template <int KF, int KT>
+static cudaError_t launch_gather_t(const SweepArgs & a, cudaStream_t st)
+{
+    // all jobs of one launch share `outer` in this variant (checked by the caller): grid.x from job 0
+    const int64_t W = (int64_t)a.job[0].outer * a.inner;
+    const int64_t total = a.n_elem * W;
+    dim3 grid((unsigned)((total + 127) / 128), (unsigned)(a.n_job * a.n_comp));
+    sweep_gather_kernel<KF, KT><<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+#define AMDG_DISPATCH_KT(KF_)                                                       \
+    switch (kt) {                                                                   \
+        case 1: return FN<KF_, 1>(a, st); case 2: return FN<KF_, 2>(a, st);          \
+        case 3: return FN<KF_, 3>(a, st); case 4: return FN<KF_, 4>(a, st);          \
+        case 5: return FN<KF_, 5>(a, st); case 6: return FN<KF_, 6>(a, st);          \
+        default: return cudaErrorInvalidValue; }
+
+bool sweep_shape_supported(int kf, int kt) { return kf >= 1 && kf <= 6 && kt >= 1 && kt <= 6; }
+
+cudaError_t launch_sweep_gather(const SweepArgs & a, int kf, int kt, cudaStream_t st)
+{
+#define FN launch_gather_t
+    switch (kf)
+    {
+        case 1: AMDG_DISPATCH_KT(1) case 2: AMDG_DISPATCH_KT(2) case 3: AMDG_DISPATCH_KT(3)
+        case 4: AMDG_DISPATCH_KT(4) case 5: AMDG_DISPATCH_KT(5) case 6: AMDG_DISPATCH_KT(6)
+        default: return cudaErrorInvalidValue;
+    }
+#undef FN
+}
+
+cudaError_t launch_sweep_fibre(const FibreSweepArgs & a, int kf, int kt, int max_fibre_len, cudaStream_t st)
+{
+    (void)a; (void)kf; (void)kt; (void)max_fibre_len; (void)st;
+    return cudaErrorNotSupported;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// K2 point-wise flux (source/Interplation.cpp:256-295; FluxFunction, source/Interplation.cpp, include/Interpolation.h:396-437)
+// -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double flux_eval(int id, const double * prm, double u, const double * x, int dim)
+{
+    switch (id)
+    {
+        case AMDG_FLUX_LINEAR: return prm[0] * u;
+        case AMDG_FLUX_BURGERS: return u * u / 2.;
+        case AMDG_FLUX_SIN: return sin(u);
+        case AMDG_FLUX_COS: return cos(u);
+        case AMDG_FLUX_BUCKLEY_X: return u * u / (u * u + (1. - u) * (1. - u));
+        case AMDG_FLUX_BUCKLEY_Y: return (u * u * (1. - 5. * (1. - u) * (1. - u))) / (u * u + (1. - u) * (1. - u));
+        case AMDG_FLUX_VLASOV_SMOOTH_E:
+        {
+            // generalised interp_Vlasov_2D2V (source/Interplation.cpp:4508-4580): component t = (int)prm[0];
+            // t < dim/2: v_t * f ; t >= dim/2: E_t(x) * f with the prescribed smooth field of the oracle harness
+            const int t = (int)prm[0], hd = dim / 2;
+            double c;
+            if (t < hd) c = x[hd + t];
+            else { c = 0.; for (int s = 0; s < hd; ++s) c += sin(2. * 3.1415926535897932384626433832795 * (x[s] + 0.125 * (t - hd + 1))); }
+            return c * u;
+        }
+    }
+    return 0.;
+}
+
+__global__ void __launch_bounds__(256) pointwise_kernel(const PointwiseArgs a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.n_points; p += stride)
+    {
+        const double u = a.up[p];
+        double x[8];
+        if (a.pts) { for (int t = 0; t < a.dim; ++t) x[t] = a.pts[p * a.dim + t]; }
+        for (int c = 0; c < a.n_flux; ++c) a.fp[(int64_t)c * a.n_points + p] = flux_eval(a.flux_id[c], a.params[c], u, x, a.dim);
+    }
+}
+
+cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st)
+{
+    const int64_t nb = (a.n_points + 255) / 256;
+    pointwise_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// interpolation point coordinates of all element points: pts[e][p][t] = pts1d[ord1d[e][t]*edge + p_t]
+__global__ void __launch_bounds__(256) point_coords_kernel(const double * __restrict__ pts1d, const int * __restrict__ ord1d,
+                                                           int64_t n_elem, int dim, int edge, int block, double * __restrict__ pts)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total = n_elem * block;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride)
+    {
+        const int64_t e = g / block; int r = (int)(g - e * block);
+        for (int t = dim - 1; t >= 0; --t)
+        {
+            const int p = r % edge; r /= edge;
+            pts[g * dim + t] = pts1d[ord1d[e * dim + t] * edge + p];
+        }
+    }
+}
+
+cudaError_t launch_point_coords(const double * pts1d, const int * ord1d, int64_t n_elem, int dim, int edge, double * pts, cudaStream_t st)
+{
+    int block = 1; for (int t = 0; t < dim; ++t) block *= edge;
+    const int64_t nb = (n_elem * block + 255) / 256;
+    point_coords_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(pts1d, ord1d, n_elem, dim, edge, block, pts);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// K4 explicit RK stage (source/ODESolver.cpp:209-301): u <- c0*u_tn + c1*(u_base + c2*dt*rhs)
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rk_stage_kernel(double c_tn, double c_u, double c_rhs, const double * __restrict__ u_tn,
+                                                       double * __restrict__ u, const double * __restrict__ rhs, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+    {
+        // same association as the reference expressions, e.g. 3/4*u_tn + 1/4*(u + dt*rhs)
+        double v = c_rhs * rhs[p];
+        if (c_u != 0.0) v = c_u * (u[p] + v);
+        u[p] = (c_tn == 1.0 ? u_tn[p] : c_tn * u_tn[p]) + v;
+    }
+}
+
+cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st)
+{
+    // u = c_tn*u_tn + [c_u != 0 ? c_u*(u + c_rhs*rhs) : c_rhs*rhs]
+    double c_tn = 1., c_u = 0., c_rhs = dt;
+    if (scheme == AMDG_RK_EULER) { if (stage != 0) return cudaErrorInvalidValue; }
+    else if (scheme == AMDG_RK_RK2SSP) { if (stage == 1) { c_tn = 0.5; c_u = 0.5; } else if (stage != 0) return cudaErrorInvalidValue; }
+    else if (scheme == AMDG_RK_RK2MID) { if (stage == 0) c_rhs = 0.5 * dt; else if (stage != 1) return cudaErrorInvalidValue; }
+    else if (scheme == AMDG_RK_RK3SSP)
+    {
+        if (stage == 1) { c_tn = 3. / 4.; c_u = 1. / 4.; }
+        else if (stage == 2) { c_tn = 1. / 3.; c_u = 2. / 3.; }
+        else if (stage != 0) return cudaErrorInvalidValue;
+    }
+    else return cudaErrorInvalidValue;
+    const int64_t nb = (n + 255) / 256;
+    rk_stage_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(c_tn, c_u, c_rhs, u_tn, u, rhs, n);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) axpby_kernel(int64_t n, double alpha, const double * __restrict__ x, double beta, double * __restrict__ y)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+        y[p] = (beta == 0.0) ? alpha * x[p] : alpha * x[p] + beta * y[p];
+}
+
+cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st)
+{
+    const int64_t nb = (n + 255) / 256;
+    axpby_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(n, alpha, x, beta, y);
+    return cudaGetLastError();
+}
+
+}  // namespace amdg

@@ -1,0 +1,87 @@
+// Device kernels of the fast sparse-grid transform path (FP64, sm_100a).
+//
+// K1 sweep1d  : FastMultiplyLU::transform_1D (reference source/FastMultiplyLU.cpp:436-512) plus the
+//               resize/zero/copy/accumulate passes around it (:666-738) folded into the epilogue.
+// K2 pointwise: LagrInterpolation::eval_fp_Lag (source/Interplation.cpp:256-295) and the Vlasov products.
+// K4 rk_stage : ExplicitRK::step_stage (source/ODESolver.cpp:209-301).
+// Hierarchisation (K3) is a K1 sweep with the stencil operator built by amdg_op_register_hier.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace amdg {
+
+struct NbrDev { int local; int pair; };
+
+// one sweep along one dimension, for a batch of `n_job` (src, dst) pairs that share operator, relation,
+// L/U part and the fibre tables but may differ in block shape (outer) -- see the shared-prefix schedule.
+struct SweepJob
+{
+    const double * src;
+    double * dst;
+    int outer;          // prod of block edges of dims < t
+    int accumulate;     // dst += result
+    double coef;
+};
+
+static const int MAX_JOBS = 32;
+
+struct SweepArgs
+{
+    // grid tables (dimension t, relation kind)
+    const int * slot_elem;      // [n]
+    const int * slot_fbase;     // [n] first slot of the slot's fibre
+    const int64_t * nbr_ptr;    // [n+1]
+    const int * nbr_split;      // [n]
+    const NbrDev * nbr;
+    const double * blocks;      // [n_pairs][KF][KT]
+    int64_t n_elem;
+    int inner;                  // prod of block edges of dims > t (same for every job)
+    int lu;                     // AMDG_LU_*
+    int n_comp;                 // components per job, consecutive n_elem*S apart
+    int n_job;
+    SweepJob job[MAX_JOBS];
+};
+
+// fibre-staged variant: work items = (fibre, column range)
+struct FibreItem { int fibre; int col0; int ncol; int pad; };
+
+struct FibreSweepArgs
+{
+    const int64_t * fibre_ptr;  // [n_fibre+1]
+    const int * slot_elem;
+    const int64_t * nbr_ptr;
+    const int * nbr_split;
+    const NbrDev * nbr;
+    const double * blocks;
+    const FibreItem * items;    // per job-independent work list for this (dim, column count)
+    int n_item;
+    int64_t n_elem;
+    int inner;
+    int lu;
+    int n_comp;
+    int n_job;
+    int smem_cols;              // padded column capacity of the staging buffer
+    SweepJob job[MAX_JOBS];
+};
+
+struct PointwiseArgs
+{
+    const double * up;      // [n_points]
+    double * fp;            // [n_flux][n_points]
+    const double * pts;     // [n_points][dim] or null
+    int64_t n_points;
+    int n_flux, dim;
+    int flux_id[8];
+    double params[8][4];
+};
+
+cudaError_t launch_sweep_gather(const SweepArgs & a, int kf, int kt, cudaStream_t st);
+cudaError_t launch_sweep_fibre(const FibreSweepArgs & a, int kf, int kt, int max_fibre_len, cudaStream_t st);
+cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
+cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);
+cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st);
+cudaError_t launch_point_coords(const double * pts1d, const int * ord1d, int64_t n_elem, int dim, int edge, double * pts, cudaStream_t st);
+bool sweep_shape_supported(int kf, int kt);
+
+}  // namespace amdg

@@ -1,0 +1,143 @@
+/* amdg.h -- C ABI of the B200-native fast sparse-grid transform path of AdaM-DG.
+ *
+ * The reference (JuntaoHuang/adaptive-multiresolution-DG) has no FFI layer: its boundary is the C++ class
+ * surface FastMultiplyLU / FastInterpolation / FastInitial / FastRHS (include/FastMultiplyLU.h:9-704),
+ * LagrInterpolation / HermInterpolation (include/Interpolation.h:36-392) and ExplicitRK
+ * (include/ODESolver.h:76-248).  Every entry point below names the reference function it replaces; the C++
+ * mirror of those classes that calls this ABI lives in adaptive-multiresolution-dg_b200/host/amdg_host.hpp and
+ * the reference-side binding is shown in INTEGRATION.md.
+ *
+ * Conventions (identical to the reference):
+ *   - an element is (level[d], suppt[d]); element rows are in the caller's order (the glue passes them in
+ *     DGSolution::dg iteration order, include/DGSolution.h:219);
+ *   - a coefficient array is `double[n_comp][n_elem][edge^dim]`, each element block row-major with the last
+ *     dimension fastest (include/VecMultiD.h:114-152); during a chain, swept dims have the target edge;
+ *   - a 1D operator is dense row-major `mat[from_basis][to_basis]`, basis index = ord1d*(pmax+1)+p
+ *     (source/FastMultiplyLU.cpp:479,497-499);
+ *   - every call returns 0 on success or a negative AMDG_E* code; nothing exits the process
+ *     (the reference prints and calls exit(1), e.g. source/FastMultiplyLU.cpp:268).
+ * All `double*` / `const double*` arguments named dev_* are DEVICE pointers; host_* are host pointers.
+ * There is no CPU fallback: compute calls on a context created without a device fail with AMDG_ENODEVICE.
+ */
+#ifndef AMDG_H
+#define AMDG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct amdg_ctx amdg_ctx;
+
+enum { AMDG_OK = 0, AMDG_EINVAL = -1, AMDG_ENODEVICE = -2, AMDG_ECUDA = -3, AMDG_ENOMEM = -4, AMDG_ESTATE = -5 };
+
+/* relation of a sweep: Element::ptr_vol_alpt / ptr_flx_alpt (include/Element.h:152-155) */
+enum { AMDG_REL_VOL = 0, AMDG_REL_FLX = 1 };
+/* part of the 1D operator: "L" = strictly finer source, "U" = same-or-coarser source, "full"
+ * (source/FastMultiplyLU.cpp:490-491) */
+enum { AMDG_LU_L = 0, AMDG_LU_U = 1, AMDG_LU_FULL = 2 };
+/* schedule of amdg_apply_tensor: the reference's literal 2^(d-1) chains (source/FastMultiplyLU.cpp:614-664) or the
+ * same sum with shared prefixes/suffixes (fewer sweeps, identical up to summation order) */
+enum { AMDG_SCHED_LITERAL = 0, AMDG_SCHED_SHARED = 1 };
+/* point-wise flux kinds: FluxFunction namespace (include/Interpolation.h:396-437) and the Vlasov products
+ * (source/Interplation.cpp:4451-4497, 4523-4573) */
+enum { AMDG_FLUX_LINEAR = 0, AMDG_FLUX_BURGERS = 1, AMDG_FLUX_SIN = 2, AMDG_FLUX_COS = 3,
+       AMDG_FLUX_BUCKLEY_X = 4, AMDG_FLUX_BUCKLEY_Y = 5, AMDG_FLUX_VLASOV_SMOOTH_E = 6 };
+/* explicit Runge-Kutta schemes: ForwardEuler, RK2SSP, RK2Midpoint, RK3SSP (source/ODESolver.cpp:203-301) */
+enum { AMDG_RK_EULER = 0, AMDG_RK_RK2SSP = 1, AMDG_RK_RK2MID = 2, AMDG_RK_RK3SSP = 3 };
+
+const char *amdg_version(void);
+const char *amdg_last_error(void);
+
+/* ---- context: snapshot of the reference's statics Element::DIM, PMAX_alpt, PMAX_intp (include/Element.h:21-24),
+ * DGSolution NMAX.  device = CUDA ordinal, or -1 for a host-only context (table building only). ---- */
+int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device, amdg_ctx **out);
+int amdg_ctx_destroy(amdg_ctx *ctx);
+int amdg_ctx_set_stream(amdg_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: a stream owned by ctx */
+int amdg_ctx_sync(amdg_ctx *ctx);
+int amdg_ctx_set_schedule(amdg_ctx *ctx, int sched);
+int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto, 1 = gather kernel, 2 = fibre-staged kernel */
+int64_t amdg_ctx_launch_count(amdg_ctx *ctx);                 /* kernels launched so far by this context */
+
+/* ---- Hash (source/Hash.cpp:55-114) and 1D element order (source/Element.cpp:388-391), bit exact ---- */
+int amdg_hash_key(int dim, const int *level, const int *suppt);
+int amdg_order_elem(int level, int suppt);
+/* Initial grid of DGSolution (source/DGSolution.cpp:10-57): fills level/suppt ([n][dim], construction order);
+ * call with level == NULL to get the count. */
+int64_t amdg_sparse_grid(int dim, int level_init, int sparse, int *level, int *suppt);
+
+/* ---- grid: replaces DGSolution::find_ptr_vol_alpt / find_ptr_flx_alpt (source/DGSolution.cpp:675-728) and
+ * the per-adapt updates (source/DGAdapt.cpp:1073-1248).  Call after construction / refine / coarsen. ---- */
+int amdg_grid_set(amdg_ctx *ctx, int64_t n_elem, const int *level, const int *suppt);
+int64_t amdg_grid_size(amdg_ctx *ctx);
+/* table export for parity: per element hash_key[n] and ord1d[n][dim] */
+int amdg_grid_keys(amdg_ctx *ctx, int *hash_key, int *ord1d);
+/* relation CSR along dim t: ptr[n+1], idx[ptr[n]] (element rows, ascending).  idx == NULL -> returns nnz. */
+int64_t amdg_grid_relation(amdg_ctx *ctx, int t, int rel, int64_t *ptr, int *idx);
+/* fibres along dim t: ptr[n_fibre+1], elems[n] sorted by ord1d inside a fibre.  elems == NULL -> returns n_fibre. */
+int64_t amdg_grid_fibres(amdg_ctx *ctx, int t, int64_t *ptr, int *elems);
+
+/* ---- operators: the dense OperatorMatrix1D tables (include/OperatorMatrix1D.h:22-121) and the transposed
+ * point tables of FastLagrIntp / FastHermIntp (source/FastMultiplyLU.cpp:1316-1360) are compacted into their
+ * (source ord1d, target ord1d) blocks.  edge_from/edge_to = pmax+1 of the row/column basis. ---- */
+int amdg_op_register(amdg_ctx *ctx, const double *host_dense, int rows, int cols, int edge_from, int edge_to, int *op_out);
+/* hierarchisation stencils pwts (include/Interpolation.h:5-11, source/Interplation.cpp:775-887, 3166-3315):
+ * anc[T-1][P1][2] = (ancestor ord1d, point index), wt[T-1][P1][P1] = wt[p0][ic], rows = 1D elements ord1d 1..T-1 */
+int amdg_op_register_hier(amdg_ctx *ctx, const int *anc, const double *wt, int p1, int *op_out);
+/* op = alpha*op_a + beta*op_b (e.g. ulft_vjp + urgt_vjp, source/FastMultiplyLU.cpp:1165) */
+int amdg_op_combine(amdg_ctx *ctx, int op_a, double alpha, int op_b, double beta, int *op_out);
+
+/* ---- K1: one 1D sweep, FastMultiplyLU::transform_1D (source/FastMultiplyLU.cpp:436-512).
+ * sizes_from[dim] = block edges of src; dst has the same edges except edge_to(op) in dim t.
+ * dst = coef * sweep(src) (+ dst if accumulate).  n_comp components, each n_elem*block apart. ---- */
+int amdg_sweep1d(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from,
+                 const double *dev_src, double *dev_dst, int n_comp, double coef, int accumulate);
+
+/* ---- sum over all orderings of the chain of sweeps: FastRHS::transform_fucoe_to_rhs (source/FastMultiplyLU.cpp:4-16),
+ * FastInterpolation::transform_ucoealpt_to_upintp (:740-819), FastInitial::transform_ucoeintp_to_ucoealpt (:1418-1445).
+ * ops[dim], rels[dim]; src blocks edge_from^dim, dst blocks edge_to^dim; dst = coef*(...) (+ dst if accumulate). ---- */
+int amdg_apply_tensor(amdg_ctx *ctx, const int *ops, const int *rels, const double *dev_src, double *dev_dst,
+                      int n_comp, double coef, int accumulate);
+
+/* ---- hierarchisation: LagrInterpolation::eval_fp_to_coe_D_Lag / eval_up_to_coe_D_Lag
+ * (source/Interplation.cpp:1222-1430, 891-1048) and the Hermite twins (:3651-3849, 3319-3479); in place allowed ---- */
+int amdg_hierarchize(amdg_ctx *ctx, int hier_op, const double *dev_src, double *dev_dst, int n_comp);
+
+/* ---- K2: point-wise flux, LagrInterpolation::eval_fp_Lag (source/Interplation.cpp:256-295):
+ * dev_fp[c] = f_{flux_id[c]}(dev_up) for c < n_flux, params[c][4].  dev_pts (optional) = coordinates
+ * [n_elem][edge^dim][dim] of the interpolation points for the Vlasov products. ---- */
+int amdg_pointwise(amdg_ctx *ctx, int n_flux, const int *flux_id, const double *params, const double *dev_up,
+                   double *dev_fp, const double *dev_pts);
+/* interpolation point coordinates of every element point from the 1D table pts1d[T*(pmax_intp+1)]
+ * (LagrBasis::intep_pt, source/LagrBasis.cpp:19-28) */
+int amdg_point_coords(amdg_ctx *ctx, const double *host_pts1d, double *dev_pts);
+
+/* ---- K4: explicit RK stage, ExplicitRK::step_stage (source/ODESolver.cpp:209-301): updates dev_u in place ---- */
+int amdg_rk_stage(amdg_ctx *ctx, int scheme, int stage, double dt, const double *dev_u_tn, double *dev_u,
+                  const double *dev_rhs, int64_t n);
+/* y = alpha*x + beta*y */
+int amdg_axpby(amdg_ctx *ctx, int64_t n, double alpha, const double *dev_x, double beta, double *dev_y);
+
+/* ---- host-buffer entry points (what the reference-facing classes call; H2D/D2H inside) ---- */
+int amdg_host_apply_tensor(amdg_ctx *ctx, const int *ops, const int *rels, const double *host_src, double *host_dst,
+                           int n_comp, double coef, int accumulate);
+int amdg_host_sweep1d(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from,
+                      const double *host_src, double *host_dst, int n_comp, double coef, int accumulate);
+int amdg_host_hierarchize(amdg_ctx *ctx, int hier_op, const double *host_src, double *host_dst, int n_comp);
+/* cfg2 round trip: Alpert -> point values -> hierarchical interpolation coefficients -> Alpert
+ * (FastLagrIntp::eval_up_Lagr, eval_up_to_coe_D_Lag, FastLagrInit::eval_ucoe_Alpt_Lagr) */
+int amdg_host_roundtrip(amdg_ctx *ctx, int op_alpt_to_pt, int hier_op, int op_intp_to_alpt,
+                        const double *host_ucoe_in, double *host_ucoe_out, int n_comp);
+
+/* ---- device memory helpers (so callers without a CUDA runtime binding can stage data) ---- */
+int amdg_dev_alloc(amdg_ctx *ctx, int64_t n_doubles, double **dev_out);
+int amdg_dev_free(amdg_ctx *ctx, double *dev);
+int amdg_dev_upload(amdg_ctx *ctx, double *dev_dst, const double *host_src, int64_t n_doubles);
+int amdg_dev_download(amdg_ctx *ctx, double *host_dst, const double *dev_src, int64_t n_doubles);
+int amdg_dev_zero(amdg_ctx *ctx, double *dev, int64_t n_doubles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMDG_H */

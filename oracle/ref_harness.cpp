@@ -344,25 +344,26 @@ int main(int argc, char ** argv)
 
     // ---- flux functions ------------------------------------------------------------------------------------
     const std::vector<double> lin_coef = { 1.0, 0.7, -0.5, 0.3, 1.3, -0.9 };
+    const std::string fname = (a.flux == "burgers1") ? std::string("burgers") : a.flux;
     auto flux = [&](std::vector<double> u, int i, int d) -> double
     {
-        if (a.flux == "burgers") return u[i] * u[i] / 2.;
-        if (a.flux == "linear") return lin_coef[d] * u[i];
-        if (a.flux == "kpp") return d == 0 ? std::sin(u[i]) : std::cos(u[i]);
+        if (fname == "burgers") return u[i] * u[i] / 2.;
+        if (fname == "linear") return lin_coef[d] * u[i];
+        if (fname == "kpp") return d == 0 ? std::sin(u[i]) : std::cos(u[i]);
         return u[i];
     };
     auto flux_d1 = [&](std::vector<double> u, int i, int d, int i1) -> double
     {
-        if (a.flux == "burgers") return u[i];
-        if (a.flux == "linear") return lin_coef[d];
-        if (a.flux == "kpp") return d == 0 ? std::cos(u[i]) : -std::sin(u[i]);
+        if (fname == "burgers") return u[i];
+        if (fname == "linear") return lin_coef[d];
+        if (fname == "kpp") return d == 0 ? std::cos(u[i]) : -std::sin(u[i]);
         return 1.;
     };
     auto flux_d2 = [&](std::vector<double> u, int i, int d, int i1, int i2) -> double
     {
-        if (a.flux == "burgers") return 1.;
-        if (a.flux == "linear") return 0.;
-        if (a.flux == "kpp") return d == 0 ? -std::sin(u[i]) : -std::cos(u[i]);
+        if (fname == "burgers") return 1.;
+        if (fname == "linear") return 0.;
+        if (fname == "kpp") return d == 0 ? -std::sin(u[i]) : -std::cos(u[i]);
         return 0.;
     };
     std::vector<std::vector<bool>> is_intp(a.vecnum, std::vector<bool>(DIM, true));

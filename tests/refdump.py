@@ -3,6 +3,7 @@
 Record layout: [u32 name_len][name][u8 dtype 'd'|'i'|'q'][u32 ndim][i64 dims...][raw little-endian data],
 after an 8-byte magic "AMDGDUMP".  Per-element arrays are sorted by ascending Hash::hash_key.
 """
+import lzma
 import struct
 import numpy as np
 
@@ -11,7 +12,8 @@ _DT = {b"d": np.float64, b"i": np.int32, b"q": np.int64}
 
 def load(path):
     out = {}
-    with open(path, "rb") as f:
+    opener = lzma.open if path.endswith(".xz") else open
+    with opener(path, "rb") as f:
         buf = f.read()
     assert buf[:8] == b"AMDGDUMP", "not an AMDG dump"
     pos = 8

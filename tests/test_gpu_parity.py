@@ -1,0 +1,192 @@
+"""Parity of the CUDA path (called through the C ABI) with the compiled reference's outputs (tests/golden/).
+Tolerance 1e-12 relative L2 per phase / RK stage, 1e-10 after a full run (BASELINE.json north_star); index work
+is covered bit-exactly by tests/test_capi_tables.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from pipeline import DevCase, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+FLUX = {"cfg4_burgers_lagr_d2_k2_n4": ("burgers", 1), "kpp_lagr_d2_k1_n4": ("kpp", None), "full_d2_k2_n3": ("linear", None),
+        "line_d1_k2_n5": ("burgers", None), "cfg1_adv_d2_k2_n4": ("burgers", None)}
+LIN = [1.0, 0.7, -0.5, 0.3, 1.3, -0.9]
+
+
+def flux_ids(A, name, dim):
+    kind, nfl = FLUX[name]
+    n = dim if nfl is None else nfl
+    if kind == "burgers":
+        return [A.FLUX_BURGERS] * n, None
+    if kind == "linear":
+        return [A.FLUX_LINEAR] * n, [[LIN[t], 0, 0, 0] for t in range(n)]
+    if kind == "kpp":
+        return [A.FLUX_SIN, A.FLUX_COS][:n], None
+
+
+@pytest.mark.parametrize("sched", [0, 1])
+@pytest.mark.parametrize("name", [n for n in golden_names() if "rt.up_intp" in load_golden(n)])
+def test_roundtrip(name, sched):
+    """cfg2: FastLagrIntp::eval_up_Lagr -> eval_up_to_coe_D_Lag -> FastLagrInit::eval_ucoe_Alpt_Lagr (and Hermite twins)"""
+    d = load_golden(name)
+    c = DevCase(d, schedule=sched)
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    up = c.eval_up(u)
+    assert rel(c.to_host(up), d["rt.up_intp"][:, 0, :]) < TOL
+    uc = c.hier(up)
+    assert rel(c.to_host(uc), d["rt.ucoe_intp"][:, 0, :]) < TOL
+    ua = c.to_alpt(uc)
+    assert rel(c.to_host(ua), d["rt.ucoe_alpt"][:, 0, :]) < TOL
+    # the host-buffer entry point does the same in one call
+    out = c.ctx.host_roundtrip(c.op_pt, c.op_hier, c.op_uv, d["ucoe_alpt.in"][:, 0, :][c.perm])
+    assert rel(out.reshape(c.ne, -1), d["rt.ucoe_alpt"][:, 0, :][c.perm]) < TOL
+    # in-place hierarchisation
+    c.ctx.hierarchize(c.op_hier, up, up)
+    assert rel(c.to_host(up), d["rt.ucoe_intp"][:, 0, :]) < TOL
+    c.close()
+
+
+def test_derivative_transform():
+    """FastLagrIntp::eval_der_up_Lagr(d0): derivative table in one dimension"""
+    d = load_golden("cfg2_rt_d4_k3_n3")
+    c = DevCase(d)
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    for d0 in range(c.dim):
+        ops = [c.op_pt_d1 if s == d0 else c.op_pt for s in range(c.dim)]
+        up = c.eval_up(u, per_dim_ops=ops)
+        assert rel(c.to_host(up), d["der%d.up_intp" % d0][:, 0, :]) < TOL
+    c.close()
+
+
+@pytest.mark.parametrize("sched", [0, 1])
+@pytest.mark.parametrize("name", sorted(FLUX))
+def test_nonlinear_rhs_lagrange(name, sched):
+    """interp -> point-wise flux -> hierarchise -> rhs_vol -> rhs_flx -> penalty"""
+    d = load_golden(name)
+    c = DevCase(d, schedule=sched)
+    A = c.amdg
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    up = c.eval_up(u)
+    assert rel(c.to_host(up), d["up_intp"][:, 0, :]) < TOL
+    ids, prm = flux_ids(A, name, c.dim)
+    fp = torch.zeros(c.dim, c.ne, c.b ** c.dim, dtype=torch.float64, device="cuda")
+    c.ctx.pointwise(ids, prm, up, fp)
+    fuc = torch.zeros_like(fp)
+    c.ctx.hierarchize(c.op_hier, fp, fuc, n_comp=len(ids))
+    for t in range(len(ids)):
+        assert rel(c.to_host(fp[t]), d["fp_intp"][:, 0, t, :]) < 1e-14
+        assert rel(c.to_host(fuc[t]), d["fucoe_intp"][:, 0, t, :]) < TOL
+    rhs = c.zeros(c.a)
+    vol = c.rhs_vol_flx([fuc[t] for t in range(c.dim)], rhs)
+    assert rel(c.to_host(vol), d["rhs_vol"][:, 0, :]) < TOL
+    assert rel(c.to_host(rhs), d["rhs_vol_flx"][:, 0, :]) < TOL
+    c.penalty(u, rhs, 1.2)
+    assert rel(c.to_host(rhs), d["rhs_all"][:, 0, :]) < TOL
+    c.close()
+
+
+def test_rk3_stages_full_step():
+    """three RK3SSP stages of the nonlinear Burgers right-hand side (ExplicitRK::step_stage)"""
+    name = "cfg1_adv_d2_k2_n4"
+    d = load_golden(name)
+    c = DevCase(d)
+    A = c.amdg
+    dt = 0.002
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    u_tn = u.clone()
+    fp = torch.zeros(c.dim, c.ne, c.b ** c.dim, dtype=torch.float64, device="cuda")
+    fuc = torch.zeros_like(fp)
+    for stage in range(3):
+        up = c.eval_up(u)
+        c.ctx.pointwise([A.FLUX_BURGERS] * c.dim, None, up, fp)
+        c.ctx.hierarchize(c.op_hier, fp, fuc, n_comp=c.dim)
+        rhs = c.zeros(c.a)
+        c.rhs_vol_flx([fuc[t] for t in range(c.dim)], rhs)
+        c.penalty(u, rhs, 1.2)
+        c.ctx.rk_stage(A.RK_RK3SSP, stage, dt, u_tn, u, rhs)
+        assert rel(c.to_host(u), d["stage%d.ucoe_alpt" % stage][:, 0, :]) < TOL
+    assert rel(c.to_host(u), d["final.ucoe_alpt"][:, 0, :]) < 1e-10
+    c.close()
+
+
+def test_linear_advection_and_wave_sweeps():
+    """cfg1 / cfg3: the assembled operator of the shipped examples as single 1D sweeps"""
+    d = load_golden("cfg1_adv_d2_k2_n4")
+    c = DevCase(d)
+    A = c.amdg
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    rhs = c.zeros(c.a)
+    for t in range(c.dim):
+        c.ctx.sweep1d(c.alpt["u_vx"], A.REL_VOL, A.LU_FULL, t, [c.a] * c.dim, u, rhs, coef=1.0, accumulate=True)
+        c.ctx.sweep1d(c.alpt["ulft_vjp"], A.REL_FLX, A.LU_FULL, t, [c.a] * c.dim, u, rhs, coef=1.0, accumulate=True)
+    assert rel(c.to_host(rhs), d["adv.rhs_sweep"][:, 0, :]) < TOL
+    assert rel(c.to_host(rhs), d["adv.rhs_spmv"][:, 0, :]) < TOL
+    # one RK3SSP::step_rk with the operator applied as sweeps
+    def L(x):
+        out = c.zeros(c.a)
+        for t in range(c.dim):
+            c.ctx.sweep1d(c.alpt["u_vx"], A.REL_VOL, A.LU_FULL, t, [c.a] * c.dim, x, out, accumulate=True)
+            c.ctx.sweep1d(c.alpt["ulft_vjp"], A.REL_FLX, A.LU_FULL, t, [c.a] * c.dim, x, out, accumulate=True)
+        return out
+    dt = 0.002
+    u_tn = u.clone()
+    for stage in range(3):
+        c.ctx.rk_stage(A.RK_RK3SSP, stage, dt, u_tn, u, L(u))
+    assert rel(c.to_host(u), d["adv.ucoe_alpt"][:, 0, :]) < 1e-10
+    c.close()
+
+    d = load_golden("cfg3_wave_d3_k2_n3")
+    c = DevCase(d)
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    sigma_dx = 20.0 * 2 ** c.nmax
+    terms = (("ux_vx", A.REL_VOL, -1.0), ("uxave_vjp", A.REL_FLX, -1.0), ("ujp_vxave", A.REL_FLX, -1.0), ("ujp_vjp", A.REL_FLX, -sigma_dx))
+    rhs = c.zeros(c.a)
+    for t in range(c.dim):
+        for nm, r, cf in terms:
+            c.ctx.sweep1d(c.alpt[nm], r, A.LU_FULL, t, [c.a] * c.dim, u, rhs, coef=cf, accumulate=True)
+    assert rel(c.to_host(rhs), d["wave.rhs_sweep"][:, 0, :]) < TOL
+    assert rel(c.to_host(rhs), d["wave.rhs_spmv"][:, 0, :]) < TOL
+    c.close()
+
+
+def test_permuted_element_order():
+    """results do not depend on the caller's element order"""
+    d = load_golden("cfg3_wave_d3_k2_n3")
+    perm = np.random.default_rng(7).permutation(d["level"].shape[0])
+    c = DevCase(d, perm=perm)
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    up = c.eval_up(u)
+    assert rel(c.to_host(up), d["rt.up_intp"][:, 0, :]) < TOL
+    c.close()
+
+
+def test_linearity_and_schedule_equivalence_large():
+    """size-independent properties on a larger grid than the fixtures: the literal and the shared schedule agree,
+    and the transform is linear"""
+    import importlib
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    d = load_golden("cfg2_rt_d4_k3_n3")
+    dim, nmax = 4, 3
+    lev, sup = A.sparse_grid(dim, nmax)
+    outs = []
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(lev.shape[0], 4 ** dim, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.rand(lev.shape[0], 4 ** dim, dtype=torch.float64, device="cuda", generator=g)
+    for sched in (0, 1):
+        ctx = A.Context(dim, nmax, 3, 3, device=0)
+        ctx.set_schedule(sched)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.grid_set(lev, sup)
+        op = ctx.op_register(d["Lag_pt_Alpt_1D"].T.copy(), 4, 4)
+        fx, fy, fxy = torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x)
+        ctx.apply_tensor([op] * dim, [0] * dim, x, fx)
+        ctx.apply_tensor([op] * dim, [0] * dim, y, fy)
+        ctx.apply_tensor([op] * dim, [0] * dim, (2.0 * x - 3.0 * y).contiguous(), fxy)
+        ctx.sync()
+        assert rel((2.0 * fx - 3.0 * fy).cpu().numpy(), fxy.cpu().numpy()) < TOL
+        outs.append(fx.cpu().numpy())
+        ctx.close()
+    assert rel(outs[0], outs[1]) < TOL

@@ -1,0 +1,182 @@
+"""The numpy restatement (oracle/amdg_oracle.py) against the outputs of the compiled reference (tests/golden/).
+CPU only.  Tolerance: the reference's own summation order is address dependent, so floating
+point phases are compared at 1e-12 relative L2 (north_star's per-stage bound); index tables are exact."""
+import numpy as np
+import pytest
+
+import amdg_oracle as O
+import refdump
+from conftest import golden_names, load_golden
+
+TOL = 1e-12
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+class Case:
+    def __init__(self, name):
+        d = self.d = load_golden(name)
+        (self.dim, self.nmax, self.n0, self.sparse, self.pa, self.pl, self.ph, self.vecnum, self.herm, self.ne) = [int(x) for x in d["config"]]
+        self.a = self.pa + 1
+        self.b = (self.ph if self.herm else self.pl) + 1
+        self.lev, self.sup, self.ord1d = d["level"], d["suppt"], d["order_elem"]
+        self.rels = None
+
+    def relations(self):
+        if self.rels is None:
+            self.rels = {k: [O.relations(self.lev, self.sup, t, k) for t in range(self.dim)] for k in ("vol", "flx")}
+        return self.rels
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_grid_tables(name):
+    c = Case(name)
+    lev, sup = O.sparse_grid(c.dim, c.n0, c.sparse == 1)
+    keys = np.array([O.hash_key(l, s) for l, s in zip(lev, sup)])
+    o = np.argsort(keys, kind="stable")
+    assert len(set(keys.tolist())) == len(keys)
+    assert (keys[o] == c.d["hash_key"]).all()
+    assert (lev[o] == c.lev).all() and (sup[o] == c.sup).all()
+    ord1d = np.array([[O.order_elem(int(n), int(j)) for n, j in zip(l, s)] for l, s in zip(c.lev, c.sup)])
+    assert (ord1d == c.ord1d).all()
+    rels = c.relations()
+    for k in ("vol", "flx"):
+        for t in range(c.dim):
+            ptr, idx = c.d["%s_d%d_ptr" % (k, t)], c.d["%s_d%d_idx" % (k, t)]
+            for e in range(c.ne):
+                assert rels[k][t][e] == list(idx[ptr[e]:ptr[e + 1]])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_input_field(name):
+    c = Case(name)
+    f = refdump.field(20240901, c.d["hash_key"], c.lev, c.vecnum, c.a ** c.dim)
+    assert np.array_equal(f, c.d["ucoe_alpt.in"])
+
+
+def _tables(c):
+    d = c.d
+    if c.herm:
+        return d["Her_pt_Alpt_1D"].T.copy(), d["herm.u_v"], d["herm.u_vx"], d["herm.ulft_vjp"] + d["herm.urgt_vjp"], d["herm.pw_anc"], d["herm.pw_wt"]
+    return d["Lag_pt_Alpt_1D"].T.copy(), d["lagr.u_v"], d["lagr.u_vx"], d["lagr.ulft_vjp"] + d["lagr.urgt_vjp"], d["lagr.pw_anc"], d["lagr.pw_wt"]
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "rt." + "up_intp" in load_golden(n)])
+def test_roundtrip(name):
+    c = Case(name)
+    if c.ne * c.b ** c.dim > 3e5:
+        pytest.skip("numpy restatement too slow for this fixture; covered by the C-ABI parity tests")
+    pt, u_v, _, _, anc, wt = _tables(c)
+    rels = c.relations()
+    u = c.d["ucoe_alpt.in"][:, 0, :]
+    up = O.apply_tensor(u, c.a, c.b, [pt] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d)
+    assert rel(up, c.d["rt.up_intp"][:, 0, :]) < TOL
+    uc = O.hierarchize(c.d["rt.up_intp"][:, 0, :], c.b, c.lev, c.sup, c.ord1d, anc, wt)
+    assert rel(uc, c.d["rt.ucoe_intp"][:, 0, :]) < TOL
+    ua = O.apply_tensor(c.d["rt.ucoe_intp"][:, 0, :], c.b, c.a, [u_v] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d)
+    assert rel(ua, c.d["rt.ucoe_alpt"][:, 0, :]) < TOL
+
+
+@pytest.mark.parametrize("name", ["cfg4_burgers_lagr_d2_k2_n4", "kpp_lagr_d2_k1_n4", "full_d2_k2_n3", "line_d1_k2_n5"])
+def test_nonlinear_rhs_lagrange(name):
+    c = Case(name)
+    d = c.d
+    pt, u_v, u_vx, uave, anc, wt = _tables(c)
+    rels = c.relations()
+    flux = {"cfg4_burgers_lagr_d2_k2_n4": "burgers", "kpp_lagr_d2_k1_n4": "kpp", "full_d2_k2_n3": "linear", "line_d1_k2_n5": "burgers"}[name]
+    n_flux = 1 if name.startswith("cfg4") else c.dim
+    u = d["ucoe_alpt.in"][:, 0, :]
+    up = O.apply_tensor(u, c.a, c.b, [pt] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d)
+    assert rel(up, d["up_intp"][:, 0, :]) < TOL
+    rhs = np.zeros_like(u)
+    fuc = []
+    for t in range(n_flux):
+        fp = O.flux_pointwise(d["up_intp"][:, 0, :], flux, t)
+        assert rel(fp, d["fp_intp"][:, 0, t, :]) < 1e-15
+        fc = O.hierarchize(fp, c.b, c.lev, c.sup, c.ord1d, anc, wt)
+        assert rel(fc, d["fucoe_intp"][:, 0, t, :]) < TOL
+        fuc.append(fc)
+    # HyperbolicLagrRHS::rhs_vol_scalar reads fucoe_intp[0][t] for every t (also the components the example did
+    # not interpolate, which stay zero): take them from the dump
+    for t in range(c.dim):
+        src = d["fucoe_intp"][:, 0, t, :]
+        mats = [u_vx if s == t else u_v for s in range(c.dim)]
+        rhs += O.apply_tensor(src, c.b, c.a, mats, ["vol"] * c.dim, rels, c.lev, c.ord1d)
+    assert rel(rhs, d["rhs_vol"][:, 0, :]) < TOL
+    for t in range(c.dim):
+        src = d["fucoe_intp"][:, 0, t, :]
+        mats = [uave if s == t else u_v for s in range(c.dim)]
+        kinds = ["flx" if s == t else "vol" for s in range(c.dim)]
+        rhs += O.apply_tensor(src, c.b, c.a, mats, kinds, rels, c.lev, c.ord1d, 0.5)
+    assert rel(rhs, d["rhs_vol_flx"][:, 0, :]) < TOL
+    if c.dim == 1:
+        # reference quirk: for DIM == 1 the single-matrix form copies twice and never sweeps
+        # (source/FastMultiplyLU.cpp:206-212 with is_first_step[0] tested first at :249), so the penalty is a no-op
+        assert rel(rhs, d["rhs_all"][:, 0, :]) < TOL
+        return
+    for t in range(c.dim):
+        rhs += O.single_sweep(u, c.a, d["alpt.ujp_vjp"], "flx", rels, c.lev, c.ord1d, t, -1.2 / 2)
+    assert rel(rhs, d["rhs_all"][:, 0, :]) < TOL
+
+
+def test_linear_sweeps_equal_assembled_operator():
+    """cfg1 / cfg3: the shipped assembled SpMV equals the sum of single 1D sweeps"""
+    c = Case("cfg1_adv_d2_k2_n4")
+    d = c.d
+    rels = c.relations()
+    u = d["ucoe_alpt.in"][:, 0, :]
+    rhs = np.zeros_like(u)
+    for t in range(c.dim):
+        rhs += O.single_sweep(u, c.a, d["alpt.u_vx"], "vol", rels, c.lev, c.ord1d, t, 1.0)
+        rhs += O.single_sweep(u, c.a, d["alpt.ulft_vjp"], "flx", rels, c.lev, c.ord1d, t, 1.0)
+    assert rel(rhs, d["adv.rhs_sweep"][:, 0, :]) < TOL
+    assert rel(rhs, d["adv.rhs_spmv"][:, 0, :]) < TOL
+    c = Case("cfg3_wave_d3_k2_n3")
+    d = c.d
+    rels = c.relations()
+    u = d["ucoe_alpt.in"][:, 0, :]
+    sigma_dx = 20.0 * 2 ** c.nmax
+    rhs = np.zeros_like(u)
+    for t in range(c.dim):
+        for nm, kind, cf in (("alpt.ux_vx", "vol", -1.0), ("alpt.uxave_vjp", "flx", -1.0), ("alpt.ujp_vxave", "flx", -1.0), ("alpt.ujp_vjp", "flx", -sigma_dx)):
+            rhs += O.single_sweep(u, c.a, d[nm], kind, rels, c.lev, c.ord1d, t, cf)
+    assert rel(rhs, d["wave.rhs_sweep"][:, 0, :]) < TOL
+    assert rel(rhs, d["wave.rhs_spmv"][:, 0, :]) < TOL
+
+
+def test_rk3ssp_and_schedule():
+    orders, lus = O.transform_order(3)
+    assert orders == [[0, 1, 2], [0, 2, 1], [1, 2, 0], [2, 0, 1]]
+    assert lus == [["L", "L", "full"], ["L", "full", "U"], ["L", "full", "U"], ["full", "U", "U"]]
+    u_tn, u, r = np.array([1.0, 2.0]), np.array([0.5, -1.0]), np.array([3.0, 4.0])
+    assert np.allclose(O.rk3ssp_stage(1, u_tn, u, r, 0.1), 0.75 * u_tn + 0.25 * (u + 0.1 * r))
+
+
+def test_hierarchisation_stencil_restated():
+    """set_pts_wts_1d_ada_Lag restated from point coordinates and level-0 basis values (Lagrange)"""
+    c = Case("cfg4_burgers_lagr_d2_k2_n4")
+    d = c.d
+    P1 = c.b
+    pts = d["lagr.intep_pt"]
+    msh0, msh1 = d["LagrBasis.intp_msh0"], d["LagrBasis.intp_msh1"]
+    # level-0 Lagrange basis r at x: the interpolating polynomial on the (sorted) level-0 nodes
+    nodes = np.sort(msh0)
+    def phi0(r, x):
+        v = 1.0
+        for s in range(P1):
+            if s != r:
+                v *= (x - nodes[s]) / (nodes[r] - nodes[s])
+        return v
+    # AllBasis order of level-0 functions follows msh0 as stored; rank -> stored index
+    stored = [int(np.argmin(np.abs(msh0 - nodes[r]))) for r in range(P1)]
+    lvl0 = [[phi0(stored.index(r) if False else list(nodes).index(msh0[r]), msh1[p0]) for p0 in range(P1)] for r in range(P1)]
+    pts_of = lambda k, i, q: pts[O.order_elem(k, i) * P1 + q]
+    row = 0
+    for n in range(1, c.nmax + 1):
+        for j in range(1, max(2, 1 << n), 2):
+            anc, wt = O.lagr_pw1d(n, j, pts_of, lvl0, P1)
+            assert [list(x) for x in anc] == d["lagr.pw_anc"][row].tolist()
+            assert np.allclose(wt, d["lagr.pw_wt"][row], atol=1e-13)
+            row += 1
