@@ -50,6 +50,9 @@ SYMBOLS = {
     "amdg_grid_relation": (_i64, [_p, _i, _i, _lp, _ip]),
     "amdg_grid_fibres": (_i64, [_p, _i, _lp, _ip]),
     "amdg_op_register": (_i, [_p, _dp, _i, _i, _i, _i, _ip]),
+    "amdg_pairs": (_i64, [_p, _ip, _ip, _ip]),
+    "amdg_op_register_compact": (_i, [_p, _dp, _i64, _i, _i, _i, _ip]),
+    "amdg_op_blocks": (_i, [_p, _i, _dp]),
     "amdg_op_register_hier": (_i, [_p, _ip, _dp, _i, _ip]),
     "amdg_op_combine": (_i, [_p, _i, _d, _i, _d, _ip]),
     "amdg_sweep1d": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _i, _d, _i]),
@@ -198,6 +201,24 @@ class Context:
         out = _i()
         _check(lib.amdg_op_register_hier(self._h, ap, wp, w.shape[-1], ctypes.byref(out)))
         return out.value
+
+    def pairs(self):
+        n = _check(lib.amdg_pairs(self._h, None, None, None))
+        src, tgt, vol = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        _check(lib.amdg_pairs(self._h, src.ctypes.data_as(_ip), tgt.ctypes.data_as(_ip), vol.ctypes.data_as(_ip)))
+        return src, tgt, vol
+
+    def op_register_compact(self, blocks, hier=False):
+        b, bp = _dbls(blocks)
+        out = _i()
+        _check(lib.amdg_op_register_compact(self._h, bp, b.shape[0], b.shape[1], b.shape[2], int(hier), ctypes.byref(out)))
+        return out.value
+
+    def op_blocks(self, op, edge_from, edge_to):
+        n = _check(lib.amdg_pairs(self._h, None, None, None))
+        out = np.zeros((n, edge_from, edge_to))
+        _check(lib.amdg_op_blocks(self._h, op, out.ctypes.data_as(_dp)))
+        return out
 
     def op_combine(self, op_a, alpha, op_b, beta):
         out = _i()

@@ -263,6 +263,31 @@ int amdg_op_register(amdg_ctx * c, const double * dense, int rows, int cols, int
     return push_op(c, std::move(op), out);
 }
 
+int64_t amdg_pairs(amdg_ctx * c, int * src, int * tgt, int * is_vol)
+{
+    if (!c) return fail(AMDG_EINVAL, "null context");
+    if (!src) return c->pairs.n_pairs;
+    for (int p = 0; p < c->pairs.n_pairs; ++p) { src[p] = c->pairs.src[p]; tgt[p] = c->pairs.tgt[p]; if (is_vol) is_vol[p] = c->pairs.vol[p]; }
+    return c->pairs.n_pairs;
+}
+
+int amdg_op_register_compact(amdg_ctx * c, const double * blocks, int64_t n_pairs, int kf, int kt, int hier, int * out)
+{
+    if (!c || !blocks || !out) return fail(AMDG_EINVAL, "null argument");
+    if (n_pairs != c->pairs.n_pairs) return fail(AMDG_EINVAL, "n_pairs does not match the canonical pair enumeration of this nmax");
+    if (!sweep_shape_supported(kf, kt)) return fail(AMDG_EINVAL, "unsupported block edge");
+    std::unique_ptr<Op> op(new Op()); op->kf = kf; op->kt = kt; op->hier = hier != 0;
+    op->blocks.assign(blocks, blocks + (size_t)n_pairs * kf * kt);
+    return push_op(c, std::move(op), out);
+}
+
+int amdg_op_blocks(amdg_ctx * c, int op, double * blocks)
+{
+    if (!c || !blocks || op < 0 || op >= (int)c->ops.size()) return fail(AMDG_EINVAL, "bad operator handle");
+    std::memcpy(blocks, c->ops[op]->blocks.data(), c->ops[op]->blocks.size() * sizeof(double));
+    return AMDG_OK;
+}
+
 int amdg_op_register_hier(amdg_ctx * c, const int * anc, const double * wt, int p1, int * out)
 {
     if (!c || !anc || !wt || !out) return fail(AMDG_EINVAL, "null argument");

@@ -82,6 +82,14 @@ int64_t amdg_grid_fibres(amdg_ctx *ctx, int t, int64_t *ptr, int *elems);
  * point tables of FastLagrIntp / FastHermIntp (source/FastMultiplyLU.cpp:1316-1360) are compacted into their
  * (source ord1d, target ord1d) blocks.  edge_from/edge_to = pmax+1 of the row/column basis. ---- */
 int amdg_op_register(amdg_ctx *ctx, const double *host_dense, int rows, int cols, int edge_from, int edge_to, int *op_out);
+/* the canonical enumeration of related 1D element pairs (depends on nmax only): pairs grouped by target ord1d,
+ * sources ascending; src/tgt/is_vol[n_pairs].  src == NULL -> returns n_pairs.  Blocks of a compact operator are
+ * stored in this order. */
+int64_t amdg_pairs(amdg_ctx *ctx, int *src_ord, int *tgt_ord, int *is_vol);
+/* register an operator from its compact form blocks[n_pairs][edge_from][edge_to] (amdg_pairs order); the inverse,
+ * amdg_op_blocks, exports the compact form of a registered operator. */
+int amdg_op_register_compact(amdg_ctx *ctx, const double *host_blocks, int64_t n_pairs, int edge_from, int edge_to, int hier, int *op_out);
+int amdg_op_blocks(amdg_ctx *ctx, int op, double *host_blocks);
 /* hierarchisation stencils pwts (include/Interpolation.h:5-11, source/Interplation.cpp:775-887, 3166-3315):
  * anc[T-1][P1][2] = (ancestor ord1d, point index), wt[T-1][P1][P1] = wt[p0][ic], rows = 1D elements ord1d 1..T-1 */
 int amdg_op_register_hier(amdg_ctx *ctx, const int *anc, const double *wt, int p1, int *op_out);
