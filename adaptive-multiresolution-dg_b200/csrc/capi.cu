@@ -5,6 +5,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 #include <cuda_runtime.h>
 
@@ -47,6 +48,10 @@ struct amdg_ctx
     double * h2d = nullptr; int64_t h2d_cap = 0;     // device staging for the host-buffer entry points
     double * d2h = nullptr; int64_t d2h_cap = 0;
     int64_t launches = 0;
+    // fibre-staged kernel: work lists per (dim, columns W, source edge)
+    struct ItemList { FibreItem * d_items = nullptr; int n = 0; int ct = 1; bool ok = false; };
+    std::map<std::tuple<int, int, int>, ItemList> items;
+    int smem_doubles = 6144, item_target = 148 * 8;
 };
 
 static int need_device(amdg_ctx * c)
@@ -65,6 +70,8 @@ static void free_dev_grid(amdg_ctx * c)
     }
     c->ddims.clear();
     cudaFree(c->d_ord1d); c->d_ord1d = nullptr;
+    for (auto & kv : c->items) cudaFree(kv.second.d_items);
+    c->items.clear();
 }
 
 template <class T>
@@ -101,6 +108,9 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     std::unique_ptr<amdg_ctx> c(new amdg_ctx());
     c->dim = dim; c->nmax = nmax; c->edge_alpt = pmax_alpt + 1; c->edge_intp = pmax_intp + 1; c->device = device;
     c->pairs.build(nmax);
+    if (const char * e = std::getenv("AMDG_SMEM_DOUBLES")) c->smem_doubles = std::max(256, std::min(atoi(e), fibre_smem_capacity_doubles()));
+    if (const char * e = std::getenv("AMDG_ITEM_TARGET")) c->item_target = std::max(1, atoi(e));
+    if (const char * e = std::getenv("AMDG_KERNEL")) c->kernel_variant = atoi(e);
     if (device >= 0)
     {
         int count = 0;
@@ -326,23 +336,116 @@ int amdg_op_combine(amdg_ctx * c, int a, double alpha, int b, double beta, int *
 // ---- sweeps ------------------------------------------------------------------------------------------------------
 static int check_op(amdg_ctx * c, int op) { return (op >= 0 && op < (int)c->ops.size()) ? AMDG_OK : fail(AMDG_EINVAL, "bad operator handle"); }
 
-// launch one sweep for a batch of jobs sharing (op, rel, lu, t, inner, outer)
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// shared-memory pitch: rows handled by one half-warp (16 lanes = (16/cx) rows x cx columns) should fall in distinct banks
+static int choose_pitch(int ncol, int kf, int cx)
+{
+    if (cx >= 16) return ncol;
+    int best = ncol, best_conf = 1 << 30;
+    for (int P = ncol; P < ncol + 16; ++P)
+    {
+        int cnt[16] = { 0 }; int conf = 0;
+        for (int lane = 0; lane < 16; ++lane) { const int tx = lane % cx, ty = lane / cx; cnt[(ty * kf * P + tx) % 16]++; }
+        for (int b = 0; b < 16; ++b) conf = std::max(conf, cnt[b]);
+        if (conf < best_conf) { best_conf = conf; best = P; }
+    }
+    return best;
+}
+
+// work list of the fibre-staged kernel for sweeps along t with W columns and source edge kf
+static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf)
+{
+    auto key = std::make_tuple(t, W, kf);
+    auto it = c->items.find(key);
+    if (it != c->items.end()) return it->second;
+    amdg_ctx::ItemList L;
+    const DimTables & H = c->grid.dims[t];
+    const int cap = c->smem_doubles;
+    const int ct = W > 128 ? 4 : (W > 16 ? 2 : 1);
+    const int64_t total = c->grid.n * (int64_t)kf * W;
+    const int64_t pack_cap = std::max<int64_t>(std::min<int64_t>(cap, total / c->item_target), (int64_t)kf * W);
+    std::vector<FibreItem> items; std::vector<double> cost;
+    auto slot_cost = [&](int64_t s) { return (double)(H.nbr_ptr[1][s + 1] - H.nbr_ptr[1][s]); };
+    FibreItem cur = { 0, 0, 0, W, 0, 0, 0, 0 }; double cur_cost = 0; bool ok = true;
+    auto flush = [&]()
+    {
+        if (cur.nslot == 0) return;
+        cur.lcx = 0; while ((1 << cur.lcx) < std::min(256, next_pow2((W + ct - 1) / ct))) cur.lcx++;
+        cur.pitch = choose_pitch(W, kf, 1 << cur.lcx);
+        items.push_back(cur); cost.push_back(cur_cost * W);
+        cur.nslot = 0; cur_cost = 0;
+    };
+    for (int64_t f = 0; f < H.n_fibre && ok; ++f)
+    {
+        const int64_t s0 = H.fibre_ptr[f]; const int m = (int)(H.fibre_ptr[f + 1] - s0);
+        double fc = 0; for (int64_t s = s0; s < s0 + m; ++s) fc += slot_cost(s);
+        if ((int64_t)m * kf * W <= cap)
+        {
+            if (cur.nslot > 0 && (int64_t)(cur.nslot + m) * kf * W > pack_cap) flush();
+            if (cur.nslot == 0) { cur.slot0 = (int)s0; cur.col0 = 0; cur.ncol = W; }
+            cur.nslot += m; cur_cost += fc;
+        }
+        else
+        {
+            flush();
+            int ncol = cap / (m * kf);
+            if (ncol < 1) { ok = false; break; }
+            const int nchunk = (W + ncol - 1) / ncol;
+            ncol = (W + nchunk - 1) / nchunk;
+            FibreItem sp = { (int)s0, m, 0, ncol, 0, 0, 0, 0 };
+            sp.lcx = 0; while ((1 << sp.lcx) < next_pow2((ncol + ct - 1) / ct)) sp.lcx++;
+            sp.pitch = choose_pitch(ncol, kf, 1 << sp.lcx);
+            if ((int64_t)m * kf * sp.pitch > fibre_smem_capacity_doubles()) sp.pitch = ncol;
+            for (int c0 = 0; c0 < W; c0 += ncol) { sp.col0 = c0; items.push_back(sp); cost.push_back(fc * std::min(ncol, W - c0)); }
+        }
+    }
+    if (ok)
+    {
+        flush();
+        std::vector<int> order(items.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+        std::vector<FibreItem> sorted(items.size());
+        for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
+        if (upload(&L.d_items, sorted.data(), sorted.size(), c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess)
+        { L.n = (int)sorted.size(); L.ct = ct; L.ok = true; }
+    }
+    return c->items.emplace(key, L).first->second;
+}
+
+// launch one sweep for a batch of jobs sharing (op, rel, lu, t, inner); jobs are grouped by equal `outer`
 static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner, const SweepJob * jobs, int n_job, int n_comp)
 {
     const Op & O = *c->ops[op];
     const DevDim & D = c->ddims[t];
-    SweepArgs a;
-    a.slot_elem = D.slot_elem; a.slot_fbase = D.slot_fbase; a.nbr_ptr = D.nbr_ptr[rel]; a.nbr_split = D.nbr_split[rel]; a.nbr = D.nbr[rel];
-    a.blocks = O.d_blocks; a.n_elem = c->grid.n; a.inner = inner; a.lu = lu; a.n_comp = n_comp;
     int done = 0;
     while (done < n_job)
     {
-        // group consecutive jobs with equal `outer`
         int cnt = 1;
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
-        a.n_job = cnt;
-        for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
-        cudaError_t e = launch_sweep_gather(a, O.kf, O.kt, c->stream);
+        const int W = jobs[done].outer * inner;
+        const amdg_ctx::ItemList * L = nullptr;
+        if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf); if (!L->ok) L = nullptr; }
+        if (c->kernel_variant == 2 && !L) return fail(AMDG_EINVAL, "fibre-staged kernel requested but a fibre does not fit in shared memory");
+        cudaError_t e;
+        if (L)
+        {
+            FibreSweepArgs a;
+            a.slot_elem = D.slot_elem; a.slot_fbase = D.slot_fbase; a.nbr_ptr = D.nbr_ptr[rel]; a.nbr_split = D.nbr_split[rel]; a.nbr = D.nbr[rel];
+            a.blocks = O.d_blocks; a.items = L->d_items; a.n_item = L->n; a.n_elem = c->grid.n; a.inner = inner; a.lu = lu; a.n_comp = n_comp;
+            a.n_job = cnt; a.smem_doubles = c->smem_doubles;
+            for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
+            e = launch_sweep_fibre(a, O.kf, O.kt, L->ct, c->stream);
+        }
+        else
+        {
+            SweepArgs a;
+            a.slot_elem = D.slot_elem; a.slot_fbase = D.slot_fbase; a.nbr_ptr = D.nbr_ptr[rel]; a.nbr_split = D.nbr_split[rel]; a.nbr = D.nbr[rel];
+            a.blocks = O.d_blocks; a.n_elem = c->grid.n; a.inner = inner; a.lu = lu; a.n_comp = n_comp; a.n_job = cnt;
+            for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
+            e = launch_sweep_gather(a, O.kf, O.kt, c->stream);
+        }
         if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
         c->launches++;
         done += cnt;

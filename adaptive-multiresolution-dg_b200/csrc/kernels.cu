@@ -1,4 +1,5 @@
 // FP64 CUDA kernels for sm_100a.  See kernels.cuh for the map to the reference functions.
+#include <algorithm>
 #include "kernels.cuh"
 #include "../../include/amdg.h"
 
@@ -96,10 +97,158 @@ cudaError_t launch_sweep_gather(const SweepArgs & a, int kf, int kt, cudaStream_
 #undef FN
 }
 
-cudaError_t launch_sweep_fibre(const FibreSweepArgs & a, int kf, int kt, int max_fibre_len, cudaStream_t st)
+// -------------------------------------------------------------------------------------------------------------
+// K1, fibre-staged form.  A CTA owns one work item = a run of whole fibres along dimension t (or, for a fibre too
+// long for shared memory, a column range of it).  Phase 1 copies the item's source entries into shared memory
+// X[row][k][column] (every source block is read from HBM exactly once per sweep); phase 2 gives every thread
+// one target row and up to CT columns: it walks the row's neighbour list, takes the KF source entries per column
+// from shared memory and the (KF x KT) operator block from L1/L2 (shared by all lanes of the row), and keeps
+// CT*KT accumulators in registers; the epilogue applies coef / accumulate and stores.
+// The thread block is 256 threads viewed as (2^lcx column lanes) x (256 >> lcx row lanes), per item.
+// -------------------------------------------------------------------------------------------------------------
+static const int FIBRE_THREADS = 256;
+static const int FIBRE_SMEM_DOUBLES = 12 * 1024;     // upper bound (96 KiB); the context picks the launch size
+
+int fibre_smem_capacity_doubles() { return FIBRE_SMEM_DOUBLES; }
+
+template <int KF, int KT, int CT>
+__global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreSweepArgs a)
 {
-    (void)a; (void)kf; (void)kt; (void)max_fibre_len; (void)st;
-    return cudaErrorNotSupported;
+    extern __shared__ double X[];
+    const FibreItem it = a.items[blockIdx.x];
+    const int jb = blockIdx.y / a.n_comp, comp = blockIdx.y % a.n_comp;
+    const SweepJob J = a.job[jb];
+    const int inner = a.inner;
+    const int W = J.outer * inner;
+    const int64_t s_from = (int64_t)W * KF, s_to = (int64_t)W * KT;
+    const double * __restrict__ src = J.src + (int64_t)comp * a.n_elem * s_from;
+    double * __restrict__ dst = J.dst + (int64_t)comp * a.n_elem * s_to;
+    const int P = it.pitch;
+    const int cx = 1 << it.lcx;
+    const int tx = threadIdx.x & (cx - 1), ty = threadIdx.x >> it.lcx, ny = FIBRE_THREADS >> it.lcx;
+    const int ncol = min(it.ncol, W - it.col0);
+
+    int cc[CT]; int off_from[CT], off_to[CT]; bool ok[CT];
+#pragma unroll
+    for (int r = 0; r < CT; ++r)
+    {
+        cc[r] = tx + r * cx;
+        ok[r] = cc[r] < ncol;
+        const int col = it.col0 + (ok[r] ? cc[r] : 0);
+        const int o = col / inner, i = col - o * inner;
+        off_from[r] = o * KF * inner + i;
+        off_to[r] = o * KT * inner + i;
+    }
+
+    // phase 1: stage
+    for (int j = ty; j < it.nslot; j += ny)
+    {
+        const int e = a.slot_elem[it.slot0 + j];
+        const double * __restrict__ g = src + (int64_t)e * s_from;
+        double * xr = X + (int64_t)j * KF * P;
+#pragma unroll
+        for (int r = 0; r < CT; ++r)
+        {
+            if (!ok[r]) continue;
+#pragma unroll
+            for (int k = 0; k < KF; ++k) xr[k * P + cc[r]] = __ldg(g + off_from[r] + (int64_t)k * inner);
+        }
+    }
+    __syncthreads();
+
+    // phase 2: per target row
+    for (int j = ty; j < it.nslot; j += ny)
+    {
+        const int slot = it.slot0 + j;
+        const int frow = a.slot_fbase[slot] - it.slot0;          // item-local row of this fibre's first element
+        int64_t n0 = a.nbr_ptr[slot], n1 = a.nbr_ptr[slot + 1];
+        const int split = a.nbr_split[slot];
+        if (a.lu == AMDG_LU_U) n1 = n0 + split;
+        else if (a.lu == AMDG_LU_L) n0 = n0 + split;
+
+        double acc[CT][KT];
+#pragma unroll
+        for (int r = 0; r < CT; ++r)
+#pragma unroll
+            for (int q = 0; q < KT; ++q) acc[r][q] = 0.0;
+
+        for (int64_t p = n0; p < n1; ++p)
+        {
+            const NbrDev nb = a.nbr[p];
+            const double * xr = X + (int64_t)(frow + nb.local) * KF * P;
+            const double * __restrict__ B = a.blocks + (int64_t)nb.pair * (KF * KT);
+#pragma unroll
+            for (int k = 0; k < KF; ++k)
+            {
+                double bk[KT];
+#pragma unroll
+                for (int q = 0; q < KT; ++q) bk[q] = __ldg(B + k * KT + q);
+#pragma unroll
+                for (int r = 0; r < CT; ++r)
+                {
+                    const double xv = ok[r] ? xr[k * P + cc[r]] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < KT; ++q) acc[r][q] = fma(xv, bk[q], acc[r][q]);
+                }
+            }
+        }
+        const int e = a.slot_elem[slot];
+        double * y = dst + (int64_t)e * s_to;
+#pragma unroll
+        for (int r = 0; r < CT; ++r)
+        {
+            if (!ok[r]) continue;
+#pragma unroll
+            for (int q = 0; q < KT; ++q)
+            {
+                double v = J.coef * acc[r][q];
+                double * yp = y + off_to[r] + (int64_t)q * inner;
+                if (J.accumulate) v += *yp;
+                *yp = v;
+            }
+        }
+    }
+}
+
+template <int KF, int KT, int CT>
+static cudaError_t launch_fibre_t(const FibreSweepArgs & a, cudaStream_t st)
+{
+    static bool configured = false;
+    const size_t smem = (size_t)std::min(std::max(a.smem_doubles, 256), FIBRE_SMEM_DOUBLES) * sizeof(double);
+    if (!configured)
+    {
+        cudaError_t e = cudaFuncSetAttribute(sweep_fibre_kernel<KF, KT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIBRE_SMEM_DOUBLES * sizeof(double)));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((unsigned)a.n_item, (unsigned)(a.n_job * a.n_comp));
+    sweep_fibre_kernel<KF, KT, CT><<<grid, FIBRE_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int KF, int KT>
+static cudaError_t launch_fibre_ct(const FibreSweepArgs & a, int ct, cudaStream_t st)
+{
+    if (ct <= 1) return launch_fibre_t<KF, KT, 1>(a, st);
+    if (ct == 2) return launch_fibre_t<KF, KT, 2>(a, st);
+    return launch_fibre_t<KF, KT, 4>(a, st);
+}
+
+#define AMDG_DISPATCH_KT_F(KF_)                                                                   \
+    switch (kt) {                                                                                 \
+        case 1: return launch_fibre_ct<KF_, 1>(a, ct, st); case 2: return launch_fibre_ct<KF_, 2>(a, ct, st); \
+        case 3: return launch_fibre_ct<KF_, 3>(a, ct, st); case 4: return launch_fibre_ct<KF_, 4>(a, ct, st); \
+        case 5: return launch_fibre_ct<KF_, 5>(a, ct, st); case 6: return launch_fibre_ct<KF_, 6>(a, ct, st); \
+        default: return cudaErrorInvalidValue; }
+
+cudaError_t launch_sweep_fibre(const FibreSweepArgs & a, int kf, int kt, int ct, cudaStream_t st)
+{
+    switch (kf)
+    {
+        case 1: AMDG_DISPATCH_KT_F(1) case 2: AMDG_DISPATCH_KT_F(2) case 3: AMDG_DISPATCH_KT_F(3)
+        case 4: AMDG_DISPATCH_KT_F(4) case 5: AMDG_DISPATCH_KT_F(5) case 6: AMDG_DISPATCH_KT_F(6)
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 // -------------------------------------------------------------------------------------------------------------

@@ -43,25 +43,35 @@ struct SweepArgs
     SweepJob job[MAX_JOBS];
 };
 
-// fibre-staged variant: work items = (fibre, column range)
-struct FibreItem { int fibre; int col0; int ncol; int pad; };
+// fibre-staged variant: one CTA stages the source entries of a run of whole fibres (or of a column range of one
+// long fibre) in shared memory, so every source block is read from HBM once per sweep.
+struct FibreItem
+{
+    int slot0;      // first slot (fibre-major element order of dimension t)
+    int nslot;      // number of slots: whole fibres
+    int col0;       // first column of the (outer x inner) plane
+    int ncol;       // columns staged by this item (the last chunk of a split fibre may hold fewer valid ones)
+    int lcx;        // log2 of the column-thread count: tid & (2^lcx-1) = column lane, tid >> lcx = row lane
+    int pitch;      // shared-memory row pitch in doubles
+    int pad0, pad1;
+};
 
 struct FibreSweepArgs
 {
-    const int64_t * fibre_ptr;  // [n_fibre+1]
     const int * slot_elem;
+    const int * slot_fbase;
     const int64_t * nbr_ptr;
     const int * nbr_split;
     const NbrDev * nbr;
     const double * blocks;
-    const FibreItem * items;    // per job-independent work list for this (dim, column count)
+    const FibreItem * items;
     int n_item;
     int64_t n_elem;
     int inner;
     int lu;
     int n_comp;
     int n_job;
-    int smem_cols;              // padded column capacity of the staging buffer
+    int smem_doubles;
     SweepJob job[MAX_JOBS];
 };
 
@@ -77,7 +87,8 @@ struct PointwiseArgs
 };
 
 cudaError_t launch_sweep_gather(const SweepArgs & a, int kf, int kt, cudaStream_t st);
-cudaError_t launch_sweep_fibre(const FibreSweepArgs & a, int kf, int kt, int max_fibre_len, cudaStream_t st);
+cudaError_t launch_sweep_fibre(const FibreSweepArgs & a, int kf, int kt, int ct, cudaStream_t st);
+int fibre_smem_capacity_doubles();
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);
 cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st);
