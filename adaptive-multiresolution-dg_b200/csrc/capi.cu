@@ -49,7 +49,7 @@ struct amdg_ctx
     double * d2h = nullptr; int64_t d2h_cap = 0;
     int64_t launches = 0;
     // fibre-staged kernel: work lists per (dim, columns W, source edge)
-    struct ItemList { FibreItem * d_items = nullptr; int n = 0; int ct = 1; bool ok = false; };
+    struct ItemList { FibreItem * d_items = nullptr; int n = 0; int ct = 1; int smem = 0; bool ok = false; };
     std::map<std::tuple<int, int, int>, ItemList> items;
     int smem_doubles = 6144, item_target = 148 * 8;
 };
@@ -363,16 +363,19 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf)
     const DimTables & H = c->grid.dims[t];
     const int cap = c->smem_doubles;
     const int ct = W > 128 ? 4 : (W > 16 ? 2 : 1);
-    const int64_t total = c->grid.n * (int64_t)kf * W;
-    const int64_t pack_cap = std::max<int64_t>(std::min<int64_t>(cap, total / c->item_target), (int64_t)kf * W);
+    int lcx_w = 0; while ((1 << lcx_w) < std::min(256, next_pow2((W + ct - 1) / ct))) lcx_w++;
+    const int pitch_w = choose_pitch(W, kf, 1 << lcx_w);
+    const int64_t total = c->grid.n * (int64_t)kf * pitch_w;
+    const int64_t pack_cap = std::max<int64_t>(std::min<int64_t>(cap, total / c->item_target), (int64_t)kf * pitch_w);
+    int64_t need = 0;
     std::vector<FibreItem> items; std::vector<double> cost;
     auto slot_cost = [&](int64_t s) { return (double)(H.nbr_ptr[1][s + 1] - H.nbr_ptr[1][s]); };
     FibreItem cur = { 0, 0, 0, W, 0, 0, 0, 0 }; double cur_cost = 0; bool ok = true;
     auto flush = [&]()
     {
         if (cur.nslot == 0) return;
-        cur.lcx = 0; while ((1 << cur.lcx) < std::min(256, next_pow2((W + ct - 1) / ct))) cur.lcx++;
-        cur.pitch = choose_pitch(W, kf, 1 << cur.lcx);
+        cur.lcx = lcx_w; cur.pitch = pitch_w;
+        need = std::max(need, (int64_t)cur.nslot * kf * cur.pitch);
         items.push_back(cur); cost.push_back(cur_cost * W);
         cur.nslot = 0; cur_cost = 0;
     };
@@ -380,9 +383,9 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf)
     {
         const int64_t s0 = H.fibre_ptr[f]; const int m = (int)(H.fibre_ptr[f + 1] - s0);
         double fc = 0; for (int64_t s = s0; s < s0 + m; ++s) fc += slot_cost(s);
-        if ((int64_t)m * kf * W <= cap)
+        if ((int64_t)m * kf * pitch_w <= cap)
         {
-            if (cur.nslot > 0 && (int64_t)(cur.nslot + m) * kf * W > pack_cap) flush();
+            if (cur.nslot > 0 && (int64_t)(cur.nslot + m) * kf * pitch_w > pack_cap) flush();
             if (cur.nslot == 0) { cur.slot0 = (int)s0; cur.col0 = 0; cur.ncol = W; }
             cur.nslot += m; cur_cost += fc;
         }
@@ -396,7 +399,8 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf)
             FibreItem sp = { (int)s0, m, 0, ncol, 0, 0, 0, 0 };
             sp.lcx = 0; while ((1 << sp.lcx) < next_pow2((ncol + ct - 1) / ct)) sp.lcx++;
             sp.pitch = choose_pitch(ncol, kf, 1 << sp.lcx);
-            if ((int64_t)m * kf * sp.pitch > fibre_smem_capacity_doubles()) sp.pitch = ncol;
+            if ((int64_t)m * kf * sp.pitch > cap) sp.pitch = ncol;
+            need = std::max(need, (int64_t)m * kf * sp.pitch);
             for (int c0 = 0; c0 < W; c0 += ncol) { sp.col0 = c0; items.push_back(sp); cost.push_back(fc * std::min(ncol, W - c0)); }
         }
     }
@@ -409,7 +413,7 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf)
         std::vector<FibreItem> sorted(items.size());
         for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
         if (upload(&L.d_items, sorted.data(), sorted.size(), c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess)
-        { L.n = (int)sorted.size(); L.ct = ct; L.ok = true; }
+        { L.n = (int)sorted.size(); L.ct = ct; L.smem = (int)need; L.ok = true; }
     }
     return c->items.emplace(key, L).first->second;
 }
@@ -434,7 +438,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
             FibreSweepArgs a;
             a.slot_elem = D.slot_elem; a.slot_fbase = D.slot_fbase; a.nbr_ptr = D.nbr_ptr[rel]; a.nbr_split = D.nbr_split[rel]; a.nbr = D.nbr[rel];
             a.blocks = O.d_blocks; a.items = L->d_items; a.n_item = L->n; a.n_elem = c->grid.n; a.inner = inner; a.lu = lu; a.n_comp = n_comp;
-            a.n_job = cnt; a.smem_doubles = c->smem_doubles;
+            a.n_job = cnt; a.smem_doubles = L->smem;
             for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
             e = launch_sweep_fibre(a, O.kf, O.kt, L->ct, c->stream);
         }
