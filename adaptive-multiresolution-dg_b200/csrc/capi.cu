@@ -49,9 +49,9 @@ struct amdg_ctx
     double * d2h = nullptr; int64_t d2h_cap = 0;
     int64_t launches = 0;
     // fibre-staged kernel: work lists per (dim, columns W, source edge)
-    struct ItemList { FibreItem * d_items = nullptr; int n = 0; int ct = 1; int smem = 0; bool ok = false; };
-    std::map<std::tuple<int, int, int>, ItemList> items;
-    int smem_doubles = 6144, item_target = 148 * 8;
+    struct ItemList { FibreItem * d_items = nullptr; int * d_nbr_lp = nullptr; int * d_item_pairs = nullptr; int n = 0; int ct = 1; int smem = 0; bool ok = false; };
+    std::map<std::tuple<int, int, int, int, int>, ItemList> items;      // key: (dim t, columns W, kf, kt, relation)
+    int smem_doubles = 8192, item_target = 148 * 8;
 };
 
 static int need_device(amdg_ctx * c)
@@ -70,7 +70,7 @@ static void free_dev_grid(amdg_ctx * c)
     }
     c->ddims.clear();
     cudaFree(c->d_ord1d); c->d_ord1d = nullptr;
-    for (auto & kv : c->items) cudaFree(kv.second.d_items);
+    for (auto & kv : c->items) { cudaFree(kv.second.d_items); cudaFree(kv.second.d_nbr_lp); cudaFree(kv.second.d_item_pairs); }
     c->items.clear();
 }
 
@@ -353,10 +353,14 @@ static int choose_pitch(int ncol, int kf, int cx)
     return best;
 }
 
-// work list of the fibre-staged kernel for sweeps along t with W columns and source edge kf
-static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf)
+// Work list of the fibre-staged kernel for sweeps along t with W columns, block edges kf -> kt and relation rel.
+// Fibres are walked in slot order.  A fibre whose staged rows fit in shared memory together with the operator
+// blocks of its distinct 1D pairs and its neighbour lists becomes (part of) a PACKED item; consecutive small
+// fibres are packed together up to a size that leaves ~item_target items per sweep.  Anything else is STREAMED:
+// one fibre, or a column range of it, with the operator blocks read from L2.
+static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, int kt, int rel)
 {
-    auto key = std::make_tuple(t, W, kf);
+    auto key = std::make_tuple(t, W, kf, kt, rel);
     auto it = c->items.find(key);
     if (it != c->items.end()) return it->second;
     amdg_ctx::ItemList L;
@@ -365,44 +369,85 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf)
     const int ct = W > 128 ? 4 : (W > 16 ? 2 : 1);
     int lcx_w = 0; while ((1 << lcx_w) < std::min(256, next_pow2((W + ct - 1) / ct))) lcx_w++;
     const int pitch_w = choose_pitch(W, kf, 1 << lcx_w);
+    const bool wide = (1 << lcx_w) * ct < W;          // more columns than one pass of the block covers: not supported by the packed path
     const int64_t total = c->grid.n * (int64_t)kf * pitch_w;
     const int64_t pack_cap = std::max<int64_t>(std::min<int64_t>(cap, total / c->item_target), (int64_t)kf * pitch_w);
-    int64_t need = 0;
+    const std::vector<int64_t> & nptr = H.nbr_ptr[rel];
+    const std::vector<Nbr> & nbr = H.nbr[rel];
     std::vector<FibreItem> items; std::vector<double> cost;
-    auto slot_cost = [&](int64_t s) { return (double)(H.nbr_ptr[1][s + 1] - H.nbr_ptr[1][s]); };
-    FibreItem cur = { 0, 0, 0, W, 0, 0, 0, 0 }; double cur_cost = 0; bool ok = true;
+    std::vector<int> nbr_lp(nbr.size(), 0), item_pairs;
+    std::vector<int> stamp(c->pairs.n_pairs, -1), lp_of(c->pairs.n_pairs, 0);
+    int64_t need = 0; bool ok = true;
+
+    // state of the packed item being built
+    FibreItem cur = { 0, 0, 0, W, lcx_w, pitch_w, 0, 0 }; double cur_cost = 0; int64_t cur_nnz = 0; int cur_id = 0;
+    auto packed_need = [&](int nslot, int npair, int64_t nnz) { return (int64_t)nslot * kf * pitch_w + (int64_t)npair * kf * kt + (2 * nnz + 2 * nslot + 2 + 1) / 2; };
     auto flush = [&]()
     {
         if (cur.nslot == 0) return;
-        cur.lcx = lcx_w; cur.pitch = pitch_w;
-        need = std::max(need, (int64_t)cur.nslot * kf * cur.pitch);
+        need = std::max(need, packed_need(cur.nslot, cur.npair, cur_nnz));
         items.push_back(cur); cost.push_back(cur_cost * W);
-        cur.nslot = 0; cur_cost = 0;
+        cur.nslot = 0; cur.npair = 0; cur_cost = 0; cur_nnz = 0; ++cur_id;
+    };
+    auto add_streamed = [&](int64_t s0, int m, double fc)
+    {
+        // column chunks: at most 32*ct columns per warp pass and m*kf*pitch <= cap
+        int ncol = std::min<int64_t>(std::min(W, 32 * ct), cap / ((int64_t)m * kf));
+        if (ncol < 1) { ok = false; return; }
+        const int nchunk = (W + ncol - 1) / ncol;
+        ncol = (W + nchunk - 1) / nchunk;
+        FibreItem sp = { (int)s0, m, 0, ncol, 0, 0, 0, 0 };
+        while ((1 << sp.lcx) < next_pow2((ncol + ct - 1) / ct)) sp.lcx++;
+        sp.pitch = choose_pitch(ncol, kf, 1 << sp.lcx);
+        if ((int64_t)m * kf * sp.pitch > cap) sp.pitch = ncol;
+        need = std::max(need, (int64_t)m * kf * sp.pitch);
+        for (int c0 = 0; c0 < W; c0 += ncol) { sp.col0 = c0; items.push_back(sp); cost.push_back(4.0 * fc * std::min(ncol, W - c0)); }
     };
     for (int64_t f = 0; f < H.n_fibre && ok; ++f)
     {
         const int64_t s0 = H.fibre_ptr[f]; const int m = (int)(H.fibre_ptr[f + 1] - s0);
-        double fc = 0; for (int64_t s = s0; s < s0 + m; ++s) fc += slot_cost(s);
-        if ((int64_t)m * kf * pitch_w <= cap)
+        const int64_t fnnz = nptr[s0 + m] - nptr[s0];
+        const double fc = (double)fnnz;
+        bool placed = false;
+        if (!wide && packed_need(m, (int)std::min<int64_t>(fnnz, c->pairs.n_pairs), fnnz) <= 4 * (int64_t)cap)     // cheap pre-filter
         {
-            if (cur.nslot > 0 && (int64_t)(cur.nslot + m) * kf * pitch_w > pack_cap) flush();
-            if (cur.nslot == 0) { cur.slot0 = (int)s0; cur.col0 = 0; cur.ncol = W; }
-            cur.nslot += m; cur_cost += fc;
+            // try to extend the current packed item
+            if (cur.nslot > 0)
+            {
+                std::vector<int> touched;
+                int nn = 0;
+                for (int64_t p = nptr[s0]; p < nptr[s0 + m]; ++p) if (stamp[nbr[p].pair] != cur_id) { stamp[nbr[p].pair] = cur_id; touched.push_back(nbr[p].pair); ++nn; }
+                if (packed_need(cur.nslot + m, cur.npair + nn, cur_nnz + fnnz) <= pack_cap)
+                {
+                    for (int pr : touched) { lp_of[pr] = cur.npair++; item_pairs.push_back(pr); }
+                    placed = true;
+                }
+                else
+                {
+                    for (int pr : touched) stamp[pr] = -1;
+                    flush();
+                }
+            }
+            if (!placed)
+            {
+                // start a new packed item with this fibre alone, if it fits
+                cur.slot0 = (int)s0; cur.pair_ofs = (int)item_pairs.size();
+                std::vector<int> touched;
+                for (int64_t p = nptr[s0]; p < nptr[s0 + m]; ++p) if (stamp[nbr[p].pair] != cur_id) { stamp[nbr[p].pair] = cur_id; touched.push_back(nbr[p].pair); }
+                if (packed_need(m, (int)touched.size(), fnnz) <= cap)
+                {
+                    for (int pr : touched) { lp_of[pr] = cur.npair++; item_pairs.push_back(pr); }
+                    placed = true;
+                }
+                else { for (int pr : touched) stamp[pr] = -1; }
+            }
+            if (placed)
+            {
+                for (int64_t p = nptr[s0]; p < nptr[s0 + m]; ++p) nbr_lp[p] = lp_of[nbr[p].pair];
+                cur.nslot += m; cur_cost += fc; cur_nnz += fnnz;
+            }
         }
-        else
-        {
-            flush();
-            int ncol = cap / (m * kf);
-            if (ncol < 1) { ok = false; break; }
-            const int nchunk = (W + ncol - 1) / ncol;
-            ncol = (W + nchunk - 1) / nchunk;
-            FibreItem sp = { (int)s0, m, 0, ncol, 0, 0, 0, 0 };
-            sp.lcx = 0; while ((1 << sp.lcx) < next_pow2((ncol + ct - 1) / ct)) sp.lcx++;
-            sp.pitch = choose_pitch(ncol, kf, 1 << sp.lcx);
-            if ((int64_t)m * kf * sp.pitch > cap) sp.pitch = ncol;
-            need = std::max(need, (int64_t)m * kf * sp.pitch);
-            for (int c0 = 0; c0 < W; c0 += ncol) { sp.col0 = c0; items.push_back(sp); cost.push_back(fc * std::min(ncol, W - c0)); }
-        }
+        if (!placed) { flush(); add_streamed(s0, m, fc); }
     }
     if (ok)
     {
@@ -412,8 +457,17 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf)
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
         std::vector<FibreItem> sorted(items.size());
         for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
-        if (upload(&L.d_items, sorted.data(), sorted.size(), c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess)
+        if (need <= fibre_smem_capacity_doubles() &&
+            upload(&L.d_items, sorted.data(), sorted.size(), c->stream) == cudaSuccess &&
+            upload(&L.d_nbr_lp, nbr_lp.data(), nbr_lp.size(), c->stream) == cudaSuccess &&
+            upload(&L.d_item_pairs, item_pairs.data(), item_pairs.size(), c->stream) == cudaSuccess &&
+            cudaStreamSynchronize(c->stream) == cudaSuccess)
         { L.n = (int)sorted.size(); L.ct = ct; L.smem = (int)need; L.ok = true; }
+        if (std::getenv("AMDG_VERBOSE"))
+        {
+            int np = 0; for (auto & x : sorted) np += x.npair > 0;
+            fprintf(stderr, "[amdg] items t=%d W=%d kf=%d kt=%d rel=%d: %d items (%d packed, %d streamed), smem %lld doubles, ct %d\n", t, W, kf, kt, rel, (int)sorted.size(), np, (int)sorted.size() - np, (long long)need, ct);
+        }
     }
     return c->items.emplace(key, L).first->second;
 }
@@ -430,13 +484,14 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
         const amdg_ctx::ItemList * L = nullptr;
-        if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf); if (!L->ok) L = nullptr; }
+        if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf, O.kt, rel); if (!L->ok) L = nullptr; }
         if (c->kernel_variant == 2 && !L) return fail(AMDG_EINVAL, "fibre-staged kernel requested but a fibre does not fit in shared memory");
         cudaError_t e;
         if (L)
         {
             FibreSweepArgs a;
             a.slot_elem = D.slot_elem; a.slot_fbase = D.slot_fbase; a.nbr_ptr = D.nbr_ptr[rel]; a.nbr_split = D.nbr_split[rel]; a.nbr = D.nbr[rel];
+            a.nbr_lp = L->d_nbr_lp; a.item_pairs = L->d_item_pairs;
             a.blocks = O.d_blocks; a.items = L->d_items; a.n_item = L->n; a.n_elem = c->grid.n; a.inner = inner; a.lu = lu; a.n_comp = n_comp;
             a.n_job = cnt; a.smem_doubles = L->smem;
             for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];

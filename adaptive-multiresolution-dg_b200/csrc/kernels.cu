@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
     double * __restrict__ dst = J.dst + (int64_t)comp * a.n_elem * s_to;
     const int P = it.pitch;
     const int cx = 1 << it.lcx;
-    const int tx = threadIdx.x & (cx - 1), ty = threadIdx.x >> it.lcx, ny = FIBRE_THREADS >> it.lcx;
+    const int tid = threadIdx.x;
+    const int tx = tid & (cx - 1);
     const int ncol = min(it.ncol, W - it.col0);
 
     int cc[CT]; int off_from[CT], off_to[CT]; bool ok[CT];
@@ -140,71 +141,172 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
         off_to[r] = o * KT * inner + i;
     }
 
-    // phase 1: stage
-    for (int j = ty; j < it.nslot; j += ny)
+    // ---- phase 1: stage the source entries X[row][k][column]
     {
-        const int e = a.slot_elem[it.slot0 + j];
-        const double * __restrict__ g = src + (int64_t)e * s_from;
-        double * xr = X + (int64_t)j * KF * P;
-#pragma unroll
-        for (int r = 0; r < CT; ++r)
+        const int ty = tid >> it.lcx, ny = FIBRE_THREADS >> it.lcx;
+        for (int j = ty; j < it.nslot; j += ny)
         {
-            if (!ok[r]) continue;
+            const int e = a.slot_elem[it.slot0 + j];
+            const double * __restrict__ g = src + (int64_t)e * s_from;
+            double * xr = X + (int64_t)j * KF * P;
 #pragma unroll
-            for (int k = 0; k < KF; ++k) xr[k * P + cc[r]] = __ldg(g + off_from[r] + (int64_t)k * inner);
+            for (int r = 0; r < CT; ++r)
+            {
+                if (!ok[r]) continue;
+#pragma unroll
+                for (int k = 0; k < KF; ++k) xr[k * P + cc[r]] = __ldg(g + off_from[r] + (int64_t)k * inner);
+            }
         }
     }
-    __syncthreads();
 
-    // phase 2: per target row
-    for (int j = ty; j < it.nslot; j += ny)
+    if (it.npair > 0)
     {
-        const int slot = it.slot0 + j;
-        const int frow = a.slot_fbase[slot] - it.slot0;          // item-local row of this fibre's first element
-        int64_t n0 = a.nbr_ptr[slot], n1 = a.nbr_ptr[slot + 1];
-        const int split = a.nbr_split[slot];
-        if (a.lu == AMDG_LU_U) n1 = n0 + split;
-        else if (a.lu == AMDG_LU_L) n0 = n0 + split;
-
-        double acc[CT][KT];
-#pragma unroll
-        for (int r = 0; r < CT; ++r)
-#pragma unroll
-            for (int q = 0; q < KT; ++q) acc[r][q] = 0.0;
-
-        for (int64_t p = n0; p < n1; ++p)
+        // ---- packed item: operator blocks of the item's distinct pairs and the neighbour lists go to shared memory too
+        double * Bs = X + (int64_t)it.nslot * KF * P;
+        int * rowptr = reinterpret_cast<int *>(Bs + (int64_t)it.npair * (KF * KT));      // [nslot+1]
+        int * rsplit = rowptr + it.nslot + 1;                                               // [nslot]
+        int * ent = rsplit + it.nslot;                                                      // [nnz][2]: item-local source row, local pair
+        const int64_t base = a.nbr_ptr[it.slot0];
+        const int nnz = (int)(a.nbr_ptr[it.slot0 + it.nslot] - base);
+        for (int idx = tid; idx < it.npair * (KF * KT); idx += FIBRE_THREADS)
         {
-            const NbrDev nb = a.nbr[p];
-            const double * xr = X + (int64_t)(frow + nb.local) * KF * P;
-            const double * __restrict__ B = a.blocks + (int64_t)nb.pair * (KF * KT);
+            const int pr = idx / (KF * KT), r = idx - pr * (KF * KT);
+            Bs[idx] = __ldg(a.blocks + (int64_t)a.item_pairs[it.pair_ofs + pr] * (KF * KT) + r);
+        }
+        for (int j = tid; j <= it.nslot; j += FIBRE_THREADS) rowptr[j] = (int)(a.nbr_ptr[it.slot0 + j] - base);
+        for (int j = tid; j < it.nslot; j += FIBRE_THREADS) rsplit[j] = a.nbr_split[it.slot0 + j];
+        for (int i = tid; i < nnz; i += FIBRE_THREADS)
+        {
+            const NbrDev nb = a.nbr[base + i];
+            ent[2 * i] = nb.local; ent[2 * i + 1] = a.nbr_lp[base + i];
+        }
+        __syncthreads();
+
+        const int ty = tid >> it.lcx, ny = FIBRE_THREADS >> it.lcx;
+        for (int j = ty; j < it.nslot; j += ny)
+        {
+            const int slot = it.slot0 + j;
+            const int frow = a.slot_fbase[slot] - it.slot0;
+            int n0 = rowptr[j], n1 = rowptr[j + 1];
+            if (a.lu == AMDG_LU_U) n1 = n0 + rsplit[j];
+            else if (a.lu == AMDG_LU_L) n0 = n0 + rsplit[j];
+            double acc[CT][KT];
 #pragma unroll
-            for (int k = 0; k < KF; ++k)
+            for (int r = 0; r < CT; ++r)
+#pragma unroll
+                for (int q = 0; q < KT; ++q) acc[r][q] = 0.0;
+            for (int p = n0; p < n1; ++p)
             {
-                double bk[KT];
+                const double * xr = X + (int64_t)(frow + ent[2 * p]) * KF * P;
+                const double * B = Bs + ent[2 * p + 1] * (KF * KT);
 #pragma unroll
-                for (int q = 0; q < KT; ++q) bk[q] = __ldg(B + k * KT + q);
-#pragma unroll
-                for (int r = 0; r < CT; ++r)
+                for (int k = 0; k < KF; ++k)
                 {
-                    const double xv = ok[r] ? xr[k * P + cc[r]] : 0.0;
+                    double bk[KT];
 #pragma unroll
-                    for (int q = 0; q < KT; ++q) acc[r][q] = fma(xv, bk[q], acc[r][q]);
+                    for (int q = 0; q < KT; ++q) bk[q] = B[k * KT + q];
+#pragma unroll
+                    for (int r = 0; r < CT; ++r)
+                    {
+                        const double xv = ok[r] ? xr[k * P + cc[r]] : 0.0;
+#pragma unroll
+                        for (int q = 0; q < KT; ++q) acc[r][q] = fma(xv, bk[q], acc[r][q]);
+                    }
+                }
+            }
+            double * y = dst + (int64_t)a.slot_elem[slot] * s_to;
+#pragma unroll
+            for (int r = 0; r < CT; ++r)
+            {
+                if (!ok[r]) continue;
+#pragma unroll
+                for (int q = 0; q < KT; ++q)
+                {
+                    double v = J.coef * acc[r][q];
+                    double * yp = y + off_to[r] + (int64_t)q * inner;
+                    if (J.accumulate) v += *yp;
+                    *yp = v;
                 }
             }
         }
-        const int e = a.slot_elem[slot];
-        double * y = dst + (int64_t)e * s_to;
-#pragma unroll
-        for (int r = 0; r < CT; ++r)
+        return;
+    }
+
+    // ---- streamed item (a long fibre, or a column range of one): one warp per target row; the 32 lanes are
+    // (32/cx neighbour slices) x (cx column lanes); neighbour entries are fetched 32 at a time (coalesced) and
+    // broadcast with shuffles, operator blocks come from L2; partial sums of the slices are reduced with shuffles.
+    __syncthreads();
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int cxw = min(cx, 32);
+        const int ns = 32 / cxw;
+        const int sl = lane / cxw;
+        for (int j = warp; j < it.nslot; j += FIBRE_THREADS / 32)
         {
-            if (!ok[r]) continue;
+            const int slot = it.slot0 + j;
+            const int frow = a.slot_fbase[slot] - it.slot0;
+            int64_t n0 = a.nbr_ptr[slot], n1 = a.nbr_ptr[slot + 1];
+            const int split = a.nbr_split[slot];
+            if (a.lu == AMDG_LU_U) n1 = n0 + split;
+            else if (a.lu == AMDG_LU_L) n0 = n0 + split;
+            double acc[CT][KT];
 #pragma unroll
-            for (int q = 0; q < KT; ++q)
+            for (int r = 0; r < CT; ++r)
+#pragma unroll
+                for (int q = 0; q < KT; ++q) acc[r][q] = 0.0;
+            for (int64_t base = n0; base < n1; base += 32)
             {
-                double v = J.coef * acc[r][q];
-                double * yp = y + off_to[r] + (int64_t)q * inner;
-                if (J.accumulate) v += *yp;
-                *yp = v;
+                const int cnt = (int)min((int64_t)32, n1 - base);
+                NbrDev mine; mine.local = 0; mine.pair = 0;
+                if (lane < cnt) mine = a.nbr[base + lane];
+                for (int i0 = 0; i0 < cnt; i0 += ns)
+                {
+                    const int i = i0 + sl;
+                    const bool valid = i < cnt;
+                    const int local = __shfl_sync(0xffffffffu, mine.local, valid ? i : 0);
+                    const int pair = __shfl_sync(0xffffffffu, mine.pair, valid ? i : 0);
+                    if (!valid) continue;
+                    const double * xr = X + (int64_t)(frow + local) * KF * P;
+                    const double * __restrict__ B = a.blocks + (int64_t)pair * (KF * KT);
+#pragma unroll
+                    for (int k = 0; k < KF; ++k)
+                    {
+                        double bk[KT];
+#pragma unroll
+                        for (int q = 0; q < KT; ++q) bk[q] = __ldg(B + k * KT + q);
+#pragma unroll
+                        for (int r = 0; r < CT; ++r)
+                        {
+                            const double xv = ok[r] ? xr[k * P + cc[r]] : 0.0;
+#pragma unroll
+                            for (int q = 0; q < KT; ++q) acc[r][q] = fma(xv, bk[q], acc[r][q]);
+                        }
+                    }
+                }
+            }
+            for (int off = cxw; off < 32; off <<= 1)
+            {
+#pragma unroll
+                for (int r = 0; r < CT; ++r)
+#pragma unroll
+                    for (int q = 0; q < KT; ++q) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], off);
+            }
+            if (sl == 0)
+            {
+                double * y = dst + (int64_t)a.slot_elem[slot] * s_to;
+#pragma unroll
+                for (int r = 0; r < CT; ++r)
+                {
+                    if (!ok[r]) continue;
+#pragma unroll
+                    for (int q = 0; q < KT; ++q)
+                    {
+                        double v = J.coef * acc[r][q];
+                        double * yp = y + off_to[r] + (int64_t)q * inner;
+                        if (J.accumulate) v += *yp;
+                        *yp = v;
+                    }
+                }
             }
         }
     }

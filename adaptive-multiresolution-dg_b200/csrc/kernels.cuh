@@ -51,9 +51,10 @@ struct FibreItem
     int nslot;      // number of slots: whole fibres
     int col0;       // first column of the (outer x inner) plane
     int ncol;       // columns staged by this item (the last chunk of a split fibre may hold fewer valid ones)
-    int lcx;        // log2 of the column-thread count: tid & (2^lcx-1) = column lane, tid >> lcx = row lane
+    int lcx;        // log2 of the column-lane count
     int pitch;      // shared-memory row pitch in doubles
-    int pad0, pad1;
+    int pair_ofs;   // packed items: first entry of the item's distinct-pair table in `item_pairs`
+    int npair;      // packed items: number of distinct 1D pairs (operator blocks staged in shared memory); 0 = streamed
 };
 
 struct FibreSweepArgs
@@ -63,6 +64,8 @@ struct FibreSweepArgs
     const int64_t * nbr_ptr;
     const int * nbr_split;
     const NbrDev * nbr;
+    const int * nbr_lp;         // per neighbour entry: index into the item's distinct-pair table (packed items)
+    const int * item_pairs;     // pool of distinct-pair tables
     const double * blocks;
     const FibreItem * items;
     int n_item;
