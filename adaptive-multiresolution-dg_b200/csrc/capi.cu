@@ -49,8 +49,12 @@ struct amdg_ctx
     double * d2h = nullptr; int64_t d2h_cap = 0;
     int64_t launches = 0;
     // fibre-staged kernel: work lists per (dim, columns W, source edge)
-    struct ItemList { FibreItem * d_items = nullptr; int * d_nbr_lp = nullptr; int * d_item_pairs = nullptr; int n = 0; int ct = 1; int smem = 0; bool ok = false; };
-    std::map<std::tuple<int, int, int, int, int>, ItemList> items;      // key: (dim t, columns W, kf, kt, relation)
+    struct ItemList
+    {
+        FibreItem * d_items = nullptr; int * d_slots = nullptr; int * d_pairs = nullptr; int * d_rowptr = nullptr; int * d_rsplit = nullptr; NbrDev * d_ent = nullptr;
+        int n = 0; int ct = 1; int smem = 0; bool ok = false;
+    };
+    std::map<std::tuple<int, int, int, int, int, int>, ItemList> items;      // key: (dim t, columns W, kf, kt, relation, parallel class)
     int smem_doubles = 8192, item_target = 148 * 8;
 };
 
@@ -70,7 +74,11 @@ static void free_dev_grid(amdg_ctx * c)
     }
     c->ddims.clear();
     cudaFree(c->d_ord1d); c->d_ord1d = nullptr;
-    for (auto & kv : c->items) { cudaFree(kv.second.d_items); cudaFree(kv.second.d_nbr_lp); cudaFree(kv.second.d_item_pairs); }
+    for (auto & kv : c->items)
+    {
+        amdg_ctx::ItemList & L = kv.second;
+        cudaFree(L.d_items); cudaFree(L.d_slots); cudaFree(L.d_pairs); cudaFree(L.d_rowptr); cudaFree(L.d_rsplit); cudaFree(L.d_ent);
+    }
     c->items.clear();
 }
 
@@ -354,104 +362,161 @@ static int choose_pitch(int ncol, int kf, int cx)
 }
 
 // Work list of the fibre-staged kernel for sweeps along t with W columns, block edges kf -> kt and relation rel.
-// Fibres are walked in slot order.  A fibre whose staged rows fit in shared memory together with the operator
-// blocks of its distinct 1D pairs and its neighbour lists becomes (part of) a PACKED item; consecutive small
-// fibres are packed together up to a size that leaves ~item_target items per sweep.  Anything else is STREAMED:
-// one fibre, or a column range of it, with the operator blocks read from L2.
-static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, int kt, int rel)
+//
+// PACKED item: a set of target rows plus the source rows they need, small enough that the staged rows, the
+//   operator blocks of the distinct 1D pairs and the item-local neighbour lists fit in shared memory together.
+//   Short fibres are packed several to an item (walked in slot order).  A long fibre is cut at a 1D level k_c:
+//   the rows of level >= k_c are grouped by their level-k_c ancestor (a subtree); a subtree's sources are the
+//   subtree itself, its ancestor chain and (flx relation) a few adjacent cells -- the union of its rows'
+//   neighbour lists, so nothing about the tree shape is assumed.
+// STREAMED item: the rows of level < k_c of a long fibre (a prefix in 1D order) have sources all over the fibre:
+//   the whole fibre is staged for a narrow column range, one warp per target row with the lanes splitting the
+//   neighbour list; operator blocks come from L2.  A fibre that cannot be cut falls back to this form entirely.
+static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, int kt, int rel, int par)
 {
-    auto key = std::make_tuple(t, W, kf, kt, rel);
+    int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
+    auto key = std::make_tuple(t, W, kf, kt, rel, pcls);
     auto it = c->items.find(key);
     if (it != c->items.end()) return it->second;
     amdg_ctx::ItemList L;
     const DimTables & H = c->grid.dims[t];
+    const int d = c->dim;
     const int cap = c->smem_doubles;
     const int ct = W > 128 ? 4 : (W > 16 ? 2 : 1);
     int lcx_w = 0; while ((1 << lcx_w) < std::min(256, next_pow2((W + ct - 1) / ct))) lcx_w++;
     const int pitch_w = choose_pitch(W, kf, 1 << lcx_w);
-    const bool wide = (1 << lcx_w) * ct < W;          // more columns than one pass of the block covers: not supported by the packed path
+    const bool wide = (1 << lcx_w) * ct < W;          // more columns than one pass of the block covers: packed path not possible
     const int64_t total = c->grid.n * (int64_t)kf * pitch_w;
-    const int64_t pack_cap = std::max<int64_t>(std::min<int64_t>(cap, total / c->item_target), (int64_t)kf * pitch_w);
+    const int64_t pack_cap = std::max<int64_t>(std::min<int64_t>(cap, total / std::max(1, c->item_target >> pcls)), (int64_t)kf * pitch_w);
     const std::vector<int64_t> & nptr = H.nbr_ptr[rel];
     const std::vector<Nbr> & nbr = H.nbr[rel];
+    const std::vector<int> & nsplit = H.nbr_split[rel];
     std::vector<FibreItem> items; std::vector<double> cost;
-    std::vector<int> nbr_lp(nbr.size(), 0), item_pairs;
-    std::vector<int> stamp(c->pairs.n_pairs, -1), lp_of(c->pairs.n_pairs, 0);
-    int64_t need = 0; bool ok = true;
+    std::vector<int> pool_slots, pool_pairs, pool_rowptr, pool_rsplit; std::vector<Nbr> pool_ent;
+    std::vector<int> pstamp(c->pairs.n_pairs, -1), plocal(c->pairs.n_pairs, 0);
+    int64_t need = 0; bool ok = true; int stamp_id = 0;
+    int n_packed = 0, n_streamed = 0;
 
-    // state of the packed item being built
-    FibreItem cur = { 0, 0, 0, W, lcx_w, pitch_w, 0, 0 }; double cur_cost = 0; int64_t cur_nnz = 0; int cur_id = 0;
-    auto packed_need = [&](int nslot, int npair, int64_t nnz) { return (int64_t)nslot * kf * pitch_w + (int64_t)npair * kf * kt + (2 * nnz + 2 * nslot + 2 + 1) / 2; };
-    auto flush = [&]()
+    auto ord_of = [&](int64_t s) { return c->grid.ord1d[(int64_t)H.slot_elem[s] * d + t]; };
+    auto need_of = [&](int64_t nsrc, int64_t npair, int64_t nnz, int64_t ntgt) { return nsrc * kf * pitch_w + npair * kf * kt + (2 * nnz + 2 * ntgt + 2 + 1) / 2; };
+
+    // emit one packed item: targets (slots) and, per target, its neighbour list; sources = union (kept in first-seen order)
+    // fibre_s0: first slot of the fibre the targets belong to (all targets of one call are of one fibre) -- for packing
+    // several fibres call begin/add/end.
+    struct Build { std::vector<int> src, tgt, rowptr, rsplit; std::vector<Nbr> ent; std::vector<int> pairs; double cost = 0; } B;
+    std::vector<int> sstamp(c->grid.n, -1), slocal(c->grid.n, 0);
+    auto begin_item = [&]() { B = Build(); B.rowptr.push_back(0); ++stamp_id; };
+    auto add_row = [&](int64_t s, int64_t fibre_s0)
     {
-        if (cur.nslot == 0) return;
-        need = std::max(need, packed_need(cur.nslot, cur.npair, cur_nnz));
-        items.push_back(cur); cost.push_back(cur_cost * W);
-        cur.nslot = 0; cur.npair = 0; cur_cost = 0; cur_nnz = 0; ++cur_id;
+        B.tgt.push_back((int)s);
+        B.rsplit.push_back(nsplit[s]);
+        for (int64_t p = nptr[s]; p < nptr[s + 1]; ++p)
+        {
+            const int ss = (int)(fibre_s0 + nbr[p].local), pr = nbr[p].pair;
+            if (sstamp[ss] != stamp_id) { sstamp[ss] = stamp_id; slocal[ss] = (int)B.src.size(); B.src.push_back(ss); }
+            if (pstamp[pr] != stamp_id) { pstamp[pr] = stamp_id; plocal[pr] = (int)B.pairs.size(); B.pairs.push_back(pr); }
+            B.ent.push_back({ slocal[ss], plocal[pr] });
+        }
+        B.rowptr.push_back((int)B.ent.size());
+        B.cost += (double)(nptr[s + 1] - nptr[s]);
     };
-    auto add_streamed = [&](int64_t s0, int m, double fc)
+    auto item_need = [&]() { return need_of((int64_t)B.src.size(), (int64_t)B.pairs.size(), (int64_t)B.ent.size(), (int64_t)B.tgt.size()); };
+    auto end_item = [&]()
     {
-        // column chunks: at most 32*ct columns per warp pass and m*kf*pitch <= cap
-        int ncol = std::min<int64_t>(std::min(W, 32 * ct), cap / ((int64_t)m * kf));
+        if (B.tgt.empty()) return;
+        FibreItem x; std::memset(&x, 0, sizeof(x));
+        x.col0 = 0; x.ncol = W; x.lcx = lcx_w; x.pitch = pitch_w;
+        x.npair = (int)B.pairs.size(); x.pair_ofs = (int)pool_pairs.size();
+        x.nsrc = (int)B.src.size(); x.src_ofs = (int)pool_slots.size();
+        pool_slots.insert(pool_slots.end(), B.src.begin(), B.src.end());
+        x.ntgt = (int)B.tgt.size(); x.tgt_ofs = (int)pool_slots.size();
+        pool_slots.insert(pool_slots.end(), B.tgt.begin(), B.tgt.end());
+        x.ent_ofs = (int)pool_ent.size(); x.row_ofs = (int)pool_rowptr.size();
+        pool_pairs.insert(pool_pairs.end(), B.pairs.begin(), B.pairs.end());
+        pool_rowptr.insert(pool_rowptr.end(), B.rowptr.begin(), B.rowptr.end());
+        pool_rsplit.insert(pool_rsplit.end(), B.rsplit.begin(), B.rsplit.end()); pool_rsplit.push_back(0);   // keep the pools aligned
+        pool_ent.insert(pool_ent.end(), B.ent.begin(), B.ent.end());
+        need = std::max(need, item_need());
+        items.push_back(x); cost.push_back(B.cost * W); ++n_packed;
+        B = Build();
+    };
+    auto add_streamed = [&](int64_t s0, int m, int ntgt, double fc, int max_cols)
+    {
+        int ncol = (int)std::min<int64_t>(std::min(std::min(W, 32 * ct), max_cols), cap / ((int64_t)m * kf));
         if (ncol < 1) { ok = false; return; }
         const int nchunk = (W + ncol - 1) / ncol;
         ncol = (W + nchunk - 1) / nchunk;
-        FibreItem sp = { (int)s0, m, 0, ncol, 0, 0, 0, 0 };
+        FibreItem sp; std::memset(&sp, 0, sizeof(sp));
+        sp.slot0 = (int)s0; sp.nslot = m; sp.ncol = ncol; sp.ntgt = ntgt;
         while ((1 << sp.lcx) < next_pow2((ncol + ct - 1) / ct)) sp.lcx++;
         sp.pitch = choose_pitch(ncol, kf, 1 << sp.lcx);
         if ((int64_t)m * kf * sp.pitch > cap) sp.pitch = ncol;
         need = std::max(need, (int64_t)m * kf * sp.pitch);
-        for (int c0 = 0; c0 < W; c0 += ncol) { sp.col0 = c0; items.push_back(sp); cost.push_back(4.0 * fc * std::min(ncol, W - c0)); }
+        for (int c0 = 0; c0 < W; c0 += ncol) { sp.col0 = c0; items.push_back(sp); cost.push_back(8.0 * fc * std::min(ncol, W - c0)); ++n_streamed; }
     };
+
+    begin_item();
     for (int64_t f = 0; f < H.n_fibre && ok; ++f)
     {
         const int64_t s0 = H.fibre_ptr[f]; const int m = (int)(H.fibre_ptr[f + 1] - s0);
         const int64_t fnnz = nptr[s0 + m] - nptr[s0];
-        const double fc = (double)fnnz;
-        bool placed = false;
-        if (!wide && packed_need(m, (int)std::min<int64_t>(fnnz, c->pairs.n_pairs), fnnz) <= 4 * (int64_t)cap)     // cheap pre-filter
+        if (wide) { add_streamed(s0, m, m, (double)fnnz, W); continue; }
+        // (1) whole fibre into the running packed item?
+        if (need_of(m, 1, fnnz, m) <= cap)
         {
-            // try to extend the current packed item
-            if (cur.nslot > 0)
-            {
-                std::vector<int> touched;
-                int nn = 0;
-                for (int64_t p = nptr[s0]; p < nptr[s0 + m]; ++p) if (stamp[nbr[p].pair] != cur_id) { stamp[nbr[p].pair] = cur_id; touched.push_back(nbr[p].pair); ++nn; }
-                if (packed_need(cur.nslot + m, cur.npair + nn, cur_nnz + fnnz) <= pack_cap)
-                {
-                    for (int pr : touched) { lp_of[pr] = cur.npair++; item_pairs.push_back(pr); }
-                    placed = true;
-                }
-                else
-                {
-                    for (int pr : touched) stamp[pr] = -1;
-                    flush();
-                }
-            }
-            if (!placed)
-            {
-                // start a new packed item with this fibre alone, if it fits
-                cur.slot0 = (int)s0; cur.pair_ofs = (int)item_pairs.size();
-                std::vector<int> touched;
-                for (int64_t p = nptr[s0]; p < nptr[s0 + m]; ++p) if (stamp[nbr[p].pair] != cur_id) { stamp[nbr[p].pair] = cur_id; touched.push_back(nbr[p].pair); }
-                if (packed_need(m, (int)touched.size(), fnnz) <= cap)
-                {
-                    for (int pr : touched) { lp_of[pr] = cur.npair++; item_pairs.push_back(pr); }
-                    placed = true;
-                }
-                else { for (int pr : touched) stamp[pr] = -1; }
-            }
-            if (placed)
-            {
-                for (int64_t p = nptr[s0]; p < nptr[s0 + m]; ++p) nbr_lp[p] = lp_of[nbr[p].pair];
-                cur.nslot += m; cur_cost += fc; cur_nnz += fnnz;
-            }
+            Build saved = B; const int saved_stamp = stamp_id;
+            for (int64_t s = s0; s < s0 + m; ++s) add_row(s, s0);
+            if (item_need() <= pack_cap || saved.tgt.empty()) { if (item_need() <= cap) continue; }
+            // does not fit together with what is already there: close the old item and retry alone
+            B = saved; (void)saved_stamp;
+            end_item(); begin_item();
+            for (int64_t s = s0; s < s0 + m; ++s) add_row(s, s0);
+            if (item_need() <= cap) continue;
+            begin_item();     // discard: falls through to the long-fibre handling
         }
-        if (!placed) { flush(); add_streamed(s0, m, fc); }
+        else { end_item(); begin_item(); }
+        // (2) long fibre: cut at level k_c
+        int lmax = 0; for (int64_t s = s0; s < s0 + m; ++s) lmax = std::max(lmax, level_of_order(ord_of(s)));
+        bool cut_ok = false;
+        for (int kc = 1; kc <= lmax && !cut_ok; ++kc)
+        {
+            // rows of level >= kc grouped by their level-kc ancestor: index (ord - 2^(n-1)) >> (n - kc)
+            std::map<int, std::vector<int64_t>> groups; int ntop = 0;
+            for (int64_t s = s0; s < s0 + m; ++s)
+            {
+                const int o = ord_of(s), n = level_of_order(o);
+                if (n < kc) { ++ntop; continue; }
+                groups[(o - (1 << (n - 1))) >> (n - kc)].push_back(s);
+            }
+            // feasibility: every group must fit
+            bool fits = true;
+            const size_t mark_items = items.size(), mark_slots = pool_slots.size(), mark_pairs = pool_pairs.size(), mark_rp = pool_rowptr.size(), mark_rs = pool_rsplit.size(), mark_ent = pool_ent.size();
+            const int64_t mark_need = need; const int mark_np = n_packed;
+            for (auto & g : groups)
+            {
+                begin_item();
+                for (int64_t s : g.second) add_row(s, s0);
+                if (item_need() > cap) { fits = false; break; }
+                end_item();
+            }
+            if (!fits)
+            {
+                items.resize(mark_items); cost.resize(mark_items); pool_slots.resize(mark_slots); pool_pairs.resize(mark_pairs);
+                pool_rowptr.resize(mark_rp); pool_rsplit.resize(mark_rs); pool_ent.resize(mark_ent); need = mark_need; n_packed = mark_np;
+                begin_item();
+                continue;
+            }
+            // the top rows (a prefix of the fibre in 1D order) as streamed items over narrow column ranges
+            double tc = 0; for (int64_t s = s0; s < s0 + ntop; ++s) tc += (double)(nptr[s + 1] - nptr[s]);
+            if (ntop > 0) add_streamed(s0, m, ntop, tc, 2 * ct);
+            cut_ok = true;
+            begin_item();
+        }
+        if (!cut_ok) { begin_item(); add_streamed(s0, m, m, (double)fnnz, W); }
     }
     if (ok)
     {
-        flush();
+        end_item();
         std::vector<int> order(items.size());
         for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
@@ -459,15 +524,16 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
         for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
         if (need <= fibre_smem_capacity_doubles() &&
             upload(&L.d_items, sorted.data(), sorted.size(), c->stream) == cudaSuccess &&
-            upload(&L.d_nbr_lp, nbr_lp.data(), nbr_lp.size(), c->stream) == cudaSuccess &&
-            upload(&L.d_item_pairs, item_pairs.data(), item_pairs.size(), c->stream) == cudaSuccess &&
+            upload(&L.d_slots, pool_slots.data(), pool_slots.size(), c->stream) == cudaSuccess &&
+            upload(&L.d_pairs, pool_pairs.data(), pool_pairs.size(), c->stream) == cudaSuccess &&
+            upload(&L.d_rowptr, pool_rowptr.data(), pool_rowptr.size(), c->stream) == cudaSuccess &&
+            upload(&L.d_rsplit, pool_rsplit.data(), pool_rsplit.size(), c->stream) == cudaSuccess &&
+            upload((Nbr **)&L.d_ent, pool_ent.data(), pool_ent.size(), c->stream) == cudaSuccess &&
             cudaStreamSynchronize(c->stream) == cudaSuccess)
         { L.n = (int)sorted.size(); L.ct = ct; L.smem = (int)need; L.ok = true; }
         if (std::getenv("AMDG_VERBOSE"))
-        {
-            int np = 0; for (auto & x : sorted) np += x.npair > 0;
-            fprintf(stderr, "[amdg] items t=%d W=%d kf=%d kt=%d rel=%d: %d items (%d packed, %d streamed), smem %lld doubles, ct %d\n", t, W, kf, kt, rel, (int)sorted.size(), np, (int)sorted.size() - np, (long long)need, ct);
-        }
+            fprintf(stderr, "[amdg] items t=%d W=%d kf=%d kt=%d rel=%d par=%d: %d items (%d packed, %d streamed), smem %lld doubles, ct %d\n",
+                    t, W, kf, kt, rel, par, (int)sorted.size(), n_packed, n_streamed, (long long)need, ct);
     }
     return c->items.emplace(key, L).first->second;
 }
@@ -484,14 +550,14 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
         const amdg_ctx::ItemList * L = nullptr;
-        if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf, O.kt, rel); if (!L->ok) L = nullptr; }
+        if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf, O.kt, rel, cnt * n_comp); if (!L->ok) L = nullptr; }
         if (c->kernel_variant == 2 && !L) return fail(AMDG_EINVAL, "fibre-staged kernel requested but a fibre does not fit in shared memory");
         cudaError_t e;
         if (L)
         {
             FibreSweepArgs a;
             a.slot_elem = D.slot_elem; a.slot_fbase = D.slot_fbase; a.nbr_ptr = D.nbr_ptr[rel]; a.nbr_split = D.nbr_split[rel]; a.nbr = D.nbr[rel];
-            a.nbr_lp = L->d_nbr_lp; a.item_pairs = L->d_item_pairs;
+            a.pool_slots = L->d_slots; a.pool_pairs = L->d_pairs; a.pool_rowptr = L->d_rowptr; a.pool_rsplit = L->d_rsplit; a.pool_ent = L->d_ent;
             a.blocks = O.d_blocks; a.items = L->d_items; a.n_item = L->n; a.n_elem = c->grid.n; a.inner = inner; a.lu = lu; a.n_comp = n_comp;
             a.n_job = cnt; a.smem_doubles = L->smem;
             for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];

@@ -141,12 +141,20 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
         off_to[r] = o * KT * inner + i;
     }
 
-    // ---- phase 1: stage the source entries X[row][k][column]
+    if (it.npair > 0)
     {
+        // ---- packed item: source rows, the operator blocks of the item's distinct pairs and the item-local
+        // neighbour lists all go to shared memory; phase 2 touches global memory only for the stores.
+        const int * __restrict__ srcs = a.pool_slots + it.src_ofs;
+        const int * __restrict__ tgts = a.pool_slots + it.tgt_ofs;
+        double * Bs = X + (int64_t)it.nsrc * KF * P;
+        int * rowptr = reinterpret_cast<int *>(Bs + (int64_t)it.npair * (KF * KT));      // [ntgt+1]
+        int * rsplit = rowptr + it.ntgt + 1;                                               // [ntgt]
+        int * ent = rsplit + it.ntgt;                                                      // [nnz][2]
         const int ty = tid >> it.lcx, ny = FIBRE_THREADS >> it.lcx;
-        for (int j = ty; j < it.nslot; j += ny)
+        for (int j = ty; j < it.nsrc; j += ny)
         {
-            const int e = a.slot_elem[it.slot0 + j];
+            const int e = a.slot_elem[srcs[j]];
             const double * __restrict__ g = src + (int64_t)e * s_from;
             double * xr = X + (int64_t)j * KF * P;
 #pragma unroll
@@ -157,36 +165,23 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
                 for (int k = 0; k < KF; ++k) xr[k * P + cc[r]] = __ldg(g + off_from[r] + (int64_t)k * inner);
             }
         }
-    }
-
-    if (it.npair > 0)
-    {
-        // ---- packed item: operator blocks of the item's distinct pairs and the neighbour lists go to shared memory too
-        double * Bs = X + (int64_t)it.nslot * KF * P;
-        int * rowptr = reinterpret_cast<int *>(Bs + (int64_t)it.npair * (KF * KT));      // [nslot+1]
-        int * rsplit = rowptr + it.nslot + 1;                                               // [nslot]
-        int * ent = rsplit + it.nslot;                                                      // [nnz][2]: item-local source row, local pair
-        const int64_t base = a.nbr_ptr[it.slot0];
-        const int nnz = (int)(a.nbr_ptr[it.slot0 + it.nslot] - base);
         for (int idx = tid; idx < it.npair * (KF * KT); idx += FIBRE_THREADS)
         {
             const int pr = idx / (KF * KT), r = idx - pr * (KF * KT);
-            Bs[idx] = __ldg(a.blocks + (int64_t)a.item_pairs[it.pair_ofs + pr] * (KF * KT) + r);
+            Bs[idx] = __ldg(a.blocks + (int64_t)a.pool_pairs[it.pair_ofs + pr] * (KF * KT) + r);
         }
-        for (int j = tid; j <= it.nslot; j += FIBRE_THREADS) rowptr[j] = (int)(a.nbr_ptr[it.slot0 + j] - base);
-        for (int j = tid; j < it.nslot; j += FIBRE_THREADS) rsplit[j] = a.nbr_split[it.slot0 + j];
+        for (int j = tid; j <= it.ntgt; j += FIBRE_THREADS) rowptr[j] = a.pool_rowptr[it.row_ofs + j];
+        for (int j = tid; j < it.ntgt; j += FIBRE_THREADS) rsplit[j] = a.pool_rsplit[it.row_ofs + j];
+        const int nnz = a.pool_rowptr[it.row_ofs + it.ntgt];
         for (int i = tid; i < nnz; i += FIBRE_THREADS)
         {
-            const NbrDev nb = a.nbr[base + i];
-            ent[2 * i] = nb.local; ent[2 * i + 1] = a.nbr_lp[base + i];
+            const NbrDev nb = a.pool_ent[it.ent_ofs + i];
+            ent[2 * i] = nb.local; ent[2 * i + 1] = nb.pair;
         }
         __syncthreads();
 
-        const int ty = tid >> it.lcx, ny = FIBRE_THREADS >> it.lcx;
-        for (int j = ty; j < it.nslot; j += ny)
+        for (int j = ty; j < it.ntgt; j += ny)
         {
-            const int slot = it.slot0 + j;
-            const int frow = a.slot_fbase[slot] - it.slot0;
             int n0 = rowptr[j], n1 = rowptr[j + 1];
             if (a.lu == AMDG_LU_U) n1 = n0 + rsplit[j];
             else if (a.lu == AMDG_LU_L) n0 = n0 + rsplit[j];
@@ -197,7 +192,7 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
                 for (int q = 0; q < KT; ++q) acc[r][q] = 0.0;
             for (int p = n0; p < n1; ++p)
             {
-                const double * xr = X + (int64_t)(frow + ent[2 * p]) * KF * P;
+                const double * xr = X + (int64_t)ent[2 * p] * KF * P;
                 const double * B = Bs + ent[2 * p + 1] * (KF * KT);
 #pragma unroll
                 for (int k = 0; k < KF; ++k)
@@ -214,7 +209,7 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
                     }
                 }
             }
-            double * y = dst + (int64_t)a.slot_elem[slot] * s_to;
+            double * y = dst + (int64_t)a.slot_elem[tgts[j]] * s_to;
 #pragma unroll
             for (int r = 0; r < CT; ++r)
             {
@@ -232,7 +227,25 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
         return;
     }
 
-    // ---- streamed item (a long fibre, or a column range of one): one warp per target row; the 32 lanes are
+    // ---- streamed item: stage the whole fibre (column range) ...
+    {
+        const int ty = tid >> it.lcx, ny = FIBRE_THREADS >> it.lcx;
+        for (int j = ty; j < it.nslot; j += ny)
+        {
+            const int e = a.slot_elem[it.slot0 + j];
+            const double * __restrict__ g = src + (int64_t)e * s_from;
+            double * xr = X + (int64_t)j * KF * P;
+#pragma unroll
+            for (int r = 0; r < CT; ++r)
+            {
+                if (!ok[r]) continue;
+#pragma unroll
+                for (int k = 0; k < KF; ++k) xr[k * P + cc[r]] = __ldg(g + off_from[r] + (int64_t)k * inner);
+            }
+        }
+    }
+
+    // ... then one warp per target row (the first ntgt rows of the fibre); the 32 lanes are
     // (32/cx neighbour slices) x (cx column lanes); neighbour entries are fetched 32 at a time (coalesced) and
     // broadcast with shuffles, operator blocks come from L2; partial sums of the slices are reduced with shuffles.
     __syncthreads();
@@ -241,10 +254,10 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
         const int cxw = min(cx, 32);
         const int ns = 32 / cxw;
         const int sl = lane / cxw;
-        for (int j = warp; j < it.nslot; j += FIBRE_THREADS / 32)
+        for (int j = warp; j < it.ntgt; j += FIBRE_THREADS / 32)
         {
             const int slot = it.slot0 + j;
-            const int frow = a.slot_fbase[slot] - it.slot0;
+            const int frow = 0;                      // a streamed item stages exactly one fibre
             int64_t n0 = a.nbr_ptr[slot], n1 = a.nbr_ptr[slot + 1];
             const int split = a.nbr_split[slot];
             if (a.lu == AMDG_LU_U) n1 = n0 + split;

@@ -47,14 +47,17 @@ struct SweepArgs
 // long fibre) in shared memory, so every source block is read from HBM once per sweep.
 struct FibreItem
 {
-    int slot0;      // first slot (fibre-major element order of dimension t)
-    int nslot;      // number of slots: whole fibres
-    int col0;       // first column of the (outer x inner) plane
-    int ncol;       // columns staged by this item (the last chunk of a split fibre may hold fewer valid ones)
-    int lcx;        // log2 of the column-lane count
-    int pitch;      // shared-memory row pitch in doubles
-    int pair_ofs;   // packed items: first entry of the item's distinct-pair table in `item_pairs`
-    int npair;      // packed items: number of distinct 1D pairs (operator blocks staged in shared memory); 0 = streamed
+    int slot0, nslot;   // streamed item: the fibre's slots [slot0, slot0+nslot) are staged
+    int col0, ncol;     // column range of the (outer x inner) plane staged by this item
+    int lcx;            // log2 of the column-lane count
+    int pitch;          // shared-memory row pitch in doubles
+    int npair;          // packed item: distinct 1D pairs whose operator blocks are staged (0 = streamed item)
+    int pair_ofs;       //   first entry in the `pairs` pool
+    int nsrc, src_ofs;  // packed item: rows to stage = slots pool[src_ofs .. +nsrc)
+    int ntgt, tgt_ofs;  // target rows: packed = slots pool[tgt_ofs .. +ntgt); streamed = the first ntgt rows of the fibre
+    int ent_ofs;        // packed item: first neighbour entry in the `ent` pool; row pointers at rowptr pool[tgt_ofs + item index ..]
+    int row_ofs;        //   first entry in the rowptr / rsplit pools (ntgt+1 / ntgt entries)
+    int pad0, pad1;
 };
 
 struct FibreSweepArgs
@@ -64,8 +67,12 @@ struct FibreSweepArgs
     const int64_t * nbr_ptr;
     const int * nbr_split;
     const NbrDev * nbr;
-    const int * nbr_lp;         // per neighbour entry: index into the item's distinct-pair table (packed items)
-    const int * item_pairs;     // pool of distinct-pair tables
+    // pools of the packed items (built per work list)
+    const int * pool_slots;     // source / target slot lists
+    const int * pool_pairs;     // distinct pair ids
+    const int * pool_rowptr;    // per target row: first entry (relative to the item's ent_ofs)
+    const int * pool_rsplit;    // per target row: number of leading U entries
+    const NbrDev * pool_ent;    // (item-local source row, item-local pair)
     const double * blocks;
     const FibreItem * items;
     int n_item;
