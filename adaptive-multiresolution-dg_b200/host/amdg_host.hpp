@@ -1,0 +1,268 @@
+// C++ host mirror of the reference's class surface for the fast-transform path, on top of the C ABI
+// (include/amdg.h).  Names, call order and argument meaning follow the reference so that an example's time loop
+// reads the same; storage moves from the hash-keyed Element map to device-resident flat arrays.
+//
+//   reference class (file:line)                                    mirror here
+//   DGSolution / DGAdapt          include/DGSolution.h:11, DGAdapt.h:6     amdg::DGSolution  (device arrays + grid tables)
+//   OperatorMatrix1D<U,V>         include/OperatorMatrix1D.h:10            amdg::OperatorMatrix1D (handles of registered tables)
+//   FastLagrIntp / FastHermIntp   include/FastMultiplyLU.h:190,224         amdg::FastLagrIntp, amdg::FastHermIntp
+//   FastLagrInit / FastHermInit   include/FastMultiplyLU.h:344,320         amdg::FastLagrInit, amdg::FastHermInit
+//   LagrInterpolation (fast part) include/Interpolation.h:36               amdg::LagrInterpolation
+//   HyperbolicLagrRHS/HermRHS     include/FastMultiplyLU.h:571,597         amdg::HyperbolicLagrRHS (Hermite: same class, Hermite tables)
+//   HyperbolicAlptRHS             include/FastMultiplyLU.h:619             amdg::HyperbolicAlptRHS
+//   ForwardEuler/RK2SSP/RK2Midpoint/RK3SSP  include/ODESolver.h:115-206    amdg::ExplicitRK + the four scheme classes
+//
+// Error convention: the reference prints and exit(1)s; the mirror throws amdg::Error carrying amdg_last_error().
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/amdg.h"
+
+namespace amdg {
+
+struct Error : std::runtime_error { explicit Error(const std::string & m) : std::runtime_error(m) {} };
+inline void check(int rc) { if (rc < 0) throw Error(std::string("amdg: ") + amdg_last_error()); }
+
+// device array of doubles owned by a context
+class DeviceArray
+{
+public:
+    DeviceArray() {}
+    DeviceArray(amdg_ctx * c, int64_t n) : ctx_(c), n_(n) { check(amdg_dev_alloc(c, n, &p_)); check(amdg_dev_zero(c, p_, n)); }
+    DeviceArray(const DeviceArray &) = delete;
+    DeviceArray & operator=(const DeviceArray &) = delete;
+    DeviceArray(DeviceArray && o) noexcept { *this = std::move(o); }
+    DeviceArray & operator=(DeviceArray && o) noexcept { release(); ctx_ = o.ctx_; p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; return *this; }
+    ~DeviceArray() { release(); }
+    double * data() const { return p_; }
+    int64_t size() const { return n_; }
+    void upload(const double * h) { check(amdg_dev_upload(ctx_, p_, h, n_)); }
+    void download(double * h) const { check(amdg_dev_download(ctx_, h, p_, n_)); }
+    void set_zero() { check(amdg_dev_zero(ctx_, p_, n_)); }
+private:
+    void release() { if (p_) amdg_dev_free(ctx_, p_); p_ = nullptr; }
+    amdg_ctx * ctx_ = nullptr; double * p_ = nullptr; int64_t n_ = 0;
+};
+
+// The device-side stand-in of DGSolution: the statics Element::DIM / PMAX_alpt / PMAX_intp / VEC_NUM
+// (include/Element.h:21-24) become constructor arguments; the element arrays of include/Element.h:76-124 become
+// flat device arrays [vec][elem][block] (fp_intp / fucoe_intp: [vec][dim][elem][block]).
+class DGSolution
+{
+public:
+    DGSolution(int dim, int nmax, int pmax_alpt, int pmax_intp, int vec_num, int device = 0)
+        : DIM(dim), NMAX(nmax), PMAX_alpt(pmax_alpt), PMAX_intp(pmax_intp), VEC_NUM(vec_num)
+    { check(amdg_ctx_create(dim, nmax, pmax_alpt, pmax_intp, device, &ctx)); }
+    ~DGSolution() { ucoe_alpt = DeviceArray(); up_intp = DeviceArray(); ucoe_intp = DeviceArray(); fp_intp = DeviceArray(); fucoe_intp = DeviceArray(); rhs = DeviceArray(); amdg_ctx_destroy(ctx); }
+    DGSolution(const DGSolution &) = delete;
+
+    // (re)build the index tables from the element list (call after construction / DGAdapt::refine / coarsen);
+    // rows in the caller's order, e.g. the iteration order of the reference's DGSolution::dg
+    void set_elements(int64_t n, const int * level, const int * suppt)
+    {
+        check(amdg_grid_set(ctx, n, level, suppt));
+        n_elem = n;
+        ucoe_alpt = DeviceArray(ctx, VEC_NUM * n * size_alpt());
+        rhs = DeviceArray(ctx, VEC_NUM * n * size_alpt());
+        up_intp = DeviceArray(ctx, VEC_NUM * n * size_intp());
+        ucoe_intp = DeviceArray(ctx, VEC_NUM * n * size_intp());
+        fp_intp = DeviceArray(ctx, (int64_t)VEC_NUM * DIM * n * size_intp());
+        fucoe_intp = DeviceArray(ctx, (int64_t)VEC_NUM * DIM * n * size_intp());
+    }
+    // DGSolution(sparse, level_init, ...) initial grid (source/DGSolution.cpp:10-57)
+    void init_sparse_grid(int level_init, bool sparse = true)
+    {
+        const int64_t n = amdg_sparse_grid(DIM, level_init, sparse, nullptr, nullptr);
+        std::vector<int> l(n * DIM), j(n * DIM);
+        amdg_sparse_grid(DIM, level_init, sparse, l.data(), j.data());
+        set_elements(n, l.data(), j.data());
+    }
+    int64_t size_alpt() const { int64_t s = 1; for (int d = 0; d < DIM; ++d) s *= PMAX_alpt + 1; return s; }
+    int64_t size_intp() const { int64_t s = 1; for (int d = 0; d < DIM; ++d) s *= PMAX_intp + 1; return s; }
+    int64_t size_basis_alpt() const { return n_elem * size_alpt(); }                       // source/DGSolution.cpp:841
+    int64_t get_dof() const { return size_basis_alpt() * VEC_NUM; }                        // source/DGSolution.cpp:846 (all variables evolve)
+    void set_rhs_zero() { rhs.set_zero(); }                                                  // source/DGSolution.cpp:1067
+    double * ucoe(int v) const { return ucoe_alpt.data() + (int64_t)v * n_elem * size_alpt(); }
+    double * rhs_v(int v) const { return rhs.data() + (int64_t)v * n_elem * size_alpt(); }
+    double * up(int v) const { return up_intp.data() + (int64_t)v * n_elem * size_intp(); }
+    double * ucoe_i(int v) const { return ucoe_intp.data() + (int64_t)v * n_elem * size_intp(); }
+    double * fp(int v, int d) const { return fp_intp.data() + ((int64_t)v * DIM + d) * n_elem * size_intp(); }
+    double * fucoe(int v, int d) const { return fucoe_intp.data() + ((int64_t)v * DIM + d) * n_elem * size_intp(); }
+
+    const int DIM, NMAX, PMAX_alpt, PMAX_intp, VEC_NUM;
+    amdg_ctx * ctx = nullptr;
+    int64_t n_elem = 0;
+    DeviceArray ucoe_alpt, up_intp, ucoe_intp, fp_intp, fucoe_intp, rhs;
+};
+
+// Handles of the registered 1D tables of one (U,V) basis pair: the members the path uses
+// (include/OperatorMatrix1D.h:24-71).  Built from the reference's dense tables (row-major [from][to]).
+struct OperatorMatrix1D
+{
+    int u_v = -1, u_vx = -1, ulft_vjp = -1, urgt_vjp = -1, ujp_vjp = -1, uave2_vjp = -1;   // uave2 = ulft_vjp + urgt_vjp (source/FastMultiplyLU.cpp:1165)
+    int edge_from = 0, edge_to = 0;
+    OperatorMatrix1D() {}
+    OperatorMatrix1D(DGSolution & dg, int edge_from_, int edge_to_, const double * t_u_v, const double * t_u_vx, const double * t_ulft_vjp,
+                     const double * t_urgt_vjp, const double * t_ujp_vjp = nullptr) : edge_from(edge_from_), edge_to(edge_to_)
+    {
+        const int T = 1 << dg.NMAX, rows = T * edge_from, cols = T * edge_to;
+        check(amdg_op_register(dg.ctx, t_u_v, rows, cols, edge_from, edge_to, &u_v));
+        check(amdg_op_register(dg.ctx, t_u_vx, rows, cols, edge_from, edge_to, &u_vx));
+        check(amdg_op_register(dg.ctx, t_ulft_vjp, rows, cols, edge_from, edge_to, &ulft_vjp));
+        check(amdg_op_register(dg.ctx, t_urgt_vjp, rows, cols, edge_from, edge_to, &urgt_vjp));
+        check(amdg_op_combine(dg.ctx, ulft_vjp, 1.0, urgt_vjp, 1.0, &uave2_vjp));
+        if (t_ujp_vjp) check(amdg_op_register(dg.ctx, t_ujp_vjp, rows, cols, edge_from, edge_to, &ujp_vjp));
+    }
+};
+
+// FastLagrIntp / FastHermIntp (source/FastMultiplyLU.cpp:1316-1390): the constructor takes the point table in the
+// reference's orientation Lag_pt_Alpt_1D[point][alpert] and transposes it like the reference does (:1350-1358).
+class FastLagrIntp
+{
+public:
+    FastLagrIntp(DGSolution & dg, const std::vector<std::vector<double>> & Lag_pt_Alpt_1D, const std::vector<std::vector<double>> & Lag_pt_Alpt_1D_d1)
+        : dg_(&dg) { op_pt_ = reg(Lag_pt_Alpt_1D); if (!Lag_pt_Alpt_1D_d1.empty()) op_d1_ = reg(Lag_pt_Alpt_1D_d1); }
+    void eval_up_Lagr() { for (int v = 0; v < dg_->VEC_NUM; ++v) eval_up_Lagr(v); }
+    void eval_up_Lagr(int vec_index)
+    {
+        std::vector<int> ops(dg_->DIM, op_pt_), rels(dg_->DIM, AMDG_REL_VOL);
+        check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->ucoe(vec_index), dg_->up(vec_index), 1, 1.0, 0));
+    }
+    void eval_der_up_Lagr(int d0)
+    {
+        std::vector<int> ops(dg_->DIM, op_pt_), rels(dg_->DIM, AMDG_REL_VOL); ops[d0] = op_d1_;
+        for (int v = 0; v < dg_->VEC_NUM; ++v) check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->ucoe(v), dg_->up(v), 1, 1.0, 0));
+    }
+protected:
+    int reg(const std::vector<std::vector<double>> & pt_alpt)
+    {
+        const size_t np = pt_alpt.size(), na = pt_alpt[0].size();
+        std::vector<double> t(na * np);
+        for (size_t r = 0; r < na; ++r) for (size_t c = 0; c < np; ++c) t[r * np + c] = pt_alpt[c][r];
+        int op; check(amdg_op_register(dg_->ctx, t.data(), (int)na, (int)np, dg_->PMAX_alpt + 1, dg_->PMAX_intp + 1, &op)); return op;
+    }
+    DGSolution * dg_; int op_pt_ = -1, op_d1_ = -1;
+};
+class FastHermIntp : public FastLagrIntp
+{
+public:
+    FastHermIntp(DGSolution & dg, const std::vector<std::vector<double>> & Her_pt_Alpt_1D) : FastLagrIntp(dg, Her_pt_Alpt_1D, {}) {}
+    void eval_up_Herm() { eval_up_Lagr(); }
+};
+
+// FastLagrInit / FastHermInit (source/FastMultiplyLU.cpp:1572-1625): ucoe_intp -> ucoe_alpt with the u_v table
+class FastLagrInit
+{
+public:
+    FastLagrInit(DGSolution & dg, const OperatorMatrix1D & matrix) : dg_(&dg), op_(matrix.u_v) {}
+    void eval_ucoe_Alpt_Lagr()
+    {
+        std::vector<int> ops(dg_->DIM, op_), rels(dg_->DIM, AMDG_REL_VOL);
+        check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->ucoe_intp.data(), dg_->ucoe_alpt.data(), dg_->VEC_NUM, 1.0, 0));
+    }
+    void eval_ucoe_Alpt_Herm() { eval_ucoe_Alpt_Lagr(); }
+private:
+    DGSolution * dg_; int op_;
+};
+typedef FastLagrInit FastHermInit;
+
+// LagrInterpolation / HermInterpolation, fast wrappers only (source/Interplation.cpp:4033-4046, 4609-4621, 891-1048,
+// 1222-1430).  The std::function flux of the reference becomes an enumerated flux id per dimension.
+class LagrInterpolation
+{
+public:
+    // pw_anc / pw_wt: the pwts stencils of every 1D element (include/Interpolation.h:5-11) in amdg_op_register_hier layout
+    LagrInterpolation(DGSolution & dg, const int * pw_anc, const double * pw_wt) : dg_(&dg)
+    { check(amdg_op_register_hier(dg.ctx, pw_anc, pw_wt, dg.PMAX_intp + 1, &op_hier_)); }
+    // nonlinear_Lagr_fast: fastLagr.eval_up_Lagr(); eval_fp_Lag(func, is_intp); eval_fp_to_coe_D_Lag(is_intp)
+    void nonlinear_Lagr_fast(const std::vector<int> & flux_id, const std::vector<double> & params, const std::vector<std::vector<bool>> & is_intp, FastLagrIntp & fastLagr)
+    {
+        fastLagr.eval_up_Lagr();
+        for (int v = 0; v < dg_->VEC_NUM; ++v)
+            for (int d = 0; d < dg_->DIM; ++d)
+            {
+                if (!is_intp[v][d]) continue;
+                const double * prm = params.empty() ? nullptr : &params[(size_t)d * 4];
+                check(amdg_pointwise(dg_->ctx, 1, &flux_id[d], prm, dg_->up(v), dg_->fp(v, d), nullptr));
+                check(amdg_hierarchize(dg_->ctx, op_hier_, dg_->fp(v, d), dg_->fucoe(v, d), 1));
+            }
+    }
+    // eval_up_to_coe_D_Lag: up_intp -> ucoe_intp
+    void eval_up_to_coe_D_Lag() { check(amdg_hierarchize(dg_->ctx, op_hier_, dg_->up_intp.data(), dg_->ucoe_intp.data(), dg_->VEC_NUM)); }
+    int hier_op() const { return op_hier_; }
+private:
+    DGSolution * dg_; int op_hier_ = -1;
+};
+
+// HyperbolicLagrRHS / HyperbolicHermRHS (source/FastMultiplyLU.cpp:1125-1267)
+class HyperbolicLagrRHS
+{
+public:
+    HyperbolicLagrRHS(DGSolution & dg, OperatorMatrix1D & oper) : dg_(&dg), m_(&oper) {}
+    void rhs_vol_scalar()
+    {
+        const int d = dg_->DIM; std::vector<int> rels(d, AMDG_REL_VOL);
+        for (int t = 0; t < d; ++t)
+        {
+            std::vector<int> ops(d, m_->u_v); ops[t] = m_->u_vx;
+            check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, t), dg_->rhs_v(0), 1, 1.0, 1));
+        }
+    }
+    void rhs_flx_intp_scalar()
+    {
+        const int d = dg_->DIM;
+        for (int t = 0; t < d; ++t)
+        {
+            std::vector<int> ops(d, m_->u_v), rels(d, AMDG_REL_VOL); ops[t] = m_->uave2_vjp; rels[t] = AMDG_REL_FLX;
+            check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, t), dg_->rhs_v(0), 1, 0.5, 1));
+        }
+    }
+private:
+    DGSolution * dg_; OperatorMatrix1D * m_;
+};
+typedef HyperbolicLagrRHS HyperbolicHermRHS;
+
+// HyperbolicAlptRHS::rhs_flx_penalty_scalar (source/FastMultiplyLU.cpp:1269-1276)
+class HyperbolicAlptRHS
+{
+public:
+    HyperbolicAlptRHS(DGSolution & dg, OperatorMatrix1D & oper_alpt) : dg_(&dg), m_(&oper_alpt) {}
+    void rhs_flx_penalty_scalar(const std::vector<double> & lax_alpha)
+    {
+        const int d = dg_->DIM;
+        if (d == 1) return;     // the reference's single-matrix form never sweeps for DIM == 1 (source/FastMultiplyLU.cpp:206-212, 249)
+        std::vector<int> sizes(d, dg_->PMAX_alpt + 1);
+        for (int t = 0; t < d; ++t)
+            check(amdg_sweep1d(dg_->ctx, m_->ujp_vjp, AMDG_REL_FLX, AMDG_LU_FULL, t, sizes.data(), dg_->ucoe(0), dg_->rhs_v(0), 1, -lax_alpha[t] / 2., 1));
+    }
+private:
+    DGSolution * dg_; OperatorMatrix1D * m_;
+};
+
+// ExplicitRK (include/ODESolver.h:76-112).  The reference packs Element arrays into Eigen vectors
+// (source/ODESolver.cpp:25-127); here ucoe_alpt / rhs already are the flat vectors, so init() only snapshots u_tn
+// and add_rhs_to_eigenvec()/final() are no-ops kept for call-order compatibility.
+class ExplicitRK
+{
+public:
+    ExplicitRK(DGSolution & dg, double dt_, int scheme, int stages) : num_stage(stages), dt(dt_), dg_(&dg), scheme_(scheme), u_tn_(dg.ctx, dg.get_dof()) {}
+    virtual ~ExplicitRK() {}
+    virtual void init() { check(amdg_axpby(dg_->ctx, dg_->get_dof(), 1.0, dg_->ucoe_alpt.data(), 0.0, u_tn_.data())); }
+    void set_rhs_zero() {}
+    void add_rhs_to_eigenvec() {}
+    virtual void step_stage(int stage) { check(amdg_rk_stage(dg_->ctx, scheme_, stage, dt, u_tn_.data(), dg_->ucoe_alpt.data(), dg_->rhs.data(), dg_->get_dof())); }
+    virtual void final() {}
+    const int num_stage;
+    const double dt;
+protected:
+    DGSolution * dg_; int scheme_; DeviceArray u_tn_;
+};
+struct ForwardEuler : ExplicitRK { ForwardEuler(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_EULER, 1) {} };
+struct RK2SSP : ExplicitRK { RK2SSP(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK2SSP, 2) {} };
+struct RK2Midpoint : ExplicitRK { RK2Midpoint(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK2MID, 2) {} };
+struct RK3SSP : ExplicitRK { RK3SSP(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK3SSP, 3) {} };
+
+}  // namespace amdg

@@ -190,3 +190,18 @@ def test_linearity_and_schedule_equivalence_large():
         outs.append(fx.cpu().numpy())
         ctx.close()
     assert rel(outs[0], outs[1]) < TOL
+
+
+def test_cpp_host_mirror_example(tmp_path):
+    """the C++ mirror of the reference's classes (host/amdg_host.hpp) drives one RK3SSP step of 2D Burgers"""
+    import lzma
+    import os
+    import subprocess
+    from conftest import GOLDEN, ROOT
+    exe = os.path.join(ROOT, "examples", "burgers_stage")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    dump = tmp_path / "burgers.dump"
+    with lzma.open(os.path.join(GOLDEN, "cfg4_burgers_lagr_d2_k2_n4.dump.xz"), "rb") as f:
+        dump.write_bytes(f.read())
+    r = subprocess.run([exe, str(dump)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout
