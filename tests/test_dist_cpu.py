@@ -1,0 +1,79 @@
+"""World-size-2 gloo tests (CPU) of the fibre-partition index logic behind the multi-GPU path
+(adaptive-multiresolution-dg_b200/dist.py): ownership keeps fibres whole, and the all-to-all layout switch is a
+permutation that lands every element block on its new owner."""
+import importlib
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, dim, nmax, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A = importlib.import_module("adaptive-multiresolution-dg_b200")
+        D = importlib.import_module("adaptive-multiresolution-dg_b200.dist")
+        lev, sup = A.sparse_grid(dim, nmax)
+        part = D.FibrePartition(lev, sup, world, rank)
+        n = lev.shape[0]
+        # every element has exactly one owner per layout, loads are balanced within 2x
+        for k in ("X", "V"):
+            cnt = np.bincount(part.owner[k], minlength=world)
+            assert cnt.sum() == n and cnt.max() <= 2 * max(1, cnt.min()) + 8, cnt
+        # fibres along the local dims are complete: all related elements (reference relation tables) are local
+        ctx = A.Context(dim, nmax, 1, 2, device=-1)
+        ctx.grid_set(lev, sup)
+        for layout, dims in (("X", part.dims_x), ("V", part.dims_v)):
+            mine = set(part.local[layout].tolist())
+            for t in dims:
+                ptr, idx = ctx.grid_relation(t, A.REL_FLX)
+                for e in part.local[layout]:
+                    assert set(idx[ptr[e]:ptr[e + 1]].tolist()) <= mine
+        ctx.close()
+        # layout switch: blocks labelled by (global id, column)
+        blk = 5
+        x = torch.tensor(part.local["X"][:, None] * 100 + np.arange(blk)[None, :], dtype=torch.float64)
+        v = part.switch(x, "X", "V")
+        assert torch.equal(v, torch.tensor(part.local["V"][:, None] * 100 + np.arange(blk)[None, :], dtype=torch.float64))
+        back = part.switch(v, "V", "X")
+        assert torch.equal(back, x)
+        q.put((rank, "ok"))
+    except Exception as e:      # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dim,nmax", [(4, 3), (6, 2), (2, 4)])
+def test_partition_and_switch_world2(dim, nmax):
+    world = 2
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, dim, nmax, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for r, msg in res:
+        assert msg == "ok", msg

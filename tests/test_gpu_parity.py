@@ -205,3 +205,16 @@ def test_cpp_host_mirror_example(tmp_path):
         dump.write_bytes(f.read())
     r = subprocess.run([exe, str(dump)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+
+
+def test_multi_gpu_fibre_partition():
+    """2-GPU parity of the fibre-partitioned path (skipped on a single-GPU box)"""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", os.path.join(ROOT, "tests", "dist_check.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "DIST_CHECK OK" in r.stdout, r.stdout[-2000:]
