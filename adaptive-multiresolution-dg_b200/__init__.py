@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libamdg_b200.so")
+LIB_PATH = os.environ.get("AMDG_LIB", os.path.join(_HERE, "libamdg_b200.so"))
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -41,6 +41,7 @@ SYMBOLS = {
     "amdg_ctx_set_schedule": (_i, [_p, _i]),
     "amdg_ctx_set_kernel": (_i, [_p, _i]),
     "amdg_ctx_launch_count": (_i64, [_p]),
+    "amdg_ctx_set_debug_buffer": (_i, [_p, _p]),
     "amdg_hash_key": (_i, [_i, _ip, _ip]),
     "amdg_order_elem": (_i, [_i, _i]),
     "amdg_sparse_grid": (_i64, [_i, _i, _i, _ip, _ip]),
@@ -155,6 +156,9 @@ class Context:
 
     def set_kernel(self, variant):
         _check(lib.amdg_ctx_set_kernel(self._h, variant))
+
+    def set_debug_buffer(self, t):
+        _check(lib.amdg_ctx_set_debug_buffer(self._h, ctypes.c_void_p(t.data_ptr()) if t is not None else None))
 
     @property
     def launch_count(self):

@@ -55,7 +55,12 @@ struct amdg_ctx
         int n = 0; int ct = 1; int smem = 0; bool ok = false;
     };
     std::map<std::tuple<int, int, int, int, int, int>, ItemList> items;      // key: (dim t, columns W, kf, kt, relation, parallel class)
-    int smem_doubles = 8192, item_target = 148 * 8;
+    int smem_doubles = 8192, item_target = 148 * 4;
+    long long * dbg = nullptr;
+    // metadata arena: index tables, work lists and operator blocks live in one allocation that is given an L2
+    // persisting access-policy window (they are re-read by every sweep while coefficient data streams through L2)
+    char * arena = nullptr; size_t arena_cap = 0, arena_lo = 0, arena_hi = 0;   // grid tables grow up from 0, operators down from cap
+    bool l2_window = false;
 };
 
 static int need_device(amdg_ctx * c)
@@ -65,21 +70,23 @@ static int need_device(amdg_ctx * c)
     return AMDG_OK;
 }
 
+static void meta_free(amdg_ctx * c, void * p);
 static void free_dev_grid(amdg_ctx * c)
 {
     for (auto & D : c->ddims)
     {
-        cudaFree(D.slot_elem); cudaFree(D.slot_fbase); cudaFree(D.fibre_ptr);
-        for (int k = 0; k < 2; ++k) { cudaFree(D.nbr_ptr[k]); cudaFree(D.nbr_split[k]); cudaFree(D.nbr[k]); }
+        meta_free(c, D.slot_elem); meta_free(c, D.slot_fbase); meta_free(c, D.fibre_ptr);
+        for (int k = 0; k < 2; ++k) { meta_free(c, D.nbr_ptr[k]); meta_free(c, D.nbr_split[k]); meta_free(c, D.nbr[k]); }
     }
     c->ddims.clear();
-    cudaFree(c->d_ord1d); c->d_ord1d = nullptr;
+    meta_free(c, c->d_ord1d); c->d_ord1d = nullptr;
     for (auto & kv : c->items)
     {
         amdg_ctx::ItemList & L = kv.second;
-        cudaFree(L.d_items); cudaFree(L.d_slots); cudaFree(L.d_pairs); cudaFree(L.d_rowptr); cudaFree(L.d_rsplit); cudaFree(L.d_ent);
+        meta_free(c, L.d_items); meta_free(c, L.d_slots); meta_free(c, L.d_pairs); meta_free(c, L.d_rowptr); meta_free(c, L.d_rsplit); meta_free(c, L.d_ent);
     }
     c->items.clear();
+    c->arena_lo = 0;
 }
 
 template <class T>
@@ -89,6 +96,34 @@ static cudaError_t upload(T ** dptr, const T * h, size_t n, cudaStream_t st)
     if (e != cudaSuccess) return e;
     if (n) e = cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
     return e;
+}
+
+
+// ---- metadata arena ------------------------------------------------------------------------------------------
+static bool in_arena(amdg_ctx * c, const void * p) { return c->arena && (const char *)p >= c->arena && (const char *)p < c->arena + c->arena_cap; }
+static void meta_free(amdg_ctx * c, void * p) { if (p && !in_arena(c, p)) cudaFree(p); }
+template <class T>
+static cudaError_t meta_upload(amdg_ctx * c, T ** dptr, const T * h, size_t n, bool is_op)
+{
+    const size_t bytes = ((std::max<size_t>(n, 1) * sizeof(T)) + 255) & ~(size_t)255;
+    if (c->arena && c->arena_lo + bytes + (c->arena_cap - c->arena_hi) <= c->arena_cap)
+    {
+        if (is_op) { c->arena_hi -= bytes; *dptr = (T *)(c->arena + c->arena_hi); }
+        else { *dptr = (T *)(c->arena + c->arena_lo); c->arena_lo += bytes; }
+        return n ? cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+    }
+    return upload(dptr, h, n, c->stream);
+}
+static void apply_l2_window(amdg_ctx * c)
+{
+    if (!c->arena || !c->l2_window) return;
+    cudaStreamAttrValue attr; std::memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = c->arena;
+    attr.accessPolicyWindow.num_bytes = c->arena_cap;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 }
 
 static int ensure_scratch(amdg_ctx * c, size_t idx, int64_t n)
@@ -128,6 +163,24 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
         CU(cudaSetDevice(device));
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
+        size_t arena_mb = 96; if (const char * e2 = std::getenv("AMDG_ARENA_MB")) arena_mb = (size_t)std::max(0, atoi(e2));
+        cudaDeviceProp prop;
+        if (arena_mb > 0 && cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+        {
+            size_t cap = arena_mb << 20;
+            if (prop.accessPolicyMaxWindowSize > 0) cap = std::min(cap, (size_t)prop.accessPolicyMaxWindowSize);
+            if (cudaMalloc((void **)&c->arena, cap) == cudaSuccess)
+            {
+                c->arena_cap = cap; c->arena_lo = 0; c->arena_hi = cap;
+                const char * w = std::getenv("AMDG_L2_PERSIST");
+                if (!(w && w[0] == '0') && prop.persistingL2CacheMaxSize > 0)
+                {
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)(32u << 20)));
+                    c->l2_window = true; apply_l2_window(c.get());
+                }
+            }
+            else { cudaGetLastError(); c->arena = nullptr; }
+        }
     }
     *out = c.release();
     return AMDG_OK;
@@ -141,7 +194,8 @@ int amdg_ctx_destroy(amdg_ctx * c)
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
         free_dev_grid(c);
-        for (auto & op : c->ops) cudaFree(op->d_blocks);
+        for (auto & op : c->ops) meta_free(c, op->d_blocks);
+        cudaFree(c->arena);
         for (double * p : c->scratch) cudaFree(p);
         cudaFree(c->h2d); cudaFree(c->d2h);
         if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -155,6 +209,7 @@ int amdg_ctx_set_stream(amdg_ctx * c, void * s)
     int r = need_device(c); if (r) return r;
     if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
     c->stream = (cudaStream_t)s;
+    apply_l2_window(c);
     return AMDG_OK;
 }
 
@@ -162,6 +217,7 @@ int amdg_ctx_sync(amdg_ctx * c) { int r = need_device(c); if (r) return r; CU(cu
 int amdg_ctx_set_schedule(amdg_ctx * c, int s) { if (!c || (s != AMDG_SCHED_LITERAL && s != AMDG_SCHED_SHARED)) return fail(AMDG_EINVAL, "bad schedule"); c->sched = s; return AMDG_OK; }
 int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 2) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
 int64_t amdg_ctx_launch_count(amdg_ctx * c) { return c ? c->launches : -1; }
+int amdg_ctx_set_debug_buffer(amdg_ctx * c, void * dev_buf) { if (!c) return fail(AMDG_EINVAL, "null context"); c->dbg = (long long *)dev_buf; return AMDG_OK; }
 
 int amdg_hash_key(int dim, const int * level, const int * suppt) { return hash_key(dim, level, suppt); }
 int amdg_order_elem(int level, int suppt) { return order_elem(level, suppt); }
@@ -189,20 +245,20 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
     CU(cudaStreamSynchronize(c->stream));
     free_dev_grid(c);
     c->ddims.resize(c->dim);
-    CU(upload(&c->d_ord1d, c->grid.ord1d.data(), c->grid.ord1d.size(), c->stream));
+    CU(meta_upload(c, &c->d_ord1d, c->grid.ord1d.data(), c->grid.ord1d.size(), false));
     for (int t = 0; t < c->dim; ++t)
     {
         const DimTables & H = c->grid.dims[t]; DevDim & D = c->ddims[t];
         std::vector<int> fbase(n);
         for (int64_t s = 0; s < n; ++s) fbase[s] = (int)H.fibre_ptr[H.slot_fibre[s]];
-        CU(upload(&D.slot_elem, H.slot_elem.data(), (size_t)n, c->stream));
-        CU(upload(&D.slot_fbase, fbase.data(), (size_t)n, c->stream));
-        CU(upload(&D.fibre_ptr, H.fibre_ptr.data(), H.fibre_ptr.size(), c->stream));
+        CU(meta_upload(c, &D.slot_elem, H.slot_elem.data(), (size_t)n, false));
+        CU(meta_upload(c, &D.slot_fbase, fbase.data(), (size_t)n, false));
+        CU(meta_upload(c, &D.fibre_ptr, H.fibre_ptr.data(), H.fibre_ptr.size(), false));
         for (int k = 0; k < 2; ++k)
         {
-            CU(upload(&D.nbr_ptr[k], H.nbr_ptr[k].data(), H.nbr_ptr[k].size(), c->stream));
-            CU(upload(&D.nbr_split[k], H.nbr_split[k].data(), H.nbr_split[k].size(), c->stream));
-            CU(upload((Nbr **)&D.nbr[k], H.nbr[k].data(), H.nbr[k].size(), c->stream));
+            CU(meta_upload(c, &D.nbr_ptr[k], H.nbr_ptr[k].data(), H.nbr_ptr[k].size(), false));
+            CU(meta_upload(c, &D.nbr_split[k], H.nbr_split[k].data(), H.nbr_split[k].size(), false));
+            CU(meta_upload(c, (Nbr **)&D.nbr[k], H.nbr[k].data(), H.nbr[k].size(), false));
         }
         CU(cudaStreamSynchronize(c->stream));   // fbase is a local
     }
@@ -256,7 +312,7 @@ static int push_op(amdg_ctx * c, std::unique_ptr<Op> op, int * out)
     if (c->device >= 0)
     {
         CU(cudaSetDevice(c->device));
-        CU(upload(&op->d_blocks, op->blocks.data(), op->blocks.size(), c->stream));
+        CU(meta_upload(c, &op->d_blocks, op->blocks.data(), op->blocks.size(), true));
         CU(cudaStreamSynchronize(c->stream));
     }
     c->ops.push_back(std::move(op));
@@ -372,18 +428,19 @@ static int choose_pitch(int ncol, int kf, int cx)
 // STREAMED item: the rows of level < k_c of a long fibre (a prefix in 1D order) have sources all over the fibre:
 //   the whole fibre is staged for a narrow column range, one warp per target row with the lanes splitting the
 //   neighbour list; operator blocks come from L2.  A fibre that cannot be cut falls back to this form entirely.
-static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, int kt, int rel, int par)
+static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, int kt, int rel, int par, int lu)
 {
     int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
-    auto key = std::make_tuple(t, W, kf, kt, rel, pcls);
+    auto key = std::make_tuple(t, W, kf, kt, rel * 4 + lu, pcls);      // the lists of a packed item hold only the entries the L/U/full part uses
     auto it = c->items.find(key);
     if (it != c->items.end()) return it->second;
     amdg_ctx::ItemList L;
     const DimTables & H = c->grid.dims[t];
     const int d = c->dim;
     const int cap = c->smem_doubles;
-    const int ct = W > 128 ? 4 : (W > 16 ? 2 : 1);
-    int lcx_w = 0; while ((1 << lcx_w) < std::min(256, next_pow2((W + ct - 1) / ct))) lcx_w++;
+    int ct = W > 128 ? 4 : (W > 16 ? 2 : 1);
+    if (const char * e = std::getenv("AMDG_CT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) ct = v; }
+    int lcx_w = 0; while ((1 << lcx_w) < std::min(fibre_threads(), next_pow2((W + ct - 1) / ct))) lcx_w++;
     const int pitch_w = choose_pitch(W, kf, 1 << lcx_w);
     const bool wide = (1 << lcx_w) * ct < W;          // more columns than one pass of the block covers: packed path not possible
     const int64_t total = c->grid.n * (int64_t)kf * pitch_w;
@@ -398,7 +455,11 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
     int n_packed = 0, n_streamed = 0;
 
     auto ord_of = [&](int64_t s) { return c->grid.ord1d[(int64_t)H.slot_elem[s] * d + t]; };
-    auto need_of = [&](int64_t nsrc, int64_t npair, int64_t nnz, int64_t ntgt) { return nsrc * kf * pitch_w + npair * kf * kt + (2 * nnz + 2 * ntgt + 2 + 1) / 2; };
+    auto need_p = [&](int64_t nsrc, int64_t npair, int64_t nnz, int64_t ntgt, int pitch) { return nsrc * kf * pitch + npair * kf * kt + (2 * nnz + 3 * ntgt + 2 + 1) / 2; };
+    auto need_of = [&](int64_t nsrc, int64_t npair, int64_t nnz, int64_t ntgt) { return need_p(nsrc, npair, nnz, ntgt, pitch_w); };
+    // column chunking of a packed item: chunk j covers W / 2^j columns
+    auto chunk_cols = [&](int j) { return std::max(1, (W + (1 << j) - 1) >> j); };
+    auto chunk_lcx = [&](int ncol) { int l = 0; while ((1 << l) < std::min(fibre_threads(), next_pow2((ncol + ct - 1) / ct))) l++; return l; };
 
     // emit one packed item: targets (slots) and, per target, its neighbour list; sources = union (kept in first-seen order)
     // fibre_s0: first slot of the fibre the targets belong to (all targets of one call are of one fibre) -- for packing
@@ -409,8 +470,10 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
     auto add_row = [&](int64_t s, int64_t fibre_s0)
     {
         B.tgt.push_back((int)s);
-        B.rsplit.push_back(nsplit[s]);
-        for (int64_t p = nptr[s]; p < nptr[s + 1]; ++p)
+        const int64_t p_lo = (lu == AMDG_LU_L) ? nptr[s] + nsplit[s] : nptr[s];
+        const int64_t p_hi = (lu == AMDG_LU_U) ? nptr[s] + nsplit[s] : nptr[s + 1];
+        B.rsplit.push_back(lu == AMDG_LU_L ? 0 : nsplit[s]);
+        for (int64_t p = p_lo; p < p_hi; ++p)
         {
             const int ss = (int)(fibre_s0 + nbr[p].local), pr = nbr[p].pair;
             if (sstamp[ss] != stamp_id) { sstamp[ss] = stamp_id; slocal[ss] = (int)B.src.size(); B.src.push_back(ss); }
@@ -418,31 +481,35 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
             B.ent.push_back({ slocal[ss], plocal[pr] });
         }
         B.rowptr.push_back((int)B.ent.size());
-        B.cost += (double)(nptr[s + 1] - nptr[s]);
+        B.cost += (double)(p_hi - p_lo) + 1.0;
     };
     auto item_need = [&]() { return need_of((int64_t)B.src.size(), (int64_t)B.pairs.size(), (int64_t)B.ent.size(), (int64_t)B.tgt.size()); };
+    auto item_need_chunk = [&](int j) { const int nc = chunk_cols(j); return need_p((int64_t)B.src.size(), (int64_t)B.pairs.size(), (int64_t)B.ent.size(), (int64_t)B.tgt.size(), choose_pitch(nc, kf, 1 << chunk_lcx(nc))); };
+    int end_chunks = 0;      // column chunking level used by end_item (0 = all columns)
     auto end_item = [&]()
     {
         if (B.tgt.empty()) return;
         FibreItem x; std::memset(&x, 0, sizeof(x));
-        x.col0 = 0; x.ncol = W; x.lcx = lcx_w; x.pitch = pitch_w;
+        x.col0 = 0; x.ncol = W; x.lcx = lcx_w; x.pitch = pitch_w; x.packed = 1;
+        if (end_chunks > 0) { x.ncol = chunk_cols(end_chunks); x.lcx = chunk_lcx(x.ncol); x.pitch = choose_pitch(x.ncol, kf, 1 << x.lcx); }
         x.npair = (int)B.pairs.size(); x.pair_ofs = (int)pool_pairs.size();
         x.nsrc = (int)B.src.size(); x.src_ofs = (int)pool_slots.size();
-        pool_slots.insert(pool_slots.end(), B.src.begin(), B.src.end());
+        for (int ss : B.src) pool_slots.push_back(H.slot_elem[ss]);          // element rows, not slots: one indirection less on the device
         x.ntgt = (int)B.tgt.size(); x.tgt_ofs = (int)pool_slots.size();
-        pool_slots.insert(pool_slots.end(), B.tgt.begin(), B.tgt.end());
+        for (int ss : B.tgt) pool_slots.push_back(H.slot_elem[ss]);
         x.ent_ofs = (int)pool_ent.size(); x.row_ofs = (int)pool_rowptr.size();
         pool_pairs.insert(pool_pairs.end(), B.pairs.begin(), B.pairs.end());
         pool_rowptr.insert(pool_rowptr.end(), B.rowptr.begin(), B.rowptr.end());
         pool_rsplit.insert(pool_rsplit.end(), B.rsplit.begin(), B.rsplit.end()); pool_rsplit.push_back(0);   // keep the pools aligned
         pool_ent.insert(pool_ent.end(), B.ent.begin(), B.ent.end());
-        need = std::max(need, item_need());
-        items.push_back(x); cost.push_back(B.cost * W); ++n_packed;
+        need = std::max(need, end_chunks > 0 ? item_need_chunk(end_chunks) : item_need());
+        for (int c0 = 0; c0 < W; c0 += x.ncol) { x.col0 = c0; items.push_back(x); cost.push_back(B.cost * std::min(x.ncol, W - c0)); ++n_packed; }
         B = Build();
     };
     auto add_streamed = [&](int64_t s0, int m, int ntgt, double fc, int max_cols)
     {
-        int ncol = (int)std::min<int64_t>(std::min(std::min(W, 32 * ct), max_cols), cap / ((int64_t)m * kf));
+        const int64_t slab = (int64_t)(fibre_threads() / 32) * 32 * (kf * kt + 2);      // per-warp operator-block slabs
+        int ncol = (int)std::min<int64_t>(std::min(std::min(W, 32 * ct), max_cols), (cap - slab) / ((int64_t)m * kf));
         if (ncol < 1) { ok = false; return; }
         const int nchunk = (W + ncol - 1) / ncol;
         ncol = (W + nchunk - 1) / nchunk;
@@ -450,8 +517,8 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
         sp.slot0 = (int)s0; sp.nslot = m; sp.ncol = ncol; sp.ntgt = ntgt;
         while ((1 << sp.lcx) < next_pow2((ncol + ct - 1) / ct)) sp.lcx++;
         sp.pitch = choose_pitch(ncol, kf, 1 << sp.lcx);
-        if ((int64_t)m * kf * sp.pitch > cap) sp.pitch = ncol;
-        need = std::max(need, (int64_t)m * kf * sp.pitch);
+        if ((int64_t)m * kf * sp.pitch + slab > cap) sp.pitch = ncol;
+        need = std::max(need, (int64_t)m * kf * sp.pitch + slab);
         for (int c0 = 0; c0 < W; c0 += ncol) { sp.col0 = c0; items.push_back(sp); cost.push_back(8.0 * fc * std::min(ncol, W - c0)); ++n_streamed; }
     };
 
@@ -492,13 +559,23 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
             bool fits = true;
             const size_t mark_items = items.size(), mark_slots = pool_slots.size(), mark_pairs = pool_pairs.size(), mark_rp = pool_rowptr.size(), mark_rs = pool_rsplit.size(), mark_ent = pool_ent.size();
             const int64_t mark_need = need; const int mark_np = n_packed;
-            for (auto & g : groups)
+            int jmax = 0;
+            for (auto & g : groups)       // pass 1: the column chunking level every group of this cut can live with (at most 4 chunks)
             {
                 begin_item();
                 for (int64_t s : g.second) add_row(s, s0);
-                if (item_need() > cap) { fits = false; break; }
-                end_item();
+                int j = 0; while (j <= 2 && item_need_chunk(j) > cap) ++j;
+                if (j > 2) { fits = false; break; }
+                jmax = std::max(jmax, j);
             }
+            begin_item();
+            if (fits)
+                for (auto & g : groups)
+                {
+                    begin_item();
+                    for (int64_t s : g.second) add_row(s, s0);
+                    end_chunks = jmax; end_item(); end_chunks = 0;
+                }
             if (!fits)
             {
                 items.resize(mark_items); cost.resize(mark_items); pool_slots.resize(mark_slots); pool_pairs.resize(mark_pairs);
@@ -508,7 +585,16 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
             }
             // the top rows (a prefix of the fibre in 1D order) as streamed items over narrow column ranges
             double tc = 0; for (int64_t s = s0; s < s0 + ntop; ++s) tc += (double)(nptr[s + 1] - nptr[s]);
-            if (ntop > 0) add_streamed(s0, m, ntop, tc, 2 * ct);
+            if (ntop > 0 && lu == AMDG_LU_U)
+            {
+                // the sources of a top row under "U" are its ancestors: top rows only -> a packed item
+                begin_item();
+                for (int64_t s = s0; s < s0 + ntop; ++s) add_row(s, s0);
+                int j = 0; while (j <= 2 && item_need_chunk(j) > cap) ++j;
+                if (j <= 2) { end_chunks = j; end_item(); end_chunks = 0; }
+                else { begin_item(); add_streamed(s0, m, ntop, tc, ct); }
+            }
+            else if (ntop > 0) add_streamed(s0, m, ntop, tc, ct);
             cut_ok = true;
             begin_item();
         }
@@ -520,20 +606,27 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
         std::vector<int> order(items.size());
         for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
-        std::vector<FibreItem> sorted(items.size());
-        for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
+        std::vector<FibreItem> sorted;
+        const char * only = std::getenv("AMDG_ONLY");     // experiment switch: "packed" / "streamed" (results are then incomplete)
+        for (size_t i = 0; i < order.size(); ++i)
+        {
+            const FibreItem & x = items[order[i]];
+            if (only && only[0] == 'p' && !x.packed) continue;
+            if (only && only[0] == 's' && x.packed) continue;
+            sorted.push_back(x);
+        }
         if (need <= fibre_smem_capacity_doubles() &&
-            upload(&L.d_items, sorted.data(), sorted.size(), c->stream) == cudaSuccess &&
-            upload(&L.d_slots, pool_slots.data(), pool_slots.size(), c->stream) == cudaSuccess &&
-            upload(&L.d_pairs, pool_pairs.data(), pool_pairs.size(), c->stream) == cudaSuccess &&
-            upload(&L.d_rowptr, pool_rowptr.data(), pool_rowptr.size(), c->stream) == cudaSuccess &&
-            upload(&L.d_rsplit, pool_rsplit.data(), pool_rsplit.size(), c->stream) == cudaSuccess &&
-            upload((Nbr **)&L.d_ent, pool_ent.data(), pool_ent.size(), c->stream) == cudaSuccess &&
+            meta_upload(c, &L.d_items, sorted.data(), sorted.size(), false) == cudaSuccess &&
+            meta_upload(c, &L.d_slots, pool_slots.data(), pool_slots.size(), false) == cudaSuccess &&
+            meta_upload(c, &L.d_pairs, pool_pairs.data(), pool_pairs.size(), false) == cudaSuccess &&
+            meta_upload(c, &L.d_rowptr, pool_rowptr.data(), pool_rowptr.size(), false) == cudaSuccess &&
+            meta_upload(c, &L.d_rsplit, pool_rsplit.data(), pool_rsplit.size(), false) == cudaSuccess &&
+            meta_upload(c, (Nbr **)&L.d_ent, pool_ent.data(), pool_ent.size(), false) == cudaSuccess &&
             cudaStreamSynchronize(c->stream) == cudaSuccess)
         { L.n = (int)sorted.size(); L.ct = ct; L.smem = (int)need; L.ok = true; }
         if (std::getenv("AMDG_VERBOSE"))
-            fprintf(stderr, "[amdg] items t=%d W=%d kf=%d kt=%d rel=%d par=%d: %d items (%d packed, %d streamed), smem %lld doubles, ct %d\n",
-                    t, W, kf, kt, rel, par, (int)sorted.size(), n_packed, n_streamed, (long long)need, ct);
+            fprintf(stderr, "[amdg] items t=%d W=%d kf=%d kt=%d rel=%d par=%d lu=%d: %d items (%d packed, %d streamed), smem %lld doubles, ct %d\n",
+                    t, W, kf, kt, rel, par, lu, (int)sorted.size(), n_packed, n_streamed, (long long)need, ct);
     }
     return c->items.emplace(key, L).first->second;
 }
@@ -550,7 +643,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
         const amdg_ctx::ItemList * L = nullptr;
-        if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf, O.kt, rel, cnt * n_comp); if (!L->ok) L = nullptr; }
+        if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf, O.kt, rel, cnt * n_comp, lu); if (!L->ok) L = nullptr; }
         if (c->kernel_variant == 2 && !L) return fail(AMDG_EINVAL, "fibre-staged kernel requested but a fibre does not fit in shared memory");
         cudaError_t e;
         if (L)
@@ -559,7 +652,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
             a.slot_elem = D.slot_elem; a.slot_fbase = D.slot_fbase; a.nbr_ptr = D.nbr_ptr[rel]; a.nbr_split = D.nbr_split[rel]; a.nbr = D.nbr[rel];
             a.pool_slots = L->d_slots; a.pool_pairs = L->d_pairs; a.pool_rowptr = L->d_rowptr; a.pool_rsplit = L->d_rsplit; a.pool_ent = L->d_ent;
             a.blocks = O.d_blocks; a.items = L->d_items; a.n_item = L->n; a.n_elem = c->grid.n; a.inner = inner; a.lu = lu; a.n_comp = n_comp;
-            a.n_job = cnt; a.smem_doubles = L->smem;
+            a.n_job = cnt; a.smem_doubles = L->smem; a.dbg = c->dbg;
             for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
             e = launch_sweep_fibre(a, O.kf, O.kt, L->ct, c->stream);
         }

@@ -106,15 +106,29 @@ cudaError_t launch_sweep_gather(const SweepArgs & a, int kf, int kt, cudaStream_
 // CT*KT accumulators in registers; the epilogue applies coef / accumulate and stores.
 // The thread block is 256 threads viewed as (2^lcx column lanes) x (256 >> lcx row lanes), per item.
 // -------------------------------------------------------------------------------------------------------------
-static const int FIBRE_THREADS = 256;
+#ifndef AMDG_FIBRE_THREADS
+#define AMDG_FIBRE_THREADS 256
+#endif
+static const int FIBRE_THREADS = AMDG_FIBRE_THREADS;
+__device__ __forceinline__ void cp_async8(void * smem, const void * gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 static const int FIBRE_SMEM_DOUBLES = 12 * 1024;     // upper bound (96 KiB); the context picks the launch size
 
 int fibre_smem_capacity_doubles() { return FIBRE_SMEM_DOUBLES; }
+int fibre_threads() { return FIBRE_THREADS; }
 
 template <int KF, int KT, int CT>
 __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreSweepArgs a)
 {
     extern __shared__ double X[];
+#define AMDG_STAMP(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[(int64_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
+    AMDG_STAMP(0);
     const FibreItem it = a.items[blockIdx.x];
     const int jb = blockIdx.y / a.n_comp, comp = blockIdx.y % a.n_comp;
     const SweepJob J = a.job[jb];
@@ -126,6 +140,8 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
     const int P = it.pitch;
     const int cx = 1 << it.lcx;
     const int tid = threadIdx.x;
+    if (a.dbg && tid == 0) { a.dbg[(int64_t)blockIdx.x * 8 + 6] = it.packed; a.dbg[(int64_t)blockIdx.x * 8 + 7] = it.packed ? it.nsrc : it.nslot; unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); a.dbg[(int64_t)blockIdx.x * 8 + 5] = smid; }
+    AMDG_STAMP(1);
     const int tx = tid & (cx - 1);
     const int ncol = min(it.ncol, W - it.col0);
 
@@ -141,44 +157,76 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
         off_to[r] = o * KT * inner + i;
     }
 
-    if (it.npair > 0)
+    if (it.packed)
     {
         // ---- packed item: source rows, the operator blocks of the item's distinct pairs and the item-local
-        // neighbour lists all go to shared memory; phase 2 touches global memory only for the stores.
-        const int * __restrict__ srcs = a.pool_slots + it.src_ofs;
-        const int * __restrict__ tgts = a.pool_slots + it.tgt_ofs;
+        // neighbour lists all go to shared memory (cp.async, everything in flight at once); phase 2 touches global
+        // memory only for the stores.
+        const int * __restrict__ srcs = a.pool_slots + it.src_ofs;       // element rows of the sources
+        const int * __restrict__ tgts = a.pool_slots + it.tgt_ofs;       // element rows of the targets
         double * Bs = X + (int64_t)it.nsrc * KF * P;
         int * rowptr = reinterpret_cast<int *>(Bs + (int64_t)it.npair * (KF * KT));      // [ntgt+1]
         int * rsplit = rowptr + it.ntgt + 1;                                               // [ntgt]
-        int * ent = rsplit + it.ntgt;                                                      // [nnz][2]
+        int * telem = rsplit + it.ntgt;                                                    // [ntgt]
+        int * ent = telem + it.ntgt;                                                       // [nnz][2]
         const int ty = tid >> it.lcx, ny = FIBRE_THREADS >> it.lcx;
-        for (int j = ty; j < it.nsrc; j += ny)
+        // all index loads first (sources and pair ids), so their latencies overlap; then every copy is issued
+        int e[4]; int pr_id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) e[u] = (ty + u * ny < it.nsrc) ? __ldg(srcs + ty + u * ny) : -1;
+        const int nb_copy = it.npair * (KF * KT);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int idx = tid + u * FIBRE_THREADS; pr_id[u] = idx < nb_copy ? __ldg(a.pool_pairs + it.pair_ofs + idx / (KF * KT)) : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
         {
-            const int e = a.slot_elem[srcs[j]];
-            const double * __restrict__ g = src + (int64_t)e * s_from;
-            double * xr = X + (int64_t)j * KF * P;
+            if (e[u] < 0) continue;
+            const double * __restrict__ g = src + (int64_t)e[u] * s_from;
+            double * xr = X + (int64_t)(ty + u * ny) * KF * P;
 #pragma unroll
             for (int r = 0; r < CT; ++r)
             {
                 if (!ok[r]) continue;
 #pragma unroll
-                for (int k = 0; k < KF; ++k) xr[k * P + cc[r]] = __ldg(g + off_from[r] + (int64_t)k * inner);
+                for (int k = 0; k < KF; ++k) cp_async8(xr + k * P + cc[r], g + off_from[r] + (int64_t)k * inner);
             }
         }
-        for (int idx = tid; idx < it.npair * (KF * KT); idx += FIBRE_THREADS)
+        for (int j0 = ty + 4 * ny; j0 < it.nsrc; j0 += ny)
+        {
+            const double * __restrict__ g = src + (int64_t)__ldg(srcs + j0) * s_from;
+            double * xr = X + (int64_t)j0 * KF * P;
+#pragma unroll
+            for (int r = 0; r < CT; ++r)
+            {
+                if (!ok[r]) continue;
+#pragma unroll
+                for (int k = 0; k < KF; ++k) cp_async8(xr + k * P + cc[r], g + off_from[r] + (int64_t)k * inner);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            const int idx = tid + u * FIBRE_THREADS;
+            if (pr_id[u] >= 0) cp_async8(Bs + idx, a.blocks + (int64_t)pr_id[u] * (KF * KT) + idx % (KF * KT));
+        }
+        for (int idx = tid + 4 * FIBRE_THREADS; idx < nb_copy; idx += FIBRE_THREADS)
         {
             const int pr = idx / (KF * KT), r = idx - pr * (KF * KT);
-            Bs[idx] = __ldg(a.blocks + (int64_t)a.pool_pairs[it.pair_ofs + pr] * (KF * KT) + r);
+            cp_async8(Bs + idx, a.blocks + (int64_t)__ldg(a.pool_pairs + it.pair_ofs + pr) * (KF * KT) + r);
         }
-        for (int j = tid; j <= it.ntgt; j += FIBRE_THREADS) rowptr[j] = a.pool_rowptr[it.row_ofs + j];
-        for (int j = tid; j < it.ntgt; j += FIBRE_THREADS) rsplit[j] = a.pool_rsplit[it.row_ofs + j];
-        const int nnz = a.pool_rowptr[it.row_ofs + it.ntgt];
+        cp_async_commit();
+        AMDG_STAMP(2);
+        for (int j = tid; j <= it.ntgt; j += FIBRE_THREADS) rowptr[j] = __ldg(a.pool_rowptr + it.row_ofs + j);
+        for (int j = tid; j < it.ntgt; j += FIBRE_THREADS) { rsplit[j] = __ldg(a.pool_rsplit + it.row_ofs + j); telem[j] = __ldg(tgts + j); }
+        const int nnz = __ldg(a.pool_rowptr + it.row_ofs + it.ntgt);
         for (int i = tid; i < nnz; i += FIBRE_THREADS)
         {
             const NbrDev nb = a.pool_ent[it.ent_ofs + i];
             ent[2 * i] = nb.local; ent[2 * i + 1] = nb.pair;
         }
+        cp_async_wait_all();
         __syncthreads();
+        AMDG_STAMP(3);
 
         for (int j = ty; j < it.ntgt; j += ny)
         {
@@ -209,7 +257,7 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
                     }
                 }
             }
-            double * y = dst + (int64_t)a.slot_elem[tgts[j]] * s_to;
+            double * y = dst + (int64_t)telem[j] * s_to;
 #pragma unroll
             for (int r = 0; r < CT; ++r)
             {
@@ -224,6 +272,7 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
                 }
             }
         }
+        AMDG_STAMP(4);
         return;
     }
 
@@ -251,6 +300,8 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
     __syncthreads();
     {
         const int lane = tid & 31, warp = tid >> 5;
+        constexpr int BWP = KF * KT + 2;                                              // slab row pitch (doubles)
+        double * Bw = X + (int64_t)it.nslot * KF * P + (int64_t)warp * 32 * BWP;      // per-warp slab behind the staged rows
         const int cxw = min(cx, 32);
         const int ns = 32 / cxw;
         const int sl = lane / cxw;
@@ -271,22 +322,31 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
             {
                 const int cnt = (int)min((int64_t)32, n1 - base);
                 NbrDev mine; mine.local = 0; mine.pair = 0;
-                if (lane < cnt) mine = a.nbr[base + lane];
+                // every lane fetches one neighbour entry and that entry's operator block (32 blocks in flight per warp)
+                // into the warp's shared-memory slab; the slices then read their blocks from there
+                __syncwarp();
+                if (lane < cnt)
+                {
+                    mine = a.nbr[base + lane];
+                    const double * __restrict__ Bg = a.blocks + (int64_t)mine.pair * (KF * KT);
+#pragma unroll
+                    for (int r = 0; r < KF * KT; ++r) Bw[lane * BWP + r] = __ldg(Bg + r);
+                }
+                __syncwarp();
                 for (int i0 = 0; i0 < cnt; i0 += ns)
                 {
                     const int i = i0 + sl;
                     const bool valid = i < cnt;
                     const int local = __shfl_sync(0xffffffffu, mine.local, valid ? i : 0);
-                    const int pair = __shfl_sync(0xffffffffu, mine.pair, valid ? i : 0);
                     if (!valid) continue;
                     const double * xr = X + (int64_t)(frow + local) * KF * P;
-                    const double * __restrict__ B = a.blocks + (int64_t)pair * (KF * KT);
+                    const double * B = Bw + i * BWP;
 #pragma unroll
                     for (int k = 0; k < KF; ++k)
                     {
                         double bk[KT];
 #pragma unroll
-                        for (int q = 0; q < KT; ++q) bk[q] = __ldg(B + k * KT + q);
+                        for (int q = 0; q < KT; ++q) bk[q] = B[k * KT + q];
 #pragma unroll
                         for (int r = 0; r < CT; ++r)
                         {

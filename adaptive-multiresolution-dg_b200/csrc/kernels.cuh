@@ -57,7 +57,8 @@ struct FibreItem
     int ntgt, tgt_ofs;  // target rows: packed = slots pool[tgt_ofs .. +ntgt); streamed = the first ntgt rows of the fibre
     int ent_ofs;        // packed item: first neighbour entry in the `ent` pool; row pointers at rowptr pool[tgt_ofs + item index ..]
     int row_ofs;        //   first entry in the rowptr / rsplit pools (ntgt+1 / ntgt entries)
-    int pad0, pad1;
+    int packed;         // 1 = packed item, 0 = streamed item
+    int pad1;
 };
 
 struct FibreSweepArgs
@@ -82,6 +83,7 @@ struct FibreSweepArgs
     int n_comp;
     int n_job;
     int smem_doubles;
+    long long * dbg;            // optional: per CTA 8 clock64 stamps (profiling builds)
     SweepJob job[MAX_JOBS];
 };
 
@@ -99,6 +101,7 @@ struct PointwiseArgs
 cudaError_t launch_sweep_gather(const SweepArgs & a, int kf, int kt, cudaStream_t st);
 cudaError_t launch_sweep_fibre(const FibreSweepArgs & a, int kf, int kt, int ct, cudaStream_t st);
 int fibre_smem_capacity_doubles();
+int fibre_threads();
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);
 cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st);

@@ -59,6 +59,8 @@ int amdg_ctx_sync(amdg_ctx *ctx);
 int amdg_ctx_set_schedule(amdg_ctx *ctx, int sched);
 int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto, 1 = gather kernel, 2 = fibre-staged kernel */
 int64_t amdg_ctx_launch_count(amdg_ctx *ctx);                 /* kernels launched so far by this context */
+/* profiling aid: device buffer of n_items*8 int64 that the sweep kernel fills with per-CTA clock64 stamps (NULL = off) */
+int amdg_ctx_set_debug_buffer(amdg_ctx *ctx, void *dev_buf);
 
 /* ---- Hash (source/Hash.cpp:55-114) and 1D element order (source/Element.cpp:388-391), bit exact ---- */
 int amdg_hash_key(int dim, const int *level, const int *suppt);
