@@ -11,6 +11,7 @@
 
 #include "../../include/amdg.h"
 #include "grid.hpp"
+#include "pipe_items.hpp"
 #include "kernels.cuh"
 
 using namespace amdg;
@@ -56,6 +57,15 @@ struct amdg_ctx
     };
     std::map<std::tuple<int, int, int, int, int, int>, ItemList> items;      // key: (dim t, columns W, kf, kt, relation, parallel class)
     int smem_doubles = 8192, item_target = 148 * 4;
+    // pipelined kernel: work lists per (dim t, columns W, kf, kt, relation*4+lu, parallel class)
+    struct PipeList
+    {
+        int * d_rec = nullptr; int2 * d_tab = nullptr; int * d_fin = nullptr; int * d_fin_ofs = nullptr; int * d_counters = nullptr;
+        int n_item = 0, n_final = 0, n_slot = 0, ct = 1, data_doubles = 0, meta_ints = 0; bool ok = false;
+    };
+    std::map<std::tuple<int, int, int, int, int, int>, PipeList> pipes;
+    int pipe_cap_doubles = 11000, pipe_meta_ints = 2560, pipe_item_target = 148 * 3;
+    int n_sm = 148;
     long long * dbg = nullptr;
     // metadata arena: index tables, work lists and operator blocks live in one allocation that is given an L2
     // persisting access-policy window (they are re-read by every sweep while coefficient data streams through L2)
@@ -80,6 +90,12 @@ static void free_dev_grid(amdg_ctx * c)
     }
     c->ddims.clear();
     meta_free(c, c->d_ord1d); c->d_ord1d = nullptr;
+    for (auto & kv : c->pipes)
+    {
+        amdg_ctx::PipeList & L = kv.second;
+        meta_free(c, L.d_rec); meta_free(c, L.d_tab); meta_free(c, L.d_fin); meta_free(c, L.d_fin_ofs); meta_free(c, L.d_counters);
+    }
+    c->pipes.clear();
     for (auto & kv : c->items)
     {
         amdg_ctx::ItemList & L = kv.second;
@@ -154,6 +170,9 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_SMEM_DOUBLES")) c->smem_doubles = std::max(256, std::min(atoi(e), fibre_smem_capacity_doubles()));
     if (const char * e = std::getenv("AMDG_ITEM_TARGET")) c->item_target = std::max(1, atoi(e));
     if (const char * e = std::getenv("AMDG_KERNEL")) c->kernel_variant = atoi(e);
+    if (const char * e = std::getenv("AMDG_PIPE_CAP")) c->pipe_cap_doubles = std::max(256, atoi(e)) & ~1;
+    if (const char * e = std::getenv("AMDG_PIPE_META")) c->pipe_meta_ints = (std::max(256, atoi(e)) + 3) & ~3;
+    if (const char * e = std::getenv("AMDG_PIPE_ITEMS")) c->pipe_item_target = std::max(1, atoi(e));
     if (device >= 0)
     {
         int count = 0;
@@ -165,6 +184,7 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
         c->own_stream = true;
         size_t arena_mb = 96; if (const char * e2 = std::getenv("AMDG_ARENA_MB")) arena_mb = (size_t)std::max(0, atoi(e2));
         cudaDeviceProp prop;
+        { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v; }
         if (arena_mb > 0 && cudaGetDeviceProperties(&prop, device) == cudaSuccess)
         {
             size_t cap = arena_mb << 20;
@@ -215,7 +235,7 @@ int amdg_ctx_set_stream(amdg_ctx * c, void * s)
 
 int amdg_ctx_sync(amdg_ctx * c) { int r = need_device(c); if (r) return r; CU(cudaStreamSynchronize(c->stream)); return AMDG_OK; }
 int amdg_ctx_set_schedule(amdg_ctx * c, int s) { if (!c || (s != AMDG_SCHED_LITERAL && s != AMDG_SCHED_SHARED)) return fail(AMDG_EINVAL, "bad schedule"); c->sched = s; return AMDG_OK; }
-int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 2) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
+int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 3) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
 int64_t amdg_ctx_launch_count(amdg_ctx * c) { return c ? c->launches : -1; }
 int amdg_ctx_set_debug_buffer(amdg_ctx * c, void * dev_buf) { if (!c) return fail(AMDG_EINVAL, "null context"); c->dbg = (long long *)dev_buf; return AMDG_OK; }
 
@@ -631,6 +651,44 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
     return c->items.emplace(key, L).first->second;
 }
 
+// work list of the pipelined kernel
+static const amdg_ctx::PipeList & get_pipe(amdg_ctx * c, int t, int W, int kf, int kt, int rel, int par, int lu)
+{
+    int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
+    auto key = std::make_tuple(t, W, kf, kt, rel * 4 + lu, pcls);
+    auto it = c->pipes.find(key);
+    if (it != c->pipes.end()) return it->second;
+    amdg_ctx::PipeList L;
+    PipeParams pp; pp.t = t; pp.W = W; pp.kf = kf; pp.kt = kt; pp.rel = rel; pp.lu = lu;
+    pp.cap_doubles = c->pipe_cap_doubles; pp.meta_cap_ints = c->pipe_meta_ints - 4; pp.item_target = std::max(1, c->pipe_item_target >> pcls); pp.threads = pipe_threads();
+    PipeBuild B;
+    build_pipe_list(c->grid, c->pairs, pp, B);
+    if (B.ok)
+    {
+        const int n = (int)B.tab.size() / 2;
+        std::vector<int> order(n); for (int i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return B.cost[x] > B.cost[y]; });
+        std::vector<int2> tab(n); for (int i = 0; i < n; ++i) { tab[i].x = B.tab[2 * order[i]]; tab[i].y = B.tab[2 * order[i] + 1]; }
+        std::vector<int> zeros((size_t)std::max(1, B.n_final) * 64, 0);
+        if (B.fin.empty()) { B.fin.push_back(0); }
+        if (B.fin_ofs.empty()) { B.fin_ofs.push_back(0); }
+        if (meta_upload(c, &L.d_rec, B.rec.data(), B.rec.size(), false) == cudaSuccess &&
+            meta_upload(c, &L.d_tab, tab.data(), tab.size(), false) == cudaSuccess &&
+            meta_upload(c, &L.d_fin, B.fin.data(), B.fin.size(), false) == cudaSuccess &&
+            meta_upload(c, &L.d_fin_ofs, B.fin_ofs.data(), B.fin_ofs.size(), false) == cudaSuccess &&
+            upload(&L.d_counters, zeros.data(), zeros.size(), c->stream) == cudaSuccess &&
+            cudaStreamSynchronize(c->stream) == cudaSuccess)
+        {
+            L.n_item = n; L.n_final = B.n_final; L.n_slot = B.n_slot; L.ct = B.ct;
+            L.data_doubles = (B.max_data + 1) & ~1; L.meta_ints = (B.max_meta + 3) & ~3; L.ok = true;
+        }
+        if (std::getenv("AMDG_VERBOSE"))
+            fprintf(stderr, "[amdg] pipe list t=%d W=%d kf=%d kt=%d rel=%d lu=%d par=%d: %d items, %d finals, %d slots, data %d doubles, meta %d ints\n",
+                    t, W, kf, kt, rel, lu, par, n, B.n_final, B.n_slot, L.data_doubles, L.meta_ints);
+    }
+    return c->pipes.emplace(key, L).first->second;
+}
+
 // launch one sweep for a batch of jobs sharing (op, rel, lu, t, inner); jobs are grouped by equal `outer`
 static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner, const SweepJob * jobs, int n_job, int n_comp)
 {
@@ -642,6 +700,33 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         int cnt = 1;
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
+        if (c->kernel_variant == 0 || c->kernel_variant == 3)
+        {
+            while (cnt * n_comp > 64 && cnt > 1) --cnt;
+            const amdg_ctx::PipeList & PL = get_pipe(c, t, W, O.kf, O.kt, rel, cnt * n_comp, lu);
+            if (PL.ok && cnt * n_comp <= 64)
+            {
+                PipeArgs a;
+                a.rec = PL.d_rec; a.tab = PL.d_tab; a.n_item = PL.n_item; a.fin = PL.d_fin; a.fin_ofs = PL.d_fin_ofs; a.counters = PL.d_counters;
+                a.n_slot = PL.n_slot; a.partial = nullptr;
+                if (PL.n_slot > 0)
+                {
+                    int64_t s_to = (int64_t)W * O.kt;
+                    int r2 = ensure_scratch(c, 200, (int64_t)cnt * n_comp * PL.n_slot * s_to); if (r2) return r2;
+                    a.partial = c->scratch[200];
+                }
+                a.blocks = O.d_blocks; a.n_elem = c->grid.n; a.inner = inner; a.n_comp = n_comp; a.n_job = cnt;
+                a.inner_magic = inner <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + (unsigned)inner - 1) / (unsigned)inner);
+                a.data_doubles = PL.data_doubles; a.meta_ints = PL.meta_ints; a.dbg = c->dbg;
+                for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
+                cudaError_t e = launch_sweep_pipe(a, O.kf, O.kt, PL.ct, c->n_sm, c->stream);
+                if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("pipelined sweep launch: ") + cudaGetErrorString(e));
+                c->launches++;
+                done += cnt;
+                continue;
+            }
+            if (c->kernel_variant == 3) return fail(AMDG_EINVAL, "pipelined kernel requested but the work list could not be built");
+        }
         const amdg_ctx::ItemList * L = nullptr;
         if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf, O.kt, rel, cnt * n_comp, lu); if (!L->ok) L = nullptr; }
         if (c->kernel_variant == 2 && !L) return fail(AMDG_EINVAL, "fibre-staged kernel requested but a fibre does not fit in shared memory");

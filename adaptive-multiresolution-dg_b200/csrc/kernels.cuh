@@ -87,6 +87,29 @@ struct FibreSweepArgs
     SweepJob job[MAX_JOBS];
 };
 
+// pipelined persistent sweep kernel (work list built by pipe_items.hpp)
+struct PipeArgs
+{
+    const int * rec;            // record pool
+    const int2 * tab;           // per item: (offset, length) into rec
+    int n_item;
+    const int * fin;            // final tables (long fibres)
+    const int * fin_ofs;
+    int * counters;             // [n_final][gy] arrival counters (zero between launches)
+    double * partial;           // [gy][n_slot][S_to] partial sums of the rows above the cut
+    int n_slot;
+    const double * blocks;
+    int64_t n_elem;
+    int inner;
+    unsigned inner_magic;       // ceil(2^32 / inner): col / inner == umulhi(col, magic) for col*inner < 2^32
+    int n_comp;
+    int n_job;
+    int data_doubles;           // shared-memory data stage size (doubles, even)
+    int meta_ints;              // shared-memory record stage size (ints, multiple of 4)
+    long long * dbg;
+    SweepJob job[MAX_JOBS];
+};
+
 struct PointwiseArgs
 {
     const double * up;      // [n_points]
@@ -102,6 +125,9 @@ cudaError_t launch_sweep_gather(const SweepArgs & a, int kf, int kt, cudaStream_
 cudaError_t launch_sweep_fibre(const FibreSweepArgs & a, int kf, int kt, int ct, cudaStream_t st);
 int fibre_smem_capacity_doubles();
 int fibre_threads();
+cudaError_t launch_sweep_pipe(const PipeArgs & a, int kf, int kt, int ct, int n_sm, cudaStream_t st);
+int pipe_threads();
+int pipe_smem_budget_bytes();
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);
 cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st);
