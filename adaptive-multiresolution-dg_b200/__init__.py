@@ -60,6 +60,7 @@ SYMBOLS = {
     "amdg_apply_tensor": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i]),
     "amdg_hierarchize": (_i, [_p, _i, _p, _p, _i]),
     "amdg_pointwise": (_i, [_p, _i, _ip, _dp, _p, _p, _p]),
+    "amdg_pointwise_hermite2d": (_i, [_p, _i, _ip, _dp, _p, _p]),
     "amdg_point_coords": (_i, [_p, _dp, _p]),
     "amdg_rk_stage": (_i, [_p, _i, _i, _d, _p, _p, _p, _i64]),
     "amdg_axpby": (_i, [_p, _i64, _d, _p, _d, _p]),
@@ -247,6 +248,12 @@ class Context:
         prm = np.zeros((len(f), 4)) if params is None else np.asarray(params, dtype=np.float64).reshape(len(f), 4)
         prm, pp = _dbls(prm)
         _check(lib.amdg_pointwise(self._h, len(f), fp_, pp, _ptr(up), _ptr(fp), _ptr(pts) if pts is not None else None))
+
+    def pointwise_hermite2d(self, flux_ids, params, up, fp):
+        f, fp_ = _ints(flux_ids)
+        prm = np.zeros((len(f), 4)) if params is None else np.asarray(params, dtype=np.float64).reshape(len(f), 4)
+        prm, pp = _dbls(prm)
+        _check(lib.amdg_pointwise_hermite2d(self._h, len(f), fp_, pp, _ptr(up), _ptr(fp)))
 
     def point_coords(self, pts1d, dev_pts):
         p, pp = _dbls(pts1d)

@@ -700,7 +700,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         int cnt = 1;
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
-        if (c->kernel_variant == 0 || c->kernel_variant == 3)
+        if (c->kernel_variant == 3)
         {
             while (cnt * n_comp > 64 && cnt > 1) --cnt;
             const amdg_ctx::PipeList & PL = get_pipe(c, t, W, O.kf, O.kt, rel, cnt * n_comp, lu);
@@ -962,6 +962,26 @@ int amdg_pointwise(amdg_ctx * c, int n_flux, const int * flux_id, const double *
     }
     CU(cudaSetDevice(c->device));
     cudaError_t e = launch_pointwise(a, c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("pointwise launch: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+int amdg_pointwise_hermite2d(amdg_ctx * c, int n_flux, const int * flux_id, const double * params, const double * up, double * fp)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (c->dim != 2 || c->edge_intp != 4) return fail(AMDG_EINVAL, "the Hermite point-wise flux exists for DIM == 2 and HermBasis::PMAX == 3 only (as in the reference)");
+    if (n_flux < 1 || n_flux > 8 || !flux_id || !up || !fp) return fail(AMDG_EINVAL, "bad arguments");
+    PointwiseArgs a; a.up = up; a.fp = fp; a.pts = nullptr; a.n_points = c->grid.n * 16; a.n_flux = n_flux; a.dim = 2;
+    for (int i = 0; i < n_flux; ++i)
+    {
+        if (flux_id[i] < AMDG_FLUX_LINEAR || flux_id[i] > AMDG_FLUX_COS) return fail(AMDG_EINVAL, "flux kind has no Hermite (derivative) form");
+        a.flux_id[i] = flux_id[i];
+        for (int k = 0; k < 4; ++k) a.params[i][k] = params ? params[i * 4 + k] : 0.0;
+    }
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_pointwise_herm2d(a, c->stream);
     if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("pointwise launch: ") + cudaGetErrorString(e));
     c->launches++;
     return AMDG_OK;

@@ -826,6 +826,50 @@ cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// Hermite (PMAX=3) point-wise flux in 2D, scalar: HermInterpolation::eval_fp_Her_2D (source/Interplation.cpp:2045-2288).
+// Local index along a dim: 0,1 = value at point 0,1; 2,3 = derivative at point 0,1 (deg_pt_deri_1d).  Block (a,b):
+//   value/value: f(u);  deriv/value: f'(u) u_x;  value/deriv: f'(u) u_y;  deriv/deriv: f''(u) u_x u_y + f'(u) u_xy
+__device__ __forceinline__ void flux_derivs(int id, const double * prm, double u, double & f, double & f1, double & f2)
+{
+    switch (id)
+    {
+        case AMDG_FLUX_LINEAR: f = prm[0] * u; f1 = prm[0]; f2 = 0.; break;
+        case AMDG_FLUX_BURGERS: f = u * u / 2.; f1 = u; f2 = 1.; break;
+        case AMDG_FLUX_SIN: f = sin(u); f1 = cos(u); f2 = -sin(u); break;
+        case AMDG_FLUX_COS: f = cos(u); f1 = -sin(u); f2 = -cos(u); break;
+        default: f = f1 = f2 = 0.;
+    }
+}
+
+__global__ void __launch_bounds__(256) pointwise_herm2d_kernel(const PointwiseArgs a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.n_points; p += stride)
+    {
+        const int64_t e = p >> 4; const int loc = (int)(p & 15);
+        const int ia = loc >> 2, ib = loc & 3;
+        const double * up = a.up + e * 16;
+        const double u = up[(ia & 1) * 4 + (ib & 1)];                    // value slot of the same point
+        const double w = up[loc];
+        for (int c = 0; c < a.n_flux; ++c)
+        {
+            double f, f1, f2; flux_derivs(a.flux_id[c], a.params[c], u, f, f1, f2);
+            double v;
+            if (ia < 2 && ib < 2) v = f;
+            else if (ia >= 2 && ib >= 2) v = f2 * up[ia * 4 + (ib - 2)] * up[(ia - 2) * 4 + ib] + f1 * w;
+            else v = f1 * w;
+            a.fp[(int64_t)c * a.n_points + p] = v;
+        }
+    }
+}
+
+cudaError_t launch_pointwise_herm2d(const PointwiseArgs & a, cudaStream_t st)
+{
+    const int64_t nb = (a.n_points + 255) / 256;
+    pointwise_herm2d_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 // interpolation point coordinates of all element points: pts[e][p][t] = pts1d[ord1d[e][t]*edge + p_t]
 __global__ void __launch_bounds__(256) point_coords_kernel(const double * __restrict__ pts1d, const int * __restrict__ ord1d,
                                                            int64_t n_elem, int dim, int edge, int block, double * __restrict__ pts)

@@ -129,6 +129,7 @@ cudaError_t launch_sweep_pipe(const PipeArgs & a, int kf, int kt, int ct, int n_
 int pipe_threads();
 int pipe_smem_budget_bytes();
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
+cudaError_t launch_pointwise_herm2d(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);
 cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st);
 cudaError_t launch_point_coords(const double * pts1d, const int * ord1d, int64_t n_elem, int dim, int edge, double * pts, cudaStream_t st);

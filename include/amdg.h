@@ -57,7 +57,7 @@ int amdg_ctx_destroy(amdg_ctx *ctx);
 int amdg_ctx_set_stream(amdg_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: a stream owned by ctx */
 int amdg_ctx_sync(amdg_ctx *ctx);
 int amdg_ctx_set_schedule(amdg_ctx *ctx, int sched);
-int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto, 1 = gather kernel, 2 = fibre-staged kernel */
+int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto (fibre-staged), 1 = gather kernel, 2 = fibre-staged kernel, 3 = pipelined persistent kernel */
 int64_t amdg_ctx_launch_count(amdg_ctx *ctx);                 /* kernels launched so far by this context */
 /* profiling aid: device buffer of n_items*8 int64 that the sweep kernel fills with per-CTA clock64 stamps (NULL = off) */
 int amdg_ctx_set_debug_buffer(amdg_ctx *ctx, void *dev_buf);
@@ -119,6 +119,9 @@ int amdg_hierarchize(amdg_ctx *ctx, int hier_op, const double *dev_src, double *
  * [n_elem][edge^dim][dim] of the interpolation points for the Vlasov products. ---- */
 int amdg_pointwise(amdg_ctx *ctx, int n_flux, const int *flux_id, const double *params, const double *dev_up,
                    double *dev_fp, const double *dev_pts);
+/* Hermite form (DIM == 2, HermBasis::PMAX == 3, scalar): HermInterpolation::eval_fp_Her_2D (source/Interplation.cpp:2045-2288):
+ * value slots f(u), first-derivative slots f'(u) u_x, mixed slot f''(u) u_x u_y + f'(u) u_xy.  Flux kinds LINEAR..COS. */
+int amdg_pointwise_hermite2d(amdg_ctx *ctx, int n_flux, const int *flux_id, const double *params, const double *dev_up, double *dev_fp);
 /* interpolation point coordinates of every element point from the 1D table pts1d[T*(pmax_intp+1)]
  * (LagrBasis::intep_pt, source/LagrBasis.cpp:19-28) */
 int amdg_point_coords(amdg_ctx *ctx, const double *host_pts1d, double *dev_pts);

@@ -218,3 +218,70 @@ def test_multi_gpu_fibre_partition():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29611", os.path.join(ROOT, "tests", "dist_check.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "DIST_CHECK OK" in r.stdout, r.stdout[-2000:]
+
+
+def test_hermite_nonlinear_stage():
+    """cfg4 as shipped: Hermite flux interpolation (FastHermIntp::eval_up_Herm -> eval_fp_Her_2D -> eval_fp_to_coe_D_Her ->
+    HyperbolicHermRHS) and three RK3SSP stages"""
+    d = load_golden("cfg4_burgers_herm_d2_k2_n4")
+    c = DevCase(d)
+    A = c.amdg
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    up = c.eval_up(u)
+    assert rel(c.to_host(up), d["up_intp"][:, 0, :]) < TOL
+    fp = torch.zeros(1, c.ne, 16, dtype=torch.float64, device="cuda")
+    c.ctx.pointwise_hermite2d([A.FLUX_BURGERS], None, up, fp)
+    assert rel(c.to_host(fp[0]), d["fp_intp"][:, 0, 0, :]) < 1e-14
+    fuc = torch.zeros(c.dim, c.ne, 16, dtype=torch.float64, device="cuda")
+    c.ctx.hierarchize(c.op_hier, fp, fuc[:1], n_comp=1)
+    assert rel(c.to_host(fuc[0]), d["fucoe_intp"][:, 0, 0, :]) < TOL
+    rhs = c.zeros(c.a)
+    c.rhs_vol_flx([fuc[t] for t in range(c.dim)], rhs)
+    assert rel(c.to_host(rhs), d["rhs_vol_flx"][:, 0, :]) < TOL
+    c.penalty(u, rhs, 1.2)
+    assert rel(c.to_host(rhs), d["rhs_all"][:, 0, :]) < TOL
+    # full RK3SSP step
+    dt = 0.002
+    u_tn = u.clone()
+    for stage in range(3):
+        up = c.eval_up(u)
+        c.ctx.pointwise_hermite2d([A.FLUX_BURGERS], None, up, fp)
+        c.ctx.hierarchize(c.op_hier, fp, fuc[:1], n_comp=1)
+        rhs = c.zeros(c.a)
+        c.rhs_vol_flx([fuc[t] for t in range(c.dim)], rhs)
+        c.penalty(u, rhs, 1.2)
+        c.ctx.rk_stage(A.RK_RK3SSP, stage, dt, u_tn, u, rhs)
+        assert rel(c.to_host(u), d["stage%d.ucoe_alpt" % stage][:, 0, :]) < TOL
+    c.close()
+
+
+def test_vlasov_6d_stage():
+    """cfg5 at reduced NMAX: generalised Vlasov products (v_t f, E_t(x) f), d=6, k=1, m=2, three RK3SSP stages"""
+    d = load_golden("cfg5_vlasov_d6_k1_n2")
+    c = DevCase(d)
+    A = c.amdg
+    dt = 0.001
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    pts = torch.zeros(c.ne, c.b ** c.dim, c.dim, dtype=torch.float64, device="cuda")
+    c.ctx.point_coords(d["lagr.intep_pt"], pts)
+    fp = torch.zeros(c.dim, c.ne, c.b ** c.dim, dtype=torch.float64, device="cuda")
+    fuc = torch.zeros_like(fp)
+    prm = [[t, 0, 0, 0] for t in range(c.dim)]
+    u_tn = u.clone()
+    for stage in range(3):
+        up = c.eval_up(u)
+        c.ctx.pointwise([A.FLUX_VLASOV_SMOOTH_E] * c.dim, prm, up, fp, pts)
+        c.ctx.hierarchize(c.op_hier, fp, fuc, n_comp=c.dim)
+        if stage == 0:
+            assert rel(c.to_host(up), d["up_intp"][:, 0, :]) < TOL
+            for t in range(c.dim):
+                assert rel(c.to_host(fp[t]), d["fp_intp"][:, 0, t, :]) < 1e-13
+                assert rel(c.to_host(fuc[t]), d["fucoe_intp"][:, 0, t, :]) < TOL
+        rhs = c.zeros(c.a)
+        c.rhs_vol_flx([fuc[t] for t in range(c.dim)], rhs)
+        c.penalty(u, rhs, 1.2)
+        if stage == 0:
+            assert rel(c.to_host(rhs), d["rhs_all"][:, 0, :]) < TOL
+        c.ctx.rk_stage(A.RK_RK3SSP, stage, dt, u_tn, u, rhs)
+        assert rel(c.to_host(u), d["stage%d.ucoe_alpt" % stage][:, 0, :]) < TOL
+    c.close()
