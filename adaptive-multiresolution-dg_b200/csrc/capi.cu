@@ -2,6 +2,7 @@
 // No torch types, no CPU compute path: a context without a device can only build and export tables.
 #include <cstdio>
 #include <cstring>
+#include <array>
 #include <map>
 #include <memory>
 #include <string>
@@ -12,6 +13,7 @@
 #include "../../include/amdg.h"
 #include "grid.hpp"
 #include "pipe_items.hpp"
+#include "mma_items.hpp"
 #include "kernels.cuh"
 
 using namespace amdg;
@@ -65,6 +67,20 @@ struct amdg_ctx
     };
     std::map<std::tuple<int, int, int, int, int, int>, PipeList> pipes;
     int pipe_cap_doubles = 11000, pipe_meta_ints = 2560, pipe_item_target = 148 * 3;
+    // tensor-core kernel: shapes of the fibres, tile programs and work lists
+    ShapeTable shapes;
+    struct MmaList
+    {
+        MmaItem * d_items = nullptr; int * d_elem_pool = nullptr; int * d_prog_ints = nullptr;
+        int n_item = 0, smem_doubles = 0; bool ok = false;
+        std::vector<int> prog_shape;                          // shape id of every program piece of this list
+        std::vector<int> prog_piece;                          // piece*1024 + number of pieces
+        std::vector<ShapeProg> progs;                         // host copies of the pieces (to build operator values)
+        std::map<int, const double **> a_tab;                 // per operator: device table of A pointers
+    };
+    std::map<std::tuple<int, int, int, int, int, int>, MmaList> mmas;       // key: (dim t, outer, kf, kt, rel*4+lu, parallel class)
+    std::map<std::tuple<int, int, int, int>, double *> mma_A;               // (op, shape, rel*4+lu, piece*1024+npieces) -> device operator values
+    int mma_cap_doubles = 9 * 1024, mma_item_target = 148 * 8, mma_ent_target = 448, mma_stage_a_max = 64;
     int n_sm = 148;
     long long * dbg = nullptr;
     // metadata arena: index tables, work lists and operator blocks live in one allocation that is given an L2
@@ -90,6 +106,15 @@ static void free_dev_grid(amdg_ctx * c)
     }
     c->ddims.clear();
     meta_free(c, c->d_ord1d); c->d_ord1d = nullptr;
+    for (auto & kv : c->mmas)
+    {
+        amdg_ctx::MmaList & L = kv.second;
+        meta_free(c, L.d_items); meta_free(c, L.d_elem_pool); meta_free(c, L.d_prog_ints);
+        for (auto & at : L.a_tab) meta_free(c, (void *)at.second);
+    }
+    c->mmas.clear();
+    for (auto & kv : c->mma_A) cudaFree(kv.second);
+    c->mma_A.clear();
     for (auto & kv : c->pipes)
     {
         amdg_ctx::PipeList & L = kv.second;
@@ -170,6 +195,10 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_SMEM_DOUBLES")) c->smem_doubles = std::max(256, std::min(atoi(e), fibre_smem_capacity_doubles()));
     if (const char * e = std::getenv("AMDG_ITEM_TARGET")) c->item_target = std::max(1, atoi(e));
     if (const char * e = std::getenv("AMDG_KERNEL")) c->kernel_variant = atoi(e);
+    if (const char * e = std::getenv("AMDG_MMA_CAP")) c->mma_cap_doubles = std::max(512, std::min(atoi(e), mma_smem_capacity_doubles())) & ~1;
+    if (const char * e = std::getenv("AMDG_MMA_ITEMS")) c->mma_item_target = std::max(1, atoi(e));
+    if (const char * e = std::getenv("AMDG_MMA_ENT")) c->mma_ent_target = std::max(16, atoi(e));
+    if (const char * e = std::getenv("AMDG_MMA_STAGE_A")) c->mma_stage_a_max = std::max(0, atoi(e));
     if (const char * e = std::getenv("AMDG_PIPE_CAP")) c->pipe_cap_doubles = std::max(256, atoi(e)) & ~1;
     if (const char * e = std::getenv("AMDG_PIPE_META")) c->pipe_meta_ints = (std::max(256, atoi(e)) + 3) & ~3;
     if (const char * e = std::getenv("AMDG_PIPE_ITEMS")) c->pipe_item_target = std::max(1, atoi(e));
@@ -235,7 +264,7 @@ int amdg_ctx_set_stream(amdg_ctx * c, void * s)
 
 int amdg_ctx_sync(amdg_ctx * c) { int r = need_device(c); if (r) return r; CU(cudaStreamSynchronize(c->stream)); return AMDG_OK; }
 int amdg_ctx_set_schedule(amdg_ctx * c, int s) { if (!c || (s != AMDG_SCHED_LITERAL && s != AMDG_SCHED_SHARED)) return fail(AMDG_EINVAL, "bad schedule"); c->sched = s; return AMDG_OK; }
-int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 3) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
+int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 4) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
 int64_t amdg_ctx_launch_count(amdg_ctx * c) { return c ? c->launches : -1; }
 int amdg_ctx_set_debug_buffer(amdg_ctx * c, void * dev_buf) { if (!c) return fail(AMDG_EINVAL, "null context"); c->dbg = (long long *)dev_buf; return AMDG_OK; }
 
@@ -260,6 +289,7 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
     Grid g;
     if (g.build(c->dim, c->nmax, n, level, suppt, c->pairs) != 0) return fail(AMDG_EINVAL, "invalid or duplicate element index");
     c->grid = std::move(g); c->have_grid = true;
+    c->shapes.build(c->grid);
     if (c->device < 0) return AMDG_OK;
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
@@ -651,6 +681,139 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
     return c->items.emplace(key, L).first->second;
 }
 
+// ---- tensor-core kernel: work list + tile programs ---------------------------------------------------------------
+static int mma_pitch(int ni, int inner) { if (inner == 1) return 1; int pk = ni; while ((pk & 7) != 4) ++pk; return pk; }
+
+static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int par, int lu)
+{
+    int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
+    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls);
+    auto it = c->mmas.find(key);
+    if (it != c->mmas.end()) return it->second;
+    amdg_ctx::MmaList L;
+    const std::map<int, std::vector<int>> & sf = c->shapes.shape_fibres[t];
+    std::vector<MmaItem> items; std::vector<double> cost; std::vector<int> elem_pool;
+    std::vector<int> prog_ints;
+    const DimTables & H = c->grid.dims[t];
+    bool ok = true; int smem_need = 0;
+    const int64_t total = c->grid.n * (int64_t)kf * outer * mma_pitch(inner, inner);
+    const int64_t target = std::max<int64_t>(1, total / std::max(1, c->mma_item_target >> pcls));
+    for (auto & kv : sf)
+    {
+        const int shape = kv.first; const std::vector<int> & fibres = kv.second;
+        if (const char * e = std::getenv("AMDG_MMA_MAXM")) { if ((int)c->shapes.ords[shape].size() > atoi(e)) continue; }     // experiment switch (results incomplete)
+        if (const char * e = std::getenv("AMDG_MMA_MINM")) { if ((int)c->shapes.ords[shape].size() < atoi(e)) continue; }
+        ShapeProg SP; build_shape_prog(c->pairs, c->shapes.ords[shape], rel, lu, kf, kt, SP);
+        const int m = SP.m;
+        // pieces: a long program is split so that one CTA walks about mma_ent_target entries
+        int np = 1;
+        const int pk_full = mma_pitch(inner, inner);
+        const bool whole_fits = (int64_t)m * outer * kf * pk_full + (2 * SP.n_rt + 1 + SP.n_ent() + m) / 2 + 4 <= c->mma_cap_doubles;
+        if (!whole_fits || SP.n_ent() > 4 * c->mma_ent_target) np = (int)std::min<int64_t>(std::max<int64_t>(1, (SP.n_ent() + c->mma_ent_target - 1) / c->mma_ent_target), std::max(1, SP.n_rt));
+        std::vector<ShapeProg> pieces; split_shape_prog(SP, np, pieces);
+        int max_piece_ints = 0; for (auto & pc : pieces) max_piece_ints = std::max(max_piece_ints, 2 * pc.n_rt + 1 + (int)pc.n_ent());
+        const bool stage_a = np == 1 && SP.n_ent() <= c->mma_stage_a_max;
+        const int a_doubles = stage_a ? (int)SP.n_ent() * 32 : 0;
+        // column rectangles
+        struct Rect { int o0, no, i0, ni, pk; };
+        std::vector<Rect> rects;
+        int nfib_max = 1;
+        const int cap = c->mma_cap_doubles - ((max_piece_ints + m + 1) / 2 + 4) - a_doubles;      // room for the piece, the element rows, staged A
+        if (cap <= 0) { ok = false; break; }
+        if ((int64_t)m * outer * kf * pk_full <= cap)
+        {
+            rects.push_back({ 0, outer, 0, inner, pk_full });
+            if (np == 1) nfib_max = (int)std::max<int64_t>(1, std::min<int64_t>(cap, target) / ((int64_t)m * outer * kf * pk_full + (m + 1) / 2));
+        }
+        else if ((int64_t)m * kf * pk_full <= cap)
+        {
+            const int no = (int)(cap / ((int64_t)m * kf * pk_full));
+            for (int o0 = 0; o0 < outer; o0 += no) rects.push_back({ o0, std::min(no, outer - o0), 0, inner, pk_full });
+        }
+        else
+        {
+            int ni = 0, pk_ni = 0;
+            for (int cand = (inner / 8) * 8; cand >= 8; cand -= 8) if ((int64_t)m * kf * mma_pitch(cand, inner) <= cap) { ni = cand; break; }
+            if (ni == 0 && inner >= 8 && (int64_t)m * kf * 8 <= cap) { ni = 8; pk_ni = 8; }      // 8 columns with a 2-way conflicting pitch beat 4 columns
+            if (ni == 0) for (int cand : { 4, 2, 1 }) if (cand <= inner && (int64_t)m * kf * mma_pitch(cand, inner) <= cap) { ni = cand; break; }
+            if (ni == 0) { ok = false; break; }
+            for (int o0 = 0; o0 < outer; ++o0) for (int i0 = 0; i0 < inner; i0 += ni) rects.push_back({ o0, 1, i0, std::min(ni, inner - i0), pk_ni ? pk_ni : mma_pitch(ni, inner) });
+        }
+        const int prog0 = (int)L.progs.size();
+        std::vector<int> piece_ofs(np);
+        for (int q = 0; q < np; ++q)
+        {
+            piece_ofs[q] = (int)prog_ints.size();
+            prog_ints.insert(prog_ints.end(), pieces[q].rt_ptr.begin(), pieces[q].rt_ptr.end());
+            prog_ints.insert(prog_ints.end(), pieces[q].rt_order.begin(), pieces[q].rt_order.end());
+            prog_ints.insert(prog_ints.end(), pieces[q].ent_src.begin(), pieces[q].ent_src.end());
+        }
+        for (size_t f0 = 0; f0 < fibres.size(); f0 += nfib_max)
+        {
+            const int nf = (int)std::min<size_t>(nfib_max, fibres.size() - f0);
+            const int eofs = (int)elem_pool.size();
+            for (int b = 0; b < nf; ++b) for (int f = 0; f < m; ++f) elem_pool.push_back(H.slot_elem[fibres[f0 + b] + f]);
+            for (const Rect & r : rects)
+                for (int q = 0; q < np; ++q)
+                {
+                    MmaItem x; std::memset(&x, 0, sizeof(x));
+                    x.prog = prog0 + q; x.elem_ofs = eofs; x.nfib = nf; x.o0 = r.o0; x.no = r.no; x.i0 = r.i0; x.ni = r.ni; x.pk = r.pk;
+                    x.m = m; x.n_rt = pieces[q].n_rt; x.prog_ofs = piece_ofs[q]; x.n_ent = (int)pieces[q].n_ent();
+                    x.ni_magic = r.ni <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + (unsigned)r.ni - 1) / (unsigned)r.ni);
+                    x.stage_a = stage_a ? 1 : 0;
+                    items.push_back(x);
+                    cost.push_back(((double)pieces[q].n_ent() + 2.0 * pieces[q].n_rt) * nf * ((r.no * r.ni + 7) / 8) + 0.01 * nf * m * r.no * r.ni);
+                    const int n_ints = 2 * pieces[q].n_rt + 1 + (int)pieces[q].n_ent();
+                    smem_need = std::max(smem_need, ((nf * m * r.no * kf * r.pk + 1) & ~1) + (n_ints + ((nf * m + 1) & ~1) + 1) / 2 + 2 + a_doubles);
+                }
+        }
+        for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(q * 1024 + np); L.progs.push_back(std::move(pieces[q])); }
+    }
+    if (ok && !items.empty())
+    {
+        std::vector<int> order(items.size()); for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+        std::vector<MmaItem> sorted(items.size()); for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
+        if (prog_ints.empty()) prog_ints.push_back(0);
+        bool up = meta_upload(c, &L.d_items, sorted.data(), sorted.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.d_elem_pool, elem_pool.data(), elem_pool.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.d_prog_ints, prog_ints.data(), prog_ints.size(), false) == cudaSuccess &&
+                  cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (up) { L.n_item = (int)sorted.size(); L.smem_doubles = (smem_need + 1) & ~1; L.ok = true; }
+        if (std::getenv("AMDG_VERBOSE"))
+            fprintf(stderr, "[amdg] mma list t=%d outer=%d inner=%d kf=%d kt=%d rel=%d lu=%d par=%d: %d items, %d programs, smem %d doubles\n",
+                    t, outer, inner, kf, kt, rel, lu, par, (int)sorted.size(), (int)L.progs.size(), L.smem_doubles);
+    }
+    return c->mmas.emplace(key, std::move(L)).first->second;
+}
+
+// device table of operator values (fragment order) for every program of a list, for operator `op`
+static const double * const * get_mma_a_tab(amdg_ctx * c, amdg_ctx::MmaList & L, int op, int rel, int lu)
+{
+    auto it = L.a_tab.find(op);
+    if (it != L.a_tab.end()) return it->second;
+    const Op & O = *c->ops[op];
+    std::vector<const double *> tab(L.progs.size());
+    for (size_t i = 0; i < L.progs.size(); ++i)
+    {
+        auto key = std::make_tuple(op, L.prog_shape[i], rel * 4 + lu, L.prog_piece[i]);
+        auto f = c->mma_A.find(key);
+        if (f == c->mma_A.end())
+        {
+            std::vector<double> A; build_shape_A(L.progs[i], O.blocks.data(), O.kf, O.kt, A);
+            if (A.empty()) A.push_back(0.0);
+            double * d = nullptr;
+            if (upload(&d, A.data(), A.size(), c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return nullptr;
+            f = c->mma_A.emplace(key, d).first;
+        }
+        tab[i] = f->second;
+    }
+    const double ** dtab = nullptr;
+    if (meta_upload(c, &dtab, tab.data(), tab.size(), false) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return nullptr;
+    L.a_tab[op] = dtab;
+    return dtab;
+}
+
 // work list of the pipelined kernel
 static const amdg_ctx::PipeList & get_pipe(amdg_ctx * c, int t, int W, int kf, int kt, int rel, int par, int lu)
 {
@@ -700,6 +863,24 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         int cnt = 1;
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
+        if (c->kernel_variant == 0 || c->kernel_variant == 4)
+        {
+            amdg_ctx::MmaList & ML = get_mma(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu);
+            const double * const * atab = ML.ok ? get_mma_a_tab(c, ML, op, rel, lu) : nullptr;
+            if (ML.ok && atab)
+            {
+                MmaArgs a;
+                a.items = ML.d_items; a.n_item = ML.n_item; a.prog_pool = ML.d_prog_ints; a.a_tab = atab; a.elem_pool = ML.d_elem_pool; a.dbg = c->dbg;
+                a.n_elem = c->grid.n; a.inner = inner; a.n_comp = n_comp; a.n_job = cnt;
+                for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
+                cudaError_t e = launch_sweep_mma(a, O.kf, O.kt, ML.smem_doubles, c->stream);
+                if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("tensor-core sweep launch: ") + cudaGetErrorString(e));
+                c->launches++;
+                done += cnt;
+                continue;
+            }
+            if (c->kernel_variant == 4) return fail(AMDG_EINVAL, "tensor-core kernel requested but the work list could not be built");
+        }
         if (c->kernel_variant == 3)
         {
             while (cnt * n_comp > 64 && cnt > 1) --cnt;

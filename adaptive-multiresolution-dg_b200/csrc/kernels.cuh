@@ -110,6 +110,35 @@ struct PipeArgs
     SweepJob job[MAX_JOBS];
 };
 
+// tensor-core sweep kernel (tile programs built by mma_items.hpp)
+struct MmaItem
+{
+    int prog;           // tile program (shape): index into a_tab
+    int elem_ofs, nfib; // element rows of this item's fibres: elem_pool[elem_ofs + b*m + f]
+    int o0, no;         // column rectangle: outer indices [o0, o0+no) ...
+    int i0, ni;         //   ... x inner indices [i0, i0+ni)
+    int pk;             // shared-memory pitch between consecutive source indices k (doubles)
+    int m, n_rt;        // fibre length, row tiles of the program piece
+    int prog_ofs;       // piece ints in prog_pool: rt_ptr[n_rt+1] | rt_id[n_rt] | ent_src[n_ent]  (row tiles in position order)
+    int n_ent;
+    unsigned ni_magic;  // ceil(2^32 / ni): c / ni == umulhi(c, magic) for the small column counts used here
+    int stage_a;        // 1: the operator values of the piece are staged in shared memory too
+    int pad[2];
+};
+struct MmaArgs
+{
+    const MmaItem * items; int n_item;
+    const int * prog_pool;          // tile programs
+    const double * const * a_tab;   // per program: operator values in fragment order [entry][32]
+    const int * elem_pool;          // element rows of the fibres of every item
+    long long * dbg;                // optional per-CTA clock stamps
+    int64_t n_elem;
+    int inner;
+    int n_comp;
+    int n_job;
+    SweepJob job[MAX_JOBS];
+};
+
 struct PointwiseArgs
 {
     const double * up;      // [n_points]
@@ -128,6 +157,8 @@ int fibre_threads();
 cudaError_t launch_sweep_pipe(const PipeArgs & a, int kf, int kt, int ct, int n_sm, cudaStream_t st);
 int pipe_threads();
 int pipe_smem_budget_bytes();
+cudaError_t launch_sweep_mma(const MmaArgs & a, int kf, int kt, int smem_doubles, cudaStream_t st);
+int mma_smem_capacity_doubles();
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_pointwise_herm2d(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);
