@@ -96,7 +96,8 @@ static inline double field_value(uint64_t seed, int hash_key, int vec, int idx, 
 struct Args
 {
     int dim = 2, nmax = 4, n0 = -1, sparse = 1, pa = 2, pl = 3, ph = 3, vecnum = 1, time_reps = 0, threads = 0, dump_tables = 0;
-    int msh_lagr = 1, msh_herm = 1, steps = 1;
+    int msh_lagr = 1, msh_herm = 1, steps = 1, rounds = 0;
+    double eps = 1e10, eta = -1.0;
     uint64_t seed = 20240901ULL;
     double dt = 1e-3;
     std::string intp = "lagr", flux = "burgers", run = "grid", out = "";
@@ -118,6 +119,8 @@ static Args parse(int argc, char ** argv)
         else if (k == "--dump-tables") a.dump_tables = std::stoi(v); else if (k == "--dt") a.dt = std::stod(v);
         else if (k == "--msh-lagr") a.msh_lagr = std::stoi(v); else if (k == "--msh-herm") a.msh_herm = std::stoi(v);
         else if (k == "--steps") a.steps = std::stoi(v);
+        else if (k == "--adapt-eps") a.eps = std::stod(v); else if (k == "--adapt-eta") a.eta = std::stod(v);
+        else if (k == "--adapt-rounds") a.rounds = std::stoi(v);
         else { std::cerr << "unknown option " << k << std::endl; exit(2); }
     }
     if (a.n0 < 0) a.n0 = a.nmax;
@@ -272,8 +275,12 @@ int main(int argc, char ** argv)
     H.timing["setup_tables"] = H.now() - t0;
 
     t0 = H.now();
-    DGAdapt dg(a.sparse == 1, a.n0, a.nmax, all_bas_alpt, all_bas_lagr, all_bas_herm, hash, 1e10, -1.0, true, false);
+    DGAdapt dg(a.sparse == 1, a.n0, a.nmax, all_bas_alpt, all_bas_lagr, all_bas_herm, hash, a.eps, a.eta, true, false);
     H.dg = &dg; H.sort_elements();
+    // adaptive (irregular) grids: DGAdapt::refine / coarsen driven by the norms of the pseudo-random field
+    // (source/DGAdapt.cpp:371-404, 675-688); the neighbour sets are then maintained by add_elem / del_elem (:1073-1248)
+    for (int r = 0; r < a.rounds; ++r) { H.fill_ucoe(a.seed); dg.refine(); H.sort_elements(); }
+    if (a.rounds > 0 && a.eta > 0) { H.fill_ucoe(a.seed); dg.coarsen(); H.sort_elements(); }
     H.timing["setup_grid"] = H.now() - t0;
 
     {

@@ -32,6 +32,9 @@ CASES = {
     "vlasov_d4_k3_m4_n2": "--dim 4 --nmax 2 --pa 3 --pl 4 --msh-lagr 2 --run grid,rhs --flux vlasov --dump-tables 1",
     # full (non-sparse) grid and a 1D grid: edge cases of the schedule (d=1 is a single full sweep)
     "full_d2_k2_n3": "--dim 2 --nmax 3 --sparse 0 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux linear --dump-tables 1",
+    # adaptive (irregular) grids produced by DGAdapt::refine / coarsen: fibres are arbitrary subsets of the 1D tree
+    "adapt_d2_k2_n6": "--dim 2 --nmax 6 --n0 2 --pa 2 --pl 3 --adapt-eps 0.02 --adapt-eta 0.012 --adapt-rounds 5 --run grid,rhs,roundtrip,stage --flux burgers --dump-tables 1 --dt 0.001",
+    "adapt_d3_k1_n4": "--dim 3 --nmax 4 --n0 1 --pa 1 --pl 2 --adapt-eps 0.05 --adapt-eta 0.03 --adapt-rounds 4 --run grid,rhs,roundtrip --flux kpp --dump-tables 1",
     "line_d1_k2_n5": "--dim 1 --nmax 5 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux burgers --dump-tables 1",
 }
 

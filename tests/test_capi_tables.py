@@ -50,12 +50,13 @@ def test_invalid_arguments(amdg):
 def test_tables_bit_exact(amdg, name):
     d = load_golden(name)
     dim, nmax, n0, sparse, pa, pl, ph, vecnum, herm, ne = [int(x) for x in d["config"]]
-    # the library's own grid generator, then sorted by its own hash key == the reference's sorted order
-    lev, sup = amdg.sparse_grid(dim, n0, sparse == 1)
-    keys = np.array([amdg.hash_key(l, s) for l, s in zip(lev, sup)])
-    o = np.argsort(keys, kind="stable")
-    assert np.array_equal(keys[o], d["hash_key"])
-    assert np.array_equal(lev[o], d["level"]) and np.array_equal(sup[o], d["suppt"])
+    if not name.startswith("adapt_"):
+        # the library's own grid generator, then sorted by its own hash key == the reference's sorted order
+        lev, sup = amdg.sparse_grid(dim, n0, sparse == 1)
+        keys = np.array([amdg.hash_key(l, s) for l, s in zip(lev, sup)])
+        o = np.argsort(keys, kind="stable")
+        assert np.array_equal(keys[o], d["hash_key"])
+        assert np.array_equal(lev[o], d["level"]) and np.array_equal(sup[o], d["suppt"])
     ctx = amdg.Context(dim, nmax, pa, ph if herm else pl, device=-1)
     ctx.grid_set(d["level"], d["suppt"])
     hk, od = ctx.grid_keys()

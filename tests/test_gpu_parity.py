@@ -11,7 +11,7 @@ from pipeline import DevCase, rel
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
-FLUX = {"cfg4_burgers_lagr_d2_k2_n4": ("burgers", 1), "kpp_lagr_d2_k1_n4": ("kpp", None), "full_d2_k2_n3": ("linear", None),
+FLUX = {"adapt_d2_k2_n6": ("burgers", None), "adapt_d3_k1_n4": ("kpp", None), "cfg4_burgers_lagr_d2_k2_n4": ("burgers", 1), "kpp_lagr_d2_k1_n4": ("kpp", None), "full_d2_k2_n3": ("linear", None),
         "line_d1_k2_n5": ("burgers", None), "cfg1_adv_d2_k2_n4": ("burgers", None)}
 LIN = [1.0, 0.7, -0.5, 0.3, 1.3, -0.9]
 
@@ -24,7 +24,7 @@ def flux_ids(A, name, dim):
     if kind == "linear":
         return [A.FLUX_LINEAR] * n, [[LIN[t], 0, 0, 0] for t in range(n)]
     if kind == "kpp":
-        return [A.FLUX_SIN, A.FLUX_COS][:n], None
+        return ([A.FLUX_SIN, A.FLUX_COS] + [A.FLUX_COS] * dim)[:n], None
 
 
 @pytest.mark.parametrize("sched", [0, 1])
@@ -284,4 +284,31 @@ def test_vlasov_6d_stage():
             assert rel(c.to_host(rhs), d["rhs_all"][:, 0, :]) < TOL
         c.ctx.rk_stage(A.RK_RK3SSP, stage, dt, u_tn, u, rhs)
         assert rel(c.to_host(u), d["stage%d.ucoe_alpt" % stage][:, 0, :]) < TOL
+    c.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
+@pytest.mark.parametrize("name", ["adapt_d2_k2_n6", "adapt_d3_k1_n4", "cfg3_wave_d3_k2_n3", "cfg5_vlasov_d6_k1_n2"])
+def test_all_kernel_variants(name, kernel):
+    """every sweep kernel (gather, fibre-staged list, pipelined list, tensor-core) on regular and adaptive grids:
+    interpolation transform, hierarchisation and the flux right-hand side against the reference"""
+    d = load_golden(name)
+    c = DevCase(d, kernel=kernel)
+    A = c.amdg
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    up = c.eval_up(u)
+    key = "up_intp" if "up_intp" in d else "rt.up_intp"
+    assert rel(c.to_host(up), d[key][:, 0, :]) < TOL
+    if "fucoe_intp" in d:
+        fuc = [c.to_dev(d["fucoe_intp"][:, 0, t, :]) for t in range(c.dim)]
+        rhs = c.zeros(c.a)
+        c.rhs_vol_flx(fuc, rhs)
+        assert rel(c.to_host(rhs), d["rhs_vol_flx"][:, 0, :]) < TOL
+        c.penalty(u, rhs, 1.2)
+        assert rel(c.to_host(rhs), d["rhs_all"][:, 0, :]) < TOL
+    if "rt.ucoe_intp" in d:
+        uc = c.hier(c.to_dev(d["rt.up_intp"][:, 0, :]))
+        assert rel(c.to_host(uc), d["rt.ucoe_intp"][:, 0, :]) < TOL
+        ua = c.to_alpt(uc)
+        assert rel(c.to_host(ua), d["rt.ucoe_alpt"][:, 0, :]) < TOL
     c.close()
