@@ -287,6 +287,25 @@ def test_vlasov_6d_stage():
     c.close()
 
 
+@pytest.mark.parametrize("name", ["cfg4_burgers_lagr_d2_k2_n4", "cfg5_vlasov_d6_k1_n2"])
+def test_merged_vol_flx_application(name):
+    """rhs_vol_scalar + rhs_flx_intp_scalar of one dimension as ONE tensor application with the combined table
+    u_vx + (ulft_vjp + urgt_vjp)/2 under the flx relation (u_vx vanishes on the pairs that only touch) -- what bench.py's
+    stage workloads run; reference source/FastMultiplyLU.cpp:1125-1189"""
+    d = load_golden(name)
+    c = DevCase(d)
+    A = c.amdg
+    op_volflx = c.ctx.op_combine(c.op_uvx, 1.0, c.op_uave, 0.5)
+    rhs = c.zeros(c.a)
+    for t in range(c.dim):
+        fuc = c.to_dev(d["fucoe_intp"][:, 0, t, :])
+        ops = [op_volflx if s == t else c.op_uv for s in range(c.dim)]
+        rels = [A.REL_FLX if s == t else A.REL_VOL for s in range(c.dim)]
+        c.ctx.apply_tensor(ops, rels, fuc, rhs, accumulate=t > 0)
+    assert rel(c.to_host(rhs), d["rhs_vol_flx"][:, 0, :]) < TOL
+    c.close()
+
+
 @pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 @pytest.mark.parametrize("name", ["adapt_d2_k2_n6", "adapt_d3_k1_n4", "cfg3_wave_d3_k2_n3", "cfg5_vlasov_d6_k1_n2"])
 def test_all_kernel_variants(name, kernel):
