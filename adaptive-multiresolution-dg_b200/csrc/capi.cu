@@ -698,18 +698,27 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
     bool ok = true; int smem_need = 0;
     const int64_t total = c->grid.n * (int64_t)kf * outer * mma_pitch(inner, inner);
     const int64_t target = std::max<int64_t>(1, total / std::max(1, c->mma_item_target >> pcls));
+    // tile programs of every shape
+    std::map<int, ShapeProg> shape_progs;
+    for (auto & kv : sf) build_shape_prog(c->pairs, c->shapes.ords[kv.first], rel, lu, kf, kt, shape_progs[kv.first]);
+    // A launch with fewer CTAs than the machine holds is bounded by its longest CTA: cut the programs finer (halve the
+    // entry target) until the grid fills the SMs or the pieces reach 32 entries.
+    int ent_target = c->mma_ent_target;
+  retry_finer:
+    const int64_t split_above = ent_target == c->mma_ent_target ? (int64_t)4 * ent_target : (int64_t)ent_target * 3 / 2;
+    items.clear(); cost.clear(); elem_pool.clear(); prog_ints.clear(); L = amdg_ctx::MmaList(); ok = true; smem_need = 0;
     for (auto & kv : sf)
     {
         const int shape = kv.first; const std::vector<int> & fibres = kv.second;
         if (const char * e = std::getenv("AMDG_MMA_MAXM")) { if ((int)c->shapes.ords[shape].size() > atoi(e)) continue; }     // experiment switch (results incomplete)
         if (const char * e = std::getenv("AMDG_MMA_MINM")) { if ((int)c->shapes.ords[shape].size() < atoi(e)) continue; }
-        ShapeProg SP; build_shape_prog(c->pairs, c->shapes.ords[shape], rel, lu, kf, kt, SP);
+        const ShapeProg & SP = shape_progs[shape];
         const int m = SP.m;
-        // pieces: a long program is split so that one CTA walks about mma_ent_target entries
+        // pieces: a long program is split so that one CTA walks about ent_target entries
         int np = 1;
         const int pk_full = mma_pitch(inner, inner);
         const bool whole_fits = (int64_t)m * outer * kf * pk_full + (2 * SP.n_rt + 1 + SP.n_ent() + m) / 2 + 4 <= c->mma_cap_doubles;
-        if (!whole_fits || SP.n_ent() > 4 * c->mma_ent_target) np = (int)std::min<int64_t>(std::max<int64_t>(1, (SP.n_ent() + c->mma_ent_target - 1) / c->mma_ent_target), std::max(1, SP.n_rt));
+        if (!whole_fits || SP.n_ent() > split_above) np = (int)std::min<int64_t>(std::max<int64_t>(1, (SP.n_ent() + ent_target - 1) / ent_target), std::max(1, SP.n_rt));
         std::vector<ShapeProg> pieces; split_shape_prog(SP, np, pieces);
         int max_piece_ints = 0; for (auto & pc : pieces) max_piece_ints = std::max(max_piece_ints, 2 * pc.n_rt + 1 + (int)pc.n_ent());
         const bool stage_a = np == 1 && SP.n_ent() <= c->mma_stage_a_max;
@@ -769,6 +778,7 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
         }
         for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(q * 1024 + np); L.progs.push_back(std::move(pieces[q])); }
     }
+    if (ok && ent_target > 32 && (int64_t)items.size() * (1 << pcls) < 3 * (int64_t)c->n_sm) { ent_target = std::max(32, ent_target / 2); goto retry_finer; }
     if (ok && !items.empty())
     {
         std::vector<int> order(items.size()); for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
