@@ -23,7 +23,7 @@ REL_VOL, REL_FLX = 0, 1
 LU_L, LU_U, LU_FULL = 0, 1, 2
 SCHED_LITERAL, SCHED_SHARED = 0, 1
 FLUX_LINEAR, FLUX_BURGERS, FLUX_SIN, FLUX_COS, FLUX_BUCKLEY_X, FLUX_BUCKLEY_Y, FLUX_VLASOV_SMOOTH_E = range(7)
-RK_EULER, RK_RK2SSP, RK_RK2MID, RK_RK3SSP = range(4)
+RK_EULER, RK_RK2SSP, RK_RK2MID, RK_RK3SSP, RK_RK3HEUN = range(5)
 
 _i, _i64, _d, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -63,6 +63,7 @@ SYMBOLS = {
     "amdg_pointwise_hermite2d": (_i, [_p, _i, _ip, _dp, _p, _p]),
     "amdg_point_coords": (_i, [_p, _dp, _p]),
     "amdg_rk_stage": (_i, [_p, _i, _i, _d, _p, _p, _p, _i64]),
+    "amdg_rk4_ode2nd_stage": (_i, [_p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _i64]),
     "amdg_axpby": (_i, [_p, _i64, _d, _p, _d, _p]),
     "amdg_host_apply_tensor": (_i, [_p, _ip, _ip, _dp, _dp, _i, _d, _i]),
     "amdg_host_sweep1d": (_i, [_p, _i, _i, _i, _i, _ip, _dp, _dp, _i, _d, _i]),
@@ -261,6 +262,9 @@ class Context:
 
     def rk_stage(self, scheme, stage, dt, u_tn, u, rhs):
         _check(lib.amdg_rk_stage(self._h, scheme, stage, dt, _ptr(u_tn), _ptr(u), _ptr(rhs), u.numel()))
+
+    def rk4_ode2nd_stage(self, stage, dt, u_tn, v_tn, u, v, rhs, ku, kv):
+        _check(lib.amdg_rk4_ode2nd_stage(self._h, stage, dt, _ptr(u_tn), _ptr(v_tn), _ptr(u), _ptr(v), _ptr(rhs), _ptr(ku), _ptr(kv), u.numel()))
 
     def axpby(self, alpha, x, beta, y):
         _check(lib.amdg_axpby(self._h, y.numel(), alpha, _ptr(x), beta, _ptr(y)))

@@ -1204,6 +1204,18 @@ int amdg_rk_stage(amdg_ctx * c, int scheme, int stage, double dt, const double *
     return AMDG_OK;
 }
 
+int amdg_rk4_ode2nd_stage(amdg_ctx * c, int stage, double dt, const double * u_tn, const double * v_tn, double * u, double * v,
+                          const double * rhs, double * ku, double * kv, int64_t n)
+{
+    int r = need_device(c); if (r) return r;
+    if (!u_tn || !v_tn || !u || !v || !rhs || !ku || !kv || n < 0) return fail(AMDG_EINVAL, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_rk4_ode2nd_stage(stage, dt, u_tn, v_tn, u, v, rhs, ku, kv, n, c->stream);
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? AMDG_EINVAL : AMDG_ECUDA, std::string("rk4_ode2nd_stage: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
 int amdg_axpby(amdg_ctx * c, int64_t n, double alpha, const double * x, double beta, double * y)
 {
     int r = need_device(c); if (r) return r;

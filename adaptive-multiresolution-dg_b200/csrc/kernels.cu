@@ -889,7 +889,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) sweep_mma_kernel(const MmaArgs
 #define MMA_STAMP(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[(int64_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
     MMA_STAMP(0);
     const MmaItem it = a.items[blockIdx.x];
-    if (a.dbg && threadIdx.x == 0) { a.dbg[(int64_t)blockIdx.x * 8 + 6] = it.m; a.dbg[(int64_t)blockIdx.x * 8 + 7] = it.nfib * 1000 + it.no * it.ni; }
+    if (a.dbg && threadIdx.x == 0)
+    {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.dbg[(int64_t)blockIdx.x * 8 + 5] = (long long)gt;
+        a.dbg[(int64_t)blockIdx.x * 8 + 6] = it.m; a.dbg[(int64_t)blockIdx.x * 8 + 7] = it.nfib * 1000000 + it.n_ent * 100 + it.no * it.ni;
+    }
     MMA_STAMP(1);
     const int jb = blockIdx.y / a.n_comp, comp = blockIdx.y % a.n_comp;
     const SweepJob J = a.job[jb];
@@ -1254,9 +1259,46 @@ cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_t
         else if (stage == 2) { c_tn = 1. / 3.; c_u = 2. / 3.; }
         else if (stage != 0) return cudaErrorInvalidValue;
     }
+    else if (scheme == AMDG_RK_RK3HEUN)            // RK3HeunLinear::step_stage, source/ODESolver.cpp:314-330
+    {
+        if (stage == 0) c_rhs = 1. / 3. * dt; else if (stage == 1) c_rhs = 1. / 2. * dt; else if (stage != 2) return cudaErrorInvalidValue;
+    }
     else return cudaErrorInvalidValue;
     const int64_t nb = (n + 255) / 256;
     rk_stage_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(c_tn, c_u, c_rhs, u_tn, u, rhs, n);
+    return cudaGetLastError();
+}
+
+// RK4ODE2nd::step_stage (source/ODESolver.cpp:578-615) for u_tt = L u written as (u, v = u_t): k_u = dt v, k_v = dt rhs are
+// kept per stage ([4][n] each); stages 0..2 set (u, v) = (u_tn, v_tn) + c k, stage 3 the classical 1/6 (k1 + 2 k2 + 2 k3 + k4)
+__global__ void __launch_bounds__(256) rk4_ode2nd_stage_kernel(int stage, double dt, const double * __restrict__ u_tn, const double * __restrict__ v_tn,
+                                                               double * __restrict__ u, double * __restrict__ v, const double * __restrict__ rhs,
+                                                               double * __restrict__ ku, double * __restrict__ kv, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+    {
+        const double a = dt * v[p], b = dt * rhs[p];
+        if (stage < 3)
+        {
+            ku[(int64_t)stage * n + p] = a; kv[(int64_t)stage * n + p] = b;
+            if (stage < 2) { u[p] = u_tn[p] + a / 2.; v[p] = v_tn[p] + b / 2.; }
+            else { u[p] = u_tn[p] + a; v[p] = v_tn[p] + b; }
+        }
+        else
+        {
+            u[p] = u_tn[p] + 1. / 6. * (ku[p] + 2 * ku[n + p] + 2 * ku[2 * n + p] + a);
+            v[p] = v_tn[p] + 1. / 6. * (kv[p] + 2 * kv[n + p] + 2 * kv[2 * n + p] + b);
+        }
+    }
+}
+
+cudaError_t launch_rk4_ode2nd_stage(int stage, double dt, const double * u_tn, const double * v_tn, double * u, double * v, const double * rhs,
+                                    double * ku, double * kv, int64_t n, cudaStream_t st)
+{
+    if (stage < 0 || stage > 3) return cudaErrorInvalidValue;
+    const int64_t nb = (n + 255) / 256;
+    rk4_ode2nd_stage_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(stage, dt, u_tn, v_tn, u, v, rhs, ku, kv, n);
     return cudaGetLastError();
 }
 

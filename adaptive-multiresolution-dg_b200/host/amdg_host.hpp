@@ -10,7 +10,10 @@
 //   LagrInterpolation (fast part) include/Interpolation.h:36               amdg::LagrInterpolation
 //   HyperbolicLagrRHS/HermRHS     include/FastMultiplyLU.h:571,597         amdg::HyperbolicLagrRHS (Hermite: same class, Hermite tables)
 //   HyperbolicAlptRHS             include/FastMultiplyLU.h:619             amdg::HyperbolicAlptRHS
-//   ForwardEuler/RK2SSP/RK2Midpoint/RK3SSP  include/ODESolver.h:115-206    amdg::ExplicitRK + the four scheme classes
+//   HyperbolicSameFlux{Lagr,Herm}RHS, HyperbolicDiffFlux{Lagr,Herm}RHS   include/FastMultiplyLU.h:477-570   same names
+//   SourceFastLagr                include/FastMultiplyLU.h:632             amdg::SourceFastLagr
+//   ForwardEuler/RK2SSP/RK2Midpoint/RK3SSP/RK3HeunLinear  include/ODESolver.h:115-230   amdg::ExplicitRK + the scheme classes
+//   RK4ODE2nd                     include/ODESolver.h (source/ODESolver.cpp:543-615)   amdg::RK4ODE2nd
 //
 // Error convention: the reference prints and exit(1)s; the mirror throws amdg::Error carrying amdg_last_error().
 #pragma once
@@ -224,6 +227,48 @@ private:
     DGSolution * dg_; OperatorMatrix1D * m_;
 };
 typedef HyperbolicLagrRHS HyperbolicHermRHS;
+// the DIM == 2 forms with one flux component per direction are the same compositions (rhs_2D(.., .., 0) and (.., .., 1),
+// source/FastMultiplyLU.cpp:1053-1058, 1089-1123)
+typedef HyperbolicLagrRHS HyperbolicDiffFluxLagrRHS;
+typedef HyperbolicLagrRHS HyperbolicDiffFluxHermRHS;
+
+// HyperbolicSameFluxHermRHS / HyperbolicSameFluxLagrRHS (source/FastMultiplyLU.cpp:970-1087): every direction uses the
+// flux component fucoe_intp[0][0]; the per-direction overloads rhs_vol_scalar(dim) / rhs_flx_intp_scalar(dim) as well
+class HyperbolicSameFluxLagrRHS
+{
+public:
+    HyperbolicSameFluxLagrRHS(DGSolution & dg, OperatorMatrix1D & oper) : dg_(&dg), m_(&oper) {}
+    void rhs_vol_scalar() { for (int t = 0; t < dg_->DIM; ++t) rhs_vol_scalar(t); }
+    void rhs_vol_scalar(int t)
+    {
+        const int d = dg_->DIM; std::vector<int> rels(d, AMDG_REL_VOL), ops(d, m_->u_v); ops[t] = m_->u_vx;
+        check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, 0), dg_->rhs_v(0), 1, 1.0, 1));
+    }
+    void rhs_flx_intp_scalar() { for (int t = 0; t < dg_->DIM; ++t) rhs_flx_intp_scalar(t); }
+    void rhs_flx_intp_scalar(int t)
+    {
+        const int d = dg_->DIM; std::vector<int> ops(d, m_->u_v), rels(d, AMDG_REL_VOL); ops[t] = m_->uave2_vjp; rels[t] = AMDG_REL_FLX;
+        check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, 0), dg_->rhs_v(0), 1, 0.5, 1));
+    }
+private:
+    DGSolution * dg_; OperatorMatrix1D * m_;
+};
+typedef HyperbolicSameFluxLagrRHS HyperbolicSameFluxHermRHS;
+
+// SourceFastLagr::rhs_source (source/FastMultiplyLU.cpp:1304-1314): rhs[v] += (u_v x ... x u_v) fucoe_intp[v][0]
+class SourceFastLagr
+{
+public:
+    SourceFastLagr(DGSolution & dg, OperatorMatrix1D & oper) : dg_(&dg), m_(&oper) {}
+    void rhs_source()
+    {
+        const int d = dg_->DIM; std::vector<int> rels(d, AMDG_REL_VOL), ops(d, m_->u_v);
+        for (int v = 0; v < dg_->VEC_NUM; ++v)
+            check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(v, 0), dg_->rhs_v(v), 1, 1.0, 1));
+    }
+private:
+    DGSolution * dg_; OperatorMatrix1D * m_;
+};
 
 // HyperbolicAlptRHS::rhs_flx_penalty_scalar (source/FastMultiplyLU.cpp:1269-1276)
 class HyperbolicAlptRHS
@@ -264,5 +309,30 @@ struct ForwardEuler : ExplicitRK { ForwardEuler(DGSolution & dg, double dt) : Ex
 struct RK2SSP : ExplicitRK { RK2SSP(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK2SSP, 2) {} };
 struct RK2Midpoint : ExplicitRK { RK2Midpoint(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK2MID, 2) {} };
 struct RK3SSP : ExplicitRK { RK3SSP(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK3SSP, 3) {} };
+struct RK3HeunLinear : ExplicitRK { RK3HeunLinear(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK3HEUN, 3) {} };
+
+// RK4ODE2nd (include/ODESolver.h, source/ODESolver.cpp:543-615): u_tt = L u as the pair (ucoe_alpt, ucoe_ut); the caller
+// evaluates rhs = L u before every step_stage, exactly as with the reference's stage interface.
+class RK4ODE2nd
+{
+public:
+    RK4ODE2nd(DGSolution & dg, DeviceArray & ucoe_ut, double dt_) : num_stage(4), dt(dt_), dg_(&dg), v_(&ucoe_ut), u_tn_(dg.ctx, dg.get_dof()),
+        v_tn_(dg.ctx, dg.get_dof()), ku_(dg.ctx, 4 * dg.get_dof()), kv_(dg.ctx, 4 * dg.get_dof()) {}
+    void init()
+    {
+        check(amdg_axpby(dg_->ctx, dg_->get_dof(), 1.0, dg_->ucoe_alpt.data(), 0.0, u_tn_.data()));
+        check(amdg_axpby(dg_->ctx, dg_->get_dof(), 1.0, v_->data(), 0.0, v_tn_.data()));
+    }
+    void step_stage(int stage)
+    {
+        check(amdg_rk4_ode2nd_stage(dg_->ctx, stage, dt, u_tn_.data(), v_tn_.data(), dg_->ucoe_alpt.data(), v_->data(), dg_->rhs.data(),
+                                    ku_.data(), kv_.data(), dg_->get_dof()));
+    }
+    void final() {}
+    const int num_stage;
+    const double dt;
+private:
+    DGSolution * dg_; DeviceArray * v_; DeviceArray u_tn_, v_tn_, ku_, kv_;
+};
 
 }  // namespace amdg

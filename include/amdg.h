@@ -45,7 +45,7 @@ enum { AMDG_SCHED_LITERAL = 0, AMDG_SCHED_SHARED = 1 };
 enum { AMDG_FLUX_LINEAR = 0, AMDG_FLUX_BURGERS = 1, AMDG_FLUX_SIN = 2, AMDG_FLUX_COS = 3,
        AMDG_FLUX_BUCKLEY_X = 4, AMDG_FLUX_BUCKLEY_Y = 5, AMDG_FLUX_VLASOV_SMOOTH_E = 6 };
 /* explicit Runge-Kutta schemes: ForwardEuler, RK2SSP, RK2Midpoint, RK3SSP (source/ODESolver.cpp:203-301) */
-enum { AMDG_RK_EULER = 0, AMDG_RK_RK2SSP = 1, AMDG_RK_RK2MID = 2, AMDG_RK_RK3SSP = 3 };
+enum { AMDG_RK_EULER = 0, AMDG_RK_RK2SSP = 1, AMDG_RK_RK2MID = 2, AMDG_RK_RK3SSP = 3, AMDG_RK_RK3HEUN = 4 };
 
 const char *amdg_version(void);
 const char *amdg_last_error(void);
@@ -129,6 +129,10 @@ int amdg_point_coords(amdg_ctx *ctx, const double *host_pts1d, double *dev_pts);
 /* ---- K4: explicit RK stage, ExplicitRK::step_stage (source/ODESolver.cpp:209-301): updates dev_u in place ---- */
 int amdg_rk_stage(amdg_ctx *ctx, int scheme, int stage, double dt, const double *dev_u_tn, double *dev_u,
                   const double *dev_rhs, int64_t n);
+/* RK4ODE2nd::step_stage (source/ODESolver.cpp:578-615) for u_tt = L u as the pair (u, v = u_t): call with dev_rhs = L u for
+ * stage 0..3; dev_ku / dev_kv are caller-owned scratch of 4*n doubles each (the k1..k4 of the reference). */
+int amdg_rk4_ode2nd_stage(amdg_ctx *ctx, int stage, double dt, const double *dev_u_tn, const double *dev_v_tn, double *dev_u,
+                          double *dev_v, const double *dev_rhs, double *dev_ku, double *dev_kv, int64_t n);
 /* y = alpha*x + beta*y */
 int amdg_axpby(amdg_ctx *ctx, int64_t n, double alpha, const double *dev_x, double beta, double *dev_y);
 

@@ -492,6 +492,34 @@ int main(int argc, char ** argv)
         }
     }
     if (has("rhs")) { nonlinear_rhs(true, ""); }
+    if (has("variants") && !herm)   // the other FastRHS compositions over the same interpolated flux: same flux in every
+    {                                // direction, one flux per direction (DIM == 2 forms), source term
+        nonlinear_rhs(false, "");
+        H.dump_flux_field("var.fucoe_intp", true);
+        if (DIM == 2)
+        {
+            dg.set_rhs_zero();
+            HyperbolicSameFluxLagrRHS same(dg, oper_lagr); same.rhs_vol_scalar(); same.rhs_flx_intp_scalar();
+            H.dump_field("var.rhs_sameflux", Harness::RHS);
+            dg.set_rhs_zero();
+            HyperbolicDiffFluxLagrRHS diff(dg, oper_lagr); diff.rhs_vol_scalar(); diff.rhs_flx_intp_scalar();
+            H.dump_field("var.rhs_diffflux", Harness::RHS);
+        }
+        dg.set_rhs_zero();
+        SourceFastLagr srcf(dg, oper_lagr); srcf.rhs_source();
+        H.dump_field("var.rhs_source", Harness::RHS);
+    }
+    if (has("variants") && herm && DIM == 2)
+    {
+        nonlinear_rhs(false, "");
+        H.dump_flux_field("var.fucoe_intp", true);
+        dg.set_rhs_zero();
+        HyperbolicSameFluxHermRHS same(dg, oper_herm); same.rhs_vol_scalar(); same.rhs_flx_intp_scalar();
+        H.dump_field("var.rhs_sameflux", Harness::RHS);
+        dg.set_rhs_zero();
+        HyperbolicDiffFluxHermRHS diff(dg, oper_herm); diff.rhs_vol_scalar(); diff.rhs_flx_intp_scalar();
+        H.dump_field("var.rhs_diffflux", Harness::RHS);
+    }
     if (has("stage"))        // full RK3SSP step with the nonlinear right-hand side, a.steps steps
     {
         for (int step = 0; step < a.steps; ++step)

@@ -35,6 +35,10 @@ CASES = {
     # adaptive (irregular) grids produced by DGAdapt::refine / coarsen: fibres are arbitrary subsets of the 1D tree
     "adapt_d2_k2_n6": "--dim 2 --nmax 6 --n0 2 --pa 2 --pl 3 --adapt-eps 0.02 --adapt-eta 0.012 --adapt-rounds 5 --run grid,rhs,roundtrip,stage --flux burgers --dump-tables 1 --dt 0.001",
     "adapt_d3_k1_n4": "--dim 3 --nmax 4 --n0 1 --pa 1 --pl 2 --adapt-eps 0.05 --adapt-eta 0.03 --adapt-rounds 4 --run grid,rhs,roundtrip --flux kpp --dump-tables 1",
+    # the other FastRHS compositions: SameFlux / DiffFlux (DIM == 2) and SourceFastLagr, Lagrange and Hermite; 3-component source
+    "variants_lagr_d2_k2_n4": "--dim 2 --nmax 4 --pa 2 --pl 3 --run grid,variants --flux kpp --dump-tables 1",
+    "variants_herm_d2_k2_n4": "--dim 2 --nmax 4 --pa 2 --ph 3 --intp herm --run grid,variants --flux burgers --dump-tables 1",
+    "variants_lagr_d3_k1_n3": "--dim 3 --nmax 3 --pa 1 --pl 2 --vecnum 2 --run grid,variants --flux kpp --dump-tables 1",
     "line_d1_k2_n5": "--dim 1 --nmax 5 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux burgers --dump-tables 1",
 }
 

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (called through the C ABI) with the compiled reference's outputs (tests/golden/).
 Tolerance 1e-12 relative L2 per phase / RK stage, 1e-10 after a full run (BASELINE.json north_star); index work
 is covered bit-exactly by tests/test_capi_tables.py."""
+import importlib
+
 import numpy as np
 import pytest
 import torch
@@ -303,6 +305,75 @@ def test_merged_vol_flx_application(name):
         rels = [A.REL_FLX if s == t else A.REL_VOL for s in range(c.dim)]
         c.ctx.apply_tensor(ops, rels, fuc, rhs, accumulate=t > 0)
     assert rel(c.to_host(rhs), d["rhs_vol_flx"][:, 0, :]) < TOL
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["variants_lagr_d2_k2_n4", "variants_herm_d2_k2_n4", "variants_lagr_d3_k1_n3"])
+def test_rhs_variants(name):
+    """HyperbolicSameFlux{Lagr,Herm}RHS, HyperbolicDiffFlux{Lagr,Herm}RHS (DIM == 2) and SourceFastLagr::rhs_source
+    (source/FastMultiplyLU.cpp:970-1123, 1304-1314) against the reference's own classes"""
+    d = load_golden(name)
+    c = DevCase(d)
+    fuc = d["var.fucoe_intp"]
+    if "var.rhs_sameflux" in d:
+        for key, comp in (("var.rhs_sameflux", lambda t: 0), ("var.rhs_diffflux", lambda t: t)):
+            rhs = c.zeros(c.a)
+            c.rhs_vol_flx([c.to_dev(fuc[:, 0, comp(t), :]) for t in range(c.dim)], rhs)
+            assert rel(c.to_host(rhs), d[key][:, 0, :]) < TOL
+    if "var.rhs_source" in d:
+        A = c.amdg
+        src = torch.stack([c.to_dev(fuc[:, v, 0, :]) for v in range(c.vecnum)])
+        rhs = torch.zeros(c.vecnum, c.ne, c.a ** c.dim, dtype=torch.float64, device="cuda")
+        c.ctx.apply_tensor([c.op_uv] * c.dim, [A.REL_VOL] * c.dim, src, rhs, n_comp=c.vecnum, accumulate=True)
+        for v in range(c.vecnum):
+            assert rel(c.to_host(rhs[v]), d["var.rhs_source"][:, v, :]) < TOL
+    c.close()
+
+
+def test_rk_schemes():
+    """amdg_rk_stage for ForwardEuler / RK2SSP / RK2Midpoint / RK3SSP / RK3HeunLinear (source/ODESolver.cpp:209-330)"""
+    import amdg_oracle as O
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    ctx = A.Context(2, 3, 2, 3, device=0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(5)
+    n = 10007
+    u_tn, u0, r = (rng.standard_normal(n) for _ in range(3))
+    for name, scheme, stages in (("euler", A.RK_EULER, 1), ("rk2ssp", A.RK_RK2SSP, 2), ("rk2mid", A.RK_RK2MID, 2), ("rk3ssp", A.RK_RK3SSP, 3), ("rk3heun", A.RK_RK3HEUN, 3)):
+        for stage in range(stages):
+            u = torch.from_numpy(u0.copy()).cuda()
+            ctx.rk_stage(scheme, stage, 0.01, torch.from_numpy(u_tn).cuda(), u, torch.from_numpy(r).cuda())
+            ref = O.rk_stage(name, stage, u_tn, u0, r, 0.01)
+            assert np.abs(u.cpu().numpy() - ref).max() < 1e-15 * np.abs(ref).max()
+        with pytest.raises(Exception):
+            ctx.rk_stage(scheme, stages, 0.01, torch.from_numpy(u_tn).cuda(), torch.from_numpy(u0.copy()).cuda(), torch.from_numpy(r).cuda())
+    ctx.close()
+
+
+def test_wave_rk4_ode2nd_stages():
+    """cfg3: one RK4ODE2nd step driven through step_stage (source/ODESolver.cpp:578-615) with the IPDG operator as single
+    sweeps, against the reference's step_rk on the assembled operator"""
+    from refdump import field
+    d = load_golden("cfg3_wave_d3_k2_n3")
+    c = DevCase(d)
+    A = c.amdg
+    sigma_dx = 20.0 * 2 ** c.nmax
+    terms = (("ux_vx", A.REL_VOL, -1.0), ("uxave_vjp", A.REL_FLX, -1.0), ("ujp_vxave", A.REL_FLX, -1.0), ("ujp_vjp", A.REL_FLX, -sigma_dx))
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    v = c.to_dev(field(20240901 + 1, d["hash_key"], d["level"], c.vecnum, c.a ** c.dim)[:, 0, :])
+    u_tn, v_tn = u.clone(), v.clone()
+    ku = torch.zeros(4, *u.shape, dtype=torch.float64, device="cuda")
+    kv = torch.zeros_like(ku)
+    rhs = c.zeros(c.a)
+    for stage in range(4):
+        first = True
+        for t in range(c.dim):
+            for nm, r, cf in terms:
+                c.ctx.sweep1d(c.alpt[nm], r, A.LU_FULL, t, [c.a] * c.dim, u, rhs, coef=cf, accumulate=not first)
+                first = False
+        c.ctx.rk4_ode2nd_stage(stage, 0.0005, u_tn, v_tn, u, v, rhs, ku, kv)
+    assert rel(c.to_host(u), d["wave.ucoe_alpt"][:, 0, :]) < 1e-10
+    assert rel(c.to_host(v), d["wave.ucoe_ut"][:, 0, :]) < 1e-10
     c.close()
 
 

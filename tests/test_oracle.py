@@ -159,6 +159,56 @@ def test_rk3ssp_and_schedule():
     assert np.allclose(O.rk3ssp_stage(1, u_tn, u, r, 0.1), 0.75 * u_tn + 0.25 * (u + 0.1 * r))
 
 
+def test_rk_schemes_and_rk4_stage_form():
+    """step_stage of every explicit scheme; RK4ODE2nd stage form == its step_rk form (the golden wave step)"""
+    u_tn, u, r = np.array([1.0, 2.0]), np.array([0.5, -1.0]), np.array([3.0, 4.0])
+    assert np.allclose(O.rk_stage("rk2ssp", 1, u_tn, u, r, 0.1), 0.5 * u_tn + 0.5 * (u + 0.1 * r))
+    assert np.allclose(O.rk_stage("rk2mid", 0, u_tn, u, r, 0.1), u_tn + 0.05 * r)
+    assert np.allclose(O.rk_stage("rk3heun", 1, u_tn, u, r, 0.1), u_tn + 0.05 * r)
+    c = Case("cfg3_wave_d3_k2_n3")
+    d = c.d
+    rels = c.relations()
+    sigma_dx = 20.0 * 2 ** c.nmax
+
+    def L(x):
+        out = np.zeros_like(x)
+        for t in range(c.dim):
+            for nm, kind, cf in (("ux_vx", "vol", -1.0), ("uxave_vjp", "flx", -1.0), ("ujp_vxave", "flx", -1.0), ("ujp_vjp", "flx", -sigma_dx)):
+                out += O.single_sweep(x, c.a, d["alpt." + nm], kind, rels, c.lev, c.ord1d, t, cf)
+        return out
+    u0 = d["ucoe_alpt.in"][:, 0, :]
+    v0 = refdump.field(20240901 + 1, d["hash_key"], c.lev, c.vecnum, c.a ** c.dim)[:, 0, :]
+    u1, v1 = O.rk4_ode2nd_stages(u0, v0, L, 0.0005)
+    assert rel(u1, d["wave.ucoe_alpt"][:, 0, :]) < 1e-10 and rel(v1, d["wave.ucoe_ut"][:, 0, :]) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["variants_lagr_d2_k2_n4", "variants_herm_d2_k2_n4", "variants_lagr_d3_k1_n3"])
+def test_rhs_variants(name):
+    """HyperbolicSameFlux*/DiffFlux* (DIM == 2) and SourceFastLagr::rhs_source as compositions of the tensor application
+    (source/FastMultiplyLU.cpp:970-1123, 1304-1314)"""
+    c = Case(name)
+    d = c.d
+    pt, u_v, u_vx, uave, anc, wt = _tables(c)
+    rels = c.relations()
+    fuc = d["var.fucoe_intp"]
+
+    def hyperbolic(comp_of_dim):
+        rhs = np.zeros((c.ne, c.a ** c.dim))
+        for t in range(c.dim):
+            src = fuc[:, 0, comp_of_dim(t), :]
+            rhs += O.apply_tensor(src, c.b, c.a, [u_vx if s == t else u_v for s in range(c.dim)], ["vol"] * c.dim, rels, c.lev, c.ord1d)
+            rhs += O.apply_tensor(src, c.b, c.a, [uave if s == t else u_v for s in range(c.dim)], ["flx" if s == t else "vol" for s in range(c.dim)],
+                                  rels, c.lev, c.ord1d, 0.5)
+        return rhs
+    if "var.rhs_sameflux" in d:
+        assert rel(hyperbolic(lambda t: 0), d["var.rhs_sameflux"][:, 0, :]) < TOL
+        assert rel(hyperbolic(lambda t: t), d["var.rhs_diffflux"][:, 0, :]) < TOL
+    if "var.rhs_source" in d:
+        for v in range(c.vecnum):
+            out = O.apply_tensor(fuc[:, v, 0, :], c.b, c.a, [u_v] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d)
+            assert rel(out, d["var.rhs_source"][:, v, :]) < TOL
+
+
 def test_hierarchisation_stencil_restated():
     """set_pts_wts_1d_ada_Lag restated from point coordinates and level-0 basis values (Lagrange)"""
     c = Case("cfg4_burgers_lagr_d2_k2_n4")
