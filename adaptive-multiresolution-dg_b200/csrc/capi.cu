@@ -682,7 +682,10 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
 }
 
 // ---- tensor-core kernel: work list + tile programs ---------------------------------------------------------------
-static int mma_pitch(int ni, int inner) { if (inner == 1) return 1; int pk = ni; while ((pk & 7) != 4) ++pk; return pk; }
+// shared-memory row of one staged element (kernels.cu, sweep_mma_kernel): X[k][col] with a column pitch = 4 (mod 8), or, for a
+// sweep along the last dimension (inner == 1), the element's own [col][k] order
+static int mma_colpitch(int ncols) { int pk = ncols; while ((pk & 7) != 4) ++pk; return pk; }
+static int64_t mma_rowsize(int kf, int no, int ni, int inner) { return inner == 1 ? (int64_t)no * ni * kf : (int64_t)kf * mma_colpitch(no * ni); }
 
 static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int par, int lu)
 {
@@ -696,7 +699,7 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
     std::vector<int> prog_ints;
     const DimTables & H = c->grid.dims[t];
     bool ok = true; int smem_need = 0;
-    const int64_t total = c->grid.n * (int64_t)kf * outer * mma_pitch(inner, inner);
+    const int64_t total = c->grid.n * mma_rowsize(kf, outer, inner, inner);
     const int64_t target = std::max<int64_t>(1, total / std::max(1, c->mma_item_target >> pcls));
     // tile programs of every shape
     std::map<int, ShapeProg> shape_progs;
@@ -716,8 +719,9 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
         const int m = SP.m;
         // pieces: a long program is split so that one CTA walks about ent_target entries
         int np = 1;
-        const int pk_full = mma_pitch(inner, inner);
-        const bool whole_fits = (int64_t)m * outer * kf * pk_full + (2 * SP.n_rt + 1 + SP.n_ent() + m) / 2 + 4 <= c->mma_cap_doubles;
+        const int64_t row_full = mma_rowsize(kf, outer, inner, inner);
+        const int slack = 32 * kf;                                   // tiles past the rectangle are read (never stored): keep them inside the allocation
+        const bool whole_fits = (int64_t)m * row_full + (2 * SP.n_rt + 1 + SP.n_ent() + m) / 2 + 4 + slack <= c->mma_cap_doubles;
         if (!whole_fits || SP.n_ent() > split_above) np = (int)std::min<int64_t>(std::max<int64_t>(1, (SP.n_ent() + ent_target - 1) / ent_target), std::max(1, SP.n_rt));
         std::vector<ShapeProg> pieces; split_shape_prog(SP, np, pieces);
         int max_piece_ints = 0; for (auto & pc : pieces) max_piece_ints = std::max(max_piece_ints, 2 * pc.n_rt + 1 + (int)pc.n_ent());
@@ -727,26 +731,25 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
         struct Rect { int o0, no, i0, ni, pk; };
         std::vector<Rect> rects;
         int nfib_max = 1;
-        const int cap = c->mma_cap_doubles - ((max_piece_ints + m + 1) / 2 + 4) - a_doubles;      // room for the piece, the element rows, staged A
+        const int cap = c->mma_cap_doubles - ((max_piece_ints + m + 1) / 2 + 4) - a_doubles - slack;      // room for the piece, the element rows, staged A
         if (cap <= 0) { ok = false; break; }
-        if ((int64_t)m * outer * kf * pk_full <= cap)
+        if ((int64_t)m * row_full <= cap)
         {
-            rects.push_back({ 0, outer, 0, inner, pk_full });
-            if (np == 1) nfib_max = (int)std::max<int64_t>(1, std::min<int64_t>(cap, target) / ((int64_t)m * outer * kf * pk_full + (m + 1) / 2));
+            rects.push_back({ 0, outer, 0, inner, mma_colpitch(outer * inner) });
+            if (np == 1) nfib_max = (int)std::max<int64_t>(1, std::min<int64_t>(cap, target) / ((int64_t)m * row_full + (m + 1) / 2));
         }
-        else if ((int64_t)m * kf * pk_full <= cap)
+        else if ((int64_t)m * mma_rowsize(kf, 1, inner, inner) <= cap)
         {
-            const int no = (int)(cap / ((int64_t)m * kf * pk_full));
-            for (int o0 = 0; o0 < outer; o0 += no) rects.push_back({ o0, std::min(no, outer - o0), 0, inner, pk_full });
+            int no = 1; while (no < outer && (int64_t)m * mma_rowsize(kf, no + 1, inner, inner) <= cap) ++no;
+            for (int o0 = 0; o0 < outer; o0 += no) { const int n = std::min(no, outer - o0); rects.push_back({ o0, n, 0, inner, mma_colpitch(n * inner) }); }
         }
         else
         {
-            int ni = 0, pk_ni = 0;
-            for (int cand = (inner / 8) * 8; cand >= 8; cand -= 8) if ((int64_t)m * kf * mma_pitch(cand, inner) <= cap) { ni = cand; break; }
-            if (ni == 0 && inner >= 8 && (int64_t)m * kf * 8 <= cap) { ni = 8; pk_ni = 8; }      // 8 columns with a 2-way conflicting pitch beat 4 columns
-            if (ni == 0) for (int cand : { 4, 2, 1 }) if (cand <= inner && (int64_t)m * kf * mma_pitch(cand, inner) <= cap) { ni = cand; break; }
+            int ni = 0;
+            for (int cand = (inner / 8) * 8; cand >= 8; cand -= 8) if ((int64_t)m * mma_rowsize(kf, 1, cand, inner) <= cap) { ni = cand; break; }
+            if (ni == 0) for (int cand : { 4, 2, 1 }) if (cand <= inner && (int64_t)m * mma_rowsize(kf, 1, cand, inner) <= cap) { ni = cand; break; }
             if (ni == 0) { ok = false; break; }
-            for (int o0 = 0; o0 < outer; ++o0) for (int i0 = 0; i0 < inner; i0 += ni) rects.push_back({ o0, 1, i0, std::min(ni, inner - i0), pk_ni ? pk_ni : mma_pitch(ni, inner) });
+            for (int o0 = 0; o0 < outer; ++o0) for (int i0 = 0; i0 < inner; i0 += ni) { const int n = std::min(ni, inner - i0); rects.push_back({ o0, 1, i0, n, mma_colpitch(n) }); }
         }
         const int prog0 = (int)L.progs.size();
         std::vector<int> piece_ofs(np);
@@ -773,7 +776,7 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
                     items.push_back(x);
                     cost.push_back(((double)pieces[q].n_ent() + 2.0 * pieces[q].n_rt) * nf * ((r.no * r.ni + 7) / 8) + 0.01 * nf * m * r.no * r.ni);
                     const int n_ints = 2 * pieces[q].n_rt + 1 + (int)pieces[q].n_ent();
-                    smem_need = std::max(smem_need, ((nf * m * r.no * kf * r.pk + 1) & ~1) + (n_ints + ((nf * m + 1) & ~1) + 1) / 2 + 2 + a_doubles);
+                    smem_need = std::max(smem_need, (int)((nf * m * mma_rowsize(kf, r.no, r.ni, inner) + 1) & ~(int64_t)1) + (n_ints + ((nf * m + 1) & ~1) + 1) / 2 + 2 + a_doubles + slack);
                 }
         }
         for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(q * 1024 + np); L.progs.push_back(std::move(pieces[q])); }
