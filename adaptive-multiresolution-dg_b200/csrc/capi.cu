@@ -81,6 +81,9 @@ struct amdg_ctx
     std::map<std::tuple<int, int, int, int, int, int>, MmaList> mmas;       // key: (dim t, outer, kf, kt, rel*4+lu, parallel class)
     std::map<std::tuple<int, int, int, int>, double *> mma_A;               // (op, shape, rel*4+lu, piece*1024+npieces) -> device operator values
     int mma_cap_doubles = 9 * 1024, mma_item_target = 148 * 8, mma_ent_target = 448, mma_stage_a_max = 64;
+    bool tc_force_stage = true; int tc_coarse_ent = 256;
+    int tc_cap_doubles = 4608, tc_item_target = 148 * 8, tc_ent_target = 48, tc_stage_a_max = 48;      // lean form (kernels_tc.cu)
+    bool lean() const { return kernel_variant == 5; }
     int n_sm = 148;
     long long * dbg = nullptr;
     // metadata arena: index tables, work lists and operator blocks live in one allocation that is given an L2
@@ -199,6 +202,12 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_MMA_ITEMS")) c->mma_item_target = std::max(1, atoi(e));
     if (const char * e = std::getenv("AMDG_MMA_ENT")) c->mma_ent_target = std::max(16, atoi(e));
     if (const char * e = std::getenv("AMDG_MMA_STAGE_A")) c->mma_stage_a_max = std::max(0, atoi(e));
+    if (const char * e = std::getenv("AMDG_TC_CAP")) c->tc_cap_doubles = std::max(512, std::min(atoi(e), tc_smem_capacity_doubles())) & ~1;
+    if (const char * e = std::getenv("AMDG_TC_ITEMS")) c->tc_item_target = std::max(1, atoi(e));
+    if (const char * e = std::getenv("AMDG_TC_ENT")) c->tc_ent_target = std::max(16, atoi(e));
+    if (const char * e = std::getenv("AMDG_TC_STAGE_A")) c->tc_stage_a_max = std::max(0, atoi(e));
+    if (const char * e = std::getenv("AMDG_TC_FORCE_STAGE")) c->tc_force_stage = atoi(e) != 0;
+    if (const char * e = std::getenv("AMDG_TC_COARSE_ENT")) c->tc_coarse_ent = std::max(16, atoi(e));
     if (const char * e = std::getenv("AMDG_PIPE_CAP")) c->pipe_cap_doubles = std::max(256, atoi(e)) & ~1;
     if (const char * e = std::getenv("AMDG_PIPE_META")) c->pipe_meta_ints = (std::max(256, atoi(e)) + 3) & ~3;
     if (const char * e = std::getenv("AMDG_PIPE_ITEMS")) c->pipe_item_target = std::max(1, atoi(e));
@@ -264,7 +273,7 @@ int amdg_ctx_set_stream(amdg_ctx * c, void * s)
 
 int amdg_ctx_sync(amdg_ctx * c) { int r = need_device(c); if (r) return r; CU(cudaStreamSynchronize(c->stream)); return AMDG_OK; }
 int amdg_ctx_set_schedule(amdg_ctx * c, int s) { if (!c || (s != AMDG_SCHED_LITERAL && s != AMDG_SCHED_SHARED)) return fail(AMDG_EINVAL, "bad schedule"); c->sched = s; return AMDG_OK; }
-int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 4) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
+int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 5) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
 int64_t amdg_ctx_launch_count(amdg_ctx * c) { return c ? c->launches : -1; }
 int amdg_ctx_set_debug_buffer(amdg_ctx * c, void * dev_buf) { if (!c) return fail(AMDG_EINVAL, "null context"); c->dbg = (long long *)dev_buf; return AMDG_OK; }
 
@@ -690,7 +699,10 @@ static int64_t mma_rowsize(int kf, int no, int ni, int inner) { return inner == 
 static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int par, int lu)
 {
     int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
-    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls);
+    const bool lean = c->lean();
+    const int cap_doubles = lean ? c->tc_cap_doubles : c->mma_cap_doubles, item_target = lean ? c->tc_item_target : c->mma_item_target;
+    const int ent_target0 = lean ? c->tc_ent_target : c->mma_ent_target, stage_a_max = lean ? c->tc_stage_a_max : c->mma_stage_a_max;
+    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls + (lean ? 16 : 0));
     auto it = c->mmas.find(key);
     if (it != c->mmas.end()) return it->second;
     amdg_ctx::MmaList L;
@@ -700,15 +712,15 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
     const DimTables & H = c->grid.dims[t];
     bool ok = true; int smem_need = 0;
     const int64_t total = c->grid.n * mma_rowsize(kf, outer, inner, inner);
-    const int64_t target = std::max<int64_t>(1, total / std::max(1, c->mma_item_target >> pcls));
+    const int64_t target = std::max<int64_t>(1, total / std::max(1, item_target >> pcls));
     // tile programs of every shape
     std::map<int, ShapeProg> shape_progs;
     for (auto & kv : sf) build_shape_prog(c->pairs, c->shapes.ords[kv.first], rel, lu, kf, kt, shape_progs[kv.first]);
     // A launch with fewer CTAs than the machine holds is bounded by its longest CTA: cut the programs finer (halve the
     // entry target) until the grid fills the SMs or the pieces reach 32 entries.
-    int ent_target = c->mma_ent_target;
+    int ent_target = ent_target0;
   retry_finer:
-    const int64_t split_above = ent_target == c->mma_ent_target ? (int64_t)4 * ent_target : (int64_t)ent_target * 3 / 2;
+    const int64_t split_above = ent_target == ent_target0 ? (int64_t)4 * ent_target : (int64_t)ent_target * 3 / 2;
     items.clear(); cost.clear(); elem_pool.clear(); prog_ints.clear(); L = amdg_ctx::MmaList(); ok = true; smem_need = 0;
     for (auto & kv : sf)
     {
@@ -721,17 +733,17 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
         int np = 1;
         const int64_t row_full = mma_rowsize(kf, outer, inner, inner);
         const int slack = 32 * kf;                                   // tiles past the rectangle are read (never stored): keep them inside the allocation
-        const bool whole_fits = (int64_t)m * row_full + (2 * SP.n_rt + 1 + SP.n_ent() + m) / 2 + 4 + slack <= c->mma_cap_doubles;
+        const bool whole_fits = (int64_t)m * row_full + (2 * SP.n_rt + 1 + SP.n_ent() + m) / 2 + 4 + slack <= cap_doubles;
         if (!whole_fits || SP.n_ent() > split_above) np = (int)std::min<int64_t>(std::max<int64_t>(1, (SP.n_ent() + ent_target - 1) / ent_target), std::max(1, SP.n_rt));
         std::vector<ShapeProg> pieces; split_shape_prog(SP, np, pieces);
         int max_piece_ints = 0; for (auto & pc : pieces) max_piece_ints = std::max(max_piece_ints, 2 * pc.n_rt + 1 + (int)pc.n_ent());
-        const bool stage_a = np == 1 && SP.n_ent() <= c->mma_stage_a_max;
+        const bool stage_a = np == 1 && SP.n_ent() <= stage_a_max;
         const int a_doubles = stage_a ? (int)SP.n_ent() * 32 : 0;
         // column rectangles
         struct Rect { int o0, no, i0, ni, pk; };
         std::vector<Rect> rects;
         int nfib_max = 1;
-        const int cap = c->mma_cap_doubles - ((max_piece_ints + m + 1) / 2 + 4) - a_doubles - slack;      // room for the piece, the element rows, staged A
+        const int cap = cap_doubles - ((max_piece_ints + m + 1) / 2 + 4) - a_doubles - slack;      // room for the piece, the element rows, staged A
         if (cap <= 0) { ok = false; break; }
         if ((int64_t)m * row_full <= cap)
         {
@@ -772,14 +784,16 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
                     x.prog = prog0 + q; x.elem_ofs = eofs; x.nfib = nf; x.o0 = r.o0; x.no = r.no; x.i0 = r.i0; x.ni = r.ni; x.pk = r.pk;
                     x.m = m; x.n_rt = pieces[q].n_rt; x.prog_ofs = piece_ofs[q]; x.n_ent = (int)pieces[q].n_ent();
                     x.ni_magic = r.ni <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + (unsigned)r.ni - 1) / (unsigned)r.ni);
-                    x.stage_a = stage_a ? 1 : 0;
+                    x.stage_a = stage_a ? 1 : 0; x.nsrc = m; x.src_ofs = eofs;
+                    x.nfib_magic = nf <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + (unsigned)nf - 1) / (unsigned)nf);
+                    { const unsigned nrf = (unsigned)(pieces[q].n_rt * nf); x.unit_magic = nrf <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + nrf - 1) / nrf); }
                     items.push_back(x);
                     cost.push_back(((double)pieces[q].n_ent() + 2.0 * pieces[q].n_rt) * nf * ((r.no * r.ni + 7) / 8) + 0.01 * nf * m * r.no * r.ni);
                     const int n_ints = 2 * pieces[q].n_rt + 1 + (int)pieces[q].n_ent();
                     smem_need = std::max(smem_need, (int)((nf * m * mma_rowsize(kf, r.no, r.ni, inner) + 1) & ~(int64_t)1) + (n_ints + ((nf * m + 1) & ~1) + 1) / 2 + 2 + a_doubles + slack);
                 }
         }
-        for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(q * 1024 + np); L.progs.push_back(std::move(pieces[q])); }
+        for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(q * 4096 + np * 2); L.progs.push_back(std::move(pieces[q])); }
     }
     if (ok && ent_target > 32 && (int64_t)items.size() * (1 << pcls) < 3 * (int64_t)c->n_sm) { ent_target = std::max(32, ent_target / 2); goto retry_finer; }
     if (ok && !items.empty())
@@ -795,6 +809,213 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
         if (up) { L.n_item = (int)sorted.size(); L.smem_doubles = (smem_need + 1) & ~1; L.ok = true; }
         if (std::getenv("AMDG_VERBOSE"))
             fprintf(stderr, "[amdg] mma list t=%d outer=%d inner=%d kf=%d kt=%d rel=%d lu=%d par=%d: %d items, %d programs, smem %d doubles\n",
+                    t, outer, inner, kf, kt, rel, lu, par, (int)sorted.size(), (int)L.progs.size(), L.smem_doubles);
+    }
+    return c->mmas.emplace(key, std::move(L)).first->second;
+}
+
+// Work list of the lean tensor-core kernel (kernels_tc.cu).  Short fibres: whole fibres x the whole column plane, several
+// fibres per item (as get_mma).  A fibre too long for that is cut by TARGETS: row tiles are walked in depth-first order of
+// the 1D tree (left end of the support, then level), and consecutive row tiles whose union of source rows still fits in
+// shared memory with a 32-column rectangle form a piece -- a subtree plus its chain of ancestors.  Only the few row tiles of
+// coarse targets, which read most of the fibre, fall back to narrow rectangles over the union of their sources.
+static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int par, int lu)
+{
+    int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
+    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls + 16);
+    auto it = c->mmas.find(key);
+    if (it != c->mmas.end()) return it->second;
+    amdg_ctx::MmaList L;
+    const std::map<int, std::vector<int>> & sf = c->shapes.shape_fibres[t];
+    std::vector<MmaItem> items; std::vector<double> cost; std::vector<int> elem_pool, prog_ints;
+    const DimTables & H = c->grid.dims[t];
+    bool ok = true; int smem_need = 0;
+    const int cap_doubles = c->tc_cap_doubles, ent_target = c->tc_ent_target, stage_a_max = c->tc_stage_a_max;
+    const int W = outer * inner;
+    const int64_t row_full = mma_rowsize(kf, outer, inner, inner);
+    const int64_t total = c->grid.n * row_full;
+    const int64_t target = std::max<int64_t>(1, total / std::max(1, c->tc_item_target >> pcls));
+    const int slack = 32 * kf;
+    struct Rect { int o0, no, i0, ni, pk; };
+    struct Piece { ShapeProg prog; std::vector<int> src; std::vector<Rect> rects; bool stage_a = false, ksplit = false; int nfib_max = 1; };
+    auto ints_doubles = [&](const ShapeProg & P, int nf, int m) { return (2 * P.n_rt + 1 + (int)P.n_ent() + ((nf * m + 1) & ~1) + 1) / 2 + 2; };
+    // a piece over the row tiles `rts` of S: piece-local source rows, remapped entries
+    auto make_piece = [&](const ShapeProg & S, const std::vector<int> & rts, Piece & P)
+    {
+        std::vector<int> loc(S.m, -1);
+        P.prog = ShapeProg(); P.src.clear();
+        ShapeProg & Q = P.prog;
+        Q.m = S.m; Q.tg = S.tg; Q.nkp = S.nkp; Q.ktp = S.ktp; Q.n_rt = (int)rts.size(); Q.rt_ptr.assign(1, 0); Q.rt_order = rts;
+        for (int rt : rts) for (int p = S.rt_ptr[rt]; p < S.rt_ptr[rt + 1]; ++p) { const int f = S.ent_src[p] / S.nkp; if (loc[f] < 0) loc[f] = 0; }
+        for (int f = 0; f < S.m; ++f) if (loc[f] == 0) { loc[f] = (int)P.src.size(); P.src.push_back(f); }
+        // longest row tiles first (the warps take them round-robin)
+        std::vector<int> order(rts.size()); for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return S.rt_ptr[rts[a] + 1] - S.rt_ptr[rts[a]] > S.rt_ptr[rts[b] + 1] - S.rt_ptr[rts[b]]; });
+        Q.rt_order.clear();
+        for (int oi : order)
+        {
+            const int rt = rts[oi];
+            Q.rt_order.push_back(rt);
+            for (int p = S.rt_ptr[rt]; p < S.rt_ptr[rt + 1]; ++p)
+            {
+                const int f = S.ent_src[p] / S.nkp, kp = S.ent_src[p] % S.nkp;
+                Q.ent_src.push_back(loc[f] * S.nkp + kp);
+                for (int g = 0; g < S.tg; ++g) Q.ent_pair.push_back(S.ent_pair[(size_t)p * S.tg + g]);
+            }
+            Q.rt_ptr.push_back((int)Q.ent_src.size());
+        }
+    };
+    for (auto & kv : sf)
+    {
+        const int shape = kv.first; const std::vector<int> & fibres = kv.second;
+        const std::vector<int> & ords = c->shapes.ords[shape];
+        ShapeProg SP; build_shape_prog(c->pairs, ords, rel, lu, kf, kt, SP);
+        const int m = SP.m;
+        std::vector<Piece> pieces;
+        const bool whole_fits = (int64_t)m * row_full + ints_doubles(SP, 1, m) + slack + (SP.n_ent() <= stage_a_max ? SP.n_ent() * 32 : 0) <= cap_doubles;
+        if (whole_fits && (SP.n_ent() <= stage_a_max || (SP.n_ent() <= 2 * (int64_t)ent_target && !c->tc_force_stage)))
+        {
+            pieces.emplace_back();
+            Piece & P = pieces.back();
+            std::vector<int> all(SP.n_rt); for (int i = 0; i < SP.n_rt; ++i) all[i] = i;
+            make_piece(SP, all, P);
+            P.stage_a = SP.n_ent() <= stage_a_max;
+            P.rects.push_back({ 0, outer, 0, inner, mma_colpitch(W) });
+            const int a_doubles = P.stage_a ? (int)SP.n_ent() * 32 : 0;
+            const int64_t room = std::min<int64_t>(cap_doubles - slack - a_doubles - (2 * SP.n_rt + 1 + (int)SP.n_ent()) / 2 - 4, target);
+            P.nfib_max = (int)std::max<int64_t>(1, room / ((int64_t)m * row_full + (m + 1) / 2 + 1));
+        }
+        else
+        {
+            // 32-column rectangles for the pieces cut by targets
+            std::vector<Rect> wide;
+            if (inner >= 32) { for (int o0 = 0; o0 < outer; ++o0) for (int i0 = 0; i0 < inner; i0 += 32) { const int n = std::min(32, inner - i0); wide.push_back({ o0, 1, i0, n, mma_colpitch(n) }); } }
+            else { const int no = std::max(1, std::min(outer, 32 / inner)); for (int o0 = 0; o0 < outer; o0 += no) { const int n = std::min(no, outer - o0); wide.push_back({ o0, n, 0, inner, mma_colpitch(n * inner) }); } }
+            int64_t row_wide = 0; for (const Rect & r : wide) row_wide = std::max(row_wide, mma_rowsize(kf, r.no, r.ni, inner));
+            // depth-first key of every fibre-local element and of every row tile (its first target)
+            std::vector<std::pair<int64_t, int>> rt_key(SP.n_rt);
+            for (int rt = 0; rt < SP.n_rt; ++rt)
+            {
+                const int o = ords[rt * SP.tg], n = level_of_order(o);
+                const int64_t left = n <= 1 ? 0 : (int64_t)(o - (1 << (n - 1))) << (c->nmax - (n - 1));
+                rt_key[rt] = { left * 64 + n, rt };
+            }
+            std::sort(rt_key.begin(), rt_key.end());
+            const int fixed = slack + (m + 1) / 2 + 8;                       // slack, element rows, alignment
+            auto rows_cap = [&](int64_t rowsize, int n_rt_, int n_ent_) { return (int)((cap_doubles - fixed - (2 * n_rt_ + 1 + n_ent_ + 1) / 2 - (n_ent_ <= stage_a_max ? n_ent_ * 32 : 0)) / rowsize); };
+            std::vector<int> coarse;
+            std::vector<int> cur; std::vector<char> mark(m, 0); int cur_src = 0, cur_ent = 0;
+            auto flush = [&]()
+            {
+                if (cur.empty()) return;
+                pieces.emplace_back(); make_piece(SP, cur, pieces.back()); pieces.back().rects = wide;
+                pieces.back().stage_a = pieces.back().prog.n_ent() <= stage_a_max;
+                cur.clear(); std::fill(mark.begin(), mark.end(), 0); cur_src = 0; cur_ent = 0;
+            };
+            for (auto & kr : rt_key)
+            {
+                const int rt = kr.second;
+                const int n_e = SP.rt_ptr[rt + 1] - SP.rt_ptr[rt];
+                if (n_e == 0) { cur.push_back(rt); continue; }               // a row tile without sources still writes zeros
+                std::vector<int> add;
+                for (int p = SP.rt_ptr[rt]; p < SP.rt_ptr[rt + 1]; ++p) { const int f = SP.ent_src[p] / SP.nkp; if (!mark[f] && (add.empty() || add.back() != f)) add.push_back(f); }
+                std::sort(add.begin(), add.end()); add.erase(std::unique(add.begin(), add.end()), add.end());
+                int own = 0; { std::vector<char> seen(m, 0); for (int p = SP.rt_ptr[rt]; p < SP.rt_ptr[rt + 1]; ++p) { const int f = SP.ent_src[p] / SP.nkp; if (!seen[f]) { seen[f] = 1; ++own; } } }
+                if (own > rows_cap(row_wide, 1, n_e)) { coarse.push_back(rt); continue; }
+                const bool fits = cur_src + (int)add.size() <= rows_cap(row_wide, (int)cur.size() + 1, cur_ent + n_e) && cur_ent + n_e <= ent_target;
+                if (!fits && cur_ent > 0)
+                {
+                    flush();
+                    add.clear();
+                    for (int p = SP.rt_ptr[rt]; p < SP.rt_ptr[rt + 1]; ++p) add.push_back(SP.ent_src[p] / SP.nkp);
+                    std::sort(add.begin(), add.end()); add.erase(std::unique(add.begin(), add.end()), add.end());
+                }
+                for (int f : add) mark[f] = 1;
+                cur_src += (int)add.size(); cur_ent += n_e; cur.push_back(rt);
+            }
+            flush();
+            // coarse row tiles: balanced groups, narrow rectangles over the union of their sources
+            if (!coarse.empty())
+            {
+                int64_t ce = 0; for (int rt : coarse) ce += SP.rt_ptr[rt + 1] - SP.rt_ptr[rt];
+                const int ng = (int)std::min<int64_t>(std::max<int64_t>(1, (ce + c->tc_coarse_ent - 1) / c->tc_coarse_ent), (int64_t)coarse.size());
+                std::stable_sort(coarse.begin(), coarse.end(), [&](int a, int b) { return SP.rt_ptr[a + 1] - SP.rt_ptr[a] > SP.rt_ptr[b + 1] - SP.rt_ptr[b]; });
+                std::vector<std::vector<int>> groups(ng); std::vector<int64_t> load(ng, 0);
+                for (int rt : coarse) { int best = 0; for (int q = 1; q < ng; ++q) if (load[q] < load[best]) best = q; groups[best].push_back(rt); load[best] += SP.rt_ptr[rt + 1] - SP.rt_ptr[rt] + 2; }
+                // coarse pieces stage nothing: their sources are streamed from L2 (entries keep fibre-local source indices), 8 columns per item
+                std::vector<Rect> narrow;
+                if (inner >= 8) { for (int o0 = 0; o0 < outer; ++o0) for (int i0 = 0; i0 < inner; i0 += 8) { const int n = std::min(8, inner - i0); narrow.push_back({ o0, 1, i0, n, mma_colpitch(n) }); } }
+                else { const int no = std::max(1, std::min(outer, 8 / inner)); for (int o0 = 0; o0 < outer; o0 += no) { const int n = std::min(no, outer - o0); narrow.push_back({ o0, n, 0, inner, mma_colpitch(n * inner) }); } }
+                for (auto & gr : groups)
+                {
+                    if (gr.empty()) continue;
+                    pieces.emplace_back(); Piece & P = pieces.back(); make_piece(SP, gr, P);
+                    for (size_t p = 0; p < P.prog.ent_src.size(); ++p) { const int e = P.prog.ent_src[p]; P.prog.ent_src[p] = P.src[e / SP.nkp] * SP.nkp + e % SP.nkp; }
+                    P.src.clear(); P.ksplit = true; P.stage_a = false; P.rects = narrow;
+                }
+                if (!ok) break;
+            }
+        }
+        // emit: programs, element rows (whole fibres for the targets, staged rows per piece), items
+        const int np = (int)pieces.size();
+        const int prog0 = (int)L.progs.size();
+        std::vector<int> piece_ofs(np);
+        for (int q = 0; q < np; ++q)
+        {
+            const ShapeProg & Q = pieces[q].prog;
+            piece_ofs[q] = (int)prog_ints.size();
+            prog_ints.insert(prog_ints.end(), Q.rt_ptr.begin(), Q.rt_ptr.end());
+            prog_ints.insert(prog_ints.end(), Q.rt_order.begin(), Q.rt_order.end());
+            prog_ints.insert(prog_ints.end(), Q.ent_src.begin(), Q.ent_src.end());
+        }
+        for (int q = 0; q < np; ++q)
+        {
+            const Piece & P = pieces[q]; const ShapeProg & Q = P.prog;
+            const int nsrc = (int)P.src.size();
+            const int a_doubles = P.stage_a ? (int)Q.n_ent() * 32 : 0;
+            for (size_t f0 = 0; f0 < fibres.size(); f0 += P.nfib_max)
+            {
+                const int nf = (int)std::min<size_t>(P.nfib_max, fibres.size() - f0);
+                const int eofs = (int)elem_pool.size();
+                for (int b = 0; b < nf; ++b) for (int f = 0; f < m; ++f) elem_pool.push_back(H.slot_elem[fibres[f0 + b] + f]);
+                int sofs = eofs;
+                if (nsrc != m && !P.ksplit)
+                {
+                    sofs = (int)elem_pool.size();
+                    for (int b = 0; b < nf; ++b) for (int s2 = 0; s2 < nsrc; ++s2) elem_pool.push_back(H.slot_elem[fibres[f0 + b] + P.src[s2]]);
+                }
+                for (const Rect & r : P.rects)
+                {
+                    MmaItem x; std::memset(&x, 0, sizeof(x));
+                    x.prog = prog0 + q; x.elem_ofs = eofs; x.nfib = nf; x.o0 = r.o0; x.no = r.no; x.i0 = r.i0; x.ni = r.ni; x.pk = r.pk;
+                    x.m = m; x.n_rt = Q.n_rt; x.prog_ofs = piece_ofs[q]; x.n_ent = (int)Q.n_ent();
+                    x.ni_magic = r.ni <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + (unsigned)r.ni - 1) / (unsigned)r.ni);
+                    x.stage_a = P.stage_a ? 1 : 0; x.nsrc = nsrc; x.src_ofs = sofs; x.ksplit = P.ksplit ? 1 : 0;
+                    x.nfib_magic = nf <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + (unsigned)nf - 1) / (unsigned)nf);
+                    { const unsigned nrf = (unsigned)(Q.n_rt * nf); x.unit_magic = nrf <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + nrf - 1) / nrf); }
+                    items.push_back(x);
+                    cost.push_back(((double)Q.n_ent() + 2.0 * Q.n_rt) * nf * ((r.no * r.ni + 7) / 8) + 0.02 * nf * nsrc * r.no * r.ni);
+                    const int n_ints = 2 * Q.n_rt + 1 + (int)Q.n_ent();
+                    smem_need = std::max(smem_need, (int)((nf * nsrc * mma_rowsize(kf, r.no, r.ni, inner) + 1) & ~(int64_t)1) + (n_ints + ((nf * m + 1) & ~1) + 1) / 2 + 2 + a_doubles + slack + (P.ksplit ? 260 : 0));
+                }
+            }
+        }
+        for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(q * 4096 + np * 2 + 1); L.progs.push_back(std::move(pieces[q].prog)); }
+    }
+    if (ok && smem_need > tc_smem_capacity_doubles()) ok = false;
+    if (ok && !items.empty())
+    {
+        std::vector<int> order(items.size()); for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+        std::vector<MmaItem> sorted(items.size()); for (size_t i = 0; i < order.size(); ++i) sorted[i] = items[order[i]];
+        if (prog_ints.empty()) prog_ints.push_back(0);
+        bool up = meta_upload(c, &L.d_items, sorted.data(), sorted.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.d_elem_pool, elem_pool.data(), elem_pool.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.d_prog_ints, prog_ints.data(), prog_ints.size(), false) == cudaSuccess &&
+                  cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (up) { L.n_item = (int)sorted.size(); L.smem_doubles = (smem_need + 1) & ~1; L.ok = true; }
+        if (std::getenv("AMDG_VERBOSE"))
+            fprintf(stderr, "[amdg] lean list t=%d outer=%d inner=%d kf=%d kt=%d rel=%d lu=%d par=%d: %d items, %d programs, smem %d doubles\n",
                     t, outer, inner, kf, kt, rel, lu, par, (int)sorted.size(), (int)L.progs.size(), L.smem_doubles);
     }
     return c->mmas.emplace(key, std::move(L)).first->second;
@@ -876,9 +1097,9 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         int cnt = 1;
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
-        if (c->kernel_variant == 0 || c->kernel_variant == 4)
+        if (c->kernel_variant == 0 || c->kernel_variant == 4 || c->kernel_variant == 5)
         {
-            amdg_ctx::MmaList & ML = get_mma(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu);
+            amdg_ctx::MmaList & ML = c->lean() ? get_mma_lean(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu) : get_mma(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu);
             const double * const * atab = ML.ok ? get_mma_a_tab(c, ML, op, rel, lu) : nullptr;
             if (ML.ok && atab)
             {
@@ -886,13 +1107,13 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
                 a.items = ML.d_items; a.n_item = ML.n_item; a.prog_pool = ML.d_prog_ints; a.a_tab = atab; a.elem_pool = ML.d_elem_pool; a.dbg = c->dbg;
                 a.n_elem = c->grid.n; a.inner = inner; a.n_comp = n_comp; a.n_job = cnt;
                 for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
-                cudaError_t e = launch_sweep_mma(a, O.kf, O.kt, ML.smem_doubles, c->stream);
+                cudaError_t e = c->lean() ? launch_sweep_tc(a, O.kf, O.kt, ML.smem_doubles, c->stream) : launch_sweep_mma(a, O.kf, O.kt, ML.smem_doubles, c->stream);
                 if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("tensor-core sweep launch: ") + cudaGetErrorString(e));
                 c->launches++;
                 done += cnt;
                 continue;
             }
-            if (c->kernel_variant == 4) return fail(AMDG_EINVAL, "tensor-core kernel requested but the work list could not be built");
+            if (c->kernel_variant == 4 || c->kernel_variant == 5) return fail(AMDG_EINVAL, "tensor-core kernel requested but the work list could not be built");
         }
         if (c->kernel_variant == 3)
         {

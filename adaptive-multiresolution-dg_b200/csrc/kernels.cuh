@@ -123,7 +123,15 @@ struct MmaItem
     int n_ent;
     unsigned ni_magic;  // ceil(2^32 / ni): c / ni == umulhi(c, magic) for the small column counts used here
     int stage_a;        // 1: the operator values of the piece are staged in shared memory too
-    int pad[2];
+    unsigned nfib_magic;    // ceil(2^32 / nfib) and ceil(2^32 / (n_rt * nfib)): unit decode of sweep_tc_kernel
+    unsigned unit_magic;
+    // sweep_tc_kernel stages only the rows the piece reads: nsrc rows per fibre, element rows at elem_pool[src_ofs + b*nsrc + s]
+    // (ent_src of the piece indexes these rows); sweep_mma_kernel stages whole fibres (nsrc == m, src_ofs == elem_ofs)
+    int nsrc, src_ofs;
+    int ksplit;             // 1: the few coarse targets of a long fibre (they read most of it): nothing is staged (nsrc == 0, ent_src holds
+                            //    fibre-local source indices, sources stream from L2), at most 8 columns, and every row tile is walked by all warps
+                            //    of the CTA: entries split four ways, partial sums added in warp order through shared memory
+    int pad2;
 };
 struct MmaArgs
 {
@@ -159,6 +167,8 @@ int pipe_threads();
 int pipe_smem_budget_bytes();
 cudaError_t launch_sweep_mma(const MmaArgs & a, int kf, int kt, int smem_doubles, cudaStream_t st);
 int mma_smem_capacity_doubles();
+cudaError_t launch_sweep_tc(const MmaArgs & a, int kf, int kt, int smem_doubles, cudaStream_t st);     // kernels_tc.cu
+int tc_smem_capacity_doubles();
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_pointwise_herm2d(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);

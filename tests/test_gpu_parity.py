@@ -377,7 +377,7 @@ def test_wave_rk4_ode2nd_stages():
     c.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("name", ["adapt_d2_k2_n6", "adapt_d3_k1_n4", "cfg3_wave_d3_k2_n3", "cfg5_vlasov_d6_k1_n2"])
 def test_all_kernel_variants(name, kernel):
     """every sweep kernel (gather, fibre-staged list, pipelined list, tensor-core) on regular and adaptive grids:

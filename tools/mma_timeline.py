@@ -7,7 +7,8 @@ A = importlib.import_module("adaptive-multiresolution-dg_b200")
 dim, nmax, k, m = 4, 8, 3, 3
 lev, sup = A.sparse_grid(dim, nmax)
 ctx = A.Context(dim, nmax, k, m, device=0)
-ctx.set_kernel(4)
+ctx.set_kernel(int(os.environ.get("KERNEL", "4")))
+SLOTS = 444 if os.environ.get("KERNEL", "4") == "4" else 148 * 6
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 ctx.grid_set(lev, sup)
 src_, tgt_, vol_ = ctx.pairs()
@@ -30,7 +31,7 @@ for nm in sys.argv[1:] or ["U", "full"]:
     t0 = d[:, 5].min()
     start = (d[:, 5] - t0) / 1e3
     end = start + (d[:, 4] - d[:, 0]) / 1965.0
-    print(nm, "t=%d" % T, "CTAs", len(d), "kernel span %.1f us; CTA lifetime sum %.0f us (/444 slots = %.1f us)" % (end.max(), (end - start).sum(), (end - start).sum() / 444))
+    print(nm, "t=%d" % T, "CTAs", len(d), "kernel span %.1f us; CTA lifetime sum %.0f us (/%d slots = %.1f us)" % (end.max(), (end - start).sum(), SLOTS, (end - start).sum() / SLOTS))
     for q in (0.5, 0.9, 0.99, 1.0):
         print("   %3.0f%% of CTAs finished by %.1f us" % (q * 100, np.quantile(end, q)))
     o = np.argsort(-end)[:6]

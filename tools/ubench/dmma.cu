@@ -24,8 +24,43 @@ __global__ void k_dfma(double * out, int iters)
     double s = 0; for (int j = 0; j < 8; ++j) s += c[j];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// latency: one warp, a dependent chain of DMMAs (ILP accumulators interleaved)
+template <int ILP>
+__global__ void k_dmma_lat(long long * out, double * sink, int iters)
+{
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+    double c[ILP][2];
+    for (int j = 0; j < ILP; ++j) { c[j][0] = 0; c[j][1] = 0; }
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i)
+#pragma unroll
+        for (int j = 0; j < ILP; ++j)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+    long long t1 = clock64();
+    double s = 0; for (int j = 0; j < ILP; ++j) s += c[j][0] + c[j][1];
+    sink[threadIdx.x] = s;
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+__global__ void k_dfma_lat(long long * out, double * sink, int iters)
+{
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4, c = 0;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) c = fma(a, b, c);
+    long long t1 = clock64();
+    sink[threadIdx.x] = c;
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+}
 int main()
 {
+    {
+        long long * d; double * sink; cudaMalloc(&d, 8); cudaMalloc(&sink, 32 * 8); long long h;
+        const int iters = 4096;
+        k_dmma_lat<1><<<1, 32>>>(d, sink, iters); cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost); printf("DMMA dependent chain: %.1f cycles per DMMA\n", (double)h / iters);
+        k_dmma_lat<2><<<1, 32>>>(d, sink, iters); cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost); printf("DMMA 2 chains: %.1f cycles per DMMA\n", (double)h / iters / 2);
+        k_dmma_lat<4><<<1, 32>>>(d, sink, iters); cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost); printf("DMMA 4 chains: %.1f cycles per DMMA\n", (double)h / iters / 4);
+        k_dmma_lat<8><<<1, 32>>>(d, sink, iters); cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost); printf("DMMA 8 chains: %.1f cycles per DMMA\n", (double)h / iters / 8);
+        k_dfma_lat<<<1, 32>>>(d, sink, iters); cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost); printf("DFMA dependent chain: %.1f cycles per DFMA\n", (double)h / iters);
+    }
     double * out; cudaMalloc(&out, 148 * 8 * 1024 * sizeof(double));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int warps = 4; warps <= 32; warps *= 2)
