@@ -81,9 +81,9 @@ struct amdg_ctx
     std::map<std::tuple<int, int, int, int, int, int>, MmaList> mmas;       // key: (dim t, outer, kf, kt, rel*4+lu, parallel class)
     std::map<std::tuple<int, int, int, int>, double *> mma_A;               // (op, shape, rel*4+lu, piece*1024+npieces) -> device operator values
     int mma_cap_doubles = 9 * 1024, mma_item_target = 148 * 8, mma_ent_target = 448, mma_stage_a_max = 64;
-    bool tc_force_stage = true; int tc_coarse_ent = 256;
+    bool tc_force_stage = true; int tc_coarse_ent = 256; int64_t tc_min_doubles = 131072;
     int tc_cap_doubles = 4608, tc_item_target = 148 * 8, tc_ent_target = 48, tc_stage_a_max = 48;      // lean form (kernels_tc.cu)
-    bool lean() const { return kernel_variant == 5; }
+    bool lean() const { return kernel_variant == 0 || kernel_variant == 5; }
     int n_sm = 148;
     long long * dbg = nullptr;
     // metadata arena: index tables, work lists and operator blocks live in one allocation that is given an L2
@@ -206,6 +206,7 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_TC_ITEMS")) c->tc_item_target = std::max(1, atoi(e));
     if (const char * e = std::getenv("AMDG_TC_ENT")) c->tc_ent_target = std::max(16, atoi(e));
     if (const char * e = std::getenv("AMDG_TC_STAGE_A")) c->tc_stage_a_max = std::max(0, atoi(e));
+    if (const char * e = std::getenv("AMDG_TC_MIN_DOUBLES")) c->tc_min_doubles = atoll(e);
     if (const char * e = std::getenv("AMDG_TC_FORCE_STAGE")) c->tc_force_stage = atoi(e) != 0;
     if (const char * e = std::getenv("AMDG_TC_COARSE_ENT")) c->tc_coarse_ent = std::max(16, atoi(e));
     if (const char * e = std::getenv("AMDG_PIPE_CAP")) c->pipe_cap_doubles = std::max(256, atoi(e)) & ~1;
@@ -699,10 +700,9 @@ static int64_t mma_rowsize(int kf, int no, int ni, int inner) { return inner == 
 static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int par, int lu)
 {
     int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
-    const bool lean = c->lean();
-    const int cap_doubles = lean ? c->tc_cap_doubles : c->mma_cap_doubles, item_target = lean ? c->tc_item_target : c->mma_item_target;
-    const int ent_target0 = lean ? c->tc_ent_target : c->mma_ent_target, stage_a_max = lean ? c->tc_stage_a_max : c->mma_stage_a_max;
-    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls + (lean ? 16 : 0));
+    const int cap_doubles = c->mma_cap_doubles, item_target = c->mma_item_target;
+    const int ent_target0 = c->mma_ent_target, stage_a_max = c->mma_stage_a_max;
+    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls);
     auto it = c->mmas.find(key);
     if (it != c->mmas.end()) return it->second;
     amdg_ctx::MmaList L;
@@ -991,6 +991,7 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
                     x.m = m; x.n_rt = Q.n_rt; x.prog_ofs = piece_ofs[q]; x.n_ent = (int)Q.n_ent();
                     x.ni_magic = r.ni <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + (unsigned)r.ni - 1) / (unsigned)r.ni);
                     x.stage_a = P.stage_a ? 1 : 0; x.nsrc = nsrc; x.src_ofs = sofs; x.ksplit = P.ksplit ? 1 : 0;
+                    { const unsigned nrun = (unsigned)(r.no * kf); x.nrun_magic = nrun <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + nrun - 1) / nrun); }
                     x.nfib_magic = nf <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + (unsigned)nf - 1) / (unsigned)nf);
                     { const unsigned nrf = (unsigned)(Q.n_rt * nf); x.unit_magic = nrf <= 1 ? 0xffffffffu : (unsigned)((0x100000000ull + nrf - 1) / nrf); }
                     items.push_back(x);
@@ -1099,20 +1100,24 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         const int W = jobs[done].outer * inner;
         if (c->kernel_variant == 0 || c->kernel_variant == 4 || c->kernel_variant == 5)
         {
-            amdg_ctx::MmaList & ML = c->lean() ? get_mma_lean(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu) : get_mma(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu);
-            const double * const * atab = ML.ok ? get_mma_a_tab(c, ML, op, rel, lu) : nullptr;
-            if (ML.ok && atab)
+            // lean tensor-core kernel first (variants 0 and 5); the whole-fibre tensor-core kernel when its list cannot be built (0) or on request (4)
+            // (auto mode keeps the whole-fibre form for sweeps of a few KB, which are bounded by the latency of one CTA, not by throughput)
+            bool launched = false;
+            const bool tiny = c->kernel_variant == 0 && (int64_t)c->grid.n * W * O.kf < c->tc_min_doubles;
+            for (int form = (c->lean() && !tiny) ? 1 : 0; form >= 0 && !launched; --form)
             {
+                amdg_ctx::MmaList & ML = form ? get_mma_lean(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu) : get_mma(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu);
+                const double * const * atab = ML.ok ? get_mma_a_tab(c, ML, op, rel, lu) : nullptr;
+                if (!(ML.ok && atab)) { if (form && c->kernel_variant == 5) break; continue; }
                 MmaArgs a;
                 a.items = ML.d_items; a.n_item = ML.n_item; a.prog_pool = ML.d_prog_ints; a.a_tab = atab; a.elem_pool = ML.d_elem_pool; a.dbg = c->dbg;
                 a.n_elem = c->grid.n; a.inner = inner; a.n_comp = n_comp; a.n_job = cnt;
                 for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
-                cudaError_t e = c->lean() ? launch_sweep_tc(a, O.kf, O.kt, ML.smem_doubles, c->stream) : launch_sweep_mma(a, O.kf, O.kt, ML.smem_doubles, c->stream);
+                cudaError_t e = form ? launch_sweep_tc(a, O.kf, O.kt, ML.smem_doubles, c->stream) : launch_sweep_mma(a, O.kf, O.kt, ML.smem_doubles, c->stream);
                 if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("tensor-core sweep launch: ") + cudaGetErrorString(e));
-                c->launches++;
-                done += cnt;
-                continue;
+                launched = true;
             }
+            if (launched) { c->launches++; done += cnt; continue; }
             if (c->kernel_variant == 4 || c->kernel_variant == 5) return fail(AMDG_EINVAL, "tensor-core kernel requested but the work list could not be built");
         }
         if (c->kernel_variant == 3)

@@ -111,7 +111,7 @@ struct PipeArgs
 };
 
 // tensor-core sweep kernel (tile programs built by mma_items.hpp)
-struct MmaItem
+struct __align__(16) MmaItem
 {
     int prog;           // tile program (shape): index into a_tab
     int elem_ofs, nfib; // element rows of this item's fibres: elem_pool[elem_ofs + b*m + f]
@@ -131,7 +131,7 @@ struct MmaItem
     int ksplit;             // 1: the few coarse targets of a long fibre (they read most of it): nothing is staged (nsrc == 0, ent_src holds
                             //    fibre-local source indices, sources stream from L2), at most 8 columns, and every row tile is walked by all warps
                             //    of the CTA: entries split four ways, partial sums added in warp order through shared memory
-    int pad2;
+    unsigned nrun_magic;    // ceil(2^32 / (no * KF)): run decode of the bulk-copy staging
 };
 struct MmaArgs
 {

@@ -20,7 +20,10 @@
 namespace amdg {
 
 static const int TC_THREADS = 128;
-static const int TC_MIN_CTAS = 6;
+#ifndef AMDG_TC_MIN_CTAS
+#define AMDG_TC_MIN_CTAS 6
+#endif
+static const int TC_MIN_CTAS = AMDG_TC_MIN_CTAS;
 static const int TC_SMEM_DOUBLES = 4608;            // upper bound (36 KiB, six CTAs per SM); typical lists need <= 27 KiB: eight CTAs per SM
 
 int tc_smem_capacity_doubles() { return TC_SMEM_DOUBLES; }
@@ -36,6 +39,12 @@ __device__ __forceinline__ void tc_cp8(void * smem, const void * gmem)
 __device__ __forceinline__ void tc_cp4(void * smem, const void * gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+// bulk (TMA) copy of one contiguous run into shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tc_bulk(void * smem, const void * gmem, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_dmma(double (&c)[2], double a, double b)
 {
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
         a.dbg[(int64_t)blockIdx.x * 8 + 6] = it.m; a.dbg[(int64_t)blockIdx.x * 8 + 7] = it.nfib * 1000000 + it.n_ent * 100 + it.no * it.ni;
     }
     TC_STAMP(1);
-    const int jb = blockIdx.y / a.n_comp, comp = blockIdx.y - jb * a.n_comp;
+    const int jb = blockIdx.y, comp = blockIdx.z;
     const SweepJob J = a.job[jb];
     const int inner = INNER1 ? 1 : a.inner;
     const int W = J.outer * inner;
@@ -176,6 +185,8 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
     const double * __restrict__ Ag = a.a_tab[it.prog];
 
     // ---- stage: the program, the element rows, (small) operator fragments and the source rows, all in flight at once
+    __shared__ __align__(8) unsigned long long s_bar;
+    bool use_bulk = false;
     {
         const int * __restrict__ ep = a.elem_pool + it.src_ofs;        // element rows of the staged rows
         // a row is nrun runs of runlen contiguous doubles: run r = (o_local, k) at global offset r*inner, shared offset k*pk + o_local*ni
@@ -183,9 +194,11 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
         const int runlen = INNER1 ? ncols * KF : it.ni;
         const int64_t col_base = INNER1 ? (int64_t)it.o0 * KF : (int64_t)it.o0 * KF * inner + it.i0;
         const bool vec = ((runlen & 1) == 0) && ((col_base & 1) == 0) && (INNER1 || (inner & 1) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((s_from & 1) == 0);
+        // runs of >= 128 aligned bytes go as one bulk copy each (one instruction per run instead of one 16-byte copy per lane)
+        use_bulk = vec && runlen >= 16;
         const int cpr = vec ? (runlen >> 1) : runlen;                 // copies per run
         const int per_row = nrun * cpr;
-        const unsigned cpr_magic = cpr <= 1 ? 0u : 0xffffffffu / (unsigned)cpr + 1u;
+        const unsigned cpr_magic = (cpr <= 1 || use_bulk) ? 0u : 0xffffffffu / (unsigned)cpr + 1u;
         for (int c = tid; c < n_prog_ints; c += TC_THREADS) tc_cp4(s_prog + c, a.prog_pool + it.prog_ofs + c);
         for (int c = tid; c < nelem; c += TC_THREADS) tc_cp4(s_elem + c, a.elem_pool + it.elem_ofs + c);
         if (it.stage_a) for (int c = tid; c < it.n_ent * 16; c += TC_THREADS) tc_cp16(s_A + 2 * c, Ag + 2 * c);
@@ -197,7 +210,27 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
             so = r * inner + w;
             dof = INNER1 ? w : k * pk + o_l * it.ni + w;
         };
-        if (per_row >= 32)
+        if (use_bulk)
+        {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+            if (tid == 0)
+            {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            const int n_copy = nrow * nrun;
+            const unsigned run_bytes = (unsigned)runlen * 8u;
+            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((unsigned)n_copy * run_bytes) : "memory");
+            for (int c = tid; c < n_copy; c += TC_THREADS)
+            {
+                const int row = nrun == 1 ? c : (int)__umulhi((unsigned)c, it.nrun_magic), r = c - row * nrun;
+                const int o_l = r / KF, k = r - o_l * KF;
+                const int e = __ldg(ep + row);
+                tc_bulk(Xs + row * rowsize + (INNER1 ? 0 : k * pk + o_l * it.ni), src + (int64_t)e * s_from + col_base + (int64_t)r * inner, run_bytes, bar);
+            }
+        }
+        else if (per_row >= 32)
         {
             // rows of this warp: warp + NW*r; lane r fetches the element row of row r, handed out by shuffles; the copy pattern
             // inside a row is the same for every row, so each lane computes its first MAXC copy offsets once
@@ -285,6 +318,13 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (use_bulk)
+    {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    }
     TC_STAMP(3);
 
     if (it.ksplit)
@@ -463,7 +503,7 @@ static cudaError_t launch_tc_t(const MmaArgs & a, int smem_doubles, cudaStream_t
         configured = true;
     }
     if (smem_doubles > TC_SMEM_DOUBLES) return cudaErrorInvalidValue;
-    dim3 grid((unsigned)a.n_item, (unsigned)(a.n_job * a.n_comp));
+    dim3 grid((unsigned)a.n_item, (unsigned)a.n_job, (unsigned)a.n_comp);
     sweep_tc_kernel<KF, KT, INNER1><<<grid, TC_THREADS, (size_t)smem_doubles * sizeof(double), st>>>(a);
     return cudaGetLastError();
 }

@@ -328,21 +328,28 @@ def main():
     nbuf = 8
     with torch.cuda.stream(stream):
         bufs = [torch.rand(ne, a ** dim, dtype=torch.float64, device="cuda") for _ in range(nbuf)]
-        dsts = [torch.empty(ne, b ** dim, dtype=torch.float64, device="cuda") for _ in range(nbuf)]
+        dsts = [torch.empty(ne, a ** (dim - 1) * b, dtype=torch.float64, device="cuda") for _ in range(nbuf)]
         for i in range(nbuf):
             ctx.sweep1d(op_pt, A.REL_VOL, A.LU_FULL, i % dim, [a] * dim, bufs[i], dsts[i])
     stream.synchronize()
-    nrep = 4 * nbuf
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        flush.fill_(0.0)
-        e0.record(stream)
+    # the launches are replayed from a CUDA graph (as in the step), so the figure is device time per launch, not host enqueue rate
+    nrep, n_replay = 4 * nbuf, 8
+    l_roof0 = ctx.launch_count
+    g_roof = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_roof, stream=stream):
         for i in range(nrep):
             ctx.sweep1d(op_pt, A.REL_VOL, A.LU_FULL, i % dim, [a] * dim, bufs[i % nbuf], dsts[i % nbuf])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        g_roof.replay()
+        flush.fill_(0.0)
+        e0.record(stream)
+        for _ in range(n_replay):
+            g_roof.replay()
         e1.record(stream)
     stream.synchronize()
-    t_launch = e0.elapsed_time(e1) / nrep * 1e-3
-    bytes_launch = 8.0 * ne * (a ** dim + b ** dim)                     # B_sweep = 8 N_e (S_from + S_to), SURVEY.md 8(d)
+    t_launch = e0.elapsed_time(e1) / (nrep * n_replay) * 1e-3
+    bytes_launch = 8.0 * ne * (a ** dim + a ** (dim - 1) * b)           # B_sweep = 8 N_e (S_from + S_to), SURVEY.md 8(d): one dimension goes from edge a to edge b
     achieved = bytes_launch / t_launch / 1e9
 
     # per-rank step time -> max over ranks
@@ -365,8 +372,9 @@ def main():
             "e2e": {"value": dof * world / t_e2e, "unit": "DoF-stage/s", "h2d_bytes_per_step": int(hin.nbytes), "d2h_bytes_per_step": int(hout.nbytes),
                     "ms_per_step": t_e2e * 1e3, "api": e2e_api},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_NCU if (args.kernel in (0, 4) and args.workload == "cfg2") else None,
-                         "kernel": "sweep_mma_kernel<%d,%d> (one 1D sweep, single job; FP64 DMMA m8n8k4)" % (a, b) if args.kernel in (0, 4) else "sweep kernel variant %d (one 1D sweep, single job)" % args.kernel, "bytes_per_launch": bytes_launch, "us_per_launch": t_launch * 1e6,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_NCU if (args.kernel in (0, 5) and args.workload == "cfg2") else None,
+                         "kernel": ("sweep_tc_kernel<%d,%d> (one 1D sweep along each dimension in turn, single job; FP64 DMMA m8n8k4)" % (a, b) if args.kernel in (0, 5) else
+                                    "sweep_mma_kernel<%d,%d> (one 1D sweep, single job; FP64 DMMA m8n8k4)" % (a, b) if args.kernel == 4 else "sweep kernel variant %d (one 1D sweep, single job)" % args.kernel), "bytes_per_launch": bytes_launch, "us_per_launch": t_launch * 1e6,
                          "peak_source": peak_src,
                          "step": {"b_alg_bytes": b_alg, "gbs": b_alg / (t_step_ms * 1e-3) / 1e9, "frac": b_alg / (t_step_ms * 1e-3) / 1e9 / peak,
                                   "note": step_note}},

@@ -57,7 +57,7 @@ int amdg_ctx_destroy(amdg_ctx *ctx);
 int amdg_ctx_set_stream(amdg_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: a stream owned by ctx */
 int amdg_ctx_sync(amdg_ctx *ctx);
 int amdg_ctx_set_schedule(amdg_ctx *ctx, int sched);
-int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto (tensor-core kernel, staged list kernel as fall-back), 1 = gather, 2 = fibre-staged list kernel, 3 = pipelined list kernel, 4 = tensor-core (FP64 MMA) kernel */
+int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto (lean tensor-core kernel; whole-fibre tensor-core and staged list kernels as fall-backs), 1 = gather, 2 = fibre-staged list kernel, 3 = pipelined list kernel, 4 = whole-fibre tensor-core (FP64 MMA) kernel, 5 = lean tensor-core kernel */
 int64_t amdg_ctx_launch_count(amdg_ctx *ctx);                 /* kernels launched so far by this context */
 /* profiling aid: device buffer of n_items*8 int64 that the sweep kernel fills with per-CTA clock64 stamps (NULL = off) */
 int amdg_ctx_set_debug_buffer(amdg_ctx *ctx, void *dev_buf);
