@@ -57,6 +57,7 @@ SYMBOLS = {
     "amdg_op_register_hier": (_i, [_p, _ip, _dp, _i, _ip]),
     "amdg_op_combine": (_i, [_p, _i, _d, _i, _d, _ip]),
     "amdg_sweep1d": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _i, _d, _i]),
+    "amdg_sweep1d_batch": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _dp, _ip, _i, _i]),
     "amdg_apply_tensor": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i]),
     "amdg_hierarchize": (_i, [_p, _i, _p, _p, _i]),
     "amdg_pointwise": (_i, [_p, _i, _ip, _dp, _p, _p, _p]),
@@ -235,6 +236,16 @@ class Context:
     def sweep1d(self, op, rel, lu, t, sizes_from, src, dst, n_comp=1, coef=1.0, accumulate=False):
         s, sp = _ints(sizes_from)
         _check(lib.amdg_sweep1d(self._h, op, rel, lu, t, sp, _ptr(src), _ptr(dst), n_comp, coef, int(accumulate)))
+
+    def sweep1d_batch(self, op, rel, lu, t, sizes_from, srcs, dsts, coefs=None, accumulates=None, n_comp=1):
+        """one launch for several (src, dst) pairs that share operator, relation, L/U part and dimension (amdg_sweep1d_batch)"""
+        n = len(srcs)
+        s, sp = _ints(np.asarray(sizes_from).reshape(n, self.dim))
+        ps = (ctypes.c_void_p * n)(*[_ptr(x) for x in srcs])
+        pd = (ctypes.c_void_p * n)(*[_ptr(x) for x in dsts])
+        cf, cp = _dbls(np.ones(n) if coefs is None else coefs)
+        ac, ap = _ints(np.zeros(n) if accumulates is None else accumulates)
+        _check(lib.amdg_sweep1d_batch(self._h, op, rel, lu, t, sp, ps, pd, cp, ap, n, n_comp))
 
     def apply_tensor(self, ops, rels, src, dst, n_comp=1, coef=1.0, accumulate=False):
         o, op = _ints(ops)

@@ -1194,6 +1194,32 @@ int amdg_sweep1d(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes
     return launch_sweep(c, op, rel, lu, t, inner, &j, 1, n_comp);
 }
 
+int amdg_sweep1d_batch(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * const * src, double * const * dst,
+                       const double * coef, const int * accumulate, int n_job, int n_comp)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if ((r = check_op(c, op))) return r;
+    if (t < 0 || t >= c->dim || rel < 0 || rel > 1 || lu < 0 || lu > 2 || !sizes_from || !src || !dst || n_comp < 1 || n_job < 1) return fail(AMDG_EINVAL, "bad sweep arguments");
+    const Op & O = *c->ops[op];
+    std::vector<SweepJob> jobs(n_job);
+    int inner0 = -1;
+    for (int i = 0; i < n_job; ++i)
+    {
+        const int * sz = sizes_from + (size_t)i * c->dim;
+        if (sz[t] != O.kf) return fail(AMDG_EINVAL, "sizes_from[t] does not match the operator's source edge");
+        if (!src[i] || !dst[i] || src[i] == dst[i]) return fail(AMDG_EINVAL, "a sweep cannot run in place");
+        int outer = 1, inner = 1;
+        for (int k = 0; k < t; ++k) outer *= sz[k];
+        for (int k = t + 1; k < c->dim; ++k) inner *= sz[k];
+        if (inner0 < 0) inner0 = inner; else if (inner != inner0) return fail(AMDG_EINVAL, "the jobs of a batch must agree in the edges of the dims after t");
+        jobs[i].src = src[i]; jobs[i].dst = dst[i]; jobs[i].outer = outer; jobs[i].accumulate = accumulate ? accumulate[i] : 0; jobs[i].coef = coef ? coef[i] : 1.0;
+    }
+    std::stable_sort(jobs.begin(), jobs.end(), [](const SweepJob & a, const SweepJob & b) { return a.outer < b.outer; });
+    CU(cudaSetDevice(c->device));
+    return launch_sweep(c, op, rel, lu, t, inner0, jobs.data(), n_job, n_comp);
+}
+
 static int64_t ipow(int b, int e) { int64_t r = 1; while (e-- > 0) r *= b; return r; }
 
 // the reference's schedule: source/FastMultiplyLU.cpp:614-664 (orderings), :121-142 (chain), :596-612 (sizes)

@@ -144,9 +144,13 @@ __device__ __forceinline__ void tc_rows_narrow(double (&acc)[4][2], const double
 // Shared-memory layout of a staged source row as in sweep_mma_kernel:
 //   INNER1 == false: X[k][col], col = o_local*ni + i_local, pitch pk = 4 (mod 8) doubles between source indices k;
 //   INNER1 == true : X[col][k], the element's own memory order (one contiguous copy per row).
-template <int KF, int KT, bool INNER1>
+// MODE 0: general; 1: sweep along the last dimension (inner == 1); 2: as 0, and the host has checked that every job overwrites its
+// destination and that all stores are aligned 16-byte pairs (the common case) -- the general store path is compiled out
+template <int KF, int KT, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const MmaArgs a)
 {
+    constexpr bool INNER1 = MODE == 1;
+    constexpr bool FAST = MODE == 2;
     extern __shared__ __align__(16) double Xs[];
     constexpr int KTP = KT <= 1 ? 1 : (KT <= 2 ? 2 : (KT <= 4 ? 4 : 8));
     constexpr int TG = 8 / KTP;
@@ -243,33 +247,28 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
                 so[i] = -1; dof[i] = 0;
                 if (c < per_row) copy_offsets(c, so[i], dof[i]);
             }
-            for (int rbase = 0; warp + NW * rbase < nrow; rbase += 32)
-            {
-                const int myrow = warp + NW * (rbase + lane);
-                const int e_lane = myrow < nrow ? __ldg(ep + myrow) : 0;
-                const int nr = min(32, (nrow - warp - NW * rbase + NW - 1) / NW);
-                for (int r = 0; r < nr; ++r)
-                {
-                    const int e = __shfl_sync(0xffffffffu, e_lane, r);
-                    const double * __restrict__ g = src + (int64_t)e * s_from + col_base;
-                    double * xr = Xs + (warp + NW * (rbase + r)) * rowsize;
-                    if (vec)
-                    {
-#pragma unroll
-                        for (int i = 0; i < MAXC; ++i) if (so[i] >= 0) tc_cp16(xr + dof[i], g + so[i]);
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int i = 0; i < MAXC; ++i) if (so[i] >= 0) tc_cp8(xr + dof[i], g + so[i]);
-                    }
-                    for (int c = lane + 32 * MAXC; c < per_row; c += 32)          // rows longer than 32*MAXC copies
-                    {
-                        int s2, d2; copy_offsets(c, s2, d2);
-                        if (vec) tc_cp16(xr + d2, g + s2); else tc_cp8(xr + d2, g + s2);
-                    }
-                }
+#define TC_ROW_LOOP(CP)                                                                                                   \
+            for (int rbase = 0; warp + NW * rbase < nrow; rbase += 32)                                                    \
+            {                                                                                                             \
+                const int myrow = warp + NW * (rbase + lane);                                                             \
+                const int e_lane = myrow < nrow ? __ldg(ep + myrow) : 0;                                                  \
+                const int nr = min(32, (nrow - warp - NW * rbase + NW - 1) / NW);                                         \
+                for (int r = 0; r < nr; ++r)                                                                              \
+                {                                                                                                         \
+                    const int e = __shfl_sync(0xffffffffu, e_lane, r);                                                    \
+                    const double * __restrict__ g = src + (int64_t)e * s_from + col_base;                                 \
+                    double * xr = Xs + (warp + NW * (rbase + r)) * rowsize;                                               \
+                    _Pragma("unroll")                                                                                     \
+                    for (int i = 0; i < MAXC; ++i) if (so[i] >= 0) CP(xr + dof[i], g + so[i]);                            \
+                    for (int c = lane + 32 * MAXC; c < per_row; c += 32)                                                  \
+                    {                                                                                                     \
+                        int s2, d2; copy_offsets(c, s2, d2);                                                              \
+                        CP(xr + d2, g + s2);                                                                              \
+                    }                                                                                                     \
+                }                                                                                                         \
             }
+            if (vec) { TC_ROW_LOOP(tc_cp16) } else { TC_ROW_LOOP(tc_cp8) }
+#undef TC_ROW_LOOP
         }
         else
         {
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
     const int n_rf = it.n_rt * it.nfib;
     const int n_units = ((ncols + 31) >> 5) * n_rf;
     const bool row_on = cq < KT;
-    const bool fast_store = vecst && !J.accumulate;
+    const bool fast_store = FAST || (vecst && !J.accumulate);
     const double coef = J.coef;
     const double * A = it.stage_a ? s_A : Ag;
     const int fib_stride = it.nsrc * rowsize;
@@ -464,13 +463,13 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
         {
             const int e = s_elem[b * m + e_loc];
             double * y = dst + (int64_t)e * s_to + q_off;
-            if (fast_store)
+            if (FAST || fast_store)
             {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if ((vmask >> j) & 1u) *reinterpret_cast<double2 *>(y + off[j]) = make_double2(coef * acc[j][0], coef * acc[j][1]);
             }
-            else
+            else if (!FAST)
             {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -492,34 +491,54 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
     TC_STAMP(4);
 }
 
-template <int KF, int KT, bool INNER1>
+template <int KF, int KT, int MODE>
 static cudaError_t launch_tc_t(const MmaArgs & a, int smem_doubles, cudaStream_t st)
 {
     static bool configured = false;
     if (!configured)
     {
-        cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<KF, KT, INNER1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_DOUBLES * sizeof(double)));
+        cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<KF, KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_DOUBLES * sizeof(double)));
         if (e != cudaSuccess) return e;
         configured = true;
     }
     if (smem_doubles > TC_SMEM_DOUBLES) return cudaErrorInvalidValue;
     dim3 grid((unsigned)a.n_item, (unsigned)a.n_job, (unsigned)a.n_comp);
-    sweep_tc_kernel<KF, KT, INNER1><<<grid, TC_THREADS, (size_t)smem_doubles * sizeof(double), st>>>(a);
+    sweep_tc_kernel<KF, KT, MODE><<<grid, TC_THREADS, (size_t)smem_doubles * sizeof(double), st>>>(a);
     return cudaGetLastError();
+}
+
+template <int KF, int KT>
+static cudaError_t launch_tc_m(const MmaArgs & a, int mode, int smem_doubles, cudaStream_t st)
+{
+    if (mode == 1) return launch_tc_t<KF, KT, 1>(a, smem_doubles, st);
+    if (mode == 2) return launch_tc_t<KF, KT, 2>(a, smem_doubles, st);
+    return launch_tc_t<KF, KT, 0>(a, smem_doubles, st);
 }
 
 #define AMDG_DISPATCH_KT_TC(KF_)                                                                  \
     switch (kt) {                                                                                 \
-        case 1: return a.inner == 1 ? launch_tc_t<KF_, 1, true>(a, smem_doubles, st) : launch_tc_t<KF_, 1, false>(a, smem_doubles, st); \
-        case 2: return a.inner == 1 ? launch_tc_t<KF_, 2, true>(a, smem_doubles, st) : launch_tc_t<KF_, 2, false>(a, smem_doubles, st); \
-        case 3: return a.inner == 1 ? launch_tc_t<KF_, 3, true>(a, smem_doubles, st) : launch_tc_t<KF_, 3, false>(a, smem_doubles, st); \
-        case 4: return a.inner == 1 ? launch_tc_t<KF_, 4, true>(a, smem_doubles, st) : launch_tc_t<KF_, 4, false>(a, smem_doubles, st); \
-        case 5: return a.inner == 1 ? launch_tc_t<KF_, 5, true>(a, smem_doubles, st) : launch_tc_t<KF_, 5, false>(a, smem_doubles, st); \
-        case 6: return a.inner == 1 ? launch_tc_t<KF_, 6, true>(a, smem_doubles, st) : launch_tc_t<KF_, 6, false>(a, smem_doubles, st); \
+        case 1: return launch_tc_m<KF_, 1>(a, mode, smem_doubles, st);                            \
+        case 2: return launch_tc_m<KF_, 2>(a, mode, smem_doubles, st);                            \
+        case 3: return launch_tc_m<KF_, 3>(a, mode, smem_doubles, st);                            \
+        case 4: return launch_tc_m<KF_, 4>(a, mode, smem_doubles, st);                            \
+        case 5: return launch_tc_m<KF_, 5>(a, mode, smem_doubles, st);                            \
+        case 6: return launch_tc_m<KF_, 6>(a, mode, smem_doubles, st);                            \
         default: return cudaErrorInvalidValue; }
 
 cudaError_t launch_sweep_tc(const MmaArgs & a, int kf, int kt, int smem_doubles, cudaStream_t st)
 {
+    // mode 2 (plain aligned 16-byte stores only): every rectangle of the lean lists has even ni and i0 when inner is even
+    int mode = a.inner == 1 ? 1 : 0;
+    if (mode == 0 && (a.inner & 1) == 0)
+    {
+        bool fast = true;
+        for (int i = 0; i < a.n_job && fast; ++i)
+        {
+            const int64_t s_to = (int64_t)a.job[i].outer * a.inner * kt;
+            fast = !a.job[i].accumulate && (s_to & 1) == 0 && (reinterpret_cast<uintptr_t>(a.job[i].dst) & 15) == 0;
+        }
+        if (fast) mode = 2;
+    }
     switch (kf)
     {
         case 1: AMDG_DISPATCH_KT_TC(1) case 2: AMDG_DISPATCH_KT_TC(2) case 3: AMDG_DISPATCH_KT_TC(3)

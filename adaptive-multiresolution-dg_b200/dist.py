@@ -64,20 +64,36 @@ class FibrePartition:
         recv_index[np.arange(len(theirs))] = recv_order                    # received row i goes to local position recv_order[i]
         return send_order, send_counts, recv_counts, recv_order
 
+    def _device_plan(self, src, dst, dev):
+        """the exchange plan as device index tensors and python count lists (cached: the layout switches of every application reuse it)"""
+        key = (src, dst, str(dev))
+        if not hasattr(self, "_plans"):
+            self._plans = {}
+        if key not in self._plans:
+            send_order, send_counts, recv_counts, recv_order = self.plan(src, dst)
+            self._plans[key] = (torch.as_tensor(send_order, device=dev), [int(c) for c in send_counts], [int(c) for c in recv_counts],
+                                torch.as_tensor(recv_order, device=dev))
+        return self._plans[key]
+
     def switch(self, x, src, dst, group=None):
         """x: [n_local(src), block] tensor in layout src -> [n_local(dst), block] in layout dst"""
-        send_order, send_counts, recv_counts, recv_order = self.plan(src, dst)
-        blk = x.shape[1]
-        dev = x.device
-        sbuf = x.index_select(0, torch.as_tensor(send_order, device=dev)).contiguous()
-        rbuf = torch.empty(int(recv_counts.sum()), blk, dtype=x.dtype, device=dev)
+        return self.switch_many([x], src, dst, group)[0]
+
+    def switch_many(self, xs, src, dst, group=None):
+        """all tensors of xs ([n_local(src), block_i]) change layout in ONE all-to-all: element rows are concatenated along the block axis"""
+        dev = xs[0].device
+        send_idx, send_counts, recv_counts, recv_idx = self._device_plan(src, dst, dev)
+        widths = [int(x.shape[1]) for x in xs]
+        cat = xs[0] if len(xs) == 1 else torch.cat(xs, dim=1)
+        sbuf = cat.index_select(0, send_idx)
+        rbuf = torch.empty(sum(recv_counts), cat.shape[1], dtype=cat.dtype, device=dev)
         if self.world == 1:
             rbuf.copy_(sbuf)
         else:
-            dist.all_to_all_single(rbuf, sbuf, [int(c) for c in recv_counts], [int(c) for c in send_counts], group=group)
+            dist.all_to_all_single(rbuf, sbuf, recv_counts, send_counts, group=group)
         out = torch.empty_like(rbuf)
-        out.index_copy_(0, torch.as_tensor(recv_order, device=dev), rbuf)
-        return out
+        out.index_copy_(0, recv_idx, rbuf)
+        return [o.contiguous() for o in torch.split(out, widths, dim=1)] if len(xs) > 1 else [out]
 
 
 class DistTensorApply:
@@ -102,25 +118,30 @@ class DistTensorApply:
             c.close()
 
     def _switch_all(self, bufs, src, dst):
-        out = {}
-        for S, x in bufs.items():
-            out[S] = self.part.switch(x, src, dst)
-            self.switches += 1
-            self.switch_bytes += x.numel() * 8
-        return out
+        """one all-to-all for all live buffers of the schedule"""
+        keys = list(bufs.keys())
+        outs = self.part.switch_many([bufs[S] for S in keys], src, dst)
+        self.switches += 1
+        self.switch_bytes += sum(bufs[S].numel() for S in keys) * 8
+        return dict(zip(keys, outs))
 
     def apply(self, op_names, rels, src_x, kf, kt, coef=1.0):
         """src_x: [n_local(X), kf^dim] in layout X -> returns [n_local(X), kt^dim] in layout X.
-        op_names[t]: operator name of dimension t (looked up per layout)."""
+        op_names[t]: operator name of dimension t (looked up per layout).  The sweeps of one level of the shared-prefix
+        schedule go out as one batched launch (amdg_sweep1d_batch); every layout switch is one all-to-all."""
         A, d, h = self.A, self.dim, self.part.h
         edge = lambda S, k: kt if (S >> k) & 1 else kf
 
-        def sweep(layout, lu, k, sizes, x, out, coef=1.0, accumulate=False):
-            c = self.ctx[layout]
-            c.sweep1d(self.ops[layout][op_names[k]], rels[k], lu, k, sizes, x, out, coef=coef, accumulate=accumulate)
-
         def alloc(layout, sizes):
-            return torch.zeros(len(self.part.local[layout]), int(np.prod(sizes)), dtype=torch.float64, device=src_x.device)
+            return torch.empty(len(self.part.local[layout]), int(np.prod(sizes)), dtype=torch.float64, device=src_x.device)
+
+        def batch(layout, lu, k, jobs, coef=1.0):
+            # jobs: (sizes_from, src, dst, accumulate)
+            if not jobs or len(self.part.local[layout]) == 0:
+                return
+            c = self.ctx[layout]
+            c.sweep1d_batch(self.ops[layout][op_names[k]], rels[k], lu, k, [j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs],
+                            coefs=[coef] * len(jobs), accumulates=[int(j[3]) for j in jobs])
 
         # down pass: X_S for S subset of {0..d-2}; sizes of X_S: dims in S have kt
         X = {0: src_x}
@@ -129,35 +150,38 @@ class DistTensorApply:
             if k == h:
                 X = self._switch_all(X, "X", "V")
                 layout = "V"
+            jobs = []
             for S in list(X.keys()):
                 sizes = [edge(S, q) if q < k else kf for q in range(d)]
                 out_sizes = list(sizes)
                 out_sizes[k] = kt
                 y = alloc(layout, out_sizes)
-                sweep(layout, A.LU_L, k, sizes, X[S], y)
+                jobs.append((sizes, X[S], y, False))
                 X[S | (1 << k)] = y
+            batch(layout, A.LU_L, k, jobs)
         if d - 1 >= h and layout == "X":
             X = self._switch_all(X, "X", "V")
             layout = "V"
         # full sweep along d-1
-        R = {}
+        R, jobs = {}, []
         for S, x in X.items():
             sizes = [edge(S, q) for q in range(d - 1)] + [kf]
-            out_sizes = sizes[:-1] + [kt]
-            y = alloc(layout, out_sizes)
-            sweep(layout, A.LU_FULL, d - 1, sizes, x, y, coef=coef)
+            y = alloc(layout, sizes[:-1] + [kt])
+            jobs.append((sizes, x, y, False))
             R[S] = y
+        batch(layout, A.LU_FULL, d - 1, jobs, coef=coef)
         # up pass: R_k(S) = U_k R_{k+1}(S) + R_{k+1}(S + {k})
         for k in range(d - 2, -1, -1):
             if k == h - 1 and layout == "V":
                 R = self._switch_all(R, "V", "X")
                 layout = "X"
-            newR = {}
+            newR, jobs = {}, []
             for S in [s for s in R if not (s >> k) & 1]:
                 sizes = [edge(S, q) if q <= k else kt for q in range(d)]
                 hi = R[S | (1 << k)]
-                sweep(layout, A.LU_U, k, sizes, R[S], hi, accumulate=True)
+                jobs.append((sizes, R[S], hi, True))
                 newR[S] = hi
+            batch(layout, A.LU_U, k, jobs)
             R = newR
         if layout == "V":
             R = self._switch_all(R, "V", "X")

@@ -104,6 +104,13 @@ int amdg_op_combine(amdg_ctx *ctx, int op_a, double alpha, int op_b, double beta
 int amdg_sweep1d(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from,
                  const double *dev_src, double *dev_dst, int n_comp, double coef, int accumulate);
 
+/* the same sweep for n_job (src, dst) pairs in one launch: the jobs share operator, relation, L/U part, dimension and the edges of
+ * the dims after t; sizes_from[n_job][dim], dev_src/dev_dst[n_job], coef[n_job], accumulate[n_job].  This is how the sweeps of one
+ * level of the shared-prefix schedule are issued (source/FastMultiplyLU.cpp:614-664 lists them one by one); the fibre-partitioned
+ * multi-GPU path drives its local phases through it. */
+int amdg_sweep1d_batch(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, const double *const *dev_src,
+                       double *const *dev_dst, const double *coef, const int *accumulate, int n_job, int n_comp);
+
 /* ---- sum over all orderings of the chain of sweeps: FastRHS::transform_fucoe_to_rhs (source/FastMultiplyLU.cpp:4-16),
  * FastInterpolation::transform_ucoealpt_to_upintp (:740-819), FastInitial::transform_ucoeintp_to_ucoealpt (:1418-1445).
  * ops[dim], rels[dim]; src blocks edge_from^dim, dst blocks edge_to^dim; dst = coef*(...) (+ dst if accumulate). ---- */
