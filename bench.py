@@ -41,9 +41,9 @@ WORKLOADS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one single-job sweep launch (ncu --set full, profiles/r01_sweep_mma_ncu.md); the
-# written half of the compulsory bytes is still in L2 when the kernel ends, so only the reads show up
-TRAFFIC_NCU = 22.87e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one single-job full sweep launch (ncu --set full, profiles/r01_sweep_tc_ncu.md,
+# launch 1); the written half of the compulsory bytes is still in L2 when the kernel ends, so only the reads show up
+TRAFFIC_NCU = 23.1e6
 
 
 def peaks():

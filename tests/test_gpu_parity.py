@@ -402,3 +402,66 @@ def test_all_kernel_variants(name, kernel):
         ua = c.to_alpt(uc)
         assert rel(c.to_host(ua), d["rt.ucoe_alpt"][:, 0, :]) < TOL
     c.close()
+
+
+def _full_size_context(A, kernel):
+    """cfg2 at BASELINE.json's size (d=4, k=3, m=3, NMAX=8) with the shipped operator tables"""
+    dim, nmax = 4, 8
+    lev, sup = A.sparse_grid(dim, nmax)
+    ctx = A.Context(dim, nmax, 3, 3, device=0)
+    ctx.set_kernel(kernel)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.grid_set(lev, sup)
+    tb = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "adaptive-multiresolution-dg_b200", "data", "tables_k3_m3_n8.npz"))
+    return ctx, lev, tb
+
+
+def test_full_size_roundtrip_identity_and_kernel_agreement():
+    """cfg2 at full size (10 496 elements, 2.69 M DoF): interpolation -> hierarchisation -> projection reproduces the input
+    (Lagrange interpolation with m >= k is exact, as in the reference's fixture), and the lean tensor-core kernel, the
+    whole-fibre tensor-core kernel and the gather kernel agree on every phase"""
+    import importlib
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    outs = {}
+    for kernel in (0, 4, 1):
+        ctx, lev, tb = _full_size_context(A, kernel)
+        dim, ne = 4, lev.shape[0]
+        rng = np.random.default_rng(20240901)
+        scale = np.ldexp(1.0, -lev.sum(axis=1).astype(np.int64))
+        u = torch.from_numpy(rng.uniform(-1, 1, size=(ne, 256)) * scale[:, None]).cuda()
+        op_pt, op_uv, op_h = ctx.op_register_compact(tb["pt"]), ctx.op_register_compact(tb["lagr.u_v"]), ctx.op_register_compact(tb["hier"], hier=True)
+        up, uc, ua = torch.zeros_like(u), torch.zeros_like(u), torch.zeros_like(u)
+        ctx.apply_tensor([op_pt] * dim, [0] * dim, u, up)
+        ctx.hierarchize(op_h, up, uc)
+        ctx.apply_tensor([op_uv] * dim, [0] * dim, uc, ua)
+        ctx.sync()
+        assert rel(ua.cpu().numpy(), u.cpu().numpy()) < 1e-10
+        outs[kernel] = (up.cpu().numpy(), uc.cpu().numpy(), ua.cpu().numpy())
+        ctx.close()
+    for kernel in (4, 1):
+        for x, y in zip(outs[0], outs[kernel]):
+            assert rel(x, y) < TOL
+
+
+def test_sweep_batch_equals_single_sweeps():
+    """amdg_sweep1d_batch: one launch for several (src, dst) pairs gives exactly what the single sweeps give (bitwise), for every
+    L/U/full part, with coef and accumulate, on the d=6 fixture grid"""
+    d = load_golden("cfg5_vlasov_d6_k1_n2")
+    c = DevCase(d)
+    A = c.amdg
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for t in (0, 3, 5):
+        for lu in (A.LU_L, A.LU_U, A.LU_FULL):
+            sizes = [[c.a] * c.dim, [c.b if q < t else c.a for q in range(c.dim)]]
+            srcs = [torch.rand(c.ne, int(np.prod(s)), dtype=torch.float64, device="cuda", generator=g) for s in sizes]
+            outs = [s[:t] + [c.b] + s[t + 1:] for s in sizes]
+            base = [torch.rand(c.ne, int(np.prod(s)), dtype=torch.float64, device="cuda", generator=g) for s in outs]
+            one = [b.clone() for b in base]
+            many = [b.clone() for b in base]
+            for i in range(2):
+                c.ctx.sweep1d(c.op_pt, A.REL_VOL, lu, t, sizes[i], srcs[i], one[i], coef=0.5 + i, accumulate=bool(i))
+            c.ctx.sweep1d_batch(c.op_pt, A.REL_VOL, lu, t, sizes, srcs, many, coefs=[0.5, 1.5], accumulates=[0, 1])
+            c.ctx.sync()
+            for i in range(2):
+                assert torch.equal(one[i], many[i])
+    c.close()
