@@ -2,6 +2,7 @@
 Tolerance 1e-12 relative L2 per phase / RK stage, 1e-10 after a full run (BASELINE.json north_star); index work
 is covered bit-exactly by tests/test_capi_tables.py."""
 import importlib
+import os
 
 import numpy as np
 import pytest
