@@ -37,6 +37,11 @@ struct DevDim
     int64_t * fibre_ptr = nullptr;
 };
 
+// plan of one fibre shape for the lean tensor-core kernel (get_mma_lean): pieces of its tile program with their source rows and
+// column rectangles; depends on the shape and the block shape only, so it is kept across grid changes
+struct LeanRect { int o0, no, i0, ni, pk; };
+struct LeanPiece { ShapeProg prog; std::vector<int> src; std::vector<LeanRect> rects; bool stage_a = false, ksplit = false, whole = false; long long hash = 0; };
+
 struct amdg_ctx
 {
     int dim = 0, nmax = 0, edge_alpt = 0, edge_intp = 0, device = -1;
@@ -74,16 +79,17 @@ struct amdg_ctx
         MmaItem * d_items = nullptr; int * d_elem_pool = nullptr; int * d_prog_ints = nullptr;
         int n_item = 0, smem_doubles = 0; bool ok = false;
         std::vector<int> prog_shape;                          // shape id of every program piece of this list
-        std::vector<int> prog_piece;                          // piece*1024 + number of pieces
+        std::vector<long long> prog_piece;                    // content hash of the piece (entries and pairs): key of its operator fragments
         std::vector<ShapeProg> progs;                         // host copies of the pieces (to build operator values)
         std::map<int, const double **> a_tab;                 // per operator: device table of A pointers
     };
     std::map<std::tuple<int, int, int, int, int, int>, MmaList> mmas;       // key: (dim t, outer, kf, kt, rel*4+lu, parallel class)
-    std::map<std::tuple<int, int, int, int>, double *> mma_A;               // (op, shape, rel*4+lu, piece*1024+npieces) -> device operator values
+    std::map<std::tuple<int, int, int, long long>, double *> mma_A;         // (op, shape, rel*4+lu, piece hash) -> device operator values
     int mma_cap_doubles = 9 * 1024, mma_item_target = 148 * 8, mma_ent_target = 448, mma_stage_a_max = 64;
     bool tc_force_stage = true; int tc_coarse_ent = 256; int64_t tc_min_doubles = 131072;
     int tc_cap_doubles = 4608, tc_item_target = 148 * 8, tc_ent_target = 48, tc_stage_a_max = 48;      // lean form (kernels_tc.cu)
     bool lean() const { return kernel_variant == 0 || kernel_variant == 5; }
+    std::map<std::tuple<int, int, int, int, int, int>, std::vector<LeanPiece>> lean_plans;   // (shape, kf, kt, rel*4+lu, outer, inner)
     int n_sm = 148;
     long long * dbg = nullptr;
     // metadata arena: index tables, work lists and operator blocks live in one allocation that is given an L2
@@ -115,9 +121,7 @@ static void free_dev_grid(amdg_ctx * c)
         meta_free(c, L.d_items); meta_free(c, L.d_elem_pool); meta_free(c, L.d_prog_ints);
         for (auto & at : L.a_tab) meta_free(c, (void *)at.second);
     }
-    c->mmas.clear();
-    for (auto & kv : c->mma_A) cudaFree(kv.second);
-    c->mma_A.clear();
+    c->mmas.clear();                     // (operator fragments, mma_A, are per shape and survive a grid change)
     for (auto & kv : c->pipes)
     {
         amdg_ctx::PipeList & L = kv.second;
@@ -253,6 +257,8 @@ int amdg_ctx_destroy(amdg_ctx * c)
         cudaSetDevice(c->device);
         cudaDeviceSynchronize();
         free_dev_grid(c);
+        for (auto & kv : c->mma_A) cudaFree(kv.second);
+        c->mma_A.clear();
         for (auto & op : c->ops) meta_free(c, op->d_blocks);
         cudaFree(c->arena);
         for (double * p : c->scratch) cudaFree(p);
@@ -694,6 +700,19 @@ static const amdg_ctx::ItemList & get_items(amdg_ctx * c, int t, int W, int kf, 
 // ---- tensor-core kernel: work list + tile programs ---------------------------------------------------------------
 // shared-memory row of one staged element (kernels.cu, sweep_mma_kernel): X[k][col] with a column pitch = 4 (mod 8), or, for a
 // sweep along the last dimension (inner == 1), the element's own [col][k] order
+// operator fragments are cached per (operator, shape, relation/part, piece): the piece is identified by its content, because the
+// same shape is cut differently for different block shapes (the rows that fit in shared memory depend on outer/inner)
+static long long piece_hash(const ShapeProg & P)
+{
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](long long v) { h ^= (unsigned long long)v; h *= 1099511628211ull; };
+    mix(P.m); mix(P.n_rt); mix(P.tg); mix(P.nkp);
+    for (int v : P.rt_ptr) mix(v);
+    for (int v : P.ent_src) mix(v % P.nkp);
+    for (int v : P.ent_pair) mix(v);
+    return (long long)(h >> 1);
+}
+
 static int mma_colpitch(int ncols) { int pk = ncols; while ((pk & 7) != 4) ++pk; return pk; }
 static int64_t mma_rowsize(int kf, int no, int ni, int inner) { return inner == 1 ? (int64_t)no * ni * kf : (int64_t)kf * mma_colpitch(no * ni); }
 
@@ -793,7 +812,7 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
                     smem_need = std::max(smem_need, (int)((nf * m * mma_rowsize(kf, r.no, r.ni, inner) + 1) & ~(int64_t)1) + (n_ints + ((nf * m + 1) & ~1) + 1) / 2 + 2 + a_doubles + slack);
                 }
         }
-        for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(q * 4096 + np * 2); L.progs.push_back(std::move(pieces[q])); }
+        for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(piece_hash(pieces[q])); L.progs.push_back(std::move(pieces[q])); }
     }
     if (ok && ent_target > 32 && (int64_t)items.size() * (1 << pcls) < 3 * (int64_t)c->n_sm) { ent_target = std::max(32, ent_target / 2); goto retry_finer; }
     if (ok && !items.empty())
@@ -836,8 +855,8 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
     const int64_t total = c->grid.n * row_full;
     const int64_t target = std::max<int64_t>(1, total / std::max(1, c->tc_item_target >> pcls));
     const int slack = 32 * kf;
-    struct Rect { int o0, no, i0, ni, pk; };
-    struct Piece { ShapeProg prog; std::vector<int> src; std::vector<Rect> rects; bool stage_a = false, ksplit = false; int nfib_max = 1; };
+    typedef LeanRect Rect;
+    typedef LeanPiece Piece;
     auto ints_doubles = [&](const ShapeProg & P, int nf, int m) { return (2 * P.n_rt + 1 + (int)P.n_ent() + ((nf * m + 1) & ~1) + 1) / 2 + 2; };
     // a piece over the row tiles `rts` of S: piece-local source rows, remapped entries
     auto make_piece = [&](const ShapeProg & S, const std::vector<int> & rts, Piece & P)
@@ -869,8 +888,12 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
     {
         const int shape = kv.first; const std::vector<int> & fibres = kv.second;
         const std::vector<int> & ords = c->shapes.ords[shape];
+        const int m = (int)ords.size();
+        auto plan_key = std::make_tuple(shape, kf, kt, rel * 4 + lu, outer, inner);
+        auto plan_it = c->lean_plans.find(plan_key);
+        if (plan_it == c->lean_plans.end())
+        {
         ShapeProg SP; build_shape_prog(c->pairs, ords, rel, lu, kf, kt, SP);
-        const int m = SP.m;
         std::vector<Piece> pieces;
         const bool whole_fits = (int64_t)m * row_full + ints_doubles(SP, 1, m) + slack + (SP.n_ent() <= stage_a_max ? SP.n_ent() * 32 : 0) <= cap_doubles;
         if (whole_fits && (SP.n_ent() <= stage_a_max || (SP.n_ent() <= 2 * (int64_t)ent_target && !c->tc_force_stage)))
@@ -879,11 +902,8 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
             Piece & P = pieces.back();
             std::vector<int> all(SP.n_rt); for (int i = 0; i < SP.n_rt; ++i) all[i] = i;
             make_piece(SP, all, P);
-            P.stage_a = SP.n_ent() <= stage_a_max;
+            P.stage_a = SP.n_ent() <= stage_a_max; P.whole = true;
             P.rects.push_back({ 0, outer, 0, inner, mma_colpitch(W) });
-            const int a_doubles = P.stage_a ? (int)SP.n_ent() * 32 : 0;
-            const int64_t room = std::min<int64_t>(cap_doubles - slack - a_doubles - (2 * SP.n_rt + 1 + (int)SP.n_ent()) / 2 - 4, target);
-            P.nfib_max = (int)std::max<int64_t>(1, room / ((int64_t)m * row_full + (m + 1) / 2 + 1));
         }
         else
         {
@@ -956,6 +976,10 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
                 if (!ok) break;
             }
         }
+        for (Piece & P : pieces) P.hash = piece_hash(P.prog);
+        plan_it = c->lean_plans.emplace(plan_key, std::move(pieces)).first;
+        }
+        const std::vector<Piece> & pieces = plan_it->second;
         // emit: programs, element rows (whole fibres for the targets, staged rows per piece), items
         const int np = (int)pieces.size();
         const int prog0 = (int)L.progs.size();
@@ -973,9 +997,15 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
             const Piece & P = pieces[q]; const ShapeProg & Q = P.prog;
             const int nsrc = (int)P.src.size();
             const int a_doubles = P.stage_a ? (int)Q.n_ent() * 32 : 0;
-            for (size_t f0 = 0; f0 < fibres.size(); f0 += P.nfib_max)
+            int nfib_max = 1;                                            // whole-fibre pieces take several fibres per item
+            if (P.whole)
             {
-                const int nf = (int)std::min<size_t>(P.nfib_max, fibres.size() - f0);
+                const int64_t room = std::min<int64_t>(cap_doubles - slack - a_doubles - (2 * Q.n_rt + 1 + (int)Q.n_ent()) / 2 - 4, target);
+                nfib_max = (int)std::max<int64_t>(1, room / ((int64_t)m * row_full + (m + 1) / 2 + 1));
+            }
+            for (size_t f0 = 0; f0 < fibres.size(); f0 += nfib_max)
+            {
+                const int nf = (int)std::min<size_t>(nfib_max, fibres.size() - f0);
                 const int eofs = (int)elem_pool.size();
                 for (int b = 0; b < nf; ++b) for (int f = 0; f < m; ++f) elem_pool.push_back(H.slot_elem[fibres[f0 + b] + f]);
                 int sofs = eofs;
@@ -1001,7 +1031,7 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
                 }
             }
         }
-        for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(q * 4096 + np * 2 + 1); L.progs.push_back(std::move(pieces[q].prog)); }
+        for (int q = 0; q < np; ++q) { L.prog_shape.push_back(shape); L.prog_piece.push_back(pieces[q].hash); L.progs.push_back(pieces[q].prog); }
     }
     if (ok && smem_need > tc_smem_capacity_doubles()) ok = false;
     if (ok && !items.empty())

@@ -30,9 +30,10 @@ struct ShapeTable
     std::vector<std::vector<int>> fibre_shape;       // [dim][fibre]
     std::vector<std::map<int, std::vector<int>>> shape_fibres;   // [dim][shape] -> slot0 list
 
+    // shape ids are stable for the lifetime of the table: a grid change (DGAdapt refine / coarsen) only appends the shapes it
+    // introduces, so that plans and operator fragments cached per shape id survive it
     void build(const Grid & G)
     {
-        id_of.clear(); ords.clear();
         fibre_shape.assign(G.dim, std::vector<int>()); shape_fibres.assign(G.dim, std::map<int, std::vector<int>>());
         for (int t = 0; t < G.dim; ++t)
         {
