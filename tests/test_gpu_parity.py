@@ -466,3 +466,70 @@ def test_sweep_batch_equals_single_sweeps():
             for i in range(2):
                 assert torch.equal(one[i], many[i])
     c.close()
+
+
+def _random_adaptive_grid(A, dim, nmax, seed, keep=0.55):
+    """a random downward-closed subset of the sparse grid: leaves (elements without children in any dimension) are removed at
+    random until about `keep` of the elements are left -- the kind of grid DGAdapt::coarsen produces"""
+    lev, sup = A.sparse_grid(dim, nmax)
+    elems = {tuple(l) + tuple(s) for l, s in zip(lev.tolist(), sup.tolist())}
+    rng = np.random.default_rng(seed)
+
+    def children(e):
+        out = []
+        for d in range(dim):
+            n, j = e[d], e[dim + d]
+            if n >= nmax:
+                continue
+            for cj in ([1] if n == 0 else [2 * j - 1, 2 * j + 1]):
+                c = list(e); c[d] = n + 1; c[dim + d] = cj
+                out.append(tuple(c))
+        return out
+    target = int(keep * len(elems))
+    while len(elems) > target:
+        leaves = [e for e in elems if sum(e[:dim]) > 0 and not any(c in elems for c in children(e))]
+        rng.shuffle(leaves)
+        for e in leaves[:max(1, len(leaves) // 3)]:
+            elems.discard(e)
+    arr = np.array(sorted(elems), dtype=np.int32)
+    return np.ascontiguousarray(arr[:, :dim]), np.ascontiguousarray(arr[:, dim:])
+
+
+@pytest.mark.parametrize("dim,nmax,a,b,seed", [(2, 7, 3, 4, 1), (3, 6, 2, 3, 2), (3, 5, 4, 4, 3), (4, 5, 3, 2, 4)])
+def test_random_adaptive_grids_lean_vs_gather(dim, nmax, a, b, seed):
+    """irregular fibre shapes that no fixture has: on random downward-closed grids the lean tensor-core kernel (subtree pieces,
+    streamed coarse targets, several fibres per item) agrees with the gather kernel -- an independent implementation that walks the
+    neighbour tables -- for every dimension, L/U/full part, both relations, with coef and accumulate"""
+    import importlib
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    lev, sup = _random_adaptive_grid(A, dim, nmax, seed)
+    ne = lev.shape[0]
+    rng = np.random.default_rng(seed)
+    res = {}
+    u = torch.from_numpy(rng.uniform(-1, 1, size=(ne, a ** dim))).cuda()
+    base = torch.from_numpy(rng.uniform(-1, 1, size=(ne, a ** (dim - 1) * b))).cuda()
+    blocks = None
+    for kernel in (5, 1):
+        ctx = A.Context(dim, nmax, max(a, b) - 1, max(a, b) - 1, device=0)
+        ctx.set_kernel(kernel)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.grid_set(lev, sup)
+        if blocks is None:
+            src_, tgt_, vol_ = ctx.pairs()
+            blocks = np.random.default_rng(100 + seed).standard_normal((len(src_), a, b))
+        op = ctx.op_register_compact(blocks)
+        outs = []
+        for t in range(dim):
+            sizes = [b if q < t else a for q in range(dim)]
+            x = u if t == 0 else torch.from_numpy(np.random.default_rng(7 + t).uniform(-1, 1, size=(ne, int(np.prod(sizes))))).cuda()
+            for relk in (A.REL_VOL, A.REL_FLX):
+                for lu in (A.LU_L, A.LU_U, A.LU_FULL):
+                    osz = sizes[:t] + [b] + sizes[t + 1:]
+                    y = torch.from_numpy(np.random.default_rng(11).uniform(-1, 1, size=(ne, int(np.prod(osz))))).cuda()
+                    ctx.sweep1d(op, relk, lu, t, sizes, x, y, coef=0.75, accumulate=(lu == A.LU_U))
+                    outs.append(y)
+        ctx.sync()
+        res[kernel] = [o.cpu().numpy() for o in outs]
+        ctx.close()
+    for x, y in zip(res[5], res[1]):
+        assert rel(x, y) < TOL
