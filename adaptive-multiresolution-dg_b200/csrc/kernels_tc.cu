@@ -234,6 +234,31 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
                 tc_bulk(Xs + row * rowsize + (INNER1 ? 0 : k * pk + o_l * it.ni), src + (int64_t)e * s_from + col_base + (int64_t)r * inner, run_bytes, bar);
             }
         }
+        else if (!INNER1 && !vec && ncols >= 32)
+        {
+            // odd block edges (no 16-byte alignment): 8-byte copies, one column (o, i) per lane and pass with its KF source indices in
+            // a row -- two multiplications per column instead of a run decode per copy
+            for (int rbase = 0; warp + NW * rbase < nrow; rbase += 32)
+            {
+                const int myrow = warp + NW * (rbase + lane);
+                const int e_lane = myrow < nrow ? __ldg(ep + myrow) : 0;
+                const int nr = min(32, (nrow - warp - NW * rbase + NW - 1) / NW);
+                for (int r = 0; r < nr; ++r)
+                {
+                    const int e = __shfl_sync(0xffffffffu, e_lane, r);
+                    const double * __restrict__ g = src + (int64_t)e * s_from + col_base;
+                    double * xr = Xs + (warp + NW * (rbase + r)) * rowsize;
+                    for (int col = lane; col < ncols; col += 32)
+                    {
+                        const int o_l = it.ni == 1 ? col : (int)__umulhi((unsigned)col, it.ni_magic), i_l = col - o_l * it.ni;
+                        const double * __restrict__ gs = g + o_l * KF * inner + i_l;
+                        double * xd = xr + col;
+#pragma unroll
+                        for (int k = 0; k < KF; ++k) tc_cp8(xd + k * pk, gs + k * inner);
+                    }
+                }
+            }
+        }
         else if (per_row >= 32)
         {
             // rows of this warp: warp + NW*r; lane r fetches the element row of row r, handed out by shuffles; the copy pattern
@@ -471,18 +496,37 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
             }
             else if (!FAST)
             {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
+                // general path.  All old values of an accumulating sweep are fetched before the first store (the stores may alias the
+                // loads for the compiler, which would serialise one L2 round trip per tile); aligned pairs go as 16-byte accesses
+                const bool accu = J.accumulate != 0;
+                if (vecst)
                 {
-                    if (!((vmask >> j) & 1u)) continue;
-                    double v0 = coef * acc[j][0];
-                    if (J.accumulate) v0 += y[off[j]];
-                    y[off[j]] = v0;
-                    if ((vmask >> j) & 16u)
+                    double2 old[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
                     {
-                        double v1 = coef * acc[j][1];
-                        if (J.accumulate) v1 += y[off[j] + second[j]];
-                        y[off[j] + second[j]] = v1;
+                        old[j] = make_double2(0.0, 0.0);
+                        if (accu && ((vmask >> j) & 1u)) old[j] = *reinterpret_cast<const double2 *>(y + off[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((vmask >> j) & 1u) *reinterpret_cast<double2 *>(y + off[j]) = make_double2(coef * acc[j][0] + old[j].x, coef * acc[j][1] + old[j].y);
+                }
+                else
+                {
+                    double old[4][2];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        old[j][0] = 0.0; old[j][1] = 0.0;
+                        if (accu && ((vmask >> j) & 1u)) old[j][0] = y[off[j]];
+                        if (accu && ((vmask >> j) & 16u)) old[j][1] = y[off[j] + second[j]];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        if ((vmask >> j) & 1u) y[off[j]] = coef * acc[j][0] + old[j][0];
+                        if ((vmask >> j) & 16u) y[off[j] + second[j]] = coef * acc[j][1] + old[j][1];
                     }
                 }
             }
