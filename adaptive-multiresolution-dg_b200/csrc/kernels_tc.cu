@@ -470,6 +470,19 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
         const int rt = s_rt_order[ri];                               // row tile id (targets rt*TG ..)
         const int p0 = s_rt_ptr[ri], p1 = s_rt_ptr[ri + 1];           // entries are stored in position order
         const double * xb = xcol + b * fib_stride;
+        const int e_loc = rt * TG + cg_;
+        const bool tgt_on = e_loc < m && row_on;
+        double * y = dst + (int64_t)(tgt_on ? s_elem[b * m + e_loc] : 0) * s_to + q_off;
+        if (!FAST && J.accumulate && tgt_on)
+        {
+            // an accumulating sweep reads its destination: start those lines towards L1 now, the MMA loop hides the trip
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                if ((vmask >> j) & 1u) asm volatile("prefetch.global.L1 [%0];" :: "l"(y + off[j]));
+                if (!vecst && ((vmask >> j) & 16u)) asm volatile("prefetch.global.L1 [%0];" :: "l"(y + off[j] + second[j]));
+            }
+        }
         double acc[4][2];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
@@ -483,11 +496,8 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
         else if (it.stage_a) tc_rows<KF, NKP, SC, true>(acc, A, s_ent, p0, p1, xb, rowsize, sk, kl, lane, nt);
         else tc_rows<KF, NKP, SC, false>(acc, A, s_ent, p0, p1, xb, rowsize, sk, kl, lane, nt);
         // epilogue: C fragment row rr = (target cg_, output cq), columns cc2, cc2+1 of every tile
-        const int e_loc = rt * TG + cg_;
-        if (e_loc < m && row_on)
+        if (tgt_on)
         {
-            const int e = s_elem[b * m + e_loc];
-            double * y = dst + (int64_t)e * s_to + q_off;
             if (FAST || fast_store)
             {
 #pragma unroll
