@@ -13,6 +13,7 @@
 // Numerics are identical to sweep_mma_kernel (same fragment order, same summation order per output).
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
@@ -159,6 +160,9 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
     constexpr int NW = TC_THREADS / 32;
 #define TC_STAMP(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[(int64_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
     TC_STAMP(0);
+    // programmatic dependent launch: the next kernel of the stream may start its CTAs as soon as every CTA of this grid has got
+    // here (they then run their own prologue and park at griddepcontrol.wait below until this grid has completed)
+    asm volatile("griddepcontrol.launch_dependents;");
     const MmaItem it = a.items[blockIdx.x];
     if (a.dbg && threadIdx.x == 0)
     {
@@ -214,6 +218,9 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
             so = r * inner + w;
             dof = INNER1 ? w : k * pk + o_l * it.ni + w;
         };
+        // everything above reads only the work lists (written once by the host); from here on the coefficient arrays of earlier
+        // kernels are touched: wait for them (returns at once when the launch carries no programmatic dependency)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         if (use_bulk)
         {
             const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
@@ -556,9 +563,19 @@ static cudaError_t launch_tc_t(const MmaArgs & a, int smem_doubles, cudaStream_t
         configured = true;
     }
     if (smem_doubles > TC_SMEM_DOUBLES) return cudaErrorInvalidValue;
-    dim3 grid((unsigned)a.n_item, (unsigned)a.n_job, (unsigned)a.n_comp);
-    sweep_tc_kernel<KF, KT, MODE><<<grid, TC_THREADS, (size_t)smem_doubles * sizeof(double), st>>>(a);
-    return cudaGetLastError();
+    // launched with programmatic stream serialization: the head of this grid (item headers, element rows, index arithmetic) overlaps
+    // the tail of the previous kernel; the kernel orders its data accesses itself (griddepcontrol.wait)
+    static const bool pdl = !(std::getenv("AMDG_TC_PDL") && std::atoi(std::getenv("AMDG_TC_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a.n_item, (unsigned)a.n_job, (unsigned)a.n_comp);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem_doubles * sizeof(double);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, sweep_tc_kernel<KF, KT, MODE>, a);
 }
 
 template <int KF, int KT>
