@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 namespace amdg {
@@ -164,9 +165,10 @@ struct Grid
             hash[e] = hash_key(dim, &level[e * dim], &suppt[e * dim]);
         }
         dims.assign(dim, DimTables());
-        std::vector<int> perm(n), pos_of_ord(P.T, -1);
-        for (int t = 0; t < dim; ++t)
+        // the tables of the dimensions are independent: one host thread per dimension
+        auto build_dim = [&](int t) -> int
         {
+            std::vector<int> perm(n), pos_of_ord(P.T, -1);
             DimTables & D = dims[t];
             std::iota(perm.begin(), perm.end(), 0);
             const int * o = ord1d.data();
@@ -186,7 +188,7 @@ struct Grid
             for (int64_t s = 0; s < n; ++s)
             {
                 if (s > 0 && !same_fibre(perm[s - 1], perm[s])) D.fibre_ptr.push_back(s);
-                else if (s > 0 && o[(int64_t)perm[s - 1] * d + t] == o[(int64_t)perm[s] * d + t]) return -1;   // duplicate element
+                else if (s > 0 && o[(int64_t)perm[s - 1] * d + t] == o[(int64_t)perm[s] * d + t]) return -1;   // duplicate element (of this dimension's pass)
                 D.elem_slot[perm[s]] = (int)s;
                 D.slot_fibre[s] = (int)D.fibre_ptr.size() - 1;
             }
@@ -231,7 +233,17 @@ struct Grid
                 }
                 for (int64_t s = s0; s < s1; ++s) pos_of_ord[o[(int64_t)perm[s] * d + t]] = -1;
             }
+                    return 0;
+        };
+        std::vector<int> rc(dim, 0);
+        if (dim > 1 && n >= 8192)
+        {
+            std::vector<std::thread> th;
+            for (int t = 0; t < dim; ++t) th.emplace_back([&, t]() { rc[t] = build_dim(t); });
+            for (auto & x : th) x.join();
         }
+        else for (int t = 0; t < dim; ++t) rc[t] = build_dim(t);
+        for (int t = 0; t < dim; ++t) if (rc[t] != 0) return -1;
         return 0;
     }
 };
