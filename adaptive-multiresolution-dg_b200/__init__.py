@@ -42,6 +42,7 @@ SYMBOLS = {
     "amdg_ctx_set_kernel": (_i, [_p, _i]),
     "amdg_ctx_launch_count": (_i64, [_p]),
     "amdg_ctx_set_debug_buffer": (_i, [_p, _p]),
+    "amdg_lean_plan_check": (_i, [_p, _i, _ip, _i, _i, _i, _i, _lp]),
     "amdg_hash_key": (_i, [_i, _ip, _ip]),
     "amdg_order_elem": (_i, [_i, _i]),
     "amdg_sparse_grid": (_i64, [_i, _i, _i, _ip, _ip]),
@@ -236,6 +237,13 @@ class Context:
     def sweep1d(self, op, rel, lu, t, sizes_from, src, dst, n_comp=1, coef=1.0, accumulate=False):
         s, sp = _ints(sizes_from)
         _check(lib.amdg_sweep1d(self._h, op, rel, lu, t, sp, _ptr(src), _ptr(dst), n_comp, coef, int(accumulate)))
+
+    def lean_plan_check(self, t, sizes_from, kf, kt, rel, lu):
+        """host-only self check of the default sweep kernel's work plans (amdg_lean_plan_check); returns a dict of counts"""
+        s, sp = _ints(sizes_from)
+        out = np.zeros(6, dtype=np.int64)
+        _check(lib.amdg_lean_plan_check(self._h, t, sp, kf, kt, rel, lu, out.ctypes.data_as(_lp)))
+        return dict(zip(("shapes", "pieces", "coarse_pieces", "entries", "max_staged_rows", "max_smem_doubles"), out.tolist()))
 
     def sweep1d_batch(self, op, rel, lu, t, sizes_from, srcs, dsts, coefs=None, accumulates=None, n_comp=1):
         """one launch for several (src, dst) pairs that share operator, relation, L/U part and dimension (amdg_sweep1d_batch)"""

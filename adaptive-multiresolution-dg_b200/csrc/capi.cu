@@ -838,25 +838,20 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
 // the 1D tree (left end of the support, then level), and consecutive row tiles whose union of source rows still fits in
 // shared memory with a 32-column rectangle form a piece -- a subtree plus its chain of ancestors.  Only the few row tiles of
 // coarse targets, which read most of the fibre, fall back to narrow rectangles over the union of their sources.
-static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int par, int lu)
+// Plan of one fibre shape for the lean tensor-core kernel: host only (no device needed), cached per (shape, block shape).
+static const std::vector<LeanPiece> & lean_plan(amdg_ctx * c, int shape, int kf, int kt, int rel, int lu, int outer, int inner)
 {
-    int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
-    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls + 16);
-    auto it = c->mmas.find(key);
-    if (it != c->mmas.end()) return it->second;
-    amdg_ctx::MmaList L;
-    const std::map<int, std::vector<int>> & sf = c->shapes.shape_fibres[t];
-    std::vector<MmaItem> items; std::vector<double> cost; std::vector<int> elem_pool, prog_ints;
-    const DimTables & H = c->grid.dims[t];
-    bool ok = true; int smem_need = 0;
+    auto plan_key = std::make_tuple(shape, kf, kt, rel * 4 + lu, outer, inner);
+    auto plan_it = c->lean_plans.find(plan_key);
+    if (plan_it != c->lean_plans.end()) return plan_it->second;
+    typedef LeanRect Rect;
+    typedef LeanPiece Piece;
+    const std::vector<int> & ords = c->shapes.ords[shape];
+    const int m = (int)ords.size();
     const int cap_doubles = c->tc_cap_doubles, ent_target = c->tc_ent_target, stage_a_max = c->tc_stage_a_max;
     const int W = outer * inner;
     const int64_t row_full = mma_rowsize(kf, outer, inner, inner);
-    const int64_t total = c->grid.n * row_full;
-    const int64_t target = std::max<int64_t>(1, total / std::max(1, c->tc_item_target >> pcls));
     const int slack = 32 * kf;
-    typedef LeanRect Rect;
-    typedef LeanPiece Piece;
     auto ints_doubles = [&](const ShapeProg & P, int nf, int m) { return (2 * P.n_rt + 1 + (int)P.n_ent() + ((nf * m + 1) & ~1) + 1) / 2 + 2; };
     // a piece over the row tiles `rts` of S: piece-local source rows, remapped entries
     auto make_piece = [&](const ShapeProg & S, const std::vector<int> & rts, Piece & P)
@@ -884,15 +879,6 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
             Q.rt_ptr.push_back((int)Q.ent_src.size());
         }
     };
-    for (auto & kv : sf)
-    {
-        const int shape = kv.first; const std::vector<int> & fibres = kv.second;
-        const std::vector<int> & ords = c->shapes.ords[shape];
-        const int m = (int)ords.size();
-        auto plan_key = std::make_tuple(shape, kf, kt, rel * 4 + lu, outer, inner);
-        auto plan_it = c->lean_plans.find(plan_key);
-        if (plan_it == c->lean_plans.end())
-        {
         ShapeProg SP; build_shape_prog(c->pairs, ords, rel, lu, kf, kt, SP);
         std::vector<Piece> pieces;
         const bool whole_fits = (int64_t)m * row_full + ints_doubles(SP, 1, m) + slack + (SP.n_ent() <= stage_a_max ? SP.n_ent() * 32 : 0) <= cap_doubles;
@@ -973,13 +959,35 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
                     for (size_t p = 0; p < P.prog.ent_src.size(); ++p) { const int e = P.prog.ent_src[p]; P.prog.ent_src[p] = P.src[e / SP.nkp] * SP.nkp + e % SP.nkp; }
                     P.src.clear(); P.ksplit = true; P.stage_a = false; P.rects = narrow;
                 }
-                if (!ok) break;
             }
         }
         for (Piece & P : pieces) P.hash = piece_hash(P.prog);
-        plan_it = c->lean_plans.emplace(plan_key, std::move(pieces)).first;
-        }
-        const std::vector<Piece> & pieces = plan_it->second;
+    return c->lean_plans.emplace(plan_key, std::move(pieces)).first->second;
+}
+
+static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int par, int lu)
+{
+    int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
+    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls + 16);
+    auto it = c->mmas.find(key);
+    if (it != c->mmas.end()) return it->second;
+    amdg_ctx::MmaList L;
+    const std::map<int, std::vector<int>> & sf = c->shapes.shape_fibres[t];
+    std::vector<MmaItem> items; std::vector<double> cost; std::vector<int> elem_pool, prog_ints;
+    const DimTables & H = c->grid.dims[t];
+    bool ok = true; int smem_need = 0;
+    const int cap_doubles = c->tc_cap_doubles;
+    const int64_t row_full = mma_rowsize(kf, outer, inner, inner);
+    const int64_t total = c->grid.n * row_full;
+    const int64_t target = std::max<int64_t>(1, total / std::max(1, c->tc_item_target >> pcls));
+    const int slack = 32 * kf;
+    typedef LeanRect Rect;
+    typedef LeanPiece Piece;
+    for (auto & kv : sf)
+    {
+        const int shape = kv.first; const std::vector<int> & fibres = kv.second;
+        const int m = (int)c->shapes.ords[shape].size();
+        const std::vector<Piece> & pieces = lean_plan(c, shape, kf, kt, rel, lu, outer, inner);
         // emit: programs, element rows (whole fibres for the targets, staged rows per piece), items
         const int np = (int)pieces.size();
         const int prog0 = (int)L.progs.size();
@@ -1050,6 +1058,76 @@ static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inne
                     t, outer, inner, kf, kt, rel, lu, par, (int)sorted.size(), (int)L.progs.size(), L.smem_doubles);
     }
     return c->mmas.emplace(key, std::move(L)).first->second;
+}
+
+// Diagnostic (host only, works without a device): builds the lean plans of every fibre shape of dimension t for a sweep with the
+// given block edges and checks their invariants -- every row tile of a shape's tile program lies in exactly one piece with all its
+// entries, staged pieces index their own source rows and fit the shared-memory capacity with at least one rectangle, coarse pieces
+// keep fibre-local sources and at most 8 columns, the rectangles of a piece tile the column plane exactly once.
+// out[0..5] = shapes, pieces, coarse (streamed) pieces, entries, largest staged row count, largest shared-memory need (doubles).
+int amdg_lean_plan_check(amdg_ctx * c, int t, const int * sizes_from, int kf, int kt, int rel, int lu, int64_t * out)
+{
+    if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (t < 0 || t >= c->dim || !sizes_from || !out || rel < 0 || rel > 1 || lu < 0 || lu > 2 || !sweep_shape_supported(kf, kt)) return fail(AMDG_EINVAL, "bad arguments");
+    int outer = 1, inner = 1;
+    for (int k = 0; k < t; ++k) outer *= sizes_from[k];
+    for (int k = t + 1; k < c->dim; ++k) inner *= sizes_from[k];
+    const int W = outer * inner, slack = 32 * kf;
+    for (int i = 0; i < 6; ++i) out[i] = 0;
+    for (auto & kv : c->shapes.shape_fibres[t])
+    {
+        const int shape = kv.first;
+        const std::vector<int> & ords = c->shapes.ords[shape];
+        const int m = (int)ords.size();
+        ShapeProg SP; build_shape_prog(c->pairs, ords, rel, lu, kf, kt, SP);
+        const std::vector<LeanPiece> & pieces = lean_plan(c, shape, kf, kt, rel, lu, outer, inner);
+        std::vector<int> seen(SP.n_rt, 0);
+        out[0]++;
+        for (const LeanPiece & P : pieces)
+        {
+            const ShapeProg & Q = P.prog;
+            out[1]++; out[2] += P.ksplit ? 1 : 0; out[3] += Q.n_ent();
+            if ((int)Q.rt_order.size() != Q.n_rt || (int)Q.rt_ptr.size() != Q.n_rt + 1) return fail(AMDG_EINVAL, "plan: inconsistent piece");
+            const int nsrc = P.ksplit ? m : (int)P.src.size();
+            for (int i = 0; i < Q.n_rt; ++i)
+            {
+                const int rt = Q.rt_order[i];
+                if (rt < 0 || rt >= SP.n_rt) return fail(AMDG_EINVAL, "plan: row tile out of range");
+                seen[rt]++;
+                const int n_e = Q.rt_ptr[i + 1] - Q.rt_ptr[i];
+                if (n_e != SP.rt_ptr[rt + 1] - SP.rt_ptr[rt]) return fail(AMDG_EINVAL, "plan: a row tile lost entries");
+                for (int p = 0; p < n_e; ++p)
+                {
+                    const int es = Q.ent_src[Q.rt_ptr[i] + p], eo = SP.ent_src[SP.rt_ptr[rt] + p];
+                    const int f = es / SP.nkp;
+                    if (f < 0 || f >= nsrc || es % SP.nkp != eo % SP.nkp) return fail(AMDG_EINVAL, "plan: bad source index");
+                    const int f_fibre = P.ksplit ? f : P.src[f];
+                    if (f_fibre != eo / SP.nkp) return fail(AMDG_EINVAL, "plan: source row mismatch");
+                    for (int g = 0; g < SP.tg; ++g)
+                        if (Q.ent_pair[(size_t)(Q.rt_ptr[i] + p) * SP.tg + g] != SP.ent_pair[(size_t)(SP.rt_ptr[rt] + p) * SP.tg + g]) return fail(AMDG_EINVAL, "plan: pair mismatch");
+                }
+            }
+            // rectangles tile the column plane
+            std::vector<char> col(W, 0);
+            for (const LeanRect & r : P.rects)
+            {
+                if (P.ksplit && r.no * r.ni > 8) return fail(AMDG_EINVAL, "plan: coarse piece wider than 8 columns");
+                for (int o = r.o0; o < r.o0 + r.no; ++o) for (int i = r.i0; i < r.i0 + r.ni; ++i)
+                {
+                    if (o < 0 || o >= outer || i < 0 || i >= inner || col[o * inner + i]) return fail(AMDG_EINVAL, "plan: rectangles overlap or leave the plane");
+                    col[o * inner + i] = 1;
+                }
+                const int64_t need = (P.ksplit ? 0 : (((int64_t)P.src.size() * mma_rowsize(kf, r.no, r.ni, inner) + 1) & ~(int64_t)1)) +
+                                     (2 * Q.n_rt + 1 + Q.n_ent() + ((m + 1) & ~1) + 1) / 2 + 2 + (P.stage_a ? Q.n_ent() * 32 : 0) + slack + (P.ksplit ? 260 : 0);
+                if (need > tc_smem_capacity_doubles()) return fail(AMDG_EINVAL, "plan: a piece does not fit in shared memory");
+                out[5] = std::max<int64_t>(out[5], need);
+            }
+            for (int i = 0; i < W; ++i) if (!col[i]) return fail(AMDG_EINVAL, "plan: rectangles do not cover the column plane");
+            if (!P.ksplit) out[4] = std::max<int64_t>(out[4], (int64_t)P.src.size());
+        }
+        for (int rt = 0; rt < SP.n_rt; ++rt) if (seen[rt] != 1) return fail(AMDG_EINVAL, "plan: a row tile is not covered exactly once");
+    }
+    return AMDG_OK;
 }
 
 // device table of operator values (fragment order) for every program of a list, for operator `op`

@@ -61,6 +61,10 @@ int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto (lean 
 int64_t amdg_ctx_launch_count(amdg_ctx *ctx);                 /* kernels launched so far by this context */
 /* profiling aid: device buffer of n_items*8 int64 that the sweep kernel fills with per-CTA clock64 stamps (NULL = off) */
 int amdg_ctx_set_debug_buffer(amdg_ctx *ctx, void *dev_buf);
+/* diagnostic, host only (no device needed): build the work plans of the default sweep kernel for every fibre shape of dimension t
+ * (a sweep with source block edges sizes_from[dim] and an operator kf -> kt) and verify their invariants; out[6] = shapes, pieces,
+ * streamed (coarse) pieces, tile entries, largest staged row count, largest shared-memory need in doubles */
+int amdg_lean_plan_check(amdg_ctx *ctx, int t, const int *sizes_from, int kf, int kt, int rel, int lu, int64_t *out);
 
 /* ---- Hash (source/Hash.cpp:55-114) and 1D element order (source/Element.cpp:388-391), bit exact ---- */
 int amdg_hash_key(int dim, const int *level, const int *suppt);
