@@ -55,6 +55,11 @@ def _worker(rank, world, port, dim, nmax, q):
         assert torch.equal(v, torch.tensor(part.local["V"][:, None] * 100 + np.arange(blk)[None, :], dtype=torch.float64))
         back = part.switch(v, "V", "X")
         assert torch.equal(back, x)
+        # several live buffers of different block sizes change layout in ONE all-to-all (switch_many), as the schedule's levels do
+        xs = [torch.tensor(part.local["X"][:, None] * 100 + 7 * i + np.arange(w)[None, :], dtype=torch.float64) for i, w in enumerate((3, 8, 1))]
+        vs = part.switch_many(xs, "X", "V")
+        for i, w in enumerate((3, 8, 1)):
+            assert vs[i].is_contiguous() and torch.equal(vs[i], torch.tensor(part.local["V"][:, None] * 100 + 7 * i + np.arange(w)[None, :], dtype=torch.float64))
         q.put((rank, "ok"))
     except Exception as e:      # pragma: no cover
         import traceback
