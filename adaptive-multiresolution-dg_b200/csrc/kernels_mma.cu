@@ -1,5 +1,6 @@
 // K1 sweep kernel, whole-fibre tensor-core form (kernel variant 4).  Split from kernels.cu so that the translation units build in parallel.
 #include <algorithm>
+#include <cstdlib>
 #include "kernels.cuh"
 #include "cp_async.cuh"
 #include "../../include/amdg.h"
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 768 / MMA_THREADS) sweep_mma_kern
     constexpr int NW = MMA_THREADS / 32;
 #define MMA_STAMP(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[(int64_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
     MMA_STAMP(0);
+    asm volatile("griddepcontrol.launch_dependents;");          // programmatic dependent launch, as in sweep_tc_kernel
     const MmaItem it = a.items[blockIdx.x];
     if (a.dbg && threadIdx.x == 0)
     {
@@ -152,6 +154,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 768 / MMA_THREADS) sweep_mma_kern
             so = r * inner + w;
             dof = INNER1 ? w : k * pk + o_l * it.ni + w;
         };
+        // from here on the coefficient arrays of earlier kernels are read: wait for them (everything above touches work lists only)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         // Rows of this warp: row = warp + NW*r.  Lane r fetches the element row of row r (one load for 32 rows, handed out
         // by shuffles).  The copy pattern inside a row is the same for every row: each lane computes its copy offsets once.
         if (per_row >= 32)
@@ -320,9 +324,19 @@ static cudaError_t launch_mma_t(const MmaArgs & a, int smem_doubles, cudaStream_
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid((unsigned)a.n_item, (unsigned)(a.n_job * a.n_comp));
-    sweep_mma_kernel<KF, KT, INNER1><<<grid, MMA_THREADS, (size_t)std::min(smem_doubles, MMA_SMEM_DOUBLES) * sizeof(double), st>>>(a);
-    return cudaGetLastError();
+    // programmatic stream serialization: the head of this grid overlaps the tail of the previous kernel (the kernel waits itself
+    // before it touches coefficient data); matters most for the small sweeps this form serves in auto mode
+    static const bool pdl = !(std::getenv("AMDG_TC_PDL") && std::atoi(std::getenv("AMDG_TC_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a.n_item, (unsigned)(a.n_job * a.n_comp), 1);
+    cfg.blockDim = dim3(MMA_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)std::min(smem_doubles, MMA_SMEM_DOUBLES) * sizeof(double);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, sweep_mma_kernel<KF, KT, INNER1>, a);
 }
 
 #define AMDG_DISPATCH_KT_M(KF_)                                                                   \
