@@ -1382,7 +1382,11 @@ static int apply_tensor_shared(amdg_ctx * c, const int * ops, const int * rels, 
     // X buffers 0..nsub-1 (X_0 = src itself), Y buffers nsub..2*nsub-1
     for (int s = 1; s < 2 * nsub; ++s) if ((r = ensure_scratch(c, (size_t)s, cap))) return r;
     auto xbuf = [&](int S) -> const double * { return S == 0 ? src : c->scratch[S]; };
-    auto ybuf = [&](int S) -> double * { return c->scratch[nsub + S]; };
+    // R_1({0}) ends up in the Y buffer of the full set S = {0..d-2} (every level accumulates into the buffer of S + {k}); its blocks
+    // have the destination's shape, so when the caller's dst is overwritten anyway that buffer IS dst and the closing
+    // "dst += R_1({0})" pass disappears
+    const bool y_in_dst = !accumulate && src != dst;
+    auto ybuf = [&](int S) -> double * { return (y_in_dst && S == nsub - 1) ? dst : c->scratch[nsub + S]; };
     auto edge = [&](int S, int k) { return ((S >> k) & 1) ? kt : kf; };   // dims in S already have the target edge
     std::vector<SweepJob> jobs;
     // down: L_k applied to every X_S with S subset of {0..k-1}
@@ -1428,8 +1432,8 @@ static int apply_tensor_shared(amdg_ctx * c, const int * ops, const int * rels, 
             SweepJob j; j.src = ybuf(lo); j.outer = outer; j.coef = 1.0;
             if (k == 0)
             {
-                // final: dst (+)= U_0 R_1({}) ; then dst += R_1({0})
-                j.dst = dst; j.accumulate = accumulate;
+                // final: dst (+)= U_0 R_1({}) ; then dst += R_1({0}) (already there when y_in_dst)
+                j.dst = dst; j.accumulate = y_in_dst ? 1 : accumulate;
             }
             else { j.dst = ybuf(hi); j.accumulate = 1; }
             nw[S] = hi;
@@ -1440,6 +1444,7 @@ static int apply_tensor_shared(amdg_ctx * c, const int * ops, const int * rels, 
         for (int S = 0; S < (1 << k); ++S) where[S] = nw[S];
     }
     // dst += R_1({0})
+    if (!y_in_dst)
     {
         const int64_t total = n * n_comp * ipow(kt, d);
         cudaError_t e = launch_axpby(total, 1.0, ybuf(where[0]), 1.0, dst, c->stream);
