@@ -1,5 +1,6 @@
 // C ABI (include/amdg.h) over the host tables (grid.hpp) and the sm_100a kernels (kernels.cu).
 // No torch types, no CPU compute path: a context without a device can only build and export tables.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <array>
@@ -303,9 +304,15 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
     if (!c || n < 1 || !level || !suppt) return fail(AMDG_EINVAL, "bad arguments to amdg_grid_set");
     if (n > 0x7fffffff) return fail(AMDG_EINVAL, "too many elements");
     Grid g;
+    const auto t0 = std::chrono::steady_clock::now();
     if (g.build(c->dim, c->nmax, n, level, suppt, c->pairs) != 0) return fail(AMDG_EINVAL, "invalid or duplicate element index");
+    const auto t1 = std::chrono::steady_clock::now();
     c->grid = std::move(g); c->have_grid = true;
     c->shapes.build(c->grid);
+    if (std::getenv("AMDG_VERBOSE"))
+        fprintf(stderr, "[amdg] grid_set: %lld elements, tables %.2f ms, shapes %.2f ms (%d shapes known)\n", (long long)n,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), (int)c->shapes.ords.size());
     if (c->device < 0) return AMDG_OK;
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));

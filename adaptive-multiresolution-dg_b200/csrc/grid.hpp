@@ -178,6 +178,21 @@ struct Grid
                 for (int k = 0; k < d; ++k) if (k != t && o[(int64_t)a * d + k] != o[(int64_t)b * d + k]) return false;
                 return true;
             };
+            if (d * nmax <= 64)
+            {
+                // the lexicographic key (1D orders of the other dims, then of dim t; each below 2^nmax) fits one 64-bit word
+                std::vector<std::pair<uint64_t, int>> keyed(n);
+                for (int64_t e = 0; e < n; ++e)
+                {
+                    uint64_t key = 0;
+                    for (int k = 0; k < d; ++k) if (k != t) key = (key << nmax) | (uint64_t)o[e * d + k];
+                    key = (key << nmax) | (uint64_t)o[e * d + t];
+                    keyed[e] = { key, (int)e };
+                }
+                std::sort(keyed.begin(), keyed.end());
+                for (int64_t s = 0; s < n; ++s) perm[s] = keyed[s].second;
+            }
+            else
             std::sort(perm.begin(), perm.end(), [o, d, t](int a, int b)
             {
                 for (int k = 0; k < d; ++k) if (k != t) { const int x = o[(int64_t)a * d + k], y = o[(int64_t)b * d + k]; if (x != y) return x < y; }
