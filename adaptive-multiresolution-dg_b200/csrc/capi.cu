@@ -15,6 +15,7 @@
 #include "grid.hpp"
 #include "pipe_items.hpp"
 #include "mma_items.hpp"
+#include "dir_items.hpp"
 #include "kernels.cuh"
 
 using namespace amdg;
@@ -90,6 +91,16 @@ struct amdg_ctx
     bool tc_force_stage = true; int tc_coarse_ent = 256; int64_t tc_min_doubles = 131072;
     int tc_cap_doubles = 4608, tc_item_target = 148 * 8, tc_ent_target = 48, tc_stage_a_max = 48;      // lean form (kernels_tc.cu)
     bool lean() const { return kernel_variant == 0 || kernel_variant == 5; }
+    // register-direct kernel (kernels_dir.cu): plans per (shape, kf, kt, rel*4+lu), lists per (dim t, outer, inner, kf, kt, rel*4+lu)
+    struct DirList
+    {
+        DirUnit * d_units = nullptr; int * d_pool = nullptr; int * d_tab_b = nullptr; int2 * d_tab_c = nullptr;
+        int n_unit = 0; bool vec_ok = false;
+        MmaList ml;                                               // programs + element rows + operator-fragment tables (get_mma_a_tab)
+    };
+    std::map<std::tuple<int, int, int, int, int, int>, DirList> dirs;
+    std::map<std::tuple<int, int, int, int>, std::vector<DirPiece>> dir_plans;
+    int dir_cost_target = 160;
     std::map<std::tuple<int, int, int, int, int, int>, std::vector<LeanPiece>> lean_plans;   // (shape, kf, kt, rel*4+lu, outer, inner)
     int n_sm = 148;
     long long * dbg = nullptr;
@@ -123,6 +134,13 @@ static void free_dev_grid(amdg_ctx * c)
         for (auto & at : L.a_tab) meta_free(c, (void *)at.second);
     }
     c->mmas.clear();                     // (operator fragments, mma_A, are per shape and survive a grid change)
+    for (auto & kv : c->dirs)
+    {
+        amdg_ctx::DirList & L = kv.second;
+        meta_free(c, L.d_units); meta_free(c, L.d_pool); meta_free(c, L.d_tab_b); meta_free(c, L.d_tab_c); meta_free(c, L.ml.d_elem_pool);
+        for (auto & at : L.ml.a_tab) meta_free(c, (void *)at.second);
+    }
+    c->dirs.clear();
     for (auto & kv : c->pipes)
     {
         amdg_ctx::PipeList & L = kv.second;
@@ -214,6 +232,7 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_TC_MIN_DOUBLES")) c->tc_min_doubles = atoll(e);
     if (const char * e = std::getenv("AMDG_TC_FORCE_STAGE")) c->tc_force_stage = atoi(e) != 0;
     if (const char * e = std::getenv("AMDG_TC_COARSE_ENT")) c->tc_coarse_ent = std::max(16, atoi(e));
+    if (const char * e = std::getenv("AMDG_DIR_COST")) c->dir_cost_target = std::max(8, atoi(e));
     if (const char * e = std::getenv("AMDG_PIPE_CAP")) c->pipe_cap_doubles = std::max(256, atoi(e)) & ~1;
     if (const char * e = std::getenv("AMDG_PIPE_META")) c->pipe_meta_ints = (std::max(256, atoi(e)) + 3) & ~3;
     if (const char * e = std::getenv("AMDG_PIPE_ITEMS")) c->pipe_item_target = std::max(1, atoi(e));
@@ -281,7 +300,7 @@ int amdg_ctx_set_stream(amdg_ctx * c, void * s)
 
 int amdg_ctx_sync(amdg_ctx * c) { int r = need_device(c); if (r) return r; CU(cudaStreamSynchronize(c->stream)); return AMDG_OK; }
 int amdg_ctx_set_schedule(amdg_ctx * c, int s) { if (!c || (s != AMDG_SCHED_LITERAL && s != AMDG_SCHED_SHARED)) return fail(AMDG_EINVAL, "bad schedule"); c->sched = s; return AMDG_OK; }
-int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 5) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
+int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 6) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
 int64_t amdg_ctx_launch_count(amdg_ctx * c) { return c ? c->launches : -1; }
 int amdg_ctx_set_debug_buffer(amdg_ctx * c, void * dev_buf) { if (!c) return fail(AMDG_EINVAL, "null context"); c->dbg = (long long *)dev_buf; return AMDG_OK; }
 
@@ -1137,6 +1156,135 @@ int amdg_lean_plan_check(amdg_ctx * c, int t, const int * sizes_from, int kf, in
     return AMDG_OK;
 }
 
+// Work list of the register-direct kernel (kernels_dir.cu, dir_items.hpp): one unit per (piece of a shape, run of fibres, range of column
+// tiles).  Host part (no device needed; also exported to the tests by amdg_dir_list_export):
+struct DirHost
+{
+    std::vector<DirUnit> units; std::vector<int> pool, elem_pool, tab_b, tab_c;
+    std::vector<ShapeProg> progs; std::vector<int> prog_shape; std::vector<long long> prog_piece;
+    int nct = 0; bool vec_ok = false;
+};
+static void build_dir_host(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int lu, DirHost & D)
+{
+    const std::map<int, std::vector<int>> & sf = c->shapes.shape_fibres[t];
+    const DimTables & H = c->grid.dims[t];
+    int nct_pad = 0;
+    build_dir_tables(outer, inner, kf, kt, D.tab_b, D.tab_c, nct_pad, D.vec_ok);
+    const int nct = (outer * inner + 7) / 8;
+    D.nct = nct;
+    std::vector<DirUnit> units; std::vector<double> cost;
+    for (auto & kv : sf)
+    {
+        const int shape = kv.first; const std::vector<int> & fibres = kv.second;
+        const int m = (int)c->shapes.ords[shape].size();
+        if (const char * e = std::getenv("AMDG_DIR_MAXM")) { if (m > atoi(e)) continue; }     // timing experiments only (results incomplete)
+        if (const char * e = std::getenv("AMDG_DIR_MINM")) { if (m < atoi(e)) continue; }
+        auto pk = std::make_tuple(shape, kf, kt, rel * 4 + lu);
+        auto pit = c->dir_plans.find(pk);
+        if (pit == c->dir_plans.end())
+        {
+            std::vector<DirPiece> pcs; build_dir_plan(c->pairs, c->shapes.ords[shape], c->nmax, rel, lu, kf, kt, pcs);
+            pit = c->dir_plans.emplace(pk, std::move(pcs)).first;
+        }
+        const std::vector<DirPiece> & pieces = pit->second;
+        const int fib0 = (int)D.elem_pool.size();
+        for (size_t b = 0; b < fibres.size(); ++b) for (int f = 0; f < m; ++f) D.elem_pool.push_back(H.slot_elem[fibres[b] + f]);
+        for (const DirPiece & P : pieces)
+        {
+            const int prog = (int)D.progs.size();
+            D.progs.push_back(P.prog); D.prog_shape.push_back(shape); D.prog_piece.push_back(P.hash);
+            const int pofs = (int)D.pool.size();
+            D.pool.insert(D.pool.end(), P.src.begin(), P.src.end());
+            D.pool.insert(D.pool.end(), P.mask.begin(), P.mask.end());
+            const int G = dir_variant_g(P.variant);
+            const double tile_cost = (double)P.src.size() + P.n_ent() + 2.0 * P.n_rt + 1.0;
+            int tpu = (int)std::max<double>(1.0, c->dir_cost_target / tile_cost);
+            tpu = std::max(G, (tpu / G) * G);
+            int nf_per = 1;
+            if (tpu >= nct) { tpu = nct; nf_per = (int)std::max<double>(1.0, c->dir_cost_target / (tile_cost * nct)); }
+            for (size_t f0 = 0; f0 < fibres.size(); f0 += nf_per)
+            {
+                const int nf = (int)std::min<size_t>(nf_per, fibres.size() - f0);
+                for (int ct0 = 0; ct0 < nct; ct0 += tpu)
+                {
+                    DirUnit x; std::memset(&x, 0, sizeof(x));
+                    x.pool_ofs = pofs; x.fib_ofs = fib0 + (int)f0 * m; x.nfib = nf; x.m = m; x.ct0 = ct0; x.nct = std::min(tpu, nct - ct0);
+                    x.n_src = (int)P.src.size(); x.prog = prog; x.variant = P.variant; x.n_rt = P.n_rt;
+                    for (int r = 0; r < 4; ++r) x.rt_id[r] = P.rt_id[r];
+                    units.push_back(x);
+                    cost.push_back(tile_cost * x.nct * nf);
+                }
+            }
+        }
+    }
+    // longest units first; equal costs keep their order (units of one fibre stay adjacent: they share sources in L1)
+    std::vector<int> order(units.size()); for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    D.units.resize(units.size()); for (size_t i = 0; i < order.size(); ++i) D.units[i] = units[order[i]];
+    if (D.pool.empty()) D.pool.push_back(0);
+}
+
+static amdg_ctx::DirList & get_dir(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int lu)
+{
+    auto key = std::make_tuple(t, outer, inner, kf, kt, rel * 4 + lu);
+    auto it = c->dirs.find(key);
+    if (it != c->dirs.end()) return it->second;
+    amdg_ctx::DirList L;
+    DirHost D; build_dir_host(c, t, outer, inner, kf, kt, rel, lu, D);
+    if (!D.units.empty())
+    {
+        bool up = meta_upload(c, &L.d_units, D.units.data(), D.units.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.d_pool, D.pool.data(), D.pool.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.ml.d_elem_pool, D.elem_pool.data(), D.elem_pool.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.d_tab_b, D.tab_b.data(), D.tab_b.size(), false) == cudaSuccess &&
+                  meta_upload(c, (int **)&L.d_tab_c, D.tab_c.data(), D.tab_c.size(), false) == cudaSuccess &&
+                  cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (up) { L.n_unit = (int)D.units.size(); L.vec_ok = D.vec_ok; L.ml.ok = true; }
+        L.ml.progs = std::move(D.progs); L.ml.prog_shape = std::move(D.prog_shape); L.ml.prog_piece = std::move(D.prog_piece);
+        if (std::getenv("AMDG_VERBOSE"))
+        {
+            int nv[4] = { 0, 0, 0, 0 }; for (auto & x : D.units) nv[x.variant]++;
+            fprintf(stderr, "[amdg] dir list t=%d outer=%d inner=%d kf=%d kt=%d rel=%d lu=%d: %d units (%d/%d/%d/%d by variant), %d programs, %d column tiles, vec %d\n",
+                    t, outer, inner, kf, kt, rel, lu, (int)D.units.size(), nv[0], nv[1], nv[2], nv[3], (int)L.ml.progs.size(), D.nct, (int)D.vec_ok);
+        }
+    }
+    return c->dirs.emplace(key, std::move(L)).first->second;
+}
+
+// Diagnostic export of the register-direct kernel's work list (host only, no device needed) so that the tests can replay it against the
+// oracle: counts[8] = units, pool ints, element rows, column tiles (padded to 8), programs, total entries, vec_ok, 0.  Call with units == NULL
+// for the counts.  units: 16 ints each (DirUnit); prog_ent_ptr[programs+1]; A[total entries][32] = operator values of `op` in fragment order.
+int amdg_dir_list_export(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, int64_t * counts, int * units, int * pool,
+                         int * elem_pool, int * tab_b, int * tab_c, int * prog_ent_ptr, double * A)
+{
+    if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (op < 0 || op >= (int)c->ops.size() || t < 0 || t >= c->dim || !sizes_from || !counts || rel < 0 || rel > 1 || lu < 0 || lu > 2) return fail(AMDG_EINVAL, "bad arguments");
+    const Op & O = *c->ops[op];
+    int outer = 1, inner = 1;
+    for (int k = 0; k < t; ++k) outer *= sizes_from[k];
+    for (int k = t + 1; k < c->dim; ++k) inner *= sizes_from[k];
+    DirHost D; build_dir_host(c, t, outer, inner, O.kf, O.kt, rel, lu, D);
+    int64_t n_ent = 0; for (auto & P : D.progs) n_ent += P.n_ent();
+    counts[0] = (int64_t)D.units.size(); counts[1] = (int64_t)D.pool.size(); counts[2] = (int64_t)D.elem_pool.size(); counts[3] = (int64_t)D.tab_b.size() / 32;
+    counts[4] = (int64_t)D.progs.size(); counts[5] = n_ent; counts[6] = D.vec_ok ? 1 : 0; counts[7] = D.nct;
+    if (!units) return AMDG_OK;
+    std::memcpy(units, D.units.data(), D.units.size() * sizeof(DirUnit));
+    std::memcpy(pool, D.pool.data(), D.pool.size() * sizeof(int));
+    std::memcpy(elem_pool, D.elem_pool.data(), D.elem_pool.size() * sizeof(int));
+    std::memcpy(tab_b, D.tab_b.data(), D.tab_b.size() * sizeof(int));
+    std::memcpy(tab_c, D.tab_c.data(), D.tab_c.size() * sizeof(int));
+    int64_t p = 0;
+    for (size_t i = 0; i < D.progs.size(); ++i)
+    {
+        prog_ent_ptr[i] = (int)p;
+        std::vector<double> Ai; build_shape_A(D.progs[i], O.blocks.data(), O.kf, O.kt, Ai);
+        std::memcpy(A + p * 32, Ai.data(), Ai.size() * sizeof(double));
+        p += D.progs[i].n_ent();
+    }
+    prog_ent_ptr[D.progs.size()] = (int)p;
+    return AMDG_OK;
+}
+
 // device table of operator values (fragment order) for every program of a list, for operator `op`
 static const double * const * get_mma_a_tab(amdg_ctx * c, amdg_ctx::MmaList & L, int op, int rel, int lu)
 {
@@ -1213,6 +1361,28 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         int cnt = 1;
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
+        if (c->kernel_variant == 6)
+        {
+            amdg_ctx::DirList & DL = get_dir(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, lu);
+            const double * const * atab = DL.ml.ok ? get_mma_a_tab(c, DL.ml, op, rel, lu) : nullptr;
+            if (!(DL.ml.ok && atab)) return fail(AMDG_EINVAL, "register-direct kernel requested but the work list could not be built");
+            DirArgs a;
+            a.units = DL.d_units; a.n_unit = DL.n_unit; a.pool = DL.d_pool; a.elem_pool = DL.ml.d_elem_pool; a.a_tab = atab;
+            a.tab_b = DL.d_tab_b; a.tab_c = DL.d_tab_c; a.n_elem = c->grid.n; a.kf = O.kf; a.kt = O.kt; a.inner = inner;
+            const int ktp = mma_ktp(O.kt);
+            a.tg = 8 / ktp; a.tg_shift = ktp == 1 ? 0 : (ktp == 2 ? 1 : (ktp == 4 ? 2 : 3)); a.dkp = 4 * inner;
+            a.n_comp = n_comp; a.n_job = cnt; a.vec_ok = 0;
+            const int64_t s_to = (int64_t)W * O.kt;
+            for (int i = 0; i < cnt; ++i)
+            {
+                a.job[i] = jobs[done + i];
+                // 16-byte accesses: the tables are pairwise aligned, block sizes even, the base aligned and (for mapped destinations) the caller built even offsets
+                if (DL.vec_ok && (s_to & 1) == 0 && (reinterpret_cast<uintptr_t>(a.job[i].dst) & 15) == 0 && !a.job[i].dst_map) a.vec_ok |= 1 << i;
+            }
+            cudaError_t e = launch_sweep_dir(a, c->stream);
+            if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("register-direct sweep launch: ") + cudaGetErrorString(e));
+            c->launches++; done += cnt; continue;
+        }
         if (c->kernel_variant == 0 || c->kernel_variant == 4 || c->kernel_variant == 5)
         {
             // lean tensor-core kernel first (variants 0 and 5); the whole-fibre tensor-core kernel when its list cannot be built (0) or on request (4)

@@ -22,6 +22,10 @@ struct SweepJob
     int outer;          // prod of block edges of dims < t
     int accumulate;     // dst += result
     double coef;
+    // optional (sweep_dir_kernel only): offset in doubles, relative to dst, of the destination block of every element row; null = row * S_to.
+    // The fibre-partitioned multi-GPU path points these at peer memory: the last sweep before a layout switch stores every element block
+    // straight into the buffer of the rank that owns it in the next layout.
+    const long long * dst_map = nullptr;
 };
 
 static const int MAX_JOBS = 32;
@@ -147,6 +151,38 @@ struct MmaArgs
     SweepJob job[MAX_JOBS];
 };
 
+// register-direct tensor-core sweep kernel (plans built by dir_items.hpp)
+struct __align__(16) DirUnit
+{
+    int pool_ofs;       // ints in `pool`: src code [n_src] | row-tile mask [n_src]
+    int fib_ofs;        // element rows of the unit's fibres: elem_pool[fib_ofs + b*m + local]
+    int nfib, m;
+    int ct0, nct;       // column tiles [ct0, ct0 + nct)
+    int n_src;
+    int prog;           // index into a_tab
+    int variant;        // dir_items.hpp
+    int n_rt;
+    int rt_id[4];
+    int pad[2];
+};
+struct DirArgs
+{
+    const DirUnit * units; int n_unit;
+    const int * pool;
+    const int * elem_pool;
+    const double * const * a_tab;   // per program: operator values in fragment order [entry][32]
+    const int * tab_b;              // [nct_pad][32] source offsets of the B fragments
+    const int2 * tab_c;             // [nct_pad][32] destination offsets of the C fragments (-1: not stored)
+    int64_t n_elem;
+    int kf, kt, inner;
+    int tg_shift;                   // log2(KTP): target slot of C row r is r >> tg_shift
+    int tg;                         // targets per row tile
+    int dkp;                        // inner * 4: source offset of the second k-part (KF > 4)
+    int vec_ok;                     // every stored column pair is an aligned 16-byte pair
+    int n_comp, n_job;
+    SweepJob job[MAX_JOBS];
+};
+
 struct PointwiseArgs
 {
     const double * up;      // [n_points]
@@ -169,6 +205,7 @@ cudaError_t launch_sweep_mma(const MmaArgs & a, int kf, int kt, int smem_doubles
 int mma_smem_capacity_doubles();
 cudaError_t launch_sweep_tc(const MmaArgs & a, int kf, int kt, int smem_doubles, cudaStream_t st);     // kernels_tc.cu
 int tc_smem_capacity_doubles();
+cudaError_t launch_sweep_dir(const DirArgs & a, cudaStream_t st);                                             // kernels_dir.cu
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_pointwise_herm2d(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);

@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--schedule", type=int, default=1)
     ap.add_argument("--ncomp", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (quick kernel comparisons)")
     ap.add_argument("--literal-rhs", action="store_true", help="stage workloads: rhs_vol and rhs_flx as separate tensor applications")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -379,7 +380,7 @@ def main():
                          "step": {"b_alg_bytes": b_alg, "gbs": b_alg / (t_step_ms * 1e-3) / 1e9, "frac": b_alg / (t_step_ms * 1e-3) / 1e9 / peak,
                                   "note": step_note}},
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             cb = run_reference(args, w, as_baseline=True)
             if cb:
                 line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
