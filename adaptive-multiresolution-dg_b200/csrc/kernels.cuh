@@ -26,6 +26,9 @@ struct SweepJob
     // The fibre-partitioned multi-GPU path points these at peer memory: the last sweep before a layout switch stores every element block
     // straight into the buffer of the rank that owns it in the next layout.
     const long long * dst_map = nullptr;
+    // optional (sweep_dir_kernel only, with accumulate): the old values are read from acc_from (plain row * S_to layout) instead of the
+    // destination -- "remote = local partial sum + sweep", the last accumulating sweep before a layout switch
+    const double * acc_from = nullptr;
 };
 
 static const int MAX_JOBS = 32;
@@ -183,6 +186,26 @@ struct DirArgs
     SweepJob job[MAX_JOBS];
 };
 
+// point-wise expressions (amdg_pointwise_expr): a small stack program per output, evaluated at every interpolation point
+enum { PW_END = 0, PW_VAR = 1, PW_X = 2, PW_OTHER = 3, PW_CONST = 4, PW_ADD = 5, PW_SUB = 6, PW_MUL = 7, PW_DIV = 8, PW_NEG = 9, PW_SIN = 10, PW_COS = 11,
+       PW_SQR = 12, PW_EXP = 13, PW_SQRT = 14, PW_ABS = 15, PW_POW = 16, PW_TANH = 17, PW_MIN = 18, PW_MAX = 19 };
+static const int PW_MAX_OPS = 192, PW_MAX_CONST = 32, PW_MAX_IO = 8, PW_STACK = 8;
+struct PwExprArgs
+{
+    const double * up[PW_MAX_IO];       // [n_points] per variable
+    const double * other[PW_MAX_IO];    // [n_other_elem][block] per field (DGSolution::copy_up_intp_to_f gathers these per element)
+    double * out[PW_MAX_IO];            // [n_points] per output
+    const int * other_map;              // element row of the field grid for every element of this grid, or null (same rows)
+    const double * pts1d;               // [T*edge] interpolation point coordinates (LagrBasis::intep_pt)
+    const int * ord1d;                  // [n_elem][dim]
+    int64_t n_points;
+    int block, edge, dim, n_out;
+    int stride[8];                      // edge^(dim-1-t)
+    int out_ptr[PW_MAX_IO + 1];         // program of output c: ops [out_ptr[c], out_ptr[c+1])
+    short op[PW_MAX_OPS], arg[PW_MAX_OPS];
+    double consts[PW_MAX_CONST];
+};
+
 struct PointwiseArgs
 {
     const double * up;      // [n_points]
@@ -207,6 +230,12 @@ cudaError_t launch_sweep_tc(const MmaArgs & a, int kf, int kt, int smem_doubles,
 int tc_smem_capacity_doubles();
 cudaError_t launch_sweep_dir(const DirArgs & a, cudaStream_t st);                                             // kernels_dir.cu
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
+cudaError_t launch_pointwise_expr(const PwExprArgs & a, cudaStream_t st);
+// rows of a local array to mapped destinations (peer memory): dst[map[e] + i] = src[e*width + i]
+cudaError_t launch_scatter_rows(const double * src, int64_t n_rows, int width, double * dst, const long long * map, cudaStream_t st);
+// cross-GPU barrier through peer-mapped flag arrays: flags_of[r] = rank r's flag array [world] (device pointers valid on this device)
+struct PeerBarrierArgs { unsigned * flags_of[16]; unsigned * epoch; unsigned * error; int world, rank; long long timeout_cycles; };
+cudaError_t launch_peer_barrier(const PeerBarrierArgs & a, cudaStream_t st);
 cudaError_t launch_pointwise_herm2d(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_tn, double * u, const double * rhs, int64_t n, cudaStream_t st);
 cudaError_t launch_rk4_ode2nd_stage(int stage, double dt, const double * u_tn, const double * v_tn, double * u, double * v, const double * rhs,

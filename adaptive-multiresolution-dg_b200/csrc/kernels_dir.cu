@@ -34,8 +34,8 @@ struct DirU { int pool_ofs, fib_ofs, nfib, m, ct0, nct, n_src, prog, variant, n_
 // NRT row tiles x G column tiles per group; NA > 1: one tile, entries spread over NA accumulators (added in a fixed order)
 template <int NRT, int G, int NA>
 __device__ __forceinline__ void dir_run(const DirArgs & a, const DirU & U, const double * __restrict__ src, double * __restrict__ dst,
-                                        const long long * __restrict__ dst_map, int64_t s_from, int64_t s_to, double coef, bool accumulate,
-                                        bool vec, int lane)
+                                        const long long * __restrict__ dst_map, const double * __restrict__ acc_from, int64_t s_from, int64_t s_to,
+                                        double coef, bool accumulate, bool vec, int lane)
 {
     constexpr int SB = NA > 1 ? 8 : 8 / G;                         // sources per batch: eight B fragments in flight
     constexpr unsigned FULL = 0xffffffffu;
@@ -52,13 +52,14 @@ __device__ __forceinline__ void dir_run(const DirArgs & a, const DirU & U, const
     for (int b = 0; b < U.nfib; ++b)
     {
         const int fo = U.fib_ofs + b * U.m;
-        long long yoff[NRT]; bool ton[NRT];
+        long long yoff[NRT]; bool ton[NRT]; int erow[NRT];
 #pragma unroll
         for (int r = 0; r < NRT; ++r)
         {
             const int tl = U.rt[r] * a.tg + g_lane;
             ton[r] = r < U.n_rt && tl < U.m;
             const int e = ton[r] ? __ldg(a.elem_pool + fo + tl) : 0;
+            erow[r] = e;
             yoff[r] = dst_map ? __ldg(dst_map + e) : (long long)e * s_to;
         }
         const int srow0 = lane < U.n_src ? __ldg(a.elem_pool + fo + (code0 >> 1)) : 0;
@@ -84,7 +85,7 @@ __device__ __forceinline__ void dir_run(const DirArgs & a, const DirU & U, const
                 for (int r = 0; r < NRT; ++r)
                 {
                     if (!ton[r]) continue;
-                    const double * y = dst + yoff[r];
+                    const double * y = acc_from ? acc_from + (long long)erow[r] * s_to : dst + yoff[r];
 #pragma unroll
                     for (int j = 0; j < G; ++j)
                     {
@@ -185,15 +186,16 @@ __global__ void __launch_bounds__(DIR_THREADS, AMDG_DIR_MIN_CTAS) sweep_dir_kern
     const double * __restrict__ src = a.job[jb].src + (int64_t)comp * a.n_elem * s_from;
     double * __restrict__ dst = a.job[jb].dst + (int64_t)comp * a.n_elem * s_to;
     const long long * __restrict__ dmap = a.job[jb].dst_map;
+    const double * __restrict__ accf = a.job[jb].acc_from ? a.job[jb].acc_from + (int64_t)comp * a.n_elem * s_to : nullptr;
     const double coef = a.job[jb].coef;
     const bool accumulate = a.job[jb].accumulate != 0;
     const bool vec = (a.vec_ok >> jb) & 1;
     switch (U.variant)
     {
-        case 0: dir_run<1, 8, 1>(a, U, src, dst, dmap, s_from, s_to, coef, accumulate, vec, lane); break;
-        case 1: dir_run<2, 4, 1>(a, U, src, dst, dmap, s_from, s_to, coef, accumulate, vec, lane); break;
-        case 2: dir_run<4, 2, 1>(a, U, src, dst, dmap, s_from, s_to, coef, accumulate, vec, lane); break;
-        default: dir_run<1, 1, 4>(a, U, src, dst, dmap, s_from, s_to, coef, accumulate, vec, lane); break;
+        case 0: dir_run<1, 8, 1>(a, U, src, dst, dmap, accf, s_from, s_to, coef, accumulate, vec, lane); break;
+        case 1: dir_run<2, 4, 1>(a, U, src, dst, dmap, accf, s_from, s_to, coef, accumulate, vec, lane); break;
+        case 2: dir_run<4, 2, 1>(a, U, src, dst, dmap, accf, s_from, s_to, coef, accumulate, vec, lane); break;
+        default: dir_run<1, 1, 4>(a, U, src, dst, dmap, accf, s_from, s_to, coef, accumulate, vec, lane); break;
     }
 }
 
