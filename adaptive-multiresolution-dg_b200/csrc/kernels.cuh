@@ -186,6 +186,36 @@ struct DirArgs
     SweepJob job[MAX_JOBS];
 };
 
+// warp-specialised streaming sweep kernel (work lists built by ws_items.hpp)
+struct __align__(16) WsItem
+{
+    int prog;                       // index into a_tab (operator values of the piece, entries row tile by row tile)
+    int pool_ofs;                   // ints in `pool`: rt_ptr[n_rt+1] | rt_id[n_rt] | ent[n_ent] (slot*2 + k-part) | src_local[n_src]
+    int fib_ofs, nfib, m;           // element rows of the item's fibres: elem_pool[fib_ofs + b*m + local]
+    int n_rt, n_src, n_ent;
+    int tab, nct;                   // tables of the rectangle shape start at tile `tab`; the rectangle has nct column tiles
+    int src_origin, dst_origin;     // offset of the rectangle's first column in a source / destination block
+    int nrun, run_len, gstride;     // a staged source = nrun runs of run_len doubles, gstride apart in global memory, back to back in the slot
+    int slot;                       // doubles per staged source (nrun * run_len)
+    int kstride;                    // doubles between consecutive source indices k inside a slot (heavy items: in global memory)
+    int heavy;                      // 1: one row tile x one column tile, not staged, the consumer warps split the entry list
+    int vec;                        // the rectangle shape allows aligned 16-byte stores
+    int pad;
+};
+struct WsArgs
+{
+    const WsItem * items; const int * cta_ptr;      // CTA c runs items [cta_ptr[c], cta_ptr[c+1])
+    const int * pool; const int * elem_pool; const double * const * a_tab;
+    const int * tab_b; const int2 * tab_c;
+    int64_t n_elem;
+    int kf, kt, inner, tg, tg_shift;
+    unsigned bulk_jobs, vec_jobs;                   // per job: bulk copies legal (16-byte aligned runs); 16-byte stores legal
+    int n_comp, n_job;
+    SweepJob job[MAX_JOBS];
+};
+int ws_stage_doubles();
+cudaError_t launch_sweep_ws(const WsArgs & a, int n_cta, cudaStream_t st);                                     // kernels_ws.cu
+
 // point-wise expressions (amdg_pointwise_expr): a small stack program per output, evaluated at every interpolation point
 enum { PW_END = 0, PW_VAR = 1, PW_X = 2, PW_OTHER = 3, PW_CONST = 4, PW_ADD = 5, PW_SUB = 6, PW_MUL = 7, PW_DIV = 8, PW_NEG = 9, PW_SIN = 10, PW_COS = 11,
        PW_SQR = 12, PW_EXP = 13, PW_SQRT = 14, PW_ABS = 15, PW_POW = 16, PW_TANH = 17, PW_MIN = 18, PW_MAX = 19 };

@@ -57,7 +57,7 @@ int amdg_ctx_destroy(amdg_ctx *ctx);
 int amdg_ctx_set_stream(amdg_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: a stream owned by ctx */
 int amdg_ctx_sync(amdg_ctx *ctx);
 int amdg_ctx_set_schedule(amdg_ctx *ctx, int sched);
-int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto (lean tensor-core kernel; whole-fibre tensor-core and staged list kernels as fall-backs), 1 = gather, 2 = fibre-staged list kernel, 3 = pipelined list kernel, 4 = whole-fibre tensor-core (FP64 MMA) kernel, 5 = lean tensor-core kernel, 6 = register-direct tensor-core kernel */
+int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto (lean tensor-core kernel; whole-fibre tensor-core and staged list kernels as fall-backs), 1 = gather, 2 = fibre-staged list kernel, 3 = pipelined list kernel, 4 = whole-fibre tensor-core (FP64 MMA) kernel, 5 = lean tensor-core kernel, 6 = register-direct tensor-core kernel, 7 = warp-specialised streaming tensor-core kernel */
 int64_t amdg_ctx_launch_count(amdg_ctx *ctx);                 /* kernels launched so far by this context */
 /* profiling aid: device buffer of n_items*8 int64 that the sweep kernel fills with per-CTA clock64 stamps (NULL = off) */
 int amdg_ctx_set_debug_buffer(amdg_ctx *ctx, void *dev_buf);
@@ -70,6 +70,11 @@ int amdg_lean_plan_check(amdg_ctx *ctx, int t, const int *sizes_from, int kf, in
  * units == NULL for the counts.  units[n][16] (DirUnit), tab_b[tiles][32], tab_c[tiles][32][2], prog_ent_ptr[programs+1], A[entries][32]. */
 int amdg_dir_list_export(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, int64_t *counts, int *units, int *pool,
                          int *elem_pool, int *tab_b, int *tab_c, int *prog_ent_ptr, double *A);
+
+/* the same for the warp-specialised streaming sweep kernel (variant 7): counts[8] = items, CTAs, pool ints, element rows, table tiles, programs,
+ * entries, bulk_ok; items[n][20] (WsItem), cta_ptr[CTAs+1] */
+int amdg_ws_list_export(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, int n_cta, int64_t *counts, int *items, int *cta_ptr,
+                        int *pool, int *elem_pool, int *tab_b, int *tab_c, int *prog_ent_ptr, double *A);
 
 /* ---- Hash (source/Hash.cpp:55-114) and 1D element order (source/Element.cpp:388-391), bit exact ---- */
 int amdg_hash_key(int dim, const int *level, const int *suppt);
