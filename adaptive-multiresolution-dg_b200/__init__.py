@@ -22,6 +22,7 @@ lib = ctypes.CDLL(LIB_PATH)
 REL_VOL, REL_FLX = 0, 1
 LU_L, LU_U, LU_FULL = 0, 1, 2
 SCHED_LITERAL, SCHED_SHARED = 0, 1
+PW = dict(VAR=1, X=2, OTHER=3, CONST=4, ADD=5, SUB=6, MUL=7, DIV=8, NEG=9, SIN=10, COS=11, SQR=12, EXP=13, SQRT=14, ABS=15, POW=16, TANH=17, MIN=18, MAX=19)
 FLUX_LINEAR, FLUX_BURGERS, FLUX_SIN, FLUX_COS, FLUX_BUCKLEY_X, FLUX_BUCKLEY_Y, FLUX_VLASOV_SMOOTH_E = range(7)
 RK_EULER, RK_RK2SSP, RK_RK2MID, RK_RK3SSP, RK_RK3HEUN = range(5)
 
@@ -69,6 +70,15 @@ SYMBOLS = {
     "amdg_rk_stage": (_i, [_p, _i, _i, _d, _p, _p, _p, _i64]),
     "amdg_rk4_ode2nd_stage": (_i, [_p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _i64]),
     "amdg_axpby": (_i, [_p, _i64, _d, _p, _d, _p]),
+    "amdg_lincomb": (_i, [_p, _i64, _i, _dp, _p, _d, _p]),
+    "amdg_sweep1d_batch_mapped": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _dp, _ip, _p, _p, _i]),
+    "amdg_points_set": (_i, [_p, _dp]),
+    "amdg_pointwise_expr": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _ip, _i, _ip, _dp, _i]),
+    "amdg_peer_export": (_i, [_p, _p, _p]),
+    "amdg_peer_open": (_i, [_p, _p, ctypes.POINTER(_p)]),
+    "amdg_peer_close": (_i, [_p, _p]),
+    "amdg_peer_barrier": (_i, [_p, _p, _i, _i, _p, _p]),
+    "amdg_scatter_rows": (_i, [_p, _p, _i64, _i, _p, _p]),
     "amdg_host_apply_tensor": (_i, [_p, _ip, _ip, _dp, _dp, _i, _d, _i]),
     "amdg_host_sweep1d": (_i, [_p, _i, _i, _i, _i, _ip, _dp, _dp, _i, _d, _i]),
     "amdg_host_hierarchize": (_i, [_p, _i, _dp, _dp, _i]),
@@ -106,10 +116,10 @@ def _dbls(a):
 
 
 def _ptr(t):
-    """device pointer of a torch tensor (must be contiguous float64 on the context's device) or a raw int"""
-    if isinstance(t, int):
-        return ctypes.c_void_p(t)
-    assert t.is_cuda and t.is_contiguous() and str(t.dtype) == "torch.float64", "need a contiguous float64 CUDA tensor"
+    """device pointer of a torch tensor (contiguous, on the context's device) or a raw int"""
+    if isinstance(t, (int, np.integer)):
+        return ctypes.c_void_p(int(t))
+    assert t.is_cuda and t.is_contiguous(), "need a contiguous CUDA tensor"
     return ctypes.c_void_p(t.data_ptr())
 
 
@@ -314,6 +324,67 @@ class Context:
 
     def rk4_ode2nd_stage(self, stage, dt, u_tn, v_tn, u, v, rhs, ku, kv):
         _check(lib.amdg_rk4_ode2nd_stage(self._h, stage, dt, _ptr(u_tn), _ptr(v_tn), _ptr(u), _ptr(v), _ptr(rhs), _ptr(ku), _ptr(kv), u.numel()))
+
+    def lincomb(self, coefs, xs, y, beta=0.0):
+        cf, cp = _dbls(coefs)
+        px = (ctypes.c_void_p * len(xs))(*[_ptr(x) for x in xs])
+        n = y.numel() if hasattr(y, "numel") else None
+        _check(lib.amdg_lincomb(self._h, n, len(xs), cp, px, beta, _ptr(y)))
+
+    def sweep1d_batch_mapped(self, op, rel, lu, t, sizes_from, srcs, dsts, coefs=None, accumulates=None, dst_maps=None, acc_froms=None):
+        """amdg_sweep1d_batch_mapped; srcs/dsts/dst_maps/acc_froms are raw device addresses (ints) or torch tensors, None entries allowed in the last two"""
+        n = len(srcs)
+        s, sp = _ints(np.asarray(sizes_from).reshape(n, self.dim))
+        ps = (ctypes.c_void_p * n)(*[_ptr(x) for x in srcs])
+        pd = (ctypes.c_void_p * n)(*[_ptr(x) for x in dsts])
+        pm = (ctypes.c_void_p * n)(*[(_ptr(x) if x is not None else None) for x in (dst_maps or [None] * n)])
+        pa = (ctypes.c_void_p * n)(*[(_ptr(x) if x is not None else None) for x in (acc_froms or [None] * n)])
+        cf, cp = _dbls(np.ones(n) if coefs is None else coefs)
+        ac, ap = _ints(np.zeros(n) if accumulates is None else accumulates)
+        _check(lib.amdg_sweep1d_batch_mapped(self._h, op, rel, lu, t, sp, ps, pd, cp, ap, pm, pa, n))
+
+    def points_set(self, pts1d):
+        p, pp = _dbls(pts1d)
+        _check(lib.amdg_points_set(self._h, pp))
+
+    def pointwise_expr(self, ups, others, other_map, outs, prog, out_ptr, consts=()):
+        """amdg_pointwise_expr: prog = [(op, arg), ...] for all outputs back to back, out_ptr[c] = first op of output c"""
+        pu = (ctypes.c_void_p * max(len(ups), 1))(*[_ptr(x) for x in ups])
+        po = (ctypes.c_void_p * max(len(others), 1))(*[_ptr(x) for x in others])
+        pout = (ctypes.c_void_p * len(outs))(*[_ptr(x) for x in outs])
+        pr, prp = _ints(np.asarray(prog, dtype=np.int32).reshape(-1, 2))
+        op_, opp = _ints(out_ptr)
+        cs, csp = _dbls(np.asarray(consts if len(consts) else [0.0]))
+        _check(lib.amdg_pointwise_expr(self._h, len(ups), pu, len(others), po, _ptr(other_map) if other_map is not None else None, len(outs), pout,
+                                       prp, pr.shape[0], opp, csp, len(consts)))
+
+    def scatter_rows(self, src, n_rows, width, dst_base, dst_map):
+        _check(lib.amdg_scatter_rows(self._h, _ptr(src), n_rows, width, _ptr(dst_base), _ptr(dst_map)))
+
+    def dev_alloc(self, n_doubles):
+        out = _p()
+        _check(lib.amdg_dev_alloc(self._h, n_doubles, ctypes.byref(out)))
+        return out.value
+
+    def dev_free(self, ptr):
+        _check(lib.amdg_dev_free(self._h, ctypes.c_void_p(ptr)))
+
+    def peer_export(self, ptr):
+        buf = ctypes.create_string_buffer(64)
+        _check(lib.amdg_peer_export(self._h, ctypes.c_void_p(ptr), buf))
+        return buf.raw
+
+    def peer_open(self, handle):
+        out = _p()
+        _check(lib.amdg_peer_open(self._h, ctypes.c_char_p(handle), ctypes.byref(out)))
+        return out.value
+
+    def peer_close(self, ptr):
+        _check(lib.amdg_peer_close(self._h, ctypes.c_void_p(ptr)))
+
+    def peer_barrier(self, flag_ptrs, rank, epoch_ptr, error_ptr):
+        fp = (ctypes.c_void_p * len(flag_ptrs))(*[ctypes.c_void_p(x) for x in flag_ptrs])
+        _check(lib.amdg_peer_barrier(self._h, fp, len(flag_ptrs), rank, ctypes.c_void_p(epoch_ptr), ctypes.c_void_p(error_ptr)))
 
     def axpby(self, alpha, x, beta, y):
         _check(lib.amdg_axpby(self._h, y.numel(), alpha, _ptr(x), beta, _ptr(y)))

@@ -111,6 +111,7 @@ struct amdg_ctx
     std::map<std::tuple<int, int, int, int, int, int, int>, WsList> wss;
     std::map<std::tuple<int, int, int, int>, std::vector<WsPiece>> ws_plans;
     int ws_items_per_cta = 12;
+    double * d_pts1d = nullptr;                                   // LagrBasis::intep_pt table [T*edge_intp] (amdg_points_set)
     int dir_cost_target = 160;
     std::map<std::tuple<int, int, int, int, int, int>, std::vector<LeanPiece>> lean_plans;   // (shape, kf, kt, rel*4+lu, outer, inner)
     int n_sm = 148;
@@ -301,7 +302,7 @@ int amdg_ctx_destroy(amdg_ctx * c)
         for (auto & op : c->ops) meta_free(c, op->d_blocks);
         cudaFree(c->arena);
         for (double * p : c->scratch) cudaFree(p);
-        cudaFree(c->h2d); cudaFree(c->d2h);
+        cudaFree(c->h2d); cudaFree(c->d2h); cudaFree(c->d_pts1d);
         if (c->own_stream) cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -1556,13 +1557,18 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
 {
     const Op & O = *c->ops[op];
     const DevDim & D = c->ddims[t];
+    // destination maps / accumulate-from exist in the lean, register-direct and streaming kernels only (even map offsets are the caller's contract
+    // whenever the block size is even: the kernels keep their 16-byte stores)
+    bool mapped = false; for (int i = 0; i < n_job; ++i) mapped = mapped || jobs[i].dst_map || jobs[i].acc_from;
+    const int variant = (mapped && c->kernel_variant != 6 && c->kernel_variant != 7) ? 5 : c->kernel_variant;
+    const bool lean = variant == 0 || variant == 5;
     int done = 0;
     while (done < n_job)
     {
         int cnt = 1;
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
-        if (c->kernel_variant == 7)
+        if (variant == 7)
         {
             const int n_cta = std::max(1, c->n_sm / std::max(1, cnt * n_comp));
             amdg_ctx::WsList & WL = get_ws(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, lu, n_cta);
@@ -1586,7 +1592,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
             if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("streaming sweep launch: ") + cudaGetErrorString(e));
             c->launches++; done += cnt; continue;
         }
-        if (c->kernel_variant == 6)
+        if (variant == 6)
         {
             amdg_ctx::DirList & DL = get_dir(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, lu);
             const double * const * atab = DL.ml.ok ? get_mma_a_tab(c, DL.ml, op, rel, lu) : nullptr;
@@ -1608,17 +1614,17 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
             if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("register-direct sweep launch: ") + cudaGetErrorString(e));
             c->launches++; done += cnt; continue;
         }
-        if (c->kernel_variant == 0 || c->kernel_variant == 4 || c->kernel_variant == 5)
+        if (variant == 0 || variant == 4 || variant == 5)
         {
             // lean tensor-core kernel first (variants 0 and 5); the whole-fibre tensor-core kernel when its list cannot be built (0) or on request (4)
             // (auto mode keeps the whole-fibre form for sweeps of a few KB, which are bounded by the latency of one CTA, not by throughput)
             bool launched = false;
-            const bool tiny = c->kernel_variant == 0 && (int64_t)c->grid.n * W * O.kf < c->tc_min_doubles;
-            for (int form = (c->lean() && !tiny) ? 1 : 0; form >= 0 && !launched; --form)
+            const bool tiny = variant == 0 && (int64_t)c->grid.n * W * O.kf < c->tc_min_doubles;
+            for (int form = (lean && !tiny) ? 1 : 0; form >= 0 && !launched; --form)
             {
                 amdg_ctx::MmaList & ML = form ? get_mma_lean(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu) : get_mma(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, cnt * n_comp, lu);
                 const double * const * atab = ML.ok ? get_mma_a_tab(c, ML, op, rel, lu) : nullptr;
-                if (!(ML.ok && atab)) { if (form && c->kernel_variant == 5) break; continue; }
+                if (!(ML.ok && atab)) { if (form && variant == 5) break; continue; }
                 MmaArgs a;
                 a.items = ML.d_items; a.n_item = ML.n_item; a.prog_pool = ML.d_prog_ints; a.a_tab = atab; a.elem_pool = ML.d_elem_pool; a.dbg = c->dbg;
                 a.n_elem = c->grid.n; a.inner = inner; a.n_comp = n_comp; a.n_job = cnt;
@@ -1628,9 +1634,9 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
                 launched = true;
             }
             if (launched) { c->launches++; done += cnt; continue; }
-            if (c->kernel_variant == 4 || c->kernel_variant == 5) return fail(AMDG_EINVAL, "tensor-core kernel requested but the work list could not be built");
+            if (variant == 4 || variant == 5) return fail(AMDG_EINVAL, "tensor-core kernel requested but the work list could not be built");
         }
-        if (c->kernel_variant == 3)
+        if (variant == 3)
         {
             while (cnt * n_comp > 64 && cnt > 1) --cnt;
             const amdg_ctx::PipeList & PL = get_pipe(c, t, W, O.kf, O.kt, rel, cnt * n_comp, lu);
@@ -1655,11 +1661,11 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
                 done += cnt;
                 continue;
             }
-            if (c->kernel_variant == 3) return fail(AMDG_EINVAL, "pipelined kernel requested but the work list could not be built");
+            if (variant == 3) return fail(AMDG_EINVAL, "pipelined kernel requested but the work list could not be built");
         }
         const amdg_ctx::ItemList * L = nullptr;
-        if (c->kernel_variant != 1) { L = &get_items(c, t, W, O.kf, O.kt, rel, cnt * n_comp, lu); if (!L->ok) L = nullptr; }
-        if (c->kernel_variant == 2 && !L) return fail(AMDG_EINVAL, "fibre-staged kernel requested but a fibre does not fit in shared memory");
+        if (variant != 1) { L = &get_items(c, t, W, O.kf, O.kt, rel, cnt * n_comp, lu); if (!L->ok) L = nullptr; }
+        if (variant == 2 && !L) return fail(AMDG_EINVAL, "fibre-staged kernel requested but a fibre does not fit in shared memory");
         cudaError_t e;
         if (L)
         {
@@ -1704,8 +1710,8 @@ int amdg_sweep1d(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes
     return launch_sweep(c, op, rel, lu, t, inner, &j, 1, n_comp);
 }
 
-int amdg_sweep1d_batch(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * const * src, double * const * dst,
-                       const double * coef, const int * accumulate, int n_job, int n_comp)
+static int sweep1d_batch_impl(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * const * src, double * const * dst,
+                             const double * coef, const int * accumulate, const long long * const * dst_map, const double * const * acc_from, int n_job, int n_comp)
 {
     int r = need_device(c); if (r) return r;
     if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
@@ -1724,10 +1730,25 @@ int amdg_sweep1d_batch(amdg_ctx * c, int op, int rel, int lu, int t, const int *
         for (int k = t + 1; k < c->dim; ++k) inner *= sz[k];
         if (inner0 < 0) inner0 = inner; else if (inner != inner0) return fail(AMDG_EINVAL, "the jobs of a batch must agree in the edges of the dims after t");
         jobs[i].src = src[i]; jobs[i].dst = dst[i]; jobs[i].outer = outer; jobs[i].accumulate = accumulate ? accumulate[i] : 0; jobs[i].coef = coef ? coef[i] : 1.0;
+        jobs[i].dst_map = dst_map ? dst_map[i] : nullptr; jobs[i].acc_from = acc_from ? acc_from[i] : nullptr;
+        if ((jobs[i].dst_map || jobs[i].acc_from) && n_comp != 1) return fail(AMDG_EINVAL, "mapped destinations take one component per job");
+        if (jobs[i].acc_from && !jobs[i].accumulate) return fail(AMDG_EINVAL, "acc_from needs accumulate");
     }
     std::stable_sort(jobs.begin(), jobs.end(), [](const SweepJob & a, const SweepJob & b) { return a.outer < b.outer; });
     CU(cudaSetDevice(c->device));
     return launch_sweep(c, op, rel, lu, t, inner0, jobs.data(), n_job, n_comp);
+}
+
+int amdg_sweep1d_batch(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * const * src, double * const * dst,
+                       const double * coef, const int * accumulate, int n_job, int n_comp)
+{
+    return sweep1d_batch_impl(c, op, rel, lu, t, sizes_from, src, dst, coef, accumulate, nullptr, nullptr, n_job, n_comp);
+}
+
+int amdg_sweep1d_batch_mapped(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * const * src, double * const * dst,
+                              const double * coef, const int * accumulate, const int64_t * const * dst_map, const double * const * acc_from, int n_job)
+{
+    return sweep1d_batch_impl(c, op, rel, lu, t, sizes_from, src, dst, coef, accumulate, reinterpret_cast<const long long * const *>(dst_map), acc_from, n_job, 1);
 }
 
 static int64_t ipow(int b, int e) { int64_t r = 1; while (e-- > 0) r *= b; return r; }
@@ -1993,6 +2014,141 @@ int amdg_axpby(amdg_ctx * c, int64_t n, double alpha, const double * x, double b
     CU(cudaSetDevice(c->device));
     cudaError_t e = launch_axpby(n, alpha, x, beta, y, c->stream);
     if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("axpby: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+// ---- point-wise expressions ---------------------------------------------------------------------------------------------
+int amdg_points_set(amdg_ctx * c, const double * host_pts1d)
+{
+    int r = need_device(c); if (r) return r;
+    if (!host_pts1d) return fail(AMDG_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n1 = (size_t)c->pairs.T * c->edge_intp;
+    if (!c->d_pts1d) CU(cudaMalloc((void **)&c->d_pts1d, n1 * sizeof(double)));
+    CU(cudaMemcpyAsync(c->d_pts1d, host_pts1d, n1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return AMDG_OK;
+}
+
+int amdg_pointwise_expr(amdg_ctx * c, int n_var, const double * const * up, int n_other, const double * const * other, const int * other_map,
+                        int n_out, double * const * out, const int * prog, int n_prog, const int * out_ptr, const double * consts, int n_const)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (n_var < 0 || n_var > PW_MAX_IO || n_other < 0 || n_other > PW_MAX_IO || n_out < 1 || n_out > PW_MAX_IO || !out || !prog || !out_ptr ||
+        n_prog < 1 || n_prog > PW_MAX_OPS || n_const < 0 || n_const > PW_MAX_CONST || (n_var && !up) || (n_other && !other) || (n_const && !consts))
+        return fail(AMDG_EINVAL, "bad point-wise expression arguments");
+    PwExprArgs a; std::memset(&a, 0, sizeof(a));
+    for (int i = 0; i < n_var; ++i) a.up[i] = up[i];
+    for (int i = 0; i < n_other; ++i) a.other[i] = other[i];
+    for (int i = 0; i < n_out; ++i) { if (!out[i]) return fail(AMDG_EINVAL, "null output"); a.out[i] = out[i]; }
+    a.other_map = other_map; a.pts1d = c->d_pts1d; a.ord1d = c->d_ord1d;
+    a.edge = c->edge_intp; a.dim = c->dim; a.n_out = n_out;
+    a.block = (int)ipow(c->edge_intp, c->dim); a.n_points = c->grid.n * a.block;
+    for (int t = 0; t < c->dim; ++t) a.stride[t] = (int)ipow(c->edge_intp, c->dim - 1 - t);
+    if (out_ptr[0] != 0 || out_ptr[n_out] != n_prog) return fail(AMDG_EINVAL, "out_ptr does not cover the program");
+    for (int i = 0; i < n_const; ++i) a.consts[i] = consts[i];
+    // validate: operand ranges and stack discipline (every output leaves exactly one value)
+    for (int cidx = 0; cidx < n_out; ++cidx)
+    {
+        a.out_ptr[cidx] = out_ptr[cidx]; a.out_ptr[cidx + 1] = out_ptr[cidx + 1];
+        int sp = 0;
+        for (int i = out_ptr[cidx]; i < out_ptr[cidx + 1]; ++i)
+        {
+            const int op = prog[2 * i], arg = prog[2 * i + 1];
+            a.op[i] = (short)op; a.arg[i] = (short)arg;
+            switch (op)
+            {
+                case PW_VAR: if (arg < 0 || arg >= n_var) return fail(AMDG_EINVAL, "expression: variable index out of range"); ++sp; break;
+                case PW_X: if (arg < 0 || arg >= c->dim) return fail(AMDG_EINVAL, "expression: coordinate index out of range");
+                           if (!c->d_pts1d) return fail(AMDG_ESTATE, "expression uses point coordinates: call amdg_points_set first"); ++sp; break;
+                case PW_OTHER: if (arg < 0 || arg >= n_other) return fail(AMDG_EINVAL, "expression: field index out of range"); ++sp; break;
+                case PW_CONST: if (arg < 0 || arg >= n_const) return fail(AMDG_EINVAL, "expression: constant index out of range"); ++sp; break;
+                case PW_ADD: case PW_SUB: case PW_MUL: case PW_DIV: case PW_POW: case PW_MIN: case PW_MAX:
+                    if (sp < 2) return fail(AMDG_EINVAL, "expression: stack underflow"); --sp; break;
+                case PW_NEG: case PW_SIN: case PW_COS: case PW_SQR: case PW_EXP: case PW_SQRT: case PW_ABS: case PW_TANH:
+                    if (sp < 1) return fail(AMDG_EINVAL, "expression: stack underflow"); break;
+                default: return fail(AMDG_EINVAL, "expression: unknown operation");
+            }
+            if (sp > PW_STACK) return fail(AMDG_EINVAL, "expression: stack too deep");
+        }
+        if (sp != 1) return fail(AMDG_EINVAL, "expression: an output must leave exactly one value");
+    }
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_pointwise_expr(a, c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("pointwise_expr launch: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+// ---- multi-GPU plumbing (one process per GPU): peer-mapped device memory, rows to mapped destinations, device-side barrier ---------
+int amdg_peer_export(amdg_ctx * c, const void * dev_ptr, void * handle64)
+{
+    int r = need_device(c); if (r) return r;
+    if (!dev_ptr || !handle64) return fail(AMDG_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    std::memcpy(handle64, &h, 64);
+    return AMDG_OK;
+}
+
+int amdg_peer_open(amdg_ctx * c, const void * handle64, void ** dev_ptr_out)
+{
+    int r = need_device(c); if (r) return r;
+    if (!handle64 || !dev_ptr_out) return fail(AMDG_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h; std::memcpy(&h, handle64, 64);
+    CU(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return AMDG_OK;
+}
+
+int amdg_peer_close(amdg_ctx * c, void * dev_ptr)
+{
+    int r = need_device(c); if (r) return r;
+    CU(cudaSetDevice(c->device));
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return AMDG_OK;
+}
+
+int amdg_peer_barrier(amdg_ctx * c, void * const * flag_ptrs, int world, int rank, void * dev_epoch, void * dev_error)
+{
+    int r = need_device(c); if (r) return r;
+    if (!flag_ptrs || world < 1 || world > 16 || rank < 0 || rank >= world || !dev_epoch || !dev_error) return fail(AMDG_EINVAL, "bad barrier arguments");
+    PeerBarrierArgs a; std::memset(&a, 0, sizeof(a));
+    for (int i = 0; i < world; ++i) { if (!flag_ptrs[i]) return fail(AMDG_EINVAL, "null flag pointer"); a.flags_of[i] = (unsigned *)flag_ptrs[i]; }
+    a.epoch = (unsigned *)dev_epoch; a.error = (unsigned *)dev_error; a.world = world; a.rank = rank; a.timeout_cycles = 6000000000ll;
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_peer_barrier(a, c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("peer barrier launch: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+int amdg_scatter_rows(amdg_ctx * c, const double * dev_src, int64_t n_rows, int width, double * dev_dst_base, const int64_t * dev_map)
+{
+    int r = need_device(c); if (r) return r;
+    if (!dev_src || !dev_dst_base || !dev_map || n_rows < 0 || width < 1) return fail(AMDG_EINVAL, "bad arguments");
+    if (n_rows == 0) return AMDG_OK;
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_scatter_rows(dev_src, n_rows, width, dev_dst_base, reinterpret_cast<const long long *>(dev_map), c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("scatter_rows launch: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+int amdg_lincomb(amdg_ctx * c, int64_t n, int k, const double * coefs, const double * const * dev_x, double beta, double * dev_y)
+{
+    int r = need_device(c); if (r) return r;
+    if (n < 0 || k < 1 || k > 16 || !coefs || !dev_x || !dev_y) return fail(AMDG_EINVAL, "bad arguments");
+    LincombArgs a; std::memset(&a, 0, sizeof(a));
+    for (int i = 0; i < k; ++i) { if (!dev_x[i]) return fail(AMDG_EINVAL, "null input"); a.x[i] = dev_x[i]; a.c[i] = coefs[i]; }
+    a.y = dev_y; a.beta = beta; a.n = n; a.k = k;
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_lincomb(a, c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("lincomb: ") + cudaGetErrorString(e));
     c->launches++;
     return AMDG_OK;
 }

@@ -467,6 +467,114 @@ cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// point-wise expressions: LagrInterpolation::eval_fp_Lag with all VEC_NUM unknowns (source/Interplation.cpp:256-295), eval_coe_u_Lag with a
+// coefficient of position (:648-698) and the Vlasov bodies with the field values of DGSolution::copy_up_intp_to_f (:4451-4497, 4523-4573;
+// source/DGSolution.cpp:1024-1065).  The reference takes a std::function; here every output is a small stack program over
+//   VAR v (point value of unknown v), X t (coordinate t of the interpolation point, from the 1D point table and the element's 1D orders),
+//   OTHER j (point value of field j at the same local point of the field element this element maps to), CONST, + - * / and a few functions.
+__global__ void __launch_bounds__(256) pointwise_expr_kernel(const PwExprArgs a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.n_points; p += stride)
+    {
+        const int64_t e = p / a.block; const int loc = (int)(p - e * a.block);
+        for (int c = 0; c < a.n_out; ++c)
+        {
+            double st[PW_STACK]; int sp = 0;
+            for (int i = a.out_ptr[c]; i < a.out_ptr[c + 1]; ++i)
+            {
+                const int op = a.op[i], arg = a.arg[i];
+                switch (op)
+                {
+                    case PW_VAR: st[sp++] = a.up[arg][p]; break;
+                    case PW_X: { const int pt = (loc / a.stride[arg]) % a.edge; st[sp++] = __ldg(a.pts1d + __ldg(a.ord1d + e * a.dim + arg) * a.edge + pt); break; }
+                    case PW_OTHER: { const int64_t eo = a.other_map ? __ldg(a.other_map + e) : e; st[sp++] = a.other[arg][eo * a.block + loc]; break; }
+                    case PW_CONST: st[sp++] = a.consts[arg]; break;
+                    case PW_ADD: --sp; st[sp - 1] += st[sp]; break;
+                    case PW_SUB: --sp; st[sp - 1] -= st[sp]; break;
+                    case PW_MUL: --sp; st[sp - 1] *= st[sp]; break;
+                    case PW_DIV: --sp; st[sp - 1] /= st[sp]; break;
+                    case PW_NEG: st[sp - 1] = -st[sp - 1]; break;
+                    case PW_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+                    case PW_COS: st[sp - 1] = cos(st[sp - 1]); break;
+                    case PW_SQR: st[sp - 1] *= st[sp - 1]; break;
+                    case PW_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+                    case PW_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+                    case PW_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+                    case PW_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+                    case PW_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
+                    case PW_MIN: --sp; st[sp - 1] = fmin(st[sp - 1], st[sp]); break;
+                    case PW_MAX: --sp; st[sp - 1] = fmax(st[sp - 1], st[sp]); break;
+                    default: break;
+                }
+            }
+            a.out[c][p] = st[0];
+        }
+    }
+}
+
+cudaError_t launch_pointwise_expr(const PwExprArgs & a, cudaStream_t st)
+{
+    const int64_t nb = (a.n_points + 255) / 256;
+    pointwise_expr_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// rows of a local array to mapped destinations (peer memory): the part of a layout switch whose data no sweep produces at the right moment
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const double * __restrict__ src, int64_t n_rows, int width, double * __restrict__ dst,
+                                                           const long long * __restrict__ map)
+{
+    const int64_t total = n_rows * width, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride)
+    {
+        const int64_t e = g / width; const int i = (int)(g - e * width);
+        dst[__ldg(map + e) + i] = src[g];
+    }
+}
+
+cudaError_t launch_scatter_rows(const double * src, int64_t n_rows, int width, double * dst, const long long * map, cudaStream_t st)
+{
+    const int64_t nb = (n_rows * width + 255) / 256;
+    scatter_rows_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(src, n_rows, width, dst, map);
+    return cudaGetLastError();
+}
+
+// Cross-GPU barrier over peer-mapped flags (one process per GPU, flags in IPC-shared device memory).  Thread r < world: publish this rank's
+// new epoch in rank r's flag array (system-scope release: everything earlier kernels of this stream stored to peers is visible first), then wait
+// until rank r's epoch has arrived here (acquire).  The epoch lives on the device so that the kernel can be replayed from a CUDA graph.  A peer
+// that never arrives makes the kernel give up after timeout_cycles and raise *error instead of hanging the device.
+__global__ void peer_barrier_kernel(const PeerBarrierArgs a)
+{
+    __shared__ unsigned s_epoch;
+    if (threadIdx.x == 0) { s_epoch = *a.epoch + 1; }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const int r = threadIdx.x;
+    if (r < a.world)
+    {
+        __threadfence_system();
+        unsigned * remote = a.flags_of[r] + a.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(remote), "r"(epoch) : "memory");
+        const unsigned * mine = a.flags_of[a.rank] + r;
+        const long long t0 = clock64();
+        unsigned v = 0;
+        while (true)
+        {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (clock64() - t0 > a.timeout_cycles) { atomicExch(a.error, 1u); break; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *a.epoch = epoch; }
+}
+
+cudaError_t launch_peer_barrier(const PeerBarrierArgs & a, cudaStream_t st)
+{
+    peer_barrier_kernel<<<1, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 // Hermite (PMAX=3) point-wise flux in 2D, scalar: HermInterpolation::eval_fp_Her_2D (source/Interplation.cpp:2045-2288).
 // Local index along a dim: 0,1 = value at point 0,1; 2,3 = derivative at point 0,1 (deg_pt_deri_1d).  Block (a,b):
 //   value/value: f(u);  deriv/value: f'(u) u_x;  value/deriv: f'(u) u_y;  deriv/deriv: f''(u) u_x u_y + f'(u) u_xy
@@ -613,6 +721,25 @@ __global__ void __launch_bounds__(256) axpby_kernel(int64_t n, double alpha, con
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
         y[p] = (beta == 0.0) ? alpha * x[p] : alpha * x[p] + beta * y[p];
+}
+
+// y = sum_i c_i x_i (+ beta y): the right-hand sides of several tensor applications, penalty terms and pushed partial sums joined in one pass
+__global__ void __launch_bounds__(256) lincomb_kernel(const LincombArgs a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.n; p += stride)
+    {
+        double v = a.beta == 0.0 ? 0.0 : a.beta * a.y[p];
+        for (int i = 0; i < a.k; ++i) v += a.c[i] * a.x[i][p];
+        a.y[p] = v;
+    }
+}
+
+cudaError_t launch_lincomb(const LincombArgs & a, cudaStream_t st)
+{
+    const int64_t nb = (a.n + 255) / 256;
+    lincomb_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st)

@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
     const int64_t s_from = (int64_t)W * KF, s_to = (int64_t)W * KT;
     const double * __restrict__ src = J.src + (int64_t)comp * a.n_elem * s_from;
     double * __restrict__ dst = J.dst + (int64_t)comp * a.n_elem * s_to;
+    // optional destination map (element row -> offset of its block relative to dst, e.g. in peer memory) and accumulate-from array (kernels.cuh)
+    const long long * __restrict__ dmap = J.dst_map;
+    const double * __restrict__ accf = J.acc_from ? J.acc_from + (int64_t)comp * a.n_elem * s_to : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = it.m;
     const int ncols = it.no * it.ni;
@@ -335,7 +338,8 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
     const int rr = lane >> 2;                                      // C fragment row -> (target g, output q)
     const int cg_ = rr / KTP, cq = rr - cg_ * KTP;
     const int * s_rt_ptr = s_prog, * s_rt_order = s_prog + it.n_rt + 1, * s_ent = s_prog + 2 * it.n_rt + 1;
-    const bool vecst = !INNER1 && ((it.ni & 1) == 0) && ((it.i0 & 1) == 0) && ((inner & 1) == 0) && ((s_to & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const bool vecst = !INNER1 && ((it.ni & 1) == 0) && ((it.i0 & 1) == 0) && ((inner & 1) == 0) && ((s_to & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                       (!accf || (reinterpret_cast<uintptr_t>(accf) & 15) == 0);
     const int q_off = (INNER1 ? it.o0 * KT + cq : it.o0 * KT * inner + cq * inner + it.i0);
     const int step_wrap = INNER1 ? KT : KT * inner - it.ni + 1;
     const int n_rf = it.n_rt * it.nfib;
@@ -425,13 +429,15 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
                 const int e_loc = rt * TG + cg_;
                 if (e_loc < m && row_on && cc2 < ncols)
                 {
-                    double * y = dst + (int64_t)sel[e_loc] * s_to + q_off;
+                    const int e_t = sel[e_loc];
+                    double * y = dst + (dmap ? __ldg(dmap + e_t) : (long long)e_t * s_to) + q_off;
+                    const double * yr = accf ? accf + (int64_t)e_t * s_to + q_off : y;
                     v0 *= coef; v1 *= coef;
-                    if (J.accumulate) v0 += y[off0];
+                    if (J.accumulate) v0 += yr[off0];
                     y[off0] = v0;
                     if (cc2 + 1 < ncols)
                     {
-                        if (J.accumulate) v1 += y[off0 + second0];
+                        if (J.accumulate) v1 += yr[off0 + second0];
                         y[off0 + second0] = v1;
                     }
                 }
@@ -479,15 +485,17 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
         const double * xb = xcol + b * fib_stride;
         const int e_loc = rt * TG + cg_;
         const bool tgt_on = e_loc < m && row_on;
-        double * y = dst + (int64_t)(tgt_on ? s_elem[b * m + e_loc] : 0) * s_to + q_off;
+        const int e_t = tgt_on ? s_elem[b * m + e_loc] : 0;
+        double * y = dst + ((!FAST && dmap) ? __ldg(dmap + e_t) : (long long)e_t * s_to) + q_off;
+        const double * yr = (!FAST && accf) ? accf + (int64_t)e_t * s_to + q_off : y;
         if (!FAST && J.accumulate && tgt_on)
         {
             // an accumulating sweep reads its destination: start those lines towards L1 now, the MMA loop hides the trip
 #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
-                if ((vmask >> j) & 1u) asm volatile("prefetch.global.L1 [%0];" :: "l"(y + off[j]));
-                if (!vecst && ((vmask >> j) & 16u)) asm volatile("prefetch.global.L1 [%0];" :: "l"(y + off[j] + second[j]));
+                if ((vmask >> j) & 1u) asm volatile("prefetch.global.L1 [%0];" :: "l"(yr + off[j]));
+                if (!vecst && ((vmask >> j) & 16u)) asm volatile("prefetch.global.L1 [%0];" :: "l"(yr + off[j] + second[j]));
             }
         }
         double acc[4][2];
@@ -523,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
                     for (int j = 0; j < 4; ++j)
                     {
                         old[j] = make_double2(0.0, 0.0);
-                        if (accu && ((vmask >> j) & 1u)) old[j] = *reinterpret_cast<const double2 *>(y + off[j]);
+                        if (accu && ((vmask >> j) & 1u)) old[j] = *reinterpret_cast<const double2 *>(yr + off[j]);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -536,8 +544,8 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
                     for (int j = 0; j < 4; ++j)
                     {
                         old[j][0] = 0.0; old[j][1] = 0.0;
-                        if (accu && ((vmask >> j) & 1u)) old[j][0] = y[off[j]];
-                        if (accu && ((vmask >> j) & 16u)) old[j][1] = y[off[j] + second[j]];
+                        if (accu && ((vmask >> j) & 1u)) old[j][0] = yr[off[j]];
+                        if (accu && ((vmask >> j) & 16u)) old[j][1] = yr[off[j] + second[j]];
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -606,7 +614,7 @@ cudaError_t launch_sweep_tc(const MmaArgs & a, int kf, int kt, int smem_doubles,
         for (int i = 0; i < a.n_job && fast; ++i)
         {
             const int64_t s_to = (int64_t)a.job[i].outer * a.inner * kt;
-            fast = !a.job[i].accumulate && (s_to & 1) == 0 && (reinterpret_cast<uintptr_t>(a.job[i].dst) & 15) == 0;
+            fast = !a.job[i].accumulate && !a.job[i].dst_map && (s_to & 1) == 0 && (reinterpret_cast<uintptr_t>(a.job[i].dst) & 15) == 0;
         }
         if (fast) mode = 2;
     }

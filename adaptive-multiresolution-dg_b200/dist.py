@@ -47,7 +47,19 @@ class FibrePartition:
         self.owner = {"X": _group_owner(level, suppt, self.dims_v, world), "V": _group_owner(level, suppt, self.dims_x, world)}
         # local element lists (ascending global id) per layout
         self.local = {k: np.nonzero(self.owner[k] == rank)[0] for k in ("X", "V")}
+        # row of every element in the local list of the rank that owns it, per layout (ascending global id inside a rank)
+        self.row_in = {}
+        for k in ("X", "V"):
+            ri = np.zeros(self.n, dtype=np.int64)
+            for r in range(world):
+                idx = np.nonzero(self.owner[k] == r)[0]
+                ri[idx] = np.arange(len(idx))
+            self.row_in[k] = ri
         self.level, self.suppt = level, suppt
+
+    def local_of(self, layout, r):
+        """global ids (ascending) of the elements rank r owns in `layout`"""
+        return np.nonzero(self.owner[layout] == r)[0]
 
     def plan(self, src, dst):
         """exchange plan src layout -> dst layout for this rank: (send_index [local src rows, grouped by destination rank],

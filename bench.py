@@ -1,21 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the fast sparse-grid transform path (BASELINE.json metric: sparse-grid DoF-stage updates/s, FP64).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5|cfg2|cfg4] [--kernel V]
 
-One "step" = one pass of the hot path over one batch of synthetic input:
-  cfg2 (default, the config the metric is quoted on that fits one GPU): the Lagrange interpolation round trip
-       d=4, k=3, m=3, NMAX=8 full sparse grid -- FastLagrIntp::eval_up_Lagr -> eval_up_to_coe_D_Lag ->
-       FastLagrInit::eval_ucoe_Alpt_Lagr (reference source/FastMultiplyLU.cpp:1362-1365, 1617-1620,
-       source/Interplation.cpp:891-1048) -- one DoF-stage update = one DoF through one forward+inverse transform.
-Multi-GPU (torchrun, one rank per GPU): the round trip has no exchange step, so the ranks run independent
-grids-worth of components (weak scaling, no data-path collective); the barrier + max-over-ranks timing uses NCCL.
+Default workload (every N): **cfg5**, example/07_vlasov_maxwell_sparse scaled to 3D3V -- d=6, k=1, m=2, NMAX=7 full sparse grid (16 172 elements,
+1.04 M DoF, 11.8 M interpolation points) -- ONE complete nonlinear RK3SSP stage: FastLagrIntp::eval_up_Lagr -> Vlasov point-wise products ->
+eval_fp_to_coe_D_Lag -> rhs_vol + rhs_flx of all six dimensions -> LxF penalty sweeps -> ExplicitRK::step_stage, as the batched program of
+adaptive-multiresolution-dg_b200/stage.py.  N = 1 runs it on one context; N > 1 (torchrun, one rank per GPU) partitions the grid by fibre
+ownership: the layout switches are stores into CUDA-IPC-mapped peer memory from the epilogues of the producing sweeps plus row scatters, separated
+by device-side barriers -- STRONG scaling, value = global DoF / max-over-ranks stage time.  Before timing, the same program is run on the reference's
+d=6 fixture (tests/golden/cfg5_vlasov_d6_k1_n2) at the same N and compared with the reference's dump: `config.parity_rel_l2`.
+At N = 1 the line also carries `secondary`: cfg2 (example/01_interp_01_high_dim, Lagrange round trip d=4, k=3, m=3, NMAX=8), the transform-only
+workload, with the roofline of its <4,4> sweep kernel.
 
-Timing: CUDA events on the stream the kernels are launched on, every timed step bracketed by its own event
-pair with an L2 flush (256 MiB write) between steps, max over ranks.  `e2e` goes through the host-buffer C-ABI
-entry point (amdg_host_roundtrip) with pinned host buffers: H2D + kernels + D2H inside the timed region.
-The reference arm (--impl reference) and `cpu_baseline` time the compiled, unmodified reference
-(oracle/_ref/ref_harness) on the host cores on a bounded sample (smaller NMAX) of the same workload.
+Timing: CUDA events on the launch stream around CUDA-graph replays of the step, an L2 flush (256 MiB write) between timed steps, max over ranks.
+`e2e`: the same step from pinned host buffers (H2D of the coefficients, the stage, D2H of the result inside the timed region).  The reference arm
+(--impl reference) and `cpu_baseline` time the compiled, unmodified reference (oracle/_ref/ref_harness) on the host cores.
 """
 import argparse
 import ctypes
@@ -33,17 +33,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: dim, k, m, nmax, sample nmax for the CPU arm
-    "cfg2": dict(kind="roundtrip", dim=4, k=3, m=3, nmax=8, cpu_nmax=7, ref_nmax=6, desc="example/01_interp_01_high_dim: Lagrange interpolation round trip d=4 k=3 m=3 NMAX=8 (full sparse grid)"),
-    # one nonlinear RK stage (interpolate -> point-wise products -> hierarchise -> vol + flx + penalty sweeps -> RK3SSP stage)
-    "cfg5": dict(kind="stage", flux="vlasov", dim=6, k=1, m=2, nmax=7, cpu_nmax=4, ref_nmax=3, desc="example/07_vlasov_maxwell_sparse scaled to 3D3V: d=6 k=1 m=2 NMAX=7, one nonlinear RK3SSP stage with a prescribed smooth field"),
+    # cpu_nmax: bounded sample for the cpu_baseline leg; ref_nmax: the --impl reference arm (same config where the reference finishes in minutes)
+    "cfg2": dict(kind="roundtrip", dim=4, k=3, m=3, nmax=8, cpu_nmax=7, ref_nmax=8, desc="example/01_interp_01_high_dim: Lagrange interpolation round trip d=4 k=3 m=3 NMAX=8 (full sparse grid)"),
+    "cfg5": dict(kind="stage", flux="vlasov", dim=6, k=1, m=2, nmax=7, cpu_nmax=4, ref_nmax=5, desc="example/07_vlasov_maxwell_sparse scaled to 3D3V: d=6 k=1 m=2 NMAX=7 full sparse grid, one nonlinear RK3SSP stage (interpolate, Vlasov products with a prescribed smooth field, hierarchise, vol+flx+penalty, RK)"),
     "cfg4": dict(kind="stage", flux="burgers", dim=2, k=2, m=3, nmax=7, cpu_nmax=7, ref_nmax=7, desc="example/02_hyperbolic_05_burgers_adapt (static upper-bound grid NMAX=7, Lagrange flux): one nonlinear RK3SSP stage"),
 }
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one single-job full sweep launch (ncu --set full, profiles/r01_sweep_tc_ncu.md,
-# launch 1); the written half of the compulsory bytes is still in L2 when the kernel ends, so only the reads show up
-TRAFFIC_NCU = 23.1e6
+LXF_ALPHA, DT = 1.2, 1e-4
 
 
 def peaks():
@@ -51,6 +46,18 @@ def peaks():
     if os.path.exists(p):
         return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the profile summary the profiling script wrote
+    (profiles/r02_traffic.json, keyed by kernel); None when there is no capture of this kernel"""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(kernel_key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -99,15 +106,15 @@ def synthetic_field(level, block, n_comp, seed):
 
 
 def run_reference(args, w, n_threads=None, as_baseline=False):
-    """the compiled, unmodified reference on the host cores, bounded sample"""
+    """the compiled, unmodified reference on the host cores"""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     if not os.path.exists(exe):
         return None
     nthr = n_threads or os.cpu_count()
-    reps = max(1, args.steps if not as_baseline else 2)
     nmax = w["cpu_nmax"] if as_baseline else w["ref_nmax"]
-    cmd = [exe, "--dim", str(w["dim"]), "--nmax", str(nmax), "--pa", str(w["k"]), "--pl", str(w["m"]),
-           "--time", str(reps + (args.warmup if not as_baseline else 1)), "--threads", str(nthr)]
+    reps = 2 if as_baseline else max(1, min(args.steps, 2 if nmax >= w["nmax"] else 5))
+    warm = 1 if (as_baseline or nmax >= w["nmax"]) else min(args.warmup, 2)
+    cmd = [exe, "--dim", str(w["dim"]), "--nmax", str(nmax), "--pa", str(w["k"]), "--pl", str(w["m"]), "--time", str(reps + warm), "--threads", str(nthr)]
     if w["kind"] == "roundtrip":
         cmd += ["--run", "roundtrip"]
         phases = ("intp", "hier", "init")
@@ -122,10 +129,241 @@ def run_reference(args, w, n_threads=None, as_baseline=False):
     r = json.loads(out)
     t_step = sum(r[p] for p in phases)          # medians over the repetitions
     dof = r["dof"]
-    return {"value": dof / t_step, "unit": "DoF-stage/s", "cores": r["threads"], "kind": "reference",
-            "sample": "%s at NMAX=%d (%d elements, %d DoF): median of %d repetitions, %.3f s per step; reference built from /root/reference/source with -O3 -fopenmp (oracle/Makefile)"
-                      % (what, nmax, r["n_elem"], dof, r["reps"], t_step),
+    same = nmax == w["nmax"]
+    return {"value": dof / t_step, "unit": "DoF-stage/s", "cores": r["threads"], "kind": "reference", "same_config": same,
+            "sample": "%s at NMAX=%d (%d elements, %d DoF)%s: median of %d repetitions, %.3f s per step; reference built from /root/reference/source with -O3 -fopenmp (oracle/Makefile)"
+                      % (what, nmax, r["n_elem"], dof, " -- the benchmark's own configuration" if same else " -- a bounded sample of the NMAX=%d workload, DoF-normalised" % w["nmax"], r["reps"], t_step),
             "ms_per_step": t_step * 1e3, "wall_s": wall}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# point-wise programs (amdg_pointwise_expr)
+def vlasov_program(A, dim):
+    """fp_t = v_t f for the x dims, E_t(x) f for the v dims, E_t(x) = sum_s sin(2 pi (x_s + (t - d/2 + 1)/8)): the generalised
+    interp_Vlasov_2D2V body (reference source/Interplation.cpp:4508-4580) with the prescribed smooth field of oracle/ref_harness.cpp"""
+    P = A.PW
+    hd = dim // 2
+    prog, ptr, consts = [], [0], [2.0 * np.pi]
+    for t in range(dim):
+        if t < hd:
+            prog += [(P["X"], hd + t), (P["VAR"], 0), (P["MUL"], 0)]
+        else:
+            consts.append(0.125 * (t - hd + 1))
+            ci = len(consts) - 1
+            for s in range(hd):
+                prog += [(P["X"], s), (P["CONST"], ci), (P["ADD"], 0), (P["CONST"], 0), (P["MUL"], 0), (P["SIN"], 0)]
+                if s:
+                    prog.append((P["ADD"], 0))
+            prog += [(P["VAR"], 0), (P["MUL"], 0)]
+        ptr.append(len(prog))
+    return prog, ptr, consts
+
+
+def burgers_program(A, dim):
+    P = A.PW
+    prog, ptr = [], [0]
+    for t in range(dim):
+        prog += [(P["VAR"], 0), (P["SQR"], 0), (P["CONST"], 0), (P["MUL"], 0)]
+        ptr.append(len(prog))
+    return prog, ptr, [0.5]
+
+
+def make_stage(A, S, D, dim, nmax, k, m, lev, sup, tables, flux, world, rank, device, stream_ptr, kernel, rk, dense=False):
+    """DeviceStage of one rank for the grid (lev, sup); tables: compact bundles (bench) or dense dump tables (fixture)"""
+    a, b = k + 1, m + 1
+    part = D.FibrePartition(lev, sup, world, rank) if world > 1 else None
+    plan = S.StagePlan(dim, a, b, dim, part=part)
+
+    def make_ops(c):
+        if dense:
+            reg = lambda nm, kf, kt: c.op_register(tables[nm], kf, kt)
+            pt = c.op_register(tables["Lag_pt_Alpt_1D"].T.copy(), a, b)
+            hier = c.op_register_hier(tables["lagr.pw_anc"], tables["lagr.pw_wt"])
+        else:
+            reg = lambda nm, kf, kt: c.op_register_compact(tables[nm])
+            pt = c.op_register_compact(tables["pt"])
+            hier = c.op_register_compact(tables["hier"], hier=True)
+        uv, uvx = reg("lagr.u_v", b, a), reg("lagr.u_vx", b, a)
+        uave = c.op_combine(reg("lagr.ulft_vjp", b, a), 1.0, reg("lagr.urgt_vjp", b, a), 1.0)      # ulft_vjp + urgt_vjp, source/FastMultiplyLU.cpp:1165
+        c.points_set(tables["lagr.intep_pt"])
+        return {"pt": pt, "uv": uv, "volflx": c.op_combine(uvx, 1.0, uave, 0.5), "pen": reg("alpt.ujp_vjp", a, a), "hier": hier}
+    prog, ptr, consts = vlasov_program(A, dim) if flux == "vlasov" else burgers_program(A, dim)
+
+    def pointwise(c, up_ptr, fp_ptrs):
+        c.pointwise_expr([up_ptr], [], None, fp_ptrs, prog, ptr, consts)
+
+    def exchange(obj):
+        import torch.distributed as dist
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    st = S.DeviceStage(A, plan, lev, sup, nmax, k, m, device, make_ops, pointwise, -LXF_ALPHA / 2.0, rk, exchange=exchange, stream_ptr=stream_ptr, kernel=kernel)
+    return st, plan, part
+
+
+def parity_check(A, S, D, world, rank, device, stream, kernel):
+    """the stage program at this N on the reference's d=6 fixture: max over (rhs, stage update) of the relative L2 error against the dump"""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refdump
+    d = refdump.load(os.path.join(ROOT, "tests", "golden", "cfg5_vlasov_d6_k1_n2.dump.xz"))
+    dim, nmax, n0, sparse, pa, pl = [int(x) for x in d["config"][:6]]
+    tables = d
+    with torch.cuda.stream(stream):
+        st, plan, part = make_stage(A, S, D, dim, nmax, pa, pl, d["level"], d["suppt"], tables, "vlasov", world, rank, device, stream.cuda_stream, kernel,
+                                    (A.RK_RK3SSP, 0, 0.001), dense=True)
+        rows = part.local["X"] if part is not None else np.arange(d["level"].shape[0])
+        u0 = torch.from_numpy(np.ascontiguousarray(d["ucoe_alpt.in"][:, 0, :][rows])).cuda()
+        if len(rows):
+            st.view("u").copy_(u0); st.view("u_tn").copy_(u0)
+        stream.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        st.run()
+    stream.synchronize()
+    err = 0.0
+    if len(rows):
+        rel = lambda x, y: float(np.linalg.norm(x - y) / max(np.linalg.norm(y), 1e-300))
+        num = np.array([np.linalg.norm(st.view("rhs").cpu().numpy() - d["rhs_all"][:, 0, :][rows]) ** 2, np.linalg.norm(st.view("u").cpu().numpy() - d["stage0.ucoe_alpt"][:, 0, :][rows]) ** 2])
+    else:
+        num = np.zeros(2)
+    t = torch.from_numpy(num).cuda()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t)
+    num = t.cpu().numpy()
+    err = max(float(np.sqrt(num[0]) / np.linalg.norm(d["rhs_all"][:, 0, :])), float(np.sqrt(num[1]) / np.linalg.norm(d["stage0.ucoe_alpt"][:, 0, :])))
+    berr = st.barrier_error()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    st.close()
+    return err, berr
+
+
+def sweep_roofline(A, ctx, stream, op, sizes_of_t, kf, kt, dim, ne, flush, label, kernel_key):
+    """device time per launch of single-job full sweeps along each dimension in turn over rotating buffers larger than L2 (graph replay)"""
+    import torch
+    peak, peak_src = peaks()
+    nbuf = 8
+    with torch.cuda.stream(stream):
+        bufs, dsts = [], []
+        for i in range(nbuf):
+            sz = sizes_of_t(i % dim)
+            bufs.append(torch.rand(ne, int(np.prod(sz)), dtype=torch.float64, device="cuda"))
+            dsts.append(torch.empty(ne, int(np.prod(sz)) // kf * kt, dtype=torch.float64, device="cuda"))
+            ctx.sweep1d(op, A.REL_VOL, A.LU_FULL, i % dim, sz, bufs[i], dsts[i])
+    stream.synchronize()
+    nrep, n_replay = 4 * nbuf, 8
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        for i in range(nrep):
+            ctx.sweep1d(op, A.REL_VOL, A.LU_FULL, i % dim, sizes_of_t(i % dim), bufs[i % nbuf], dsts[i % nbuf])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        g.replay()
+        flush.fill_(0.0)
+        e0.record(stream)
+        for _ in range(n_replay):
+            g.replay()
+        e1.record(stream)
+    stream.synchronize()
+    t_launch = e0.elapsed_time(e1) / (nrep * n_replay) * 1e-3
+    bytes_launch = float(np.mean([8.0 * ne * (np.prod(sizes_of_t(t)) + np.prod(sizes_of_t(t)) // kf * kt) for t in range(dim)]))    # B_sweep = 8 N_e (S_from + S_to)
+    achieved = bytes_launch / t_launch / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kernel_key),
+            "kernel": label, "bytes_per_launch": bytes_launch, "us_per_launch": t_launch * 1e6, "peak_source": peak_src}
+
+
+KERNEL_NAMES = {0: "sweep_tc_kernel", 5: "sweep_tc_kernel", 4: "sweep_mma_kernel", 6: "sweep_dir_kernel", 7: "sweep_ws_kernel"}
+
+
+def timed_replays(torch, stream, flush, run_step, steps, barrier):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    with torch.cuda.stream(stream):
+        for s in range(steps):
+            flush.fill_(0.0)                  # L2 flush between timed steps (outside the event pair)
+            ev[s][0].record(stream)
+            run_step()
+            ev[s][1].record(stream)
+    barrier()
+    return float(np.sum([e0.elapsed_time(e1) for e0, e1 in ev])) / steps
+
+
+def roundtrip_record(args, A, torch, stream, flush, local_rank, w, with_cpu):
+    """cfg2: Alpert -> point values -> hierarchical coefficients -> Alpert on one GPU"""
+    dim, k, m, nmax = w["dim"], w["k"], w["m"], w["nmax"]
+    a, b = k + 1, m + 1
+    lev, sup = A.sparse_grid(dim, nmax)
+    keys = np.array([A.hash_key(l, s) for l, s in zip(lev, sup)])
+    o = np.argsort(keys, kind="stable")
+    lev, sup = lev[o], sup[o]
+    ne = lev.shape[0]
+    dof = ne * a ** dim
+    ctx = A.Context(dim, nmax, k, m, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_schedule(args.schedule)
+    ctx.set_kernel(args.kernel)
+    ctx.grid_set(lev, sup)
+    tb = load_tables(A, w)
+    op_pt, op_uv, op_hier = ctx.op_register_compact(tb["pt"]), ctx.op_register_compact(tb["lagr.u_v"]), ctx.op_register_compact(tb["hier"], hier=True)
+    vol = [A.REL_VOL] * dim
+    host_in = torch.from_numpy(synthetic_field(lev, a ** dim, 1, 20240901)).pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    hin, hout = host_in.numpy(), host_out.numpy()
+    with torch.cuda.stream(stream):
+        u = host_in.to("cuda", non_blocking=True)
+        up = torch.zeros(1, ne, b ** dim, dtype=torch.float64, device="cuda")
+        out = torch.zeros(1, ne, a ** dim, dtype=torch.float64, device="cuda")
+
+    def step():
+        ctx.apply_tensor([op_pt] * dim, vol, u, up)                # Alpert -> point values
+        ctx.hierarchize(op_hier, up, up)                            # point values -> hierarchical coefficients
+        ctx.apply_tensor([op_uv] * dim, vol, up, out)               # -> Alpert
+    sync = lambda: torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+    sync()
+    l_before = ctx.launch_count
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        step()
+    launches_per_step = ctx.launch_count - l_before
+    with torch.cuda.stream(stream):
+        graph.replay()
+    sync()
+    t_ms = timed_replays(torch, stream, flush, graph.replay, args.steps, sync)
+    for _ in range(2):
+        ctx.host_roundtrip(op_pt, op_hier, op_uv, hin, out=hout)
+    sync()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        ctx.host_roundtrip(op_pt, op_hier, op_uv, hin, out=hout)
+    sync()
+    t_e2e = (time.perf_counter() - t0) / n_e2e
+    kname = KERNEL_NAMES.get(args.kernel, "sweep kernel %d" % args.kernel)
+    roof = sweep_roofline(A, ctx, stream, op_pt, lambda t: [a] * dim, a, b, dim, ne, flush,
+                          "%s<%d,%d> (one 1D sweep along each dimension in turn, single job; FP64 DMMA m8n8k4)" % (kname, a, b), "%s<%d,%d>" % (kname, a, b))
+    chain = sum((a ** (dim - i) * b ** i + a ** (dim - i - 1) * b ** (i + 1)) for i in range(dim))
+    b_alg = 8.0 * ne * (2 * 2 ** (dim - 1) * chain + dim * 2 * b ** dim)          # SURVEY.md 8(d)
+    peak = roof["peak"]
+    roof["step"] = {"b_alg_bytes": b_alg, "gbs": b_alg / (t_ms * 1e-3) / 1e9, "frac": b_alg / (t_ms * 1e-3) / 1e9 / peak,
+                    "note": "reference sweep list bytes / measured step time; the shared-prefix schedule runs %d instead of %d sweeps per transform" % (3 * 2 ** (dim - 1) - 2, dim * 2 ** (dim - 1))}
+    rec = {"workload": w["desc"], "metric": "sparse-grid DoF-stage updates/sec (FP64)", "value": dof / (t_ms * 1e-3), "unit": "DoF-stage/s", "ms_per_step": t_ms,
+           "n_elem": int(ne), "dof": int(dof), "gpu_launches": int(launches_per_step * args.steps), "kernel": args.kernel,
+           "e2e": {"value": dof / t_e2e, "unit": "DoF-stage/s", "h2d_bytes_per_step": int(hin.nbytes), "d2h_bytes_per_step": int(hout.nbytes), "ms_per_step": t_e2e * 1e3,
+                   "api": "amdg_host_roundtrip (pinned host buffers)"},
+           "roofline": roof}
+    if with_cpu:
+        cb = run_reference(args, w, as_baseline=True)
+        if cb:
+            rec["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+    ctx.close()
+    return rec
 
 
 def main():
@@ -134,13 +372,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default="cfg5")
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--schedule", type=int, default=1)
-    ap.add_argument("--ncomp", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (quick kernel comparisons)")
-    ap.add_argument("--literal-rhs", action="store_true", help="stage workloads: rhs_vol and rhs_flx as separate tensor applications")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 secondary record at N = 1")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -152,9 +389,9 @@ def main():
             return 0
         r = run_reference(args, w)
         line = {"impl": "reference", "metric": "sparse-grid DoF-stage updates/sec (FP64)", "value": r["value"], "unit": "DoF-stage/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong" if w["kind"] == "stage" else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["desc"], "sample": r["sample"]},
+                "config": {"workload": w["desc"], "sample": r["sample"], "same_config": r["same_config"]},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "DoF-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -167,151 +404,92 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     A = importlib.import_module("adaptive-multiresolution-dg_b200")
-
-    dim, k, m, nmax = w["dim"], w["k"], w["m"], w["nmax"]
-    a, b = k + 1, m + 1
-    lev, sup = A.sparse_grid(dim, nmax)
-    keys = np.array([A.hash_key(l, s) for l, s in zip(lev, sup)])
-    o = np.argsort(keys, kind="stable")
-    lev, sup = lev[o], sup[o]
-    ne = lev.shape[0]
-    ncomp = args.ncomp
-    dof = ne * a ** dim * ncomp
-
+    S = importlib.import_module("adaptive-multiresolution-dg_b200.stage")
+    D = importlib.import_module("adaptive-multiresolution-dg_b200.dist")
     stream = torch.cuda.Stream()
-    ctx = A.Context(dim, nmax, k, m, device=local_rank)
-    ctx.set_stream(stream.cuda_stream)
-    ctx.set_schedule(args.schedule)
-    ctx.set_kernel(args.kernel)
-    ctx.grid_set(lev, sup)
-    tb = load_tables(A, w)
-    op_pt = ctx.op_register_compact(tb["pt"])
-    op_uv = ctx.op_register_compact(tb["lagr.u_v"])
-    op_hier = ctx.op_register_compact(tb["hier"], hier=True)
-    vol = [A.REL_VOL] * dim
-
-    host_in = torch.from_numpy(synthetic_field(lev, a ** dim, ncomp, 20240901 + rank)).pin_memory()
-    host_out = torch.empty_like(host_in).pin_memory()
-    hin, hout = host_in.numpy(), host_out.numpy()
     with torch.cuda.stream(stream):
-        u = host_in.to("cuda", non_blocking=True)
         flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
-
-    if w["kind"] == "roundtrip":
-        with torch.cuda.stream(stream):
-            up = torch.zeros(ncomp, ne, b ** dim, dtype=torch.float64, device="cuda")
-            out = torch.zeros(ncomp, ne, a ** dim, dtype=torch.float64, device="cuda")
-        ops_f, ops_i = [op_pt] * dim, [op_uv] * dim
-
-        def step():
-            ctx.apply_tensor(ops_f, vol, u, up, n_comp=ncomp)          # Alpert -> point values
-            ctx.hierarchize(op_hier, up, up, n_comp=ncomp)              # point values -> hierarchical coefficients
-            ctx.apply_tensor(ops_i, vol, up, out, n_comp=ncomp)         # -> Alpert
-
-        def e2e_call():
-            ctx.host_roundtrip(op_pt, op_hier, op_uv, hin, n_comp=ncomp, out=hout)
-        e2e_api = "amdg_host_roundtrip (pinned host buffers)"
-        # algorithmic bytes of the reference's sweep list: 2*2^(d-1)*C(d,a,b) + d*2*b^d doubles per element
-        chain = sum((a ** (dim - i) * b ** i + a ** (dim - i - 1) * b ** (i + 1)) for i in range(dim))
-        b_alg = 8.0 * ne * ncomp * (2 * 2 ** (dim - 1) * chain + dim * 2 * b ** dim)
-        step_note = "reference sweep list bytes / measured step time; the shared-prefix schedule runs %d instead of %d sweeps per transform" % (3 * 2 ** (dim - 1) - 2, dim * 2 ** (dim - 1))
-    else:
-        assert ncomp == 1
-        # one nonlinear RK3SSP stage of a scalar conservation law, Lagrange flux interpolation
-        # (the loop of example/07_vlasov_ampere_02_2D2V_accuracy.cpp:247-303)
-        op_uvx = ctx.op_register_compact(tb["lagr.u_vx"])
-        op_ul = ctx.op_register_compact(tb["lagr.ulft_vjp"])
-        op_ur = ctx.op_register_compact(tb["lagr.urgt_vjp"])
-        op_uave = ctx.op_combine(op_ul, 1.0, op_ur, 1.0)                 # ulft_vjp + urgt_vjp, source/FastMultiplyLU.cpp:1165
-        op_volflx = ctx.op_combine(op_uvx, 1.0, op_uave, 0.5)            # u_vx + (ulft_vjp + urgt_vjp)/2 under the flx relation
-        op_pen = ctx.op_register_compact(tb["alpt.ujp_vjp"])
-        nf = dim
-        flux_ids = [A.FLUX_VLASOV_SMOOTH_E if w["flux"] == "vlasov" else A.FLUX_BURGERS] * nf
-        prm = [[t, 0, 0, 0] for t in range(nf)]
-        lxf_alpha, dt = 1.2, 1e-4
-        with torch.cuda.stream(stream):
-            up = torch.zeros(ne, b ** dim, dtype=torch.float64, device="cuda")
-            pts = torch.zeros(ne, b ** dim, dim, dtype=torch.float64, device="cuda")
-            fp = torch.zeros(nf, ne, b ** dim, dtype=torch.float64, device="cuda")
-            fuc = torch.zeros_like(fp)
-            rhs = torch.zeros(ne, a ** dim, dtype=torch.float64, device="cuda")
-            u_tn = u.clone()
-            ctx.point_coords(tb["lagr.intep_pt"], pts)
-        merged = not args.literal_rhs
-
-        def step():
-            ctx.apply_tensor([op_pt] * dim, vol, u, up)                                  # FastLagrIntp::eval_up_Lagr
-            ctx.pointwise(flux_ids, prm, up, fp, pts)                                    # eval_fp_Lag / Vlasov products
-            ctx.hierarchize(op_hier, fp, fuc, n_comp=nf)                                 # eval_fp_to_coe_D_Lag
-            for t in range(dim):
-                if merged:      # rhs_vol_scalar + rhs_flx_intp_scalar of dim t as ONE tensor application
-                    ops = [op_volflx if s == t else op_uv for s in range(dim)]
-                    rels = [A.REL_FLX if s == t else A.REL_VOL for s in range(dim)]
-                    ctx.apply_tensor(ops, rels, fuc[t], rhs, accumulate=t > 0)           # t == 0 overwrites: DGSolution::set_rhs_zero
-                else:
-                    ctx.apply_tensor([op_uvx if s == t else op_uv for s in range(dim)], vol, fuc[t], rhs, accumulate=t > 0)
-                    ctx.apply_tensor([op_uave if s == t else op_uv for s in range(dim)], [A.REL_FLX if s == t else A.REL_VOL for s in range(dim)],
-                                     fuc[t], rhs, coef=0.5, accumulate=True)
-            for t in range(dim):                                                         # HyperbolicAlptRHS::rhs_flx_penalty_scalar
-                ctx.sweep1d(op_pen, A.REL_FLX, A.LU_FULL, t, [a] * dim, u, rhs, coef=-lxf_alpha / 2.0, accumulate=True)
-            ctx.rk_stage(A.RK_RK3SSP, 1, dt, u_tn, u, rhs)                               # RK3SSP::step_stage(1): u <- 3/4 u_n + 1/4 (u + dt rhs)
-
-        d_u = ctypes.c_void_p(u.data_ptr())
-
-        def e2e_call():
-            A.lib.amdg_dev_upload(ctx._h, d_u, hin.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), hin.size)
-            step()
-            A.lib.amdg_dev_download(ctx._h, hout.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), d_u, hout.size)
-            ctx.sync()
-        e2e_api = "amdg_dev_upload + the stage's C-ABI calls + amdg_dev_download (pinned host buffers)"
-        C = lambda p, q: sum((p ** (dim - i) * q ** i + p ** (dim - i - 1) * q ** (i + 1)) for i in range(dim))
-        n_ch = 2 ** (dim - 1)
-        # interpolation + point-wise + hierarchisation + vol and flx tensor applications + penalty sweeps + 4 axpy vectors
-        b_alg = 8.0 * ne * (n_ch * C(a, b) + (1 + nf) * b ** dim + nf * dim * 2 * b ** dim + 2 * nf * n_ch * C(b, a) + dim * 2 * a ** dim + 4 * a ** dim)
-        step_note = ("reference sweep list bytes / measured step time; here every tensor application runs %d instead of %d sweeps (shared-prefix schedule)%s"
-                     % (3 * n_ch - 2, dim * n_ch, " and vol + flx of a dimension are one application (u_vx + (ulft_vjp+urgt_vjp)/2 under the flx relation)" if merged else ""))
-    stream.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    if w["kind"] == "roundtrip":
+        if world > 1:
+            raise SystemExit("the round trip has no exchange step: run it on one GPU (the multi-GPU benchmark is the cfg5 stage)")
+        rec = roundtrip_record(args, A, torch, stream, flush, local_rank, w, with_cpu=not args.no_cpu)
+        line = {"metric": rec["metric"], "value": rec["value"], "unit": rec["unit"], "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rec["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["desc"], "n_elem": rec["n_elem"], "dof": rec["dof"], "kernel": args.kernel, "cuda_graph": True,
+                           "l2": "flushed (256 MiB write) between timed steps; per-step CUDA event pairs on the launch stream"},
+                "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"]}
+        if "cpu_baseline" in rec:
+            line["cpu_baseline"] = rec["cpu_baseline"]
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- the stage workloads (cfg5 default, cfg4)
+    dim, k, m, nmax = w["dim"], w["k"], w["m"], w["nmax"]
+    a, b = k + 1, m + 1
+    parity = parity_check(A, S, D, world, rank, local_rank, stream, args.kernel) if dim == 6 else None
+    lev, sup = A.sparse_grid(dim, nmax)
+    keys = np.array([A.hash_key(l, s) for l, s in zip(lev, sup)])
+    o = np.argsort(keys, kind="stable")
+    lev, sup = lev[o], sup[o]
+    ne = lev.shape[0]
+    dof = ne * a ** dim
+    tb = load_tables(A, w)
+    with torch.cuda.stream(stream):
+        st, plan, part = make_stage(A, S, D, dim, nmax, k, m, lev, sup, tb, w["flux"], world, rank, local_rank, stream.cuda_stream, args.kernel, (A.RK_RK3SSP, 1, DT))
+    rows = part.local["X"] if part is not None else np.arange(ne)
+    u_all = synthetic_field(lev, a ** dim, 1, 20240901)[0]
+    host_in = torch.from_numpy(np.ascontiguousarray(u_all[rows])).pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    hin, hout = host_in.numpy(), host_out.numpy()
+    d_u = ctypes.c_void_p(st.local_ptr("u"))
+    c0 = st.ctx["X"]
+    dp = ctypes.POINTER(ctypes.c_double)
+    with torch.cuda.stream(stream):
+        if len(rows):
+            st.view("u").copy_(host_in, non_blocking=True)
+            st.view("u_tn").copy_(host_in, non_blocking=True)
+    stream.synchronize()
+    barrier()
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
-            step()
+            st.run()
     barrier()
-    # the step is a fixed sequence of ~36 kernel launches: capture it once into a CUDA graph and replay it
-    graph = None
-    launches_per_step = None
+    graph, launches_per_step = None, None
+    l_before = st.launch_count()
     if not args.no_graph:
-        l_before = ctx.launch_count
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
-            step()
-        launches_per_step = ctx.launch_count - l_before
+            st.run()
+        launches_per_step = st.launch_count() - l_before
         with torch.cuda.stream(stream):
             graph.replay()
         barrier()
-    run_step = (lambda: graph.replay()) if graph is not None else step
+    else:
+        with torch.cuda.stream(stream):
+            st.run()
+        launches_per_step = st.launch_count() - l_before
+        barrier()
+    run_step = (lambda: graph.replay()) if graph is not None else st.run
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    l0 = ctx.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    with torch.cuda.stream(stream):
-        for s in range(args.steps):
-            flush.fill_(0.0)                  # L2 flush between timed steps (outside the event pair)
-            ev[s][0].record(stream)
-            run_step()
-            ev[s][1].record(stream)
-    barrier()
-    launches = (launches_per_step * args.steps) if graph is not None else (ctx.launch_count - l0)
-    times = np.array([e0.elapsed_time(e1) for e0, e1 in ev])          # ms
-    t_total = float(times.sum())
+    t_step_ms = timed_replays(torch, stream, flush, run_step, args.steps, barrier)
 
-    # ---- e2e through the host-buffer entry point, pinned host memory, copies inside the timed region
+    # ---- e2e: host buffers -> device, the stage, device -> host, every step
+    def e2e_call():
+        if len(rows):
+            A.lib.amdg_dev_upload(c0._h, d_u, hin.ctypes.data_as(dp), hin.size)
+        with torch.cuda.stream(stream):
+            run_step()
+        if len(rows):
+            A.lib.amdg_dev_download(c0._h, hout.ctypes.data_as(dp), d_u, hout.size)
+        c0.sync()
     for _ in range(2):
         e2e_call()
     barrier()
@@ -319,75 +497,66 @@ def main():
     n_e2e = max(3, min(args.steps, 10))
     for _ in range(n_e2e):
         e2e_call()
-    torch.cuda.synchronize()
+    barrier()
     t_e2e = (time.perf_counter() - t0) / n_e2e
     clocks = sampler.finish()
+    berr = st.barrier_error()
 
-    # ---- roofline of the dominant kernel (the 1D sweep): single-job launches over a rotating set of buffers larger
-    # than L2, so that every launch streams its source from HBM
-    peak, peak_src = peaks()
-    nbuf = 8
-    with torch.cuda.stream(stream):
-        bufs = [torch.rand(ne, a ** dim, dtype=torch.float64, device="cuda") for _ in range(nbuf)]
-        dsts = [torch.empty(ne, a ** (dim - 1) * b, dtype=torch.float64, device="cuda") for _ in range(nbuf)]
-        for i in range(nbuf):
-            ctx.sweep1d(op_pt, A.REL_VOL, A.LU_FULL, i % dim, [a] * dim, bufs[i], dsts[i])
-    stream.synchronize()
-    # the launches are replayed from a CUDA graph (as in the step), so the figure is device time per launch, not host enqueue rate
-    nrep, n_replay = 4 * nbuf, 8
-    l_roof0 = ctx.launch_count
-    g_roof = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g_roof, stream=stream):
-        for i in range(nrep):
-            ctx.sweep1d(op_pt, A.REL_VOL, A.LU_FULL, i % dim, [a] * dim, bufs[i % nbuf], dsts[i % nbuf])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        g_roof.replay()
-        flush.fill_(0.0)
-        e0.record(stream)
-        for _ in range(n_replay):
-            g_roof.replay()
-        e1.record(stream)
-    stream.synchronize()
-    t_launch = e0.elapsed_time(e1) / (nrep * n_replay) * 1e-3
-    bytes_launch = 8.0 * ne * (a ** dim + a ** (dim - 1) * b)           # B_sweep = 8 N_e (S_from + S_to), SURVEY.md 8(d): one dimension goes from edge a to edge b
-    achieved = bytes_launch / t_launch / 1e9
-
-    # per-rank step time -> max over ranks
-    t_step_ms = t_total / args.steps
+    tt = torch.tensor([t_step_ms, t_e2e, float(len(rows)), float(len(part.local["V"]) if part is not None else ne), float(st.sent_bytes), float(berr)], dtype=torch.float64, device="cuda")
+    mx, sm = tt.clone(), tt.clone()
     if world > 1:
-        tt = torch.tensor([t_step_ms, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_step_ms, t_e2e = float(tt[0]), float(tt[1])
-    value = dof * world / (t_step_ms * 1e-3)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    t_step_ms, t_e2e = float(mx[0]), float(mx[1])
+    value = dof / (t_step_ms * 1e-3)
 
+    roof = None
     if rank == 0:
+        # roofline of the dominant kernel of the stage: the b -> a sweeps of the right-hand-side applications (d of the d+1 tensor applications)
+        rctx = A.Context(dim, nmax, k, m, device=local_rank)
+        rctx.set_stream(stream.cuda_stream); rctx.set_kernel(args.kernel); rctx.grid_set(lev, sup)
+        op_uv = rctx.op_register_compact(tb["lagr.u_v"])
+        kname = KERNEL_NAMES.get(args.kernel, "sweep kernel %d" % args.kernel)
+        roof = sweep_roofline(A, rctx, stream, op_uv, lambda t: [a if q < t else b for q in range(dim)], b, a, dim, ne, flush,
+                              "%s<%d,%d> (one 1D sweep of the right-hand-side chain along each dimension in turn, single job, whole grid on one GPU; FP64 DMMA m8n8k4)" % (kname, b, a),
+                              "%s<%d,%d>" % (kname, b, a))
+        C = lambda p, q: sum((p ** (dim - i) * q ** i + p ** (dim - i - 1) * q ** (i + 1)) for i in range(dim))
+        n_ch, nf = 2 ** (dim - 1), dim
+        b_alg = 8.0 * ne * (n_ch * C(a, b) + (1 + nf) * b ** dim + nf * dim * 2 * b ** dim + 2 * nf * n_ch * C(b, a) + dim * 2 * a ** dim + 4 * a ** dim)        # SURVEY.md 8(d)
+        roof["step"] = {"b_alg_bytes": b_alg, "gbs": b_alg / (t_step_ms * 1e-3) / 1e9, "frac_of_n_gpus": b_alg / (t_step_ms * 1e-3) / 1e9 / (roof["peak"] * world),
+                        "note": "reference sweep list bytes / measured stage time / (N x measured HBM peak); every tensor application runs %d instead of %d sweeps (shared-prefix schedule), vol + flx of a dimension are one application" % (3 * n_ch - 2, dim * n_ch)}
+        rctx.close()
         line = {
             "metric": "sparse-grid DoF-stage updates/sec (FP64)", "value": value, "unit": "DoF-stage/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": max(args.warmup, 3), "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "n_elem": int(ne), "dof_per_gpu": int(dof), "components": ncomp, "schedule": "shared-prefix" if args.schedule else "literal",
-                       "kernel": args.kernel, "cuda_graph": graph is not None, "l2": "flushed (256 MiB write) between timed steps; per-step CUDA event pairs on the launch stream",
-                       "multi_gpu": "independent replicas per rank (no exchange step in this workload)" if world > 1 else "single GPU"},
+            "config": {"workload": w["desc"], "n_elem": int(ne), "dof": int(dof), "points": int(ne * b ** dim), "kernel": args.kernel, "cuda_graph": graph is not None,
+                       "l2": "flushed (256 MiB write) between timed steps; per-step CUDA event pairs on the launch stream",
+                       "multi_gpu": ("fibre-partitioned: %d ranks, layout switches = stores into IPC-mapped peer memory from the sweep epilogues + row scatters, %d device-side barriers per stage"
+                                     % (world, plan.n_barrier)) if world > 1 else "single GPU (same batched program, one layout)",
+                       "launches_per_stage": int(launches_per_step), "barriers_per_stage": int(plan.n_barrier),
+                       "exchange_bytes_per_stage_all_ranks": float(sm[4]), "exchange_doubles_per_element": int(plan.push_bytes) if world > 1 else 0,
+                       "max_local_elements": [int(mx[2]), int(mx[3])], "ideal_local_elements": ne / world,
+                       "parity_rel_l2": (parity[0] if parity else None), "parity_fixture": "tests/golden/cfg5_vlasov_d6_k1_n2 (reference dump): rhs and RK stage after one stage at this N" if parity else None,
+                       "barrier_timeouts": int(mx[5]) + (parity[1] if parity else 0)},
             "clocks": clocks,
-            "e2e": {"value": dof * world / t_e2e, "unit": "DoF-stage/s", "h2d_bytes_per_step": int(hin.nbytes), "d2h_bytes_per_step": int(hout.nbytes),
-                    "ms_per_step": t_e2e * 1e3, "api": e2e_api},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_NCU if (args.kernel in (0, 5) and args.workload == "cfg2") else None,
-                         "kernel": ("sweep_tc_kernel<%d,%d> (one 1D sweep along each dimension in turn, single job; FP64 DMMA m8n8k4)" % (a, b) if args.kernel in (0, 5) else
-                                    "sweep_mma_kernel<%d,%d> (one 1D sweep, single job; FP64 DMMA m8n8k4)" % (a, b) if args.kernel == 4 else "sweep kernel variant %d (one 1D sweep, single job)" % args.kernel), "bytes_per_launch": bytes_launch, "us_per_launch": t_launch * 1e6,
-                         "peak_source": peak_src,
-                         "step": {"b_alg_bytes": b_alg, "gbs": b_alg / (t_step_ms * 1e-3) / 1e9, "frac": b_alg / (t_step_ms * 1e-3) / 1e9 / peak,
-                                  "note": step_note}},
+            "e2e": {"value": dof / t_e2e, "unit": "DoF-stage/s", "h2d_bytes_per_step": int(dof * 8), "d2h_bytes_per_step": int(dof * 8), "ms_per_step": t_e2e * 1e3,
+                    "api": "amdg_dev_upload + the stage's C-ABI calls (CUDA-graph replay) + amdg_dev_download, pinned host buffers, per rank its own rows"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roof,
         }
+    st.close()
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             cb = run_reference(args, w, as_baseline=True)
             if cb:
                 line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+        if world == 1 and not args.no_secondary and args.workload == "cfg5":
+            line["secondary"] = roundtrip_record(args, A, torch, stream, flush, local_rank, WORKLOADS["cfg2"], with_cpu=not args.no_cpu)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
     return 0
 
 

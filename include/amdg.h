@@ -125,6 +125,14 @@ int amdg_sweep1d(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes
 int amdg_sweep1d_batch(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, const double *const *dev_src,
                        double *const *dev_dst, const double *coef, const int *accumulate, int n_job, int n_comp);
 
+/* the same with mapped destinations (register-direct / streaming kernels only, one component per job): dev_dst_map[j] (or NULL) = per element row the
+ * offset in doubles, relative to dev_dst[j], of the element's destination block -- possibly in peer memory: the last sweep before a layout
+ * switch of the fibre-partitioned multi-GPU path stores every block straight into the rank that owns it next; dev_acc_from[j] (or NULL, needs
+ * accumulate[j]) = array in the plain row layout whose values are added instead of the destination's ("remote = local partial sum + sweep") */
+int amdg_sweep1d_batch_mapped(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, const double *const *dev_src,
+                              double *const *dev_dst, const double *coef, const int *accumulate, const int64_t *const *dev_dst_map,
+                              const double *const *dev_acc_from, int n_job);
+
 /* ---- sum over all orderings of the chain of sweeps: FastRHS::transform_fucoe_to_rhs (source/FastMultiplyLU.cpp:4-16),
  * FastInterpolation::transform_ucoealpt_to_upintp (:740-819), FastInitial::transform_ucoeintp_to_ucoealpt (:1418-1445).
  * ops[dim], rels[dim]; src blocks edge_from^dim, dst blocks edge_to^dim; dst = coef*(...) (+ dst if accumulate). ---- */
@@ -147,6 +155,21 @@ int amdg_pointwise_hermite2d(amdg_ctx *ctx, int n_flux, const int *flux_id, cons
  * (LagrBasis::intep_pt, source/LagrBasis.cpp:19-28) */
 int amdg_point_coords(amdg_ctx *ctx, const double *host_pts1d, double *dev_pts);
 
+/* point-wise expressions: LagrInterpolation::eval_fp_Lag with all VEC_NUM unknowns (source/Interplation.cpp:256-295), eval_coe_u_Lag with a
+ * coefficient of position (:648-698, wrappers :4159-4225) and the Vlasov bodies (:4451-4497, 4523-4573) with the field values that
+ * DGSolution::copy_up_intp_to_f (source/DGSolution.cpp:1024-1065) broadcasts.  The reference passes std::function objects; here every output is a
+ * stack program prog[n_prog][2] = (operation, argument), output c = ops [out_ptr[c], out_ptr[c+1]):
+ *   VAR v: point value dev_up[v][point];  X t: coordinate t of the point (amdg_points_set);  OTHER j: dev_other[j][map[element]][local point]
+ *   (dev_other_map = element row of the field grid for every element, NULL = same rows);  CONST k: consts[k];  binary + - * / pow min max;
+ *   unary neg sin cos sqr exp sqrt abs tanh.  Only outputs listed are written (the reference's is_intp mask). */
+enum { AMDG_PW_VAR = 1, AMDG_PW_X = 2, AMDG_PW_OTHER = 3, AMDG_PW_CONST = 4, AMDG_PW_ADD = 5, AMDG_PW_SUB = 6, AMDG_PW_MUL = 7, AMDG_PW_DIV = 8,
+       AMDG_PW_NEG = 9, AMDG_PW_SIN = 10, AMDG_PW_COS = 11, AMDG_PW_SQR = 12, AMDG_PW_EXP = 13, AMDG_PW_SQRT = 14, AMDG_PW_ABS = 15, AMDG_PW_POW = 16,
+       AMDG_PW_TANH = 17, AMDG_PW_MIN = 18, AMDG_PW_MAX = 19 };
+/* the 1D table of interpolation point coordinates pts1d[T*(pmax_intp+1)] (LagrBasis::intep_pt, source/LagrBasis.cpp:19-28), kept on the device */
+int amdg_points_set(amdg_ctx *ctx, const double *host_pts1d);
+int amdg_pointwise_expr(amdg_ctx *ctx, int n_var, const double *const *dev_up, int n_other, const double *const *dev_other, const int *dev_other_map,
+                        int n_out, double *const *dev_out, const int *prog, int n_prog, const int *out_ptr, const double *consts, int n_const);
+
 /* ---- K4: explicit RK stage, ExplicitRK::step_stage (source/ODESolver.cpp:209-301): updates dev_u in place ---- */
 int amdg_rk_stage(amdg_ctx *ctx, int scheme, int stage, double dt, const double *dev_u_tn, double *dev_u,
                   const double *dev_rhs, int64_t n);
@@ -156,6 +179,8 @@ int amdg_rk4_ode2nd_stage(amdg_ctx *ctx, int stage, double dt, const double *dev
                           double *dev_v, const double *dev_rhs, double *dev_ku, double *dev_kv, int64_t n);
 /* y = alpha*x + beta*y */
 int amdg_axpby(amdg_ctx *ctx, int64_t n, double alpha, const double *dev_x, double beta, double *dev_y);
+/* y = sum_{i<k} coefs[i]*x_i + beta*y (k <= 16): DGSolution rhs accumulated from several FastRHS calls (source/FastMultiplyLU.cpp:69-93) in one pass */
+int amdg_lincomb(amdg_ctx *ctx, int64_t n, int k, const double *coefs, const double *const *dev_x, double beta, double *dev_y);
 
 /* ---- host-buffer entry points (what the reference-facing classes call; H2D/D2H inside) ---- */
 int amdg_host_apply_tensor(amdg_ctx *ctx, const int *ops, const int *rels, const double *host_src, double *host_dst,
@@ -167,6 +192,15 @@ int amdg_host_hierarchize(amdg_ctx *ctx, int hier_op, const double *host_src, do
  * (FastLagrIntp::eval_up_Lagr, eval_up_to_coe_D_Lag, FastLagrInit::eval_ucoe_Alpt_Lagr) */
 int amdg_host_roundtrip(amdg_ctx *ctx, int op_alpt_to_pt, int hier_op, int op_intp_to_alpt,
                         const double *host_ucoe_in, double *host_ucoe_out, int n_comp);
+
+/* ---- multi-GPU plumbing (one process per GPU; the fibre-partitioned path of SURVEY.md 8e): device memory of the other ranks mapped through CUDA IPC,
+ * a copy of element rows to mapped destinations, and a device-side barrier over peer-mapped flags (graph-capturable; gives up and raises *dev_error
+ * instead of hanging when a peer never arrives).  flag_ptrs[r] = rank r's flag array unsigned[world] as mapped on this device. ---- */
+int amdg_peer_export(amdg_ctx *ctx, const void *dev_ptr, void *handle64);
+int amdg_peer_open(amdg_ctx *ctx, const void *handle64, void **dev_ptr_out);
+int amdg_peer_close(amdg_ctx *ctx, void *dev_ptr);
+int amdg_peer_barrier(amdg_ctx *ctx, void *const *flag_ptrs, int world, int rank, void *dev_epoch, void *dev_error);
+int amdg_scatter_rows(amdg_ctx *ctx, const double *dev_src, int64_t n_rows, int width, double *dev_dst_base, const int64_t *dev_map);
 
 /* ---- device memory helpers (so callers without a CUDA runtime binding can stage data) ---- */
 int amdg_dev_alloc(amdg_ctx *ctx, int64_t n_doubles, double **dev_out);

@@ -45,6 +45,14 @@ def main():
         if rank == 0:
             print("%s: rel-L2 %.3e, switches %d (%.2f MB sent by rank 0)" % (name, e, T.switches, T.switch_bytes / 1e6))
         T.close()
+    # the whole nonlinear stage program at this world size against the reference's dump (bench.py runs the same check before timing)
+    import bench
+    S = importlib.import_module("adaptive-multiresolution-dg_b200.stage")
+    stream = torch.cuda.Stream()
+    err, berr = bench.parity_check(A, S, D, world, rank, local, stream, 0)
+    worst = max(worst, err, float(berr))
+    if rank == 0:
+        print("stage program (cfg5 fixture, %d ranks): rel-L2 %.3e, barrier time-outs %d" % (world, err, berr))
     w = torch.tensor([worst], device="cuda", dtype=torch.float64)
     dist.all_reduce(w, op=dist.ReduceOp.MAX)
     if rank == 0:

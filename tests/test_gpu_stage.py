@@ -1,0 +1,158 @@
+"""GPU tests of the pieces the batched / partitioned stage is made of (adaptive-multiresolution-dg_b200/stage.py): mapped destinations and
+accumulate-from in the sweep kernels, row scatter, point-wise expressions, linear combination, the device-side barrier, and the whole stage
+program on one GPU against the reference's dumps."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from pipeline import DevCase, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("kernel", [5, 6, 7])
+@pytest.mark.parametrize("name", ["cfg5_vlasov_d6_k1_n2", "adapt_d2_k2_n6", "cfg2_rt_d4_k3_n3"])
+def test_mapped_destination_and_accumulate_from(name, kernel):
+    """a sweep with a destination map writes every element block where the map says (here: a permuted, padded array); with acc_from the old
+    values come from a second array in the plain layout"""
+    d = load_golden(name)
+    c = DevCase(d, kernel=kernel)
+    A = c.amdg
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in sorted({0, c.dim - 1}):
+        for lu in (A.LU_L, A.LU_U, A.LU_FULL):
+            sizes = [c.b if q < t else c.a for q in range(c.dim)]
+            s_from = int(np.prod(sizes)); s_to = s_from // c.a * c.b
+            x = torch.rand(c.ne, s_from, dtype=torch.float64, device="cuda", generator=g)
+            base = torch.rand(c.ne, s_to, dtype=torch.float64, device="cuda", generator=g)
+            plain = base.clone()
+            c.ctx.sweep1d(c.op_pt, A.REL_VOL, lu, t, sizes, x, plain, coef=0.5, accumulate=True)
+            perm = torch.randperm(c.ne, device="cuda", generator=g)
+            pitch = s_to + (2 if s_to % 2 == 0 else 1)                       # even offsets whenever the block size is even
+            out = torch.full((c.ne + 3, pitch), -7.0, dtype=torch.float64, device="cuda")
+            dmap = (perm * pitch).to(torch.int64).contiguous()
+            c.ctx.sweep1d_batch_mapped(c.op_pt, A.REL_VOL, lu, t, [sizes], [x], [out], coefs=[0.5], accumulates=[1], dst_maps=[dmap], acc_froms=[base])
+            c.ctx.sync()
+            got = out[perm][:, :s_to]
+            assert torch.allclose(got, plain, rtol=0, atol=1e-14 * float(plain.abs().max()))
+            assert float(out[:, s_to:].min()) == -7.0 and float(out[:, s_to:].max()) == -7.0      # nothing written outside the mapped blocks
+            # without accumulate
+            plain2 = torch.empty_like(base)
+            c.ctx.sweep1d(c.op_pt, A.REL_VOL, lu, t, sizes, x, plain2)
+            c.ctx.sweep1d_batch_mapped(c.op_pt, A.REL_VOL, lu, t, [sizes], [x], [out], dst_maps=[dmap])
+            c.ctx.sync()
+            assert torch.equal(out[perm][:, :s_to], plain2) or torch.allclose(out[perm][:, :s_to], plain2, rtol=0, atol=1e-14 * float(plain2.abs().max()))
+    c.close()
+
+
+def test_scatter_rows_lincomb_barrier():
+    d = load_golden("cfg4_burgers_lagr_d2_k2_n4")
+    c = DevCase(d)
+    A = c.amdg
+    n, w = 37, 24
+    src = torch.rand(n, w, dtype=torch.float64, device="cuda")
+    perm = torch.randperm(n, device="cuda")
+    dst = torch.zeros(n + 2, w + 4, dtype=torch.float64, device="cuda")
+    mp = (perm * (w + 4)).to(torch.int64).contiguous()
+    c.ctx.scatter_rows(src, n, w, dst, mp)
+    xs = [torch.rand(1000, dtype=torch.float64, device="cuda") for _ in range(5)]
+    y = torch.rand(1000, dtype=torch.float64, device="cuda")
+    y0 = y.clone()
+    c.ctx.lincomb([1.0, -2.0, 0.5, 3.0, 1.0], xs, y, beta=0.25)
+    # a barrier of a single rank with itself (flags, epoch and error words in one small buffer), three times, also from a CUDA graph
+    st = torch.zeros(64, dtype=torch.int32, device="cuda")
+    flags, epoch, error = st.data_ptr(), st.data_ptr() + 128, st.data_ptr() + 136
+    for _ in range(3):
+        c.ctx.peer_barrier([flags], 0, epoch, error)
+    c.ctx.sync()
+    assert torch.equal(dst[perm][:, :w], src) and float(dst[:, w:].abs().max()) == 0.0
+    assert torch.allclose(y, 0.25 * y0 + xs[0] - 2 * xs[1] + 0.5 * xs[2] + 3 * xs[3] + xs[4], rtol=1e-14, atol=1e-14)
+    assert int(st[0]) == 3 and int(st[32]) == 3 and int(st[34]) == 0
+    c.close()
+
+
+def test_pointwise_expressions_match_enumerated_and_oracle():
+    """amdg_pointwise_expr: the enumerated fluxes as stack programs; coordinates from the 1D table; a two-variable flux; a field through an element map"""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = load_golden("cfg5_vlasov_d6_k1_n2")
+    c = DevCase(d)
+    A = c.amdg
+    P = A.PW
+    c.ctx.points_set(d["lagr.intep_pt"])
+    up = c.to_dev(d["up_intp"][:, 0, :])
+    npts = c.b ** c.dim
+    # 1. the Vlasov products of the fixture (v_t f, E_t(x) f with the harness' analytic field): program vs the reference's fp_intp
+    prog, ptr, consts = bench.vlasov_program(A, c.dim)
+    outs = [torch.zeros(c.ne, npts, dtype=torch.float64, device="cuda") for _ in range(c.dim)]
+    c.ctx.pointwise_expr([up], [], None, outs, prog, ptr, consts)
+    for t in range(c.dim):
+        assert rel(c.to_host(outs[t]), d["fp_intp"][:, 0, t, :]) < 1e-14
+    # 2. two unknowns: the coupled Schroedinger source of example/06_schrodinger_02_coupled_adapt.cpp:183-194, component 0: -(u0^2 + u1^2) u1
+    u1 = torch.rand_like(up)
+    o = torch.zeros_like(up)
+    c.ctx.pointwise_expr([up, u1], [], None, [o], [(P["VAR"], 0), (P["SQR"], 0), (P["VAR"], 1), (P["SQR"], 0), (P["ADD"], 0), (P["VAR"], 1), (P["MUL"], 0), (P["NEG"], 0)], [0, 8])
+    assert torch.allclose(o, -(up * up + u1 * u1) * u1, rtol=1e-15, atol=0)
+    # 3. a field living on another grid's elements, gathered through an element map (DGSolution::copy_up_intp_to_f): E * f
+    nE = 11
+    E = torch.rand(nE, npts, dtype=torch.float64, device="cuda")
+    emap = torch.randint(0, nE, (c.ne,), dtype=torch.int32, device="cuda")
+    c.ctx.pointwise_expr([up], [E], emap, [o], [(P["OTHER"], 0), (P["VAR"], 0), (P["MUL"], 0)], [0, 3])
+    assert torch.equal(o, E[emap.long()] * up)
+    # 4. malformed programs are rejected, nothing is launched
+    with pytest.raises(A.AmdgError):
+        c.ctx.pointwise_expr([up], [], None, [o], [(P["VAR"], 0), (P["ADD"], 0)], [0, 2])
+    with pytest.raises(A.AmdgError):
+        c.ctx.pointwise_expr([up], [], None, [o], [(P["VAR"], 3)], [0, 1])
+    c.close()
+
+
+@pytest.mark.parametrize("kernel", [0, 7])
+def test_stage_program_single_gpu_vs_reference(kernel):
+    """the whole batched stage program (stage.py) on one GPU: right-hand side and RK stage 0 of the d=6 Vlasov fixture against the reference"""
+    sys.path.insert(0, ROOT)
+    import bench
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    S = importlib.import_module("adaptive-multiresolution-dg_b200.stage")
+    D = importlib.import_module("adaptive-multiresolution-dg_b200.dist")
+    err, berr = bench.parity_check(A, S, D, 1, 0, 0, torch.cuda.current_stream(), kernel)
+    assert err < TOL and berr == 0
+
+
+def test_stage_program_burgers_2d_vs_reference():
+    """the same program in 2D (cfg4, Burgers, one flux component per dimension) against the reference's nonlinear right-hand side"""
+    sys.path.insert(0, ROOT)
+    import bench
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    S = importlib.import_module("adaptive-multiresolution-dg_b200.stage")
+    D = importlib.import_module("adaptive-multiresolution-dg_b200.dist")
+    d = load_golden("cfg1_adv_d2_k2_n4")           # Burgers flux in both dimensions, RK3SSP stages dumped
+    dim, nmax, n0, sparse, pa, pl = [int(x) for x in d["config"][:6]]
+    stream = torch.cuda.current_stream()
+    st, plan, part = bench.make_stage(A, S, D, dim, nmax, pa, pl, d["level"], d["suppt"], d, "burgers", 1, 0, 0, stream.cuda_stream, 0, (A.RK_RK3SSP, 0, 0.002), dense=True)
+    u0 = torch.from_numpy(np.ascontiguousarray(d["ucoe_alpt.in"][:, 0, :])).cuda()
+    st.view("u").copy_(u0); st.view("u_tn").copy_(u0)
+    st.run()
+    torch.cuda.synchronize()
+    assert rel(st.view("rhs").cpu().numpy(), d["rhs_all"][:, 0, :]) < TOL
+    assert rel(st.view("u").cpu().numpy(), d["stage0.ucoe_alpt"][:, 0, :]) < TOL
+    st.close()
+
+
+def _n_gpus():
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs (the driver's 1-GPU box runs the same check inside `bench.py --gpus 2`)")
+def test_two_gpu_stage_parity():
+    import subprocess
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29671",
+                        os.path.join(ROOT, "tests", "dist_check.py")], capture_output=True, text=True, timeout=900)
+    assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
