@@ -105,6 +105,7 @@ struct amdg_ctx
     struct WsList
     {
         WsItem * d_items = nullptr; int * d_cta_ptr = nullptr; int * d_pool = nullptr; int * d_tab_b = nullptr; int2 * d_tab_c = nullptr;
+        int * d_rows = nullptr; int * d_rows_ptr = nullptr;
         int n_cta = 0; bool bulk_ok = false;
         MmaList ml;
     };
@@ -157,6 +158,7 @@ static void free_dev_grid(amdg_ctx * c)
     {
         amdg_ctx::WsList & L = kv.second;
         meta_free(c, L.d_items); meta_free(c, L.d_cta_ptr); meta_free(c, L.d_pool); meta_free(c, L.d_tab_b); meta_free(c, L.d_tab_c); meta_free(c, L.ml.d_elem_pool);
+        meta_free(c, L.d_rows); meta_free(c, L.d_rows_ptr);
         for (auto & at : L.ml.a_tab) meta_free(c, (void *)at.second);
     }
     c->wss.clear();
@@ -1309,7 +1311,7 @@ int amdg_dir_list_export(amdg_ctx * c, int op, int rel, int lu, int t, const int
 // amdg_ws_list_export): items per persistent CTA, balanced by longest-processing-time-first on a cost estimate.
 struct WsHost
 {
-    std::vector<WsItem> items; std::vector<int> cta_ptr, pool, elem_pool, tab_b, tab_c;
+    std::vector<WsItem> items; std::vector<int> cta_ptr, pool, elem_pool, tab_b, tab_c, rows, rows_ptr;
     std::vector<ShapeProg> progs; std::vector<int> prog_shape; std::vector<long long> prog_piece;
     bool bulk_ok = true;
 };
@@ -1423,6 +1425,33 @@ static void build_ws_host(amdg_ctx * c, int t, int outer, int inner, int kf, int
     for (int q = 0; q < n_cta; ++q) { for (int i : bins[q]) sorted.push_back(D.items[i]); D.cta_ptr.push_back((int)sorted.size()); }
     D.items.swap(sorted);
     D.pool.push_back(0);                                           // padding: the kernel fetches one entry ahead
+    // resolved element rows per CTA (the kernel keeps them in shared memory): sources of every slot / entry, targets of every row tile
+    const int tg = 8 / mma_ktp(kt);
+    D.rows.clear(); D.rows_ptr.assign(1, 0);
+    for (int q = 0; q < n_cta; ++q)
+    {
+        const int base = (int)D.rows.size();
+        for (int i = D.cta_ptr[q]; i < D.cta_ptr[q + 1]; ++i)
+        {
+            WsItem & x = D.items[i];
+            x.rows_ofs = (int)D.rows.size() - base;
+            const int * P = D.pool.data() + x.pool_ofs;
+            const int * rt_id = P + x.n_rt + 1, * ent = P + 2 * x.n_rt + 1, * src_local = ent + x.n_ent;
+            if (x.heavy)
+            {
+                for (int p = 0; p < x.n_ent; ++p) D.rows.push_back(D.elem_pool[x.fib_ofs + (ent[p] >> 1)]);
+                for (int g = 0; g < tg; ++g) { const int tl = rt_id[0] * tg + g; D.rows.push_back(tl < x.m ? D.elem_pool[x.fib_ofs + tl] : -1); }
+            }
+            else
+            {
+                for (int b = 0; b < x.nfib; ++b) for (int s2 = 0; s2 < x.n_src; ++s2) D.rows.push_back(D.elem_pool[x.fib_ofs + b * x.m + src_local[s2]]);
+                for (int b = 0; b < x.nfib; ++b) for (int ri = 0; ri < x.n_rt; ++ri) for (int g = 0; g < tg; ++g)
+                { const int tl = rt_id[ri] * tg + g; D.rows.push_back(tl < x.m ? D.elem_pool[x.fib_ofs + b * x.m + tl] : -1); }
+            }
+        }
+        D.rows_ptr.push_back((int)D.rows.size());
+    }
+    if (D.rows.empty()) D.rows.push_back(0);
 }
 
 static amdg_ctx::WsList & get_ws(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int lu, int n_cta)
@@ -1440,6 +1469,8 @@ static amdg_ctx::WsList & get_ws(amdg_ctx * c, int t, int outer, int inner, int 
                   meta_upload(c, &L.ml.d_elem_pool, D.elem_pool.data(), D.elem_pool.size(), false) == cudaSuccess &&
                   meta_upload(c, &L.d_tab_b, D.tab_b.data(), D.tab_b.size(), false) == cudaSuccess &&
                   meta_upload(c, (int **)&L.d_tab_c, D.tab_c.data(), D.tab_c.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.d_rows, D.rows.data(), D.rows.size(), false) == cudaSuccess &&
+                  meta_upload(c, &L.d_rows_ptr, D.rows_ptr.data(), D.rows_ptr.size(), false) == cudaSuccess &&
                   cudaStreamSynchronize(c->stream) == cudaSuccess;
         if (up) { L.n_cta = n_cta; L.bulk_ok = D.bulk_ok; L.ml.ok = true; }
         if (std::getenv("AMDG_VERBOSE"))
@@ -1456,7 +1487,7 @@ static amdg_ctx::WsList & get_ws(amdg_ctx * c, int t, int outer, int inner, int 
 // Diagnostic export of the streaming kernel's work list (host only): counts[8] = items, CTAs, pool ints, element rows, table tiles, programs,
 // entries, bulk_ok.  Call with items == NULL for the counts.  items[n][20] (WsItem), cta_ptr[CTAs+1], tab_b[tiles][32], tab_c[tiles][32][2].
 int amdg_ws_list_export(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, int n_cta, int64_t * counts, int * items, int * cta_ptr,
-                        int * pool, int * elem_pool, int * tab_b, int * tab_c, int * prog_ent_ptr, double * A)
+                        int * pool, int * elem_pool, int * tab_b, int * tab_c, int * prog_ent_ptr, double * A, int * rows, int * rows_ptr)
 {
     if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
     if (op < 0 || op >= (int)c->ops.size() || t < 0 || t >= c->dim || !sizes_from || !counts || rel < 0 || rel > 1 || lu < 0 || lu > 2 || n_cta < 1) return fail(AMDG_EINVAL, "bad arguments");
@@ -1467,8 +1498,10 @@ int amdg_ws_list_export(amdg_ctx * c, int op, int rel, int lu, int t, const int 
     WsHost D; build_ws_host(c, t, outer, inner, O.kf, O.kt, rel, lu, n_cta, D);
     int64_t n_ent = 0; for (auto & P : D.progs) n_ent += P.n_ent();
     counts[0] = (int64_t)D.items.size(); counts[1] = n_cta; counts[2] = (int64_t)D.pool.size(); counts[3] = (int64_t)D.elem_pool.size();
-    counts[4] = (int64_t)D.tab_b.size() / 32; counts[5] = (int64_t)D.progs.size(); counts[6] = n_ent; counts[7] = D.bulk_ok ? 1 : 0;
+    counts[4] = (int64_t)D.tab_b.size() / 32; counts[5] = (int64_t)D.progs.size(); counts[6] = n_ent; counts[7] = (D.bulk_ok ? 1 : 0) + 2 * (int64_t)D.rows.size();
     if (!items) return AMDG_OK;
+    if (rows) std::memcpy(rows, D.rows.data(), D.rows.size() * sizeof(int));
+    if (rows_ptr) std::memcpy(rows_ptr, D.rows_ptr.data(), D.rows_ptr.size() * sizeof(int));
     std::memcpy(items, D.items.data(), D.items.size() * sizeof(WsItem));
     std::memcpy(cta_ptr, D.cta_ptr.data(), D.cta_ptr.size() * sizeof(int));
     std::memcpy(pool, D.pool.data(), D.pool.size() * sizeof(int));
@@ -1575,7 +1608,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
             const double * const * atab = WL.ml.ok ? get_mma_a_tab(c, WL.ml, op, rel, lu) : nullptr;
             if (!(WL.ml.ok && atab)) return fail(AMDG_EINVAL, "streaming kernel requested but the work list could not be built");
             WsArgs a;
-            a.items = WL.d_items; a.cta_ptr = WL.d_cta_ptr; a.pool = WL.d_pool; a.elem_pool = WL.ml.d_elem_pool; a.a_tab = atab;
+            a.items = WL.d_items; a.cta_ptr = WL.d_cta_ptr; a.rows = WL.d_rows; a.rows_ptr = WL.d_rows_ptr; a.pool = WL.d_pool; a.elem_pool = WL.ml.d_elem_pool; a.a_tab = atab;
             a.tab_b = WL.d_tab_b; a.tab_c = WL.d_tab_c; a.n_elem = c->grid.n; a.kf = O.kf; a.kt = O.kt; a.inner = inner;
             const int ktp = mma_ktp(O.kt);
             a.tg = 8 / ktp; a.tg_shift = ktp == 1 ? 0 : (ktp == 2 ? 1 : (ktp == 4 ? 2 : 3));

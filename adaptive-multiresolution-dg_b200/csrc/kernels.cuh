@@ -200,11 +200,14 @@ struct __align__(16) WsItem
     int kstride;                    // doubles between consecutive source indices k inside a slot (heavy items: in global memory)
     int heavy;                      // 1: one row tile x one column tile, not staged, the consumer warps split the entry list
     int vec;                        // the rectangle shape allows aligned 16-byte stores
-    int pad;
+    int rows_ofs;                   // element rows of the item in the CTA's part of `rows`: staged: source row of every slot [nfib*n_src], then the target
+                                    // row of every (fibre, row tile, target slot) [nfib*n_rt*tg] (-1: no such target); heavy: source row of every entry
+                                    // [n_ent], then target rows [tg]
 };
 struct WsArgs
 {
     const WsItem * items; const int * cta_ptr;      // CTA c runs items [cta_ptr[c], cta_ptr[c+1])
+    const int * rows; const int * rows_ptr;         // resolved element rows of CTA c's items: rows[rows_ptr[c] + item.rows_ofs + ...]
     const int * pool; const int * elem_pool; const double * const * a_tab;
     const int * tab_b; const int2 * tab_c;
     int64_t n_elem;

@@ -26,6 +26,8 @@ static const int WS_THREADS = (WS_NC + 1) * 32;
 static const int WS_STAGES = 4;
 static const int WS_STAGE_DOUBLES = 4096;         // 32 KiB
 static const int WS_RED_DOUBLES = WS_NC * 64;
+static const int WS_HDR_ITEMS = 96;               // item headers of the CTA kept in shared memory (more: read from global memory)
+static const int WS_ROWS_INTS = 4096;             // resolved element rows of the CTA's items kept in shared memory
 
 int ws_stage_doubles() { return WS_STAGE_DOUBLES; }
 
@@ -49,15 +51,15 @@ __device__ __forceinline__ void ws_wait(unsigned bar, unsigned parity)
     }
 }
 
-struct WsHdr { int prog, pool_ofs, fib_ofs, nfib, m, n_rt, n_src, n_ent, tab, nct, src_origin, dst_origin, nrun, run_len, gstride, slot, kstride, heavy, vec; };
-__device__ __forceinline__ WsHdr ws_header(const WsItem * it, int lane)
+struct WsHdr { int prog, pool_ofs, fib_ofs, nfib, m, n_rt, n_src, n_ent, tab, nct, src_origin, dst_origin, nrun, run_len, gstride, slot, kstride, heavy, vec, rows_ofs; };
+__device__ __forceinline__ WsHdr ws_header(const int * it, int lane)
 {
     int hv = 0;
-    if (lane < 19) hv = __ldg(reinterpret_cast<const int *>(it) + lane);
+    if (lane < 20) hv = it[lane];
     WsHdr h;
 #define WS_F(name, i) h.name = __shfl_sync(0xffffffffu, hv, i)
     WS_F(prog, 0); WS_F(pool_ofs, 1); WS_F(fib_ofs, 2); WS_F(nfib, 3); WS_F(m, 4); WS_F(n_rt, 5); WS_F(n_src, 6); WS_F(n_ent, 7); WS_F(tab, 8); WS_F(nct, 9);
-    WS_F(src_origin, 10); WS_F(dst_origin, 11); WS_F(nrun, 12); WS_F(run_len, 13); WS_F(gstride, 14); WS_F(slot, 15); WS_F(kstride, 16); WS_F(heavy, 17); WS_F(vec, 18);
+    WS_F(src_origin, 10); WS_F(dst_origin, 11); WS_F(nrun, 12); WS_F(run_len, 13); WS_F(gstride, 14); WS_F(slot, 15); WS_F(kstride, 16); WS_F(heavy, 17); WS_F(vec, 18); WS_F(rows_ofs, 19);
 #undef WS_F
     return h;
 }
@@ -83,6 +85,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
     const int64_t s_from = (int64_t)W * a.kf, s_to = (int64_t)W * a.kt;
     const double * __restrict__ src = a.job[jb].src + (int64_t)comp * a.n_elem * s_from;
     const int it0 = __ldg(a.cta_ptr + blockIdx.x), it1 = __ldg(a.cta_ptr + blockIdx.x + 1);
+    // the CTA's item headers and resolved element rows move to shared memory once (one round trip to L2 for all of them, under the tail of the
+    // previous kernel): neither the producer nor the consumers wait for work-list loads per item afterwards
+    int * s_hdr = reinterpret_cast<int *>(ws_smem + WS_STAGES * WS_STAGE_DOUBLES + WS_RED_DOUBLES);
+    int * s_rows = s_hdr + WS_HDR_ITEMS * 20;
+    const int r0 = __ldg(a.rows_ptr + blockIdx.x), r1 = __ldg(a.rows_ptr + blockIdx.x + 1);
+    const int n_items = it1 - it0, n_rows = r1 - r0;
+    const bool hdr_sm = n_items <= WS_HDR_ITEMS, rows_sm = n_rows <= WS_ROWS_INTS;
+    if (hdr_sm) for (int i = tid; i < n_items * 20; i += WS_THREADS) s_hdr[i] = __ldg(reinterpret_cast<const int *>(a.items + it0) + i);
+    if (rows_sm) for (int i = tid; i < n_rows; i += WS_THREADS) s_rows[i] = __ldg(a.rows + r0 + i);
+    const int * hdrs = hdr_sm ? s_hdr : reinterpret_cast<const int *>(a.items + it0);
+    const int * rows = rows_sm ? s_rows : a.rows + r0;
+    __syncthreads();
     // the work lists are host-written; from here on the coefficient arrays of earlier kernels are read and written
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -91,12 +105,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
         // ---------------------------------------------------------------- producer
         const bool bulk = (a.bulk_jobs >> jb) & 1u;
         int stage = 0; unsigned phase = 0;
-        for (int it = it0; it < it1; ++it)
+        for (int it = 0; it < n_items; ++it)
         {
-            const WsHdr h = ws_header(a.items + it, lane);
+            const WsHdr h = ws_header(hdrs + it * 20, lane);
             if (h.heavy) continue;
             ws_wait(ws_sptr(&bar_empty[stage]), phase ^ 1u);
-            const int * __restrict__ src_local = a.pool + h.pool_ofs + 2 * h.n_rt + 1 + h.n_ent;
+            const int * srow = rows + h.rows_ofs;
             const int n_slots = h.nfib * h.n_src;
             double * sbase = ws_smem + stage * WS_STAGE_DOUBLES;
             const unsigned bar = ws_sptr(&bar_full[stage]);
@@ -107,9 +121,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
                 const unsigned run_bytes = (unsigned)h.run_len * 8u;
                 for (int sl = lane; sl < n_slots; sl += 32)
                 {
-                    const int b = sl / h.n_src, s = sl - b * h.n_src;
-                    const int row = __ldg(a.elem_pool + h.fib_ofs + b * h.m + __ldg(src_local + s));
-                    const double * g = src + (int64_t)row * s_from + h.src_origin;
+                    const double * g = src + (int64_t)srow[sl] * s_from + h.src_origin;
                     const unsigned d = ws_sptr(sbase + (int64_t)sl * h.slot);
                     for (int r = 0; r < h.nrun; ++r)
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -120,9 +132,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
             {
                 for (int sl = 0; sl < n_slots; ++sl)
                 {
-                    const int b = sl / h.n_src, s = sl - b * h.n_src;
-                    const int row = __ldg(a.elem_pool + h.fib_ofs + b * h.m + __ldg(src_local + s));
-                    const double * g = src + (int64_t)row * s_from + h.src_origin;
+                    const double * g = src + (int64_t)srow[sl] * s_from + h.src_origin;
                     double * d = sbase + (int64_t)sl * h.slot;
                     for (int r = 0; r < h.nrun; ++r)
                         for (int x = lane; x < h.run_len; x += 32)
@@ -147,9 +157,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
     const int dk = min(4 + kk, a.kf - 1) - min(kk, a.kf - 1);        // second k-part (KF > 4), in units of the k stride
     double * red = ws_smem + WS_STAGES * WS_STAGE_DOUBLES;
     int stage = 0; unsigned phase = 0;
-    for (int it = it0; it < it1; ++it)
+    for (int it = 0; it < n_items; ++it)
     {
-        const WsHdr h = ws_header(a.items + it, lane);
+        const WsHdr h = ws_header(hdrs + it * 20, lane);
         const int * __restrict__ rt_ptr = a.pool + h.pool_ofs;
         const int * __restrict__ rt_id = rt_ptr + h.n_rt + 1;
         const int * __restrict__ ent = rt_id + h.n_rt;
@@ -167,10 +177,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
             {
                 const int g = su % ngroups, rem = su / ngroups;
                 const int ri = rem % h.n_rt, b = rem / h.n_rt;
-                const int rt = __ldg(rt_id + ri), p0 = __ldg(rt_ptr + ri), p1 = __ldg(rt_ptr + ri + 1);
-                const int tl = rt * a.tg + g_lane;
-                const bool ton = tl < h.m;
-                const int e = ton ? __ldg(a.elem_pool + h.fib_ofs + b * h.m + tl) : 0;
+                const int p0 = __ldg(rt_ptr + ri), p1 = __ldg(rt_ptr + ri + 1);
+                const int e_t = rows[h.rows_ofs + h.nfib * h.n_src + (b * h.n_rt + ri) * a.tg + g_lane];
+                const bool ton = e_t >= 0;
+                const int e = ton ? e_t : 0;
                 const long long yoff = (dmap ? __ldg(dmap + e) : (long long)e * s_to) + h.dst_origin;
                 const int tile0 = h.tab + g * 8;
                 const int gv = min(8, h.nct - g * 8);
@@ -260,16 +270,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
         else
         {
             // heavy item: one row tile, one column tile (tables of the whole plane: B offsets are global), the warps split the entries
-            const int p0 = __ldg(rt_ptr), p1 = __ldg(rt_ptr + 1), rt = __ldg(rt_id);
+            const int p0 = __ldg(rt_ptr), p1 = __ldg(rt_ptr + 1);
             const int n = p1 - p0;
             const int chunk = (((n + WS_NC - 1) / WS_NC) + 3) & ~3;
             const int q0 = min(p1, p0 + warp * chunk), q1 = min(p1, q0 + chunk);
             const int bo = __ldg(a.tab_b + h.tab * 32 + lane);
-            const int tl = rt * a.tg + g_lane;
-            const bool ton = tl < h.m;
-            for (int b = 0; b < h.nfib; ++b)
+            const int e_t = rows[h.rows_ofs + h.n_ent + g_lane];
+            const bool ton = e_t >= 0;
+            for (int b = 0; b < h.nfib; ++b)              // (heavy items carry one fibre)
             {
-                const int fo = h.fib_ofs + b * h.m;
                 double acc[4][2];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
                     // lane l holds entry qb + l: its code and the element row of its source
                     const int ql = qb + lane;
                     int code = 0, row = 0;
-                    if (ql < q1) { code = __ldg(ent + ql); row = __ldg(a.elem_pool + fo + (code >> 1)); }
+                    if (ql < q1) { code = __ldg(ent + ql); row = rows[h.rows_ofs + ql - p0]; }
                     const int nb = min(32, q1 - qb);
                     for (int i0 = 0; i0 < nb; i0 += 16)
                     {
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
                     double v0 = 0.0, v1 = 0.0;
 #pragma unroll
                     for (int w = 0; w < WS_NC; ++w) { v0 += red[(w * 32 + lane) * 2]; v1 += red[(w * 32 + lane) * 2 + 1]; }
-                    const int e = __ldg(a.elem_pool + fo + tl);
+                    const int e = e_t;
                     const long long yoff = (dmap ? __ldg(dmap + e) : (long long)e * s_to) + h.dst_origin;
                     const int2 co = __ldg(a.tab_c + h.tab * 32 + lane);
                     if (co.x >= 0)
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) sweep_ws_kernel(const WsArgs a)
 
 cudaError_t launch_sweep_ws(const WsArgs & a, int n_cta, cudaStream_t st)
 {
-    const size_t smem = (size_t)(WS_STAGES * WS_STAGE_DOUBLES + WS_RED_DOUBLES) * sizeof(double);
+    const size_t smem = (size_t)(WS_STAGES * WS_STAGE_DOUBLES + WS_RED_DOUBLES) * sizeof(double) + (size_t)(WS_HDR_ITEMS * 20 + WS_ROWS_INTS) * sizeof(int);
     // the opt-in is per device: set it on every launch (cheap), not once per process
     cudaError_t e = cudaFuncSetAttribute(sweep_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -246,7 +246,7 @@ def sweep_roofline(A, ctx, stream, op, sizes_of_t, kf, kt, dim, ne, flush, label
     """device time per launch of single-job full sweeps along each dimension in turn over rotating buffers larger than L2 (graph replay)"""
     import torch
     peak, peak_src = peaks()
-    nbuf = 8
+    nbuf = dim * ((8 + dim - 1) // dim)           # buffer i is always swept along dimension i % dim (the block shapes differ per dimension)
     with torch.cuda.stream(stream):
         bufs, dsts = [], []
         for i in range(nbuf):

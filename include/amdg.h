@@ -72,9 +72,9 @@ int amdg_dir_list_export(amdg_ctx *ctx, int op, int rel, int lu, int t, const in
                          int *elem_pool, int *tab_b, int *tab_c, int *prog_ent_ptr, double *A);
 
 /* the same for the warp-specialised streaming sweep kernel (variant 7): counts[8] = items, CTAs, pool ints, element rows, table tiles, programs,
- * entries, bulk_ok; items[n][20] (WsItem), cta_ptr[CTAs+1] */
+ * entries, bulk_ok + 2 * resolved rows; items[n][20] (WsItem), cta_ptr[CTAs+1], rows[], rows_ptr[CTAs+1] (resolved element rows per CTA) */
 int amdg_ws_list_export(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, int n_cta, int64_t *counts, int *items, int *cta_ptr,
-                        int *pool, int *elem_pool, int *tab_b, int *tab_c, int *prog_ent_ptr, double *A);
+                        int *pool, int *elem_pool, int *tab_b, int *tab_c, int *prog_ent_ptr, double *A, int *rows, int *rows_ptr);
 
 /* ---- Hash (source/Hash.cpp:55-114) and 1D element order (source/Element.cpp:388-391), bit exact ---- */
 int amdg_hash_key(int dim, const int *level, const int *suppt);

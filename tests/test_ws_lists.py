@@ -12,7 +12,7 @@ from conftest import load_golden
 
 A = importlib.import_module("adaptive-multiresolution-dg_b200")
 F = ("prog", "pool_ofs", "fib_ofs", "nfib", "m", "n_rt", "n_src", "n_ent", "tab", "nct", "src_origin", "dst_origin", "nrun", "run_len", "gstride", "slot",
-     "kstride", "heavy", "vec")
+     "kstride", "heavy", "vec", "rows_ofs")
 
 
 def replay(L, src, n_elem, s_to, kf, kt, coef=1.0, old=None, stage_cap=4096):
@@ -25,8 +25,10 @@ def replay(L, src, n_elem, s_to, kf, kt, coef=1.0, old=None, stage_cap=4096):
     written = np.zeros((n_elem, s_to), dtype=np.int32)
     pool, ep = L["pool"], L["elem_pool"]
     assert L["cta_ptr"][0] == 0 and L["cta_ptr"][-1] == len(L["items"]) and (np.diff(L["cta_ptr"]) >= 0).all()
-    for it in L["items"]:
-        h = dict(zip(F, [int(x) for x in it[:19]]))
+    cta_of = np.searchsorted(L["cta_ptr"], np.arange(len(L["items"])), side="right") - 1
+    for ii, it in enumerate(L["items"]):
+        h = dict(zip(F, [int(x) for x in it[:20]]))
+        rows = L["rows"][L["rows_ptr"][cta_of[ii]] + h["rows_ofs"]:]            # the kernel reads sources and targets from here (shared memory copy)
         rt_ptr = pool[h["pool_ofs"]:h["pool_ofs"] + h["n_rt"] + 1]
         rt_id = pool[h["pool_ofs"] + h["n_rt"] + 1:h["pool_ofs"] + 2 * h["n_rt"] + 1]
         ent = pool[h["pool_ofs"] + 2 * h["n_rt"] + 1:h["pool_ofs"] + 2 * h["n_rt"] + 1 + h["n_ent"]]
@@ -42,7 +44,8 @@ def replay(L, src, n_elem, s_to, kf, kt, coef=1.0, old=None, stage_cap=4096):
             slots = []
             if not h["heavy"]:
                 for s in range(h["n_src"]):
-                    row = ep[fo + src_local[s]]
+                    row = rows[b * h["n_src"] + s]
+                    assert row == ep[fo + src_local[s]]
                     slots.append(np.concatenate([src[row, h["src_origin"] + r * h["gstride"]:h["src_origin"] + r * h["gstride"] + h["run_len"]] for r in range(h["nrun"])]))
             for ri in range(h["n_rt"]):
                 rt = int(rt_id[ri])
@@ -54,16 +57,18 @@ def replay(L, src, n_elem, s_to, kf, kt, coef=1.0, old=None, stage_cap=4096):
                         boff = L["tab_b"][tile] + (code & 1) * dk * h["kstride"]
                         B = np.zeros((4, 8))
                         if h["heavy"]:
-                            B[kk, nn] = src[ep[fo + (code >> 1)], h["src_origin"] + boff]
+                            B[kk, nn] = src[rows[p], h["src_origin"] + boff]
                         else:
                             B[kk, nn] = slots[code >> 1][boff]
                         Am = np.zeros((8, 4)); Am[row8, kk] = Ap[p]
                         acc += Am @ B
                     for lane in range(32):
                         tl = rt * tg + (row8[lane] // ktp)
-                        if tl >= h["m"]:
+                        e = rows[(h["n_ent"] if h["heavy"] else h["nfib"] * h["n_src"] + (b * h["n_rt"] + ri) * tg) + (row8[lane] // ktp)]
+                        assert (e < 0) == (tl >= h["m"])
+                        if e < 0:
                             continue
-                        e = ep[fo + tl]
+                        assert e == ep[fo + tl]
                         for hh in range(2):
                             off = L["tab_c"][tile, lane, hh]
                             if off >= 0:
