@@ -234,7 +234,19 @@ class StagePlan:
         fuc = cur
         # 4. right-hand side: rhs_vol + rhs_flx of dimension t as one application (u_vx + (ulft_vjp + urgt_vjp)/2 under the flx relation in dim t)
         apps = [dict(src=fuc[t], ops=["volflx" if s == t else "uv" for s in range(d)], rels=[REL_FLX if s == t else REL_VOL for s in range(d)]) for t in range(nf)]
-        res = self.apply_batch("rhs", apps, b, a, final_layout="X")
+        rhs = self.buf("rhs", "X", A)
+        first = True
+        if self.dist:
+            # all applications in lockstep: two barriers for the whole right-hand side
+            res = self.apply_batch("rhs", apps, b, a, final_layout="X")
+        else:
+            # one GPU: one application at a time over the same scratch buffers (the working set of a schedule level stays near the L2 size),
+            # each result added to rhs before the next application overwrites it
+            res = []
+            for t in range(nf):
+                r1 = self.apply_batch("rhs", [apps[t]], b, a, final_layout="X")
+                self.ops.append(("lincomb", rhs, r1, 0.0 if first else 1.0))
+                first = False
         # 5. penalty sweeps of the X dims, all parts joined, RK stage
         if d > 1:
             px2 = self.buf("pen@X", "X", A)
@@ -242,8 +254,8 @@ class StagePlan:
                 self.ops.append(("sweep", "X", "pen", REL_FLX, LU_FULL, t, [dict(sizes=[a] * d, src=u, dst=px2, coef="pen", acc=n_ > 0, push=False)]))
             if x_dims:
                 pen_parts.append(px2)
-        rhs = self.buf("rhs", "X", A)
-        self.ops.append(("lincomb", rhs, res + pen_parts))
+        if res + pen_parts:
+            self.ops.append(("lincomb", rhs, res + pen_parts, 0.0 if first else 1.0))
         self.ops.append(("rk", "u_tn", u, rhs))
         self.result, self.rhs, self.up, self.fuc = u, rhs, up, fuc
 
@@ -399,13 +411,13 @@ class DeviceStage:
                 if len(self.rows[lay]):
                     self.pointwise(self.ctx[lay], self.local_ptr(up), [self.local_ptr(f) for f in fps])
             elif kind == "lincomb":
-                _, dst, parts = o
+                _, dst, parts, beta = o
                 n = len(self.rows["X"]) * plan.bufs[dst].width
                 if n:
                     c = self.ctx["X"]
                     cf = np.ones(len(parts))
                     px = (ctypes.c_void_p * len(parts))(*[ctypes.c_void_p(self.local_ptr(p)) for p in parts])
-                    A._check(A.lib.amdg_lincomb(c._h, n, len(parts), cf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), px, 0.0, ctypes.c_void_p(self.local_ptr(dst))))
+                    A._check(A.lib.amdg_lincomb(c._h, n, len(parts), cf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), px, beta, ctypes.c_void_p(self.local_ptr(dst))))
             elif kind == "rk":
                 _, u_tn, u, rhs = o
                 n = len(self.rows["X"]) * plan.bufs[u].width

@@ -144,8 +144,8 @@ class Emulator:
                     for c, f in enumerate(fps):
                         self.view(r, f)[:] = flux(c, self.view(r, up))
                 elif o[0] == "lincomb":
-                    _, dst, parts = o
-                    self.view(r, dst)[:] = sum(self.view(r, p) for p in parts)
+                    _, dst, parts, beta = o
+                    self.view(r, dst)[:] = sum(self.view(r, p) for p in parts) + (beta * self.view(r, dst) if beta else 0.0)
                 elif o[0] == "rk":
                     _, u_tn, u, rhs = o
                     self.view(r, u)[:] = 0.75 * self.view(r, u_tn) + 0.25 * (self.view(r, u) + DT * self.view(r, rhs))
@@ -196,6 +196,6 @@ def test_plan_summary_cfg5():
     p1 = S.StagePlan(6, 2, 3, 6)
     p8 = S.StagePlan(6, 2, 3, 6, part=part)
     assert p1.n_barrier == 0 and p8.n_barrier == 6
-    assert sum(1 for o in p1.ops if o[0] == "sweep") < 60
+    assert sum(1 for o in p8.ops if o[0] == "sweep") < 70
     # exchange volume per element and stage: interpolation 1000 + 3375 + u 64 + pen 64 + up 729 + hierarchisation 6*729 + rhs 6*(3375 + 1000)
     assert p8.push_bytes == 64 + 1000 + 3375 + 64 + 729 + 6 * 729 + 6 * (3375 + 1000)
