@@ -200,6 +200,29 @@ private:
     DGSolution * dg_; int op_hier_ = -1;
 };
 
+// HermInterpolation, fast wrapper (source/Interplation.cpp:4609-4621): fastHerm.eval_up_Herm(); eval_fp_Her_2D(func, func_d1, func_d2, is_intp);
+// eval_fp_to_coe_D_Her(is_intp).  DIM == 2, HermBasis::PMAX == 3, scalar, as in the reference; the flux and its derivatives are an enumerated id.
+class HermInterpolation
+{
+public:
+    HermInterpolation(DGSolution & dg, const int * pw_anc, const double * pw_wt) : dg_(&dg)
+    { check(amdg_op_register_hier(dg.ctx, pw_anc, pw_wt, dg.PMAX_intp + 1, &op_hier_)); }
+    void nonlinear_Herm_2D_fast(const std::vector<int> & flux_id, const std::vector<std::vector<bool>> & is_intp, FastLagrIntp & fastHerm, const std::vector<double> & params = {})
+    {
+        fastHerm.eval_up_Lagr();
+        for (int d = 0; d < dg_->DIM; ++d)
+        {
+            if (!is_intp[0][d]) continue;
+            const double * prm = params.empty() ? nullptr : &params[(size_t)d * 4];
+            check(amdg_pointwise_hermite2d(dg_->ctx, 1, &flux_id[d], prm, dg_->up(0), dg_->fp(0, d)));
+            check(amdg_hierarchize(dg_->ctx, op_hier_, dg_->fp(0, d), dg_->fucoe(0, d), 1));
+        }
+    }
+    void eval_up_to_coe_D_Her() { check(amdg_hierarchize(dg_->ctx, op_hier_, dg_->up_intp.data(), dg_->ucoe_intp.data(), dg_->VEC_NUM)); }
+private:
+    DGSolution * dg_; int op_hier_ = -1;
+};
+
 // HyperbolicLagrRHS / HyperbolicHermRHS (source/FastMultiplyLU.cpp:1125-1267)
 class HyperbolicLagrRHS
 {

@@ -156,3 +156,16 @@ def test_two_gpu_stage_parity():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29671",
                         os.path.join(ROOT, "tests", "dist_check.py")], capture_output=True, text=True, timeout=900)
     assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_live_reference_dropin_burgers_adapt():
+    """examples/live_burgers_adapt: the reference's own DGAdapt / OperatorMatrix1D / HermInterpolation objects (oracle/_ref/libsgdg_ref.a, unmodified)
+    with every fast class replaced by the mirror over the C ABI, ten adaptive Burgers steps with refine() and coarsen() each step
+    (example/02_hyperbolic_05_burgers_adapt.cpp:223-470, -imex 0 -v 0) in lockstep with the stock reference run: same element sets, coefficients
+    within 1e-10, identical L2 error against the exact solution"""
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "live_burgers_adapt")
+    if not os.path.exists(exe):
+        pytest.skip("examples/live_burgers_adapt is built only where the reference sources exist (__graft_entry__.build())")
+    r = subprocess.run([exe, "-NM", "6", "-N0", "2", "-steps", "10"], capture_output=True, text=True, timeout=900)
+    assert "LIVE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
