@@ -86,7 +86,7 @@ struct amdg_ctx
         std::vector<ShapeProg> progs;                         // host copies of the pieces (to build operator values)
         std::map<int, const double **> a_tab;                 // per operator: device table of A pointers
     };
-    std::map<std::tuple<int, int, int, int, int, int>, MmaList> mmas;       // key: (dim t, outer, kf, kt, rel*4+lu, parallel class)
+    std::map<std::tuple<int, int, int, int, int, int>, MmaList> mmas;       // key: (dim t * 16 + kf, outer, inner, kt, rel*4+lu, parallel class)
     std::map<std::tuple<int, int, int, long long>, double *> mma_A;         // (op, shape, rel*4+lu, piece hash) -> device operator values
     int mma_cap_doubles = 9 * 1024, mma_item_target = 148 * 8, mma_ent_target = 448, mma_stage_a_max = 64;
     bool tc_force_stage = true; int tc_coarse_ent = 256; int64_t tc_min_doubles = 131072;
@@ -225,6 +225,28 @@ static int ensure_scratch(amdg_ctx * c, size_t idx, int64_t n)
     return AMDG_OK;
 }
 
+// Per-shape caches (plans on the host, operator fragments on the device) survive grid changes on purpose; over a long adaptive run the
+// set of shapes ever seen keeps growing, so once the known shapes exceed twice the live ones (and a floor, AMDG_CACHE_SHAPES, default 4096)
+// everything belonging to shapes the new grid does not have is dropped.  Called from amdg_grid_set after the shape table was rebuilt.
+static void evict_shape_caches(amdg_ctx * c)
+{
+    const size_t floor_shapes = std::getenv("AMDG_CACHE_SHAPES") ? (size_t)std::max(0, atoi(std::getenv("AMDG_CACHE_SHAPES"))) : 4096;
+    const std::vector<char> live = c->shapes.live_flags();
+    size_t n_live = 0; for (char f : live) n_live += f;
+    if (c->shapes.n_known() <= std::max(floor_shapes, 2 * n_live)) return;
+    const size_t before = c->shapes.n_known(), frags_before = c->mma_A.size();
+    if (c->device >= 0 && !c->mma_A.empty()) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    for (auto it = c->mma_A.begin(); it != c->mma_A.end();)
+    {
+        if (!live[std::get<1>(it->first)]) { cudaFree(it->second); it = c->mma_A.erase(it); } else ++it;
+    }
+    auto prune = [&](auto & m) { for (auto it = m.begin(); it != m.end();) { if (!live[std::get<0>(it->first)]) it = m.erase(it); else ++it; } };
+    prune(c->lean_plans); prune(c->dir_plans); prune(c->ws_plans);
+    c->shapes.retire(live);
+    if (std::getenv("AMDG_VERBOSE"))
+        fprintf(stderr, "[amdg] cache eviction: shapes %zu -> %zu, operator fragments %zu -> %zu\n", before, c->shapes.n_known(), frags_before, c->mma_A.size());
+}
+
 extern "C" {
 
 const char * amdg_version(void) { return "amdg-b200 0.1 (sm_100a, fp64)"; }
@@ -350,6 +372,7 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
     const auto t1 = std::chrono::steady_clock::now();
     c->grid = std::move(g); c->have_grid = true;
     c->shapes.build(c->grid);
+    evict_shape_caches(c);
     if (std::getenv("AMDG_VERBOSE"))
         fprintf(stderr, "[amdg] grid_set: %lld elements, tables %.2f ms, shapes %.2f ms (%d shapes known)\n", (long long)n,
                 std::chrono::duration<double, std::milli>(t1 - t0).count(),
@@ -358,23 +381,35 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     free_dev_grid(c);
-    c->ddims.resize(c->dim);
-    CU(meta_upload(c, &c->d_ord1d, c->grid.ord1d.data(), c->grid.ord1d.size(), false));
-    for (int t = 0; t < c->dim; ++t)
+    // the device tables are committed as a whole: a failed upload leaves the context without a grid (host tables included), never with partial tables
+    auto up_all = [&]() -> cudaError_t
     {
-        const DimTables & H = c->grid.dims[t]; DevDim & D = c->ddims[t];
-        std::vector<int> fbase(n);
-        for (int64_t s = 0; s < n; ++s) fbase[s] = (int)H.fibre_ptr[H.slot_fibre[s]];
-        CU(meta_upload(c, &D.slot_elem, H.slot_elem.data(), (size_t)n, false));
-        CU(meta_upload(c, &D.slot_fbase, fbase.data(), (size_t)n, false));
-        CU(meta_upload(c, &D.fibre_ptr, H.fibre_ptr.data(), H.fibre_ptr.size(), false));
-        for (int k = 0; k < 2; ++k)
+        cudaError_t e;
+        c->ddims.resize(c->dim);
+        if ((e = meta_upload(c, &c->d_ord1d, c->grid.ord1d.data(), c->grid.ord1d.size(), false)) != cudaSuccess) return e;
+        for (int t = 0; t < c->dim; ++t)
         {
-            CU(meta_upload(c, &D.nbr_ptr[k], H.nbr_ptr[k].data(), H.nbr_ptr[k].size(), false));
-            CU(meta_upload(c, &D.nbr_split[k], H.nbr_split[k].data(), H.nbr_split[k].size(), false));
-            CU(meta_upload(c, (Nbr **)&D.nbr[k], H.nbr[k].data(), H.nbr[k].size(), false));
+            const DimTables & H = c->grid.dims[t]; DevDim & D = c->ddims[t];
+            std::vector<int> fbase(n);
+            for (int64_t s = 0; s < n; ++s) fbase[s] = (int)H.fibre_ptr[H.slot_fibre[s]];
+            if ((e = meta_upload(c, &D.slot_elem, H.slot_elem.data(), (size_t)n, false)) != cudaSuccess) return e;
+            if ((e = meta_upload(c, &D.slot_fbase, fbase.data(), (size_t)n, false)) != cudaSuccess) return e;
+            if ((e = meta_upload(c, &D.fibre_ptr, H.fibre_ptr.data(), H.fibre_ptr.size(), false)) != cudaSuccess) return e;
+            for (int k = 0; k < 2; ++k)
+            {
+                if ((e = meta_upload(c, &D.nbr_ptr[k], H.nbr_ptr[k].data(), H.nbr_ptr[k].size(), false)) != cudaSuccess) return e;
+                if ((e = meta_upload(c, &D.nbr_split[k], H.nbr_split[k].data(), H.nbr_split[k].size(), false)) != cudaSuccess) return e;
+                if ((e = meta_upload(c, (Nbr **)&D.nbr[k], H.nbr[k].data(), H.nbr[k].size(), false)) != cudaSuccess) return e;
+            }
+            if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;   // fbase is a local
         }
-        CU(cudaStreamSynchronize(c->stream));   // fbase is a local
+        return cudaSuccess;
+    };
+    const cudaError_t ue = up_all();
+    if (ue != cudaSuccess)
+    {
+        free_dev_grid(c); c->have_grid = false; cudaGetLastError();
+        return fail(AMDG_ECUDA, std::string("amdg_grid_set: table upload failed: ") + cudaGetErrorString(ue));
     }
     return AMDG_OK;
 }
@@ -769,7 +804,7 @@ static amdg_ctx::MmaList & get_mma(amdg_ctx * c, int t, int outer, int inner, in
     int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
     const int cap_doubles = c->mma_cap_doubles, item_target = c->mma_item_target;
     const int ent_target0 = c->mma_ent_target, stage_a_max = c->mma_stage_a_max;
-    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls);
+    auto key = std::make_tuple(t * 16 + kf, outer, inner, kt, rel * 4 + lu, pcls);          // kf <= 6: (t, kf) share a field, outer and inner keep their own
     auto it = c->mmas.find(key);
     if (it != c->mmas.end()) return it->second;
     amdg_ctx::MmaList L;
@@ -1016,7 +1051,7 @@ static const std::vector<LeanPiece> & lean_plan(amdg_ctx * c, int shape, int kf,
 static amdg_ctx::MmaList & get_mma_lean(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int par, int lu)
 {
     int pcls = 0; while ((1 << (pcls + 1)) <= par && pcls < 5) ++pcls;
-    auto key = std::make_tuple(t, outer * 65536 + inner, kf, kt, rel * 4 + lu, pcls + 16);
+    auto key = std::make_tuple(t * 16 + kf, outer, inner, kt, rel * 4 + lu, pcls + 16);
     auto it = c->mmas.find(key);
     if (it != c->mmas.end()) return it->second;
     amdg_ctx::MmaList L;

@@ -383,13 +383,13 @@ __global__ void __launch_bounds__(FIBRE_THREADS) sweep_fibre_kernel(const FibreS
 template <int KF, int KT, int CT>
 static cudaError_t launch_fibre_t(const FibreSweepArgs & a, cudaStream_t st)
 {
-    static bool configured = false;
+    static PerDeviceOnce configured;
     const size_t smem = (size_t)std::min(std::max(a.smem_doubles, 256), FIBRE_SMEM_DOUBLES) * sizeof(double);
-    if (!configured)
+    if (!configured.done())
     {
         cudaError_t e = cudaFuncSetAttribute(sweep_fibre_kernel<KF, KT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FIBRE_SMEM_DOUBLES * sizeof(double)));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark();
     }
     dim3 grid((unsigned)a.n_item, (unsigned)(a.n_job * a.n_comp));
     sweep_fibre_kernel<KF, KT, CT><<<grid, FIBRE_THREADS, smem, st>>>(a);

@@ -6,10 +6,21 @@
 // K4 rk_stage : ExplicitRK::step_stage (source/ODESolver.cpp:209-301).
 // Hierarchisation (K3) is a K1 sweep with the stencil operator built by amdg_op_register_hier.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace amdg {
+
+// Function attributes (the dynamic shared-memory opt-in) are per device: every launch wrapper keeps one of these per kernel
+// instantiation and sets the attribute the first time it launches on a device (the C ABI makes the context's device current first).
+struct PerDeviceOnce
+{
+    std::atomic<unsigned long long> mask{0};
+    static unsigned long long bit() { int d = 0; cudaGetDevice(&d); return 1ull << (d & 63); }
+    bool done() const { return (mask.load(std::memory_order_acquire) & bit()) != 0; }
+    void mark() { mask.fetch_or(bit(), std::memory_order_release); }
+};
 
 struct NbrDev { int local; int pair; };
 

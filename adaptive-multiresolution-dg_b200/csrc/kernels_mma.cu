@@ -317,12 +317,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 768 / MMA_THREADS) sweep_mma_kern
 template <int KF, int KT, bool INNER1>
 static cudaError_t launch_mma_t(const MmaArgs & a, int smem_doubles, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured)
+    static PerDeviceOnce configured;
+    if (!configured.done())
     {
         cudaError_t e = cudaFuncSetAttribute(sweep_mma_kernel<KF, KT, INNER1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MMA_SMEM_DOUBLES * sizeof(double)));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark();
     }
     // programmatic stream serialization: the head of this grid overlaps the tail of the previous kernel (the kernel waits itself
     // before it touches coefficient data); matters most for the small sweeps this form serves in auto mode

@@ -563,12 +563,12 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) sweep_tc_kernel(const
 template <int KF, int KT, int MODE>
 static cudaError_t launch_tc_t(const MmaArgs & a, int smem_doubles, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured)
+    static PerDeviceOnce configured;
+    if (!configured.done())
     {
         cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<KF, KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TC_SMEM_DOUBLES * sizeof(double)));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark();
     }
     if (smem_doubles > TC_SMEM_DOUBLES) return cudaErrorInvalidValue;
     // launched with programmatic stream serialization: the head of this grid (item headers, element rows, index arithmetic) overlaps

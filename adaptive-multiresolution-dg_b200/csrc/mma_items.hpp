@@ -30,8 +30,23 @@ struct ShapeTable
     std::vector<std::vector<int>> fibre_shape;       // [dim][fibre]
     std::vector<std::map<int, std::vector<int>>> shape_fibres;   // [dim][shape] -> slot0 list
 
-    // shape ids are stable for the lifetime of the table: a grid change (DGAdapt refine / coarsen) only appends the shapes it
-    // introduces, so that plans and operator fragments cached per shape id survive it
+    // shape ids are stable while a shape is known: a grid change (DGAdapt refine / coarsen) only appends the shapes it
+    // introduces, so that plans and operator fragments cached per shape id survive it.  retire() forgets shapes the current
+    // grid no longer has (their ids are never reused; a shape that comes back gets a fresh id), which bounds the table over a long adaptive run.
+    std::vector<char> live_flags() const
+    {
+        std::vector<char> live(ords.size(), 0);
+        for (const auto & per_dim : shape_fibres) for (const auto & kv : per_dim) live[kv.first] = 1;
+        return live;
+    }
+    size_t n_known() const { return id_of.size(); }
+    void retire(const std::vector<char> & live)
+    {
+        for (auto it = id_of.begin(); it != id_of.end();)
+        {
+            if (!live[it->second]) { std::vector<int>().swap(ords[it->second]); it = id_of.erase(it); } else ++it;
+        }
+    }
     void build(const Grid & G)
     {
         fibre_shape.assign(G.dim, std::vector<int>()); shape_fibres.assign(G.dim, std::map<int, std::vector<int>>());

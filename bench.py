@@ -384,6 +384,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # the ONE JSON line goes to the real stdout; everything else a library prints there (NCCL's version banner, ...) is sent to stderr
+    out_fd = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(out_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -394,7 +402,7 @@ def main():
                 "config": {"workload": w["desc"], "sample": r["sample"], "same_config": r["same_config"]},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "DoF-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -426,7 +434,7 @@ def main():
                 "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"]}
         if "cpu_baseline" in rec:
             line["cpu_baseline"] = rec["cpu_baseline"]
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------- the stage workloads (cfg5 default, cfg4)
@@ -553,7 +561,7 @@ def main():
                 line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
         if world == 1 and not args.no_secondary and args.workload == "cfg5":
             line["secondary"] = roundtrip_record(args, A, torch, stream, flush, local_rank, WORKLOADS["cfg2"], with_cpu=not args.no_cpu)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

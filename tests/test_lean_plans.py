@@ -70,3 +70,20 @@ def test_plans_on_random_adaptive_grids(dim, nmax, k, m, seed):
     ctx.grid_set(lev2, sup2)
     check_all(ctx, dim, k + 1, m + 1)
     ctx.close()
+
+
+def test_shape_cache_eviction(monkeypatch, capfd):
+    """a long adaptive run keeps meeting new fibre shapes: once the known shapes exceed the eviction threshold, plans of shapes the
+    current grid no longer has are dropped (csrc/capi.cu: evict_shape_caches) and the plans of the surviving / returning shapes stay valid"""
+    monkeypatch.setenv("AMDG_CACHE_SHAPES", "0")
+    monkeypatch.setenv("AMDG_VERBOSE", "1")
+    dim, nmax, k, m = 2, 8, 2, 3
+    ctx = A.Context(dim, nmax, k, m, device=-1)
+    evictions = 0
+    for seed in range(6):
+        lev, sup = random_adaptive_grid(dim, nmax, 100 + seed, keep=0.3 + 0.1 * (seed % 3))
+        ctx.grid_set(lev, sup)
+        check_all(ctx, dim, k + 1, m + 1)
+        evictions += capfd.readouterr().err.count("cache eviction")
+    assert evictions >= 1
+    ctx.close()
