@@ -230,6 +230,25 @@ struct WsArgs
 int ws_stage_doubles();
 cudaError_t launch_sweep_ws(const WsArgs & a, int n_cta, cudaStream_t st);                                     // kernels_ws.cu
 
+// column-form sweep kernel (kernels_col.cu): one thread per column, no staging
+struct __align__(16) ColUnit { int tgt; int ent0; int n_ent; int g; };     // target element row, first entry, entries, column group (32*NC columns)
+static const int COL_PFR = 4;               // prefetch sectors per lane and source row: a column group reads at most 32 * COL_PFR sectors of a row
+struct ColArgs
+{
+    const ColUnit * units; int n_unit;      // heavy units first (one CTA each: (target, 32 columns)), then the normal ones, fibre by fibre
+    int n_heavy;
+    const int * cta_ptr; int n_cta;         // normal CTA c runs the units [cta_ptr[c], cta_ptr[c+1])
+    const int * pf;                         // [groups][COL_PFR][32] byte offsets (from the start of an element row) of the sectors a column group reads, -1 = none
+    const int2 * ent;                       // per (dimension, relation): (source element row, canonical 1D pair id), slot by slot, "U" sources first
+    const double * blocks;                  // operator blocks [pair][KF][KT]
+    int64_t n_elem;
+    int inner;
+    int n_comp, n_job;
+    SweepJob job[MAX_JOBS];
+};
+cudaError_t launch_sweep_col(const ColArgs & a, int kf, int kt, int nc, cudaStream_t st);                       // kernels_col.cu
+int col_max_nc(int kf, int kt);
+
 // point-wise expressions (amdg_pointwise_expr): a small stack program per output, evaluated at every interpolation point
 enum { PW_END = 0, PW_VAR = 1, PW_X = 2, PW_OTHER = 3, PW_CONST = 4, PW_ADD = 5, PW_SUB = 6, PW_MUL = 7, PW_DIV = 8, PW_NEG = 9, PW_SIN = 10, PW_COS = 11,
        PW_SQR = 12, PW_EXP = 13, PW_SQRT = 14, PW_ABS = 15, PW_POW = 16, PW_TANH = 17, PW_MIN = 18, PW_MAX = 19 };
