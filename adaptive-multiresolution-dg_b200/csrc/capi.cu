@@ -114,10 +114,10 @@ struct amdg_ctx
     int ws_items_per_cta = 12;
     // column kernel (kernels_col.cu): resolved entry table per (dim t, relation); unit list per (dim t, rel*4+lu, column groups, columns per lane)
     std::map<std::pair<int, int>, int2 *> col_ents;
-    struct ColList { ColUnit * d_units = nullptr; int * d_cta_ptr = nullptr; int n_unit = 0, n_heavy = 0, n_cta = 0; };
-    std::map<std::tuple<int, int, int, int, int>, ColList> cols;               // (dim t, rel*4+lu, column groups, 32-column groups, CTA target)
-    std::map<std::tuple<int, int, int, int>, int *> col_pfs;                   // (outer, inner, kf, columns per lane) -> prefetch sector table
-    int col_heavy_ent = 24, col_cta_per_sm = 4, col_force_nc = 0;
+    struct ColList { ColUnit * d_units = nullptr; int n_unit = 0, n_heavy = 0; };
+    std::map<std::tuple<int, int, int, int>, ColList> cols;                    // (dim t, rel*4+lu, column groups, heavy threshold)
+    int col_heavy_ent = 24, col_upc = 8, col_force_nc = 0;
+    int64_t col_min_block = 64; int col_max_kk = 9;                            // auto mode: column kernel for blocks >= col_min_block doubles with KF*KT <= col_max_kk (measured: profiles/r02_sweep_kernels.md)
     double * d_pts1d = nullptr;                                   // LagrBasis::intep_pt table [T*edge_intp] (amdg_points_set)
     int dir_cost_target = 160;
     std::map<std::tuple<int, int, int, int, int, int>, std::vector<LeanPiece>> lean_plans;   // (shape, kf, kt, rel*4+lu, outer, inner)
@@ -170,10 +170,8 @@ static void free_dev_grid(amdg_ctx * c)
     c->wss.clear();
     for (auto & kv : c->col_ents) meta_free(c, kv.second);
     c->col_ents.clear();
-    for (auto & kv : c->cols) { meta_free(c, kv.second.d_units); meta_free(c, kv.second.d_cta_ptr); }
+    for (auto & kv : c->cols) meta_free(c, kv.second.d_units);
     c->cols.clear();
-    for (auto & kv : c->col_pfs) meta_free(c, kv.second);
-    c->col_pfs.clear();
     for (auto & kv : c->pipes)
     {
         amdg_ctx::PipeList & L = kv.second;
@@ -277,7 +275,9 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_ITEM_TARGET")) c->item_target = std::max(1, atoi(e));
     if (const char * e = std::getenv("AMDG_KERNEL")) c->kernel_variant = atoi(e);
     if (const char * e = std::getenv("AMDG_COL_HEAVY")) c->col_heavy_ent = std::max(1, std::min(32, atoi(e)));
-    if (const char * e = std::getenv("AMDG_COL_CTAS")) c->col_cta_per_sm = std::max(1, atoi(e));
+    if (const char * e = std::getenv("AMDG_COL_UPC")) c->col_upc = std::max(1, atoi(e));
+    if (const char * e = std::getenv("AMDG_COL_MIN_BLOCK")) c->col_min_block = std::max(1, atoi(e));
+    if (const char * e = std::getenv("AMDG_COL_MAX_KK")) c->col_max_kk = std::max(1, atoi(e));
     if (const char * e = std::getenv("AMDG_COL_NC")) c->col_force_nc = std::max(0, std::min(4, atoi(e)));
     if (const char * e = std::getenv("AMDG_MMA_CAP")) c->mma_cap_doubles = std::max(512, std::min(atoi(e), mma_smem_capacity_doubles())) & ~1;
     if (const char * e = std::getenv("AMDG_MMA_ITEMS")) c->mma_item_target = std::max(1, atoi(e));
@@ -1669,97 +1669,30 @@ static const int2 * get_col_ent(amdg_ctx * c, int t, int rel)
     return d;
 }
 
-// bytes a lane group reads from one source row, as 32-byte sectors: table [groups][COL_PFR][32] of byte offsets from the row start (-1 = none).
-// Rows need not be sector aligned (odd block sizes): every run of touched bytes is covered from its first byte in steps of 32 plus its last word.
-static const int * get_col_pf(amdg_ctx * c, int outer, int inner, int kf, int nc)
+// units = (target, column group): heavy ones (long entry lists, longest first) then the rest fibre by fibre, column group by column group
+static amdg_ctx::ColList & get_col(amdg_ctx * c, int t, int rel, int lu, int ng)
 {
-    auto key = std::make_tuple(outer, inner, kf, nc);
-    auto it = c->col_pfs.find(key);
-    if (it != c->col_pfs.end()) return it->second;
-    const int W = outer * inner, ng = (W + 32 * nc - 1) / (32 * nc);
-    const bool aligned = (((int64_t)W * kf * 8) % 32) == 0;
-    std::vector<int> tab((size_t)ng * COL_PFR * 32, -1);
-    for (int g = 0; g < ng; ++g)
-    {
-        std::vector<int> words;                                     // touched 8-byte words of the row (element offsets)
-        for (int cidx = g * 32 * nc; cidx < std::min(W, (g + 1) * 32 * nc); ++cidx)
-        {
-            const int o = cidx / inner, i = cidx - o * inner;
-            for (int k = 0; k < kf; ++k) words.push_back((o * kf + k) * inner + i);
-        }
-        std::sort(words.begin(), words.end());
-        std::vector<int> offs;
-        size_t p = 0;
-        while (p < words.size())
-        {
-            size_t q = p; while (q + 1 < words.size() && words[q + 1] == words[q] + 1) ++q;       // run [p, q] of consecutive words
-            const int lo = words[p] * 8, hi = words[q] * 8 + 8;
-            if (aligned) { for (int sct = lo / 32; sct <= (hi - 1) / 32; ++sct) if (offs.empty() || offs.back() != sct * 32) offs.push_back(sct * 32); }
-            else { for (int b = lo; b < hi; b += 32) offs.push_back(b); if ((hi - 8 - lo) % 32 != 0) offs.push_back(hi - 8); }
-            p = q + 1;
-        }
-        for (size_t i = 0; i < offs.size() && i < (size_t)COL_PFR * 32; ++i) tab[(size_t)g * COL_PFR * 32 + i] = offs[i];
-    }
-    int * d = nullptr;
-    if (meta_upload(c, &d, tab.data(), tab.size(), false) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) return nullptr;
-    c->col_pfs[key] = d;
-    return d;
-}
-
-// units = (target, column group): heavy ones (long entry lists: one CTA per (target, 32 columns), longest first), then the rest fibre by fibre,
-// column group by column group, cut into n_cta contiguous ranges of about equal cost
-static amdg_ctx::ColList & get_col(amdg_ctx * c, int t, int rel, int lu, int ng, int ngh, int cta_target)
-{
-    auto key = std::make_tuple(t, rel * 4 + lu, ng, ngh * 64 + c->col_heavy_ent, cta_target);
+    auto key = std::make_tuple(t, rel * 4 + lu, ng, c->col_heavy_ent);
     auto it = c->cols.find(key);
     if (it != c->cols.end()) return it->second;
     const DimTables & H = c->grid.dims[t];
     std::vector<ColUnit> heavy, normal;
     normal.reserve((size_t)c->grid.n * ng);
-    auto range = [&](int64_t s, int64_t & p0, int64_t & p1)
-    {
-        p0 = H.nbr_ptr[rel][s]; p1 = H.nbr_ptr[rel][s + 1];
-        if (lu == AMDG_LU_U) p1 = p0 + H.nbr_split[rel][s]; else if (lu == AMDG_LU_L) p0 += H.nbr_split[rel][s];
-    };
     for (int64_t f = 0; f < H.n_fibre; ++f)
-    {
         for (int g = 0; g < ng; ++g)
             for (int64_t s = H.fibre_ptr[f]; s < H.fibre_ptr[f + 1]; ++s)
             {
-                int64_t p0, p1; range(s, p0, p1);
-                if (p1 - p0 > c->col_heavy_ent) continue;
+                int64_t p0 = H.nbr_ptr[rel][s], p1 = H.nbr_ptr[rel][s + 1];
+                if (lu == AMDG_LU_U) p1 = p0 + H.nbr_split[rel][s]; else if (lu == AMDG_LU_L) p0 += H.nbr_split[rel][s];
                 ColUnit u; u.tgt = H.slot_elem[s]; u.ent0 = (int)p0; u.n_ent = (int)(p1 - p0); u.g = g;
-                normal.push_back(u);
+                (u.n_ent > c->col_heavy_ent ? heavy : normal).push_back(u);
             }
-        for (int64_t s = H.fibre_ptr[f]; s < H.fibre_ptr[f + 1]; ++s)
-        {
-            int64_t p0, p1; range(s, p0, p1);
-            if (p1 - p0 <= c->col_heavy_ent) continue;
-            for (int g = 0; g < ngh; ++g) { ColUnit u; u.tgt = H.slot_elem[s]; u.ent0 = (int)p0; u.n_ent = (int)(p1 - p0); u.g = g; heavy.push_back(u); }
-        }
-    }
     std::stable_sort(heavy.begin(), heavy.end(), [](const ColUnit & x, const ColUnit & y) { return x.n_ent > y.n_ent; });
     amdg_ctx::ColList L;
     L.n_heavy = (int)heavy.size(); L.n_unit = (int)(heavy.size() + normal.size());
-    // contiguous ranges of normal units with about equal cost (entries + a fixed part per unit)
-    const int n_cta = (int)std::max<size_t>(1, std::min<size_t>((normal.size() + 3) / 4, (size_t)cta_target));
-    std::vector<int> cta_ptr(n_cta + 1, L.n_unit);
-    {
-        double total = 0; for (const ColUnit & u : normal) total += 2.0 + u.n_ent;
-        double run = 0; int cta = 0; cta_ptr[0] = L.n_heavy;
-        for (size_t i = 0; i < normal.size(); ++i)
-        {
-            run += 2.0 + normal[i].n_ent;
-            while (cta + 1 < n_cta && run >= total * (cta + 1) / n_cta) { ++cta; cta_ptr[cta] = L.n_heavy + (int)i + 1; }
-        }
-        for (int k = cta + 1; k <= n_cta; ++k) cta_ptr[k] = L.n_unit;
-    }
-    L.n_cta = n_cta;
     heavy.insert(heavy.end(), normal.begin(), normal.end());
-    if (meta_upload(c, &L.d_units, heavy.data(), heavy.size(), false) != cudaSuccess ||
-        meta_upload(c, &L.d_cta_ptr, cta_ptr.data(), cta_ptr.size(), false) != cudaSuccess ||
-        cudaStreamSynchronize(c->stream) != cudaSuccess) { L.d_units = nullptr; L.n_unit = 0; }
-    if (std::getenv("AMDG_VERBOSE")) fprintf(stderr, "[amdg] column list t=%d rel=%d lu=%d groups=%d/%d: %d units, %d heavy, %d CTAs\n", t, rel, lu, ng, ngh, L.n_unit, L.n_heavy, n_cta);
+    if (meta_upload(c, &L.d_units, heavy.data(), heavy.size(), false) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { L.d_units = nullptr; L.n_unit = 0; }
+    if (std::getenv("AMDG_VERBOSE")) fprintf(stderr, "[amdg] column list t=%d rel=%d lu=%d groups=%d: %d units, %d heavy\n", t, rel, lu, ng, L.n_unit, L.n_heavy);
     return c->cols.emplace(key, L).first->second;
 }
 
@@ -1771,25 +1704,27 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
     // destination maps / accumulate-from exist in the lean, register-direct and streaming kernels only (even map offsets are the caller's contract
     // whenever the block size is even: the kernels keep their 16-byte stores)
     bool mapped = false; for (int i = 0; i < n_job; ++i) mapped = mapped || jobs[i].dst_map || jobs[i].acc_from;
-    const int variant = (mapped && c->kernel_variant != 6 && c->kernel_variant != 7 && c->kernel_variant != 8) ? 5 : c->kernel_variant;
-    const bool lean = variant == 0 || variant == 5;
+    const int variant0 = (mapped && c->kernel_variant < 6) ? 5 : c->kernel_variant;
     int done = 0;
     while (done < n_job)
     {
         int cnt = 1;
         while (done + cnt < n_job && cnt < MAX_JOBS && jobs[done + cnt].outer == jobs[done].outer) ++cnt;
         const int W = jobs[done].outer * inner;
+        // auto mode picks per block shape (measured, profiles/r02_sweep_kernels.md): the column kernel for large blocks with small operator blocks
+        // (the 6-D shapes), the lean tensor-core kernel otherwise
+        int variant = variant0;
+        if (c->kernel_variant == 0 && W >= 32 && (int64_t)W * O.kf >= c->col_min_block && O.kf * O.kt <= c->col_max_kk) variant = 8;
+        const bool lean = variant == 0 || variant == 5;
         if (variant == 8)
         {
             const int nc = col_pick_nc(c, W, O.kf, O.kt);
             const int ng = (W + 32 * nc - 1) / (32 * nc);
             const int2 * ent = get_col_ent(c, t, rel);
-            const int * pf = get_col_pf(c, jobs[done].outer, inner, O.kf, nc);
-            const int cta_target = std::max(1, c->n_sm * c->col_cta_per_sm / std::max(1, cnt * n_comp));
-            amdg_ctx::ColList & CL = get_col(c, t, rel, lu, ng, (W + 31) / 32, cta_target);
-            if (!ent || !pf || !CL.d_units) return fail(AMDG_ENOMEM, "column kernel: the work list could not be uploaded");
+            amdg_ctx::ColList & CL = get_col(c, t, rel, lu, ng);
+            if (!ent || !CL.d_units) return fail(AMDG_ENOMEM, "column kernel: the work list could not be uploaded");
             ColArgs a;
-            a.units = CL.d_units; a.n_unit = CL.n_unit; a.n_heavy = CL.n_heavy; a.cta_ptr = CL.d_cta_ptr; a.n_cta = CL.n_cta; a.pf = pf; a.ent = ent; a.blocks = O.d_blocks;
+            a.units = CL.d_units; a.n_unit = CL.n_unit; a.n_heavy = CL.n_heavy; a.upc = c->col_upc; a.ent = ent; a.blocks = O.d_blocks;
             a.n_elem = c->grid.n; a.inner = inner; a.n_comp = n_comp; a.n_job = cnt;
             for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
             cudaError_t e = launch_sweep_col(a, O.kf, O.kt, nc, c->stream);

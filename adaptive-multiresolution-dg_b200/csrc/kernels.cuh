@@ -232,13 +232,10 @@ cudaError_t launch_sweep_ws(const WsArgs & a, int n_cta, cudaStream_t st);      
 
 // column-form sweep kernel (kernels_col.cu): one thread per column, no staging
 struct __align__(16) ColUnit { int tgt; int ent0; int n_ent; int g; };     // target element row, first entry, entries, column group (32*NC columns)
-static const int COL_PFR = 4;               // prefetch sectors per lane and source row: a column group reads at most 32 * COL_PFR sectors of a row
 struct ColArgs
 {
-    const ColUnit * units; int n_unit;      // heavy units first (one CTA each: (target, 32 columns)), then the normal ones, fibre by fibre
-    int n_heavy;
-    const int * cta_ptr; int n_cta;         // normal CTA c runs the units [cta_ptr[c], cta_ptr[c+1])
-    const int * pf;                         // [groups][COL_PFR][32] byte offsets (from the start of an element row) of the sectors a column group reads, -1 = none
+    const ColUnit * units; int n_unit;      // heavy units first (one CTA each), then the normal ones (upc per CTA), fibre by fibre
+    int n_heavy, upc;
     const int2 * ent;                       // per (dimension, relation): (source element row, canonical 1D pair id), slot by slot, "U" sources first
     const double * blocks;                  // operator blocks [pair][KF][KT]
     int64_t n_elem;

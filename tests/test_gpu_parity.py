@@ -592,7 +592,7 @@ def test_live_reference_cfg2_n6(kernel, sched, tmp_path_factory):
     c.close()
 
 
-@pytest.mark.parametrize("kernel", [0, 6, 7, 8])
+@pytest.mark.parametrize("kernel", [0, 5, 6, 7, 8])
 def test_live_reference_cfg5_n4(kernel, tmp_path_factory):
     """cfg5 at d=6, k=1, m=2, N=4 (501 elements): one nonlinear stage (interpolate, Vlasov products, hierarchise, vol + flx + penalty, RK3SSP
     stage 0) against the reference run on this machine -- the <2,3>, <3,3>, <3,2> and <2,2> instantiations of the 6-D benchmark"""

@@ -114,7 +114,7 @@ def test_pointwise_expressions_match_enumerated_and_oracle():
     c.close()
 
 
-@pytest.mark.parametrize("kernel", [0, 7, 8])
+@pytest.mark.parametrize("kernel", [0, 5, 7, 8])
 def test_stage_program_single_gpu_vs_reference(kernel):
     """the whole batched stage program (stage.py) on one GPU: right-hand side and RK stage 0 of the d=6 Vlasov fixture against the reference"""
     sys.path.insert(0, ROOT)
