@@ -44,8 +44,6 @@ SYMBOLS = {
     "amdg_ctx_launch_count": (_i64, [_p]),
     "amdg_ctx_set_debug_buffer": (_i, [_p, _p]),
     "amdg_lean_plan_check": (_i, [_p, _i, _ip, _i, _i, _i, _i, _lp]),
-    "amdg_dir_list_export": (_i, [_p, _i, _i, _i, _i, _ip, _lp, _ip, _ip, _ip, _ip, _ip, _ip, _dp]),
-    "amdg_ws_list_export": (_i, [_p, _i, _i, _i, _i, _ip, _i, _lp, _ip, _ip, _ip, _ip, _ip, _ip, _ip, _dp, _ip, _ip]),
     "amdg_hash_key": (_i, [_i, _ip, _ip]),
     "amdg_order_elem": (_i, [_i, _i]),
     "amdg_sparse_grid": (_i64, [_i, _i, _i, _ip, _ip]),
@@ -256,37 +254,6 @@ class Context:
         out = np.zeros(6, dtype=np.int64)
         _check(lib.amdg_lean_plan_check(self._h, t, sp, kf, kt, rel, lu, out.ctypes.data_as(_lp)))
         return dict(zip(("shapes", "pieces", "coarse_pieces", "entries", "max_staged_rows", "max_smem_doubles"), out.tolist()))
-
-    def dir_list_export(self, op, rel, lu, t, sizes_from):
-        """work list of the register-direct sweep kernel for one sweep (amdg_dir_list_export), as numpy arrays"""
-        s, sp = _ints(sizes_from)
-        cnt = np.zeros(8, dtype=np.int64)
-        _check(lib.amdg_dir_list_export(self._h, op, rel, lu, t, sp, cnt.ctypes.data_as(_lp), None, None, None, None, None, None, None))
-        nu, npool, nel, ntile, nprog, nent = [int(x) for x in cnt[:6]]
-        units = np.zeros((nu, 16), dtype=np.int32); pool = np.zeros(npool, dtype=np.int32); elem = np.zeros(max(nel, 1), dtype=np.int32)
-        tab_b = np.zeros((ntile, 32), dtype=np.int32); tab_c = np.zeros((ntile, 32, 2), dtype=np.int32)
-        pptr = np.zeros(nprog + 1, dtype=np.int32); A_ = np.zeros((max(nent, 1), 32))
-        _check(lib.amdg_dir_list_export(self._h, op, rel, lu, t, sp, cnt.ctypes.data_as(_lp), units.ctypes.data_as(_ip), pool.ctypes.data_as(_ip),
-                                        elem.ctypes.data_as(_ip), tab_b.ctypes.data_as(_ip), tab_c.ctypes.data_as(_ip), pptr.ctypes.data_as(_ip),
-                                        A_.ctypes.data_as(_dp)))
-        return dict(units=units, pool=pool, elem_pool=elem, tab_b=tab_b, tab_c=tab_c, prog_ent_ptr=pptr, A=A_, vec_ok=bool(cnt[6]), nct=int(cnt[7]))
-
-    def ws_list_export(self, op, rel, lu, t, sizes_from, n_cta=148):
-        """work list of the warp-specialised streaming sweep kernel for one sweep (amdg_ws_list_export), as numpy arrays"""
-        s, sp = _ints(sizes_from)
-        cnt = np.zeros(8, dtype=np.int64)
-        _check(lib.amdg_ws_list_export(self._h, op, rel, lu, t, sp, n_cta, cnt.ctypes.data_as(_lp), None, None, None, None, None, None, None, None, None, None))
-        ni, ncta, npool, nel, ntile, nprog, nent = [int(x) for x in cnt[:7]]
-        nrows = int(cnt[7]) // 2
-        rows = np.zeros(max(nrows, 1), dtype=np.int32); rows_ptr = np.zeros(ncta + 1, dtype=np.int32)
-        items = np.zeros((ni, 20), dtype=np.int32); cta = np.zeros(ncta + 1, dtype=np.int32); pool = np.zeros(npool, dtype=np.int32)
-        elem = np.zeros(max(nel, 1), dtype=np.int32); tab_b = np.zeros((ntile, 32), dtype=np.int32); tab_c = np.zeros((ntile, 32, 2), dtype=np.int32)
-        pptr = np.zeros(nprog + 1, dtype=np.int32); A_ = np.zeros((max(nent, 1), 32))
-        _check(lib.amdg_ws_list_export(self._h, op, rel, lu, t, sp, n_cta, cnt.ctypes.data_as(_lp), items.ctypes.data_as(_ip), cta.ctypes.data_as(_ip),
-                                       pool.ctypes.data_as(_ip), elem.ctypes.data_as(_ip), tab_b.ctypes.data_as(_ip), tab_c.ctypes.data_as(_ip),
-                                       pptr.ctypes.data_as(_ip), A_.ctypes.data_as(_dp), rows.ctypes.data_as(_ip), rows_ptr.ctypes.data_as(_ip)))
-        return dict(items=items, cta_ptr=cta, pool=pool, elem_pool=elem, tab_b=tab_b, tab_c=tab_c, prog_ent_ptr=pptr, A=A_, bulk_ok=bool(int(cnt[7]) & 1),
-                    rows=rows, rows_ptr=rows_ptr)
 
     def sweep1d_batch(self, op, rel, lu, t, sizes_from, srcs, dsts, coefs=None, accumulates=None, n_comp=1):
         """one launch for several (src, dst) pairs that share operator, relation, L/U part and dimension (amdg_sweep1d_batch)"""

@@ -15,8 +15,6 @@
 #include "grid.hpp"
 #include "pipe_items.hpp"
 #include "mma_items.hpp"
-#include "dir_items.hpp"
-#include "ws_items.hpp"
 #include "kernels.cuh"
 
 using namespace amdg;
@@ -92,26 +90,6 @@ struct amdg_ctx
     bool tc_force_stage = true; int tc_coarse_ent = 256; int64_t tc_min_doubles = 131072;
     int tc_cap_doubles = 4608, tc_item_target = 148 * 8, tc_ent_target = 48, tc_stage_a_max = 48;      // lean form (kernels_tc.cu)
     bool lean() const { return kernel_variant == 0 || kernel_variant == 5; }
-    // register-direct kernel (kernels_dir.cu): plans per (shape, kf, kt, rel*4+lu), lists per (dim t, outer, inner, kf, kt, rel*4+lu)
-    struct DirList
-    {
-        DirUnit * d_units = nullptr; int * d_pool = nullptr; int * d_tab_b = nullptr; int2 * d_tab_c = nullptr;
-        int n_unit = 0; bool vec_ok = false;
-        MmaList ml;                                               // programs + element rows + operator-fragment tables (get_mma_a_tab)
-    };
-    std::map<std::tuple<int, int, int, int, int, int>, DirList> dirs;
-    std::map<std::tuple<int, int, int, int>, std::vector<DirPiece>> dir_plans;
-    // warp-specialised streaming kernel (kernels_ws.cu): plans per (shape, kf, kt, rel*4+lu), lists per (dim t, outer, inner, kf, kt, rel*4+lu, CTAs per job)
-    struct WsList
-    {
-        WsItem * d_items = nullptr; int * d_cta_ptr = nullptr; int * d_pool = nullptr; int * d_tab_b = nullptr; int2 * d_tab_c = nullptr;
-        int * d_rows = nullptr; int * d_rows_ptr = nullptr;
-        int n_cta = 0; bool bulk_ok = false;
-        MmaList ml;
-    };
-    std::map<std::tuple<int, int, int, int, int, int, int>, WsList> wss;
-    std::map<std::tuple<int, int, int, int>, std::vector<WsPiece>> ws_plans;
-    int ws_items_per_cta = 12;
     // column kernel (kernels_col.cu): resolved entry table per (dim t, relation); unit list per (dim t, rel*4+lu, column groups, columns per lane)
     std::map<std::pair<int, int>, int2 *> col_ents;
     struct ColList { ColUnit * d_units = nullptr; int n_unit = 0, n_heavy = 0; };
@@ -119,7 +97,6 @@ struct amdg_ctx
     int col_heavy_ent = 24, col_upc = 8, col_force_nc = 0;
     int64_t col_min_block = 64; int col_max_kk = 9;                            // auto mode: column kernel for blocks >= col_min_block doubles with KF*KT <= col_max_kk (measured: profiles/r02_sweep_kernels.md)
     double * d_pts1d = nullptr;                                   // LagrBasis::intep_pt table [T*edge_intp] (amdg_points_set)
-    int dir_cost_target = 160;
     std::map<std::tuple<int, int, int, int, int, int>, std::vector<LeanPiece>> lean_plans;   // (shape, kf, kt, rel*4+lu, outer, inner)
     int n_sm = 148;
     long long * dbg = nullptr;
@@ -153,21 +130,6 @@ static void free_dev_grid(amdg_ctx * c)
         for (auto & at : L.a_tab) meta_free(c, (void *)at.second);
     }
     c->mmas.clear();                     // (operator fragments, mma_A, are per shape and survive a grid change)
-    for (auto & kv : c->dirs)
-    {
-        amdg_ctx::DirList & L = kv.second;
-        meta_free(c, L.d_units); meta_free(c, L.d_pool); meta_free(c, L.d_tab_b); meta_free(c, L.d_tab_c); meta_free(c, L.ml.d_elem_pool);
-        for (auto & at : L.ml.a_tab) meta_free(c, (void *)at.second);
-    }
-    c->dirs.clear();
-    for (auto & kv : c->wss)
-    {
-        amdg_ctx::WsList & L = kv.second;
-        meta_free(c, L.d_items); meta_free(c, L.d_cta_ptr); meta_free(c, L.d_pool); meta_free(c, L.d_tab_b); meta_free(c, L.d_tab_c); meta_free(c, L.ml.d_elem_pool);
-        meta_free(c, L.d_rows); meta_free(c, L.d_rows_ptr);
-        for (auto & at : L.ml.a_tab) meta_free(c, (void *)at.second);
-    }
-    c->wss.clear();
     for (auto & kv : c->col_ents) meta_free(c, kv.second);
     c->col_ents.clear();
     for (auto & kv : c->cols) meta_free(c, kv.second.d_units);
@@ -251,7 +213,7 @@ static void evict_shape_caches(amdg_ctx * c)
         if (!live[std::get<1>(it->first)]) { cudaFree(it->second); it = c->mma_A.erase(it); } else ++it;
     }
     auto prune = [&](auto & m) { for (auto it = m.begin(); it != m.end();) { if (!live[std::get<0>(it->first)]) it = m.erase(it); else ++it; } };
-    prune(c->lean_plans); prune(c->dir_plans); prune(c->ws_plans);
+    prune(c->lean_plans);
     c->shapes.retire(live);
     if (std::getenv("AMDG_VERBOSE"))
         fprintf(stderr, "[amdg] cache eviction: shapes %zu -> %zu, operator fragments %zu -> %zu\n", before, c->shapes.n_known(), frags_before, c->mma_A.size());
@@ -290,8 +252,6 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_TC_MIN_DOUBLES")) c->tc_min_doubles = atoll(e);
     if (const char * e = std::getenv("AMDG_TC_FORCE_STAGE")) c->tc_force_stage = atoi(e) != 0;
     if (const char * e = std::getenv("AMDG_TC_COARSE_ENT")) c->tc_coarse_ent = std::max(16, atoi(e));
-    if (const char * e = std::getenv("AMDG_WS_ITEMS")) c->ws_items_per_cta = std::max(1, atoi(e));
-    if (const char * e = std::getenv("AMDG_DIR_COST")) c->dir_cost_target = std::max(8, atoi(e));
     if (const char * e = std::getenv("AMDG_PIPE_CAP")) c->pipe_cap_doubles = std::max(256, atoi(e)) & ~1;
     if (const char * e = std::getenv("AMDG_PIPE_META")) c->pipe_meta_ints = (std::max(256, atoi(e)) + 3) & ~3;
     if (const char * e = std::getenv("AMDG_PIPE_ITEMS")) c->pipe_item_target = std::max(1, atoi(e));
@@ -359,7 +319,7 @@ int amdg_ctx_set_stream(amdg_ctx * c, void * s)
 
 int amdg_ctx_sync(amdg_ctx * c) { int r = need_device(c); if (r) return r; CU(cudaStreamSynchronize(c->stream)); return AMDG_OK; }
 int amdg_ctx_set_schedule(amdg_ctx * c, int s) { if (!c || (s != AMDG_SCHED_LITERAL && s != AMDG_SCHED_SHARED)) return fail(AMDG_EINVAL, "bad schedule"); c->sched = s; return AMDG_OK; }
-int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 8) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
+int amdg_ctx_set_kernel(amdg_ctx * c, int v) { if (!c || v < 0 || v > 8 || v == 6 || v == 7) return fail(AMDG_EINVAL, "bad kernel variant"); c->kernel_variant = v; return AMDG_OK; }
 int64_t amdg_ctx_launch_count(amdg_ctx * c) { return c ? c->launches : -1; }
 int amdg_ctx_set_debug_buffer(amdg_ctx * c, void * dev_buf) { if (!c) return fail(AMDG_EINVAL, "null context"); c->dbg = (long long *)dev_buf; return AMDG_OK; }
 
@@ -1228,348 +1188,6 @@ int amdg_lean_plan_check(amdg_ctx * c, int t, const int * sizes_from, int kf, in
     return AMDG_OK;
 }
 
-// Work list of the register-direct kernel (kernels_dir.cu, dir_items.hpp): one unit per (piece of a shape, run of fibres, range of column
-// tiles).  Host part (no device needed; also exported to the tests by amdg_dir_list_export):
-struct DirHost
-{
-    std::vector<DirUnit> units; std::vector<int> pool, elem_pool, tab_b, tab_c;
-    std::vector<ShapeProg> progs; std::vector<int> prog_shape; std::vector<long long> prog_piece;
-    int nct = 0; bool vec_ok = false;
-};
-static void build_dir_host(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int lu, DirHost & D)
-{
-    const std::map<int, std::vector<int>> & sf = c->shapes.shape_fibres[t];
-    const DimTables & H = c->grid.dims[t];
-    int nct_pad = 0;
-    build_dir_tables(outer, inner, kf, kt, D.tab_b, D.tab_c, nct_pad, D.vec_ok);
-    const int nct = (outer * inner + 7) / 8;
-    D.nct = nct;
-    std::vector<DirUnit> units; std::vector<double> cost;
-    for (auto & kv : sf)
-    {
-        const int shape = kv.first; const std::vector<int> & fibres = kv.second;
-        const int m = (int)c->shapes.ords[shape].size();
-        if (const char * e = std::getenv("AMDG_DIR_MAXM")) { if (m > atoi(e)) continue; }     // timing experiments only (results incomplete)
-        if (const char * e = std::getenv("AMDG_DIR_MINM")) { if (m < atoi(e)) continue; }
-        auto pk = std::make_tuple(shape, kf, kt, rel * 4 + lu);
-        auto pit = c->dir_plans.find(pk);
-        if (pit == c->dir_plans.end())
-        {
-            std::vector<DirPiece> pcs; build_dir_plan(c->pairs, c->shapes.ords[shape], c->nmax, rel, lu, kf, kt, pcs);
-            pit = c->dir_plans.emplace(pk, std::move(pcs)).first;
-        }
-        const std::vector<DirPiece> & pieces = pit->second;
-        const int fib0 = (int)D.elem_pool.size();
-        for (size_t b = 0; b < fibres.size(); ++b) for (int f = 0; f < m; ++f) D.elem_pool.push_back(H.slot_elem[fibres[b] + f]);
-        for (const DirPiece & P : pieces)
-        {
-            const int prog = (int)D.progs.size();
-            D.progs.push_back(P.prog); D.prog_shape.push_back(shape); D.prog_piece.push_back(P.hash);
-            const int pofs = (int)D.pool.size();
-            D.pool.insert(D.pool.end(), P.src.begin(), P.src.end());
-            D.pool.insert(D.pool.end(), P.mask.begin(), P.mask.end());
-            const int G = dir_variant_g(P.variant);
-            const double tile_cost = (double)P.src.size() + P.n_ent() + 2.0 * P.n_rt + 1.0;
-            int tpu = (int)std::max<double>(1.0, c->dir_cost_target / tile_cost);
-            tpu = std::max(G, (tpu / G) * G);
-            int nf_per = 1;
-            if (tpu >= nct) { tpu = nct; nf_per = (int)std::max<double>(1.0, c->dir_cost_target / (tile_cost * nct)); }
-            for (size_t f0 = 0; f0 < fibres.size(); f0 += nf_per)
-            {
-                const int nf = (int)std::min<size_t>(nf_per, fibres.size() - f0);
-                for (int ct0 = 0; ct0 < nct; ct0 += tpu)
-                {
-                    DirUnit x; std::memset(&x, 0, sizeof(x));
-                    x.pool_ofs = pofs; x.fib_ofs = fib0 + (int)f0 * m; x.nfib = nf; x.m = m; x.ct0 = ct0; x.nct = std::min(tpu, nct - ct0);
-                    x.n_src = (int)P.src.size(); x.prog = prog; x.variant = P.variant; x.n_rt = P.n_rt;
-                    for (int r = 0; r < 4; ++r) x.rt_id[r] = P.rt_id[r];
-                    units.push_back(x);
-                    cost.push_back(tile_cost * x.nct * nf);
-                }
-            }
-        }
-    }
-    // longest units first; equal costs keep their order (units of one fibre stay adjacent: they share sources in L1)
-    std::vector<int> order(units.size()); for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
-    D.units.resize(units.size()); for (size_t i = 0; i < order.size(); ++i) D.units[i] = units[order[i]];
-    if (D.pool.empty()) D.pool.push_back(0);
-}
-
-static amdg_ctx::DirList & get_dir(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int lu)
-{
-    auto key = std::make_tuple(t, outer, inner, kf, kt, rel * 4 + lu);
-    auto it = c->dirs.find(key);
-    if (it != c->dirs.end()) return it->second;
-    amdg_ctx::DirList L;
-    DirHost D; build_dir_host(c, t, outer, inner, kf, kt, rel, lu, D);
-    if (!D.units.empty())
-    {
-        bool up = meta_upload(c, &L.d_units, D.units.data(), D.units.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.d_pool, D.pool.data(), D.pool.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.ml.d_elem_pool, D.elem_pool.data(), D.elem_pool.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.d_tab_b, D.tab_b.data(), D.tab_b.size(), false) == cudaSuccess &&
-                  meta_upload(c, (int **)&L.d_tab_c, D.tab_c.data(), D.tab_c.size(), false) == cudaSuccess &&
-                  cudaStreamSynchronize(c->stream) == cudaSuccess;
-        if (up) { L.n_unit = (int)D.units.size(); L.vec_ok = D.vec_ok; L.ml.ok = true; }
-        L.ml.progs = std::move(D.progs); L.ml.prog_shape = std::move(D.prog_shape); L.ml.prog_piece = std::move(D.prog_piece);
-        if (std::getenv("AMDG_VERBOSE"))
-        {
-            int nv[4] = { 0, 0, 0, 0 }; for (auto & x : D.units) nv[x.variant]++;
-            fprintf(stderr, "[amdg] dir list t=%d outer=%d inner=%d kf=%d kt=%d rel=%d lu=%d: %d units (%d/%d/%d/%d by variant), %d programs, %d column tiles, vec %d\n",
-                    t, outer, inner, kf, kt, rel, lu, (int)D.units.size(), nv[0], nv[1], nv[2], nv[3], (int)L.ml.progs.size(), D.nct, (int)D.vec_ok);
-        }
-    }
-    return c->dirs.emplace(key, std::move(L)).first->second;
-}
-
-// Diagnostic export of the register-direct kernel's work list (host only, no device needed) so that the tests can replay it against the
-// oracle: counts[8] = units, pool ints, element rows, column tiles (padded to 8), programs, total entries, vec_ok, 0.  Call with units == NULL
-// for the counts.  units: 16 ints each (DirUnit); prog_ent_ptr[programs+1]; A[total entries][32] = operator values of `op` in fragment order.
-int amdg_dir_list_export(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, int64_t * counts, int * units, int * pool,
-                         int * elem_pool, int * tab_b, int * tab_c, int * prog_ent_ptr, double * A)
-{
-    if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
-    if (op < 0 || op >= (int)c->ops.size() || t < 0 || t >= c->dim || !sizes_from || !counts || rel < 0 || rel > 1 || lu < 0 || lu > 2) return fail(AMDG_EINVAL, "bad arguments");
-    const Op & O = *c->ops[op];
-    int outer = 1, inner = 1;
-    for (int k = 0; k < t; ++k) outer *= sizes_from[k];
-    for (int k = t + 1; k < c->dim; ++k) inner *= sizes_from[k];
-    DirHost D; build_dir_host(c, t, outer, inner, O.kf, O.kt, rel, lu, D);
-    int64_t n_ent = 0; for (auto & P : D.progs) n_ent += P.n_ent();
-    counts[0] = (int64_t)D.units.size(); counts[1] = (int64_t)D.pool.size(); counts[2] = (int64_t)D.elem_pool.size(); counts[3] = (int64_t)D.tab_b.size() / 32;
-    counts[4] = (int64_t)D.progs.size(); counts[5] = n_ent; counts[6] = D.vec_ok ? 1 : 0; counts[7] = D.nct;
-    if (!units) return AMDG_OK;
-    std::memcpy(units, D.units.data(), D.units.size() * sizeof(DirUnit));
-    std::memcpy(pool, D.pool.data(), D.pool.size() * sizeof(int));
-    std::memcpy(elem_pool, D.elem_pool.data(), D.elem_pool.size() * sizeof(int));
-    std::memcpy(tab_b, D.tab_b.data(), D.tab_b.size() * sizeof(int));
-    std::memcpy(tab_c, D.tab_c.data(), D.tab_c.size() * sizeof(int));
-    int64_t p = 0;
-    for (size_t i = 0; i < D.progs.size(); ++i)
-    {
-        prog_ent_ptr[i] = (int)p;
-        std::vector<double> Ai; build_shape_A(D.progs[i], O.blocks.data(), O.kf, O.kt, Ai);
-        std::memcpy(A + p * 32, Ai.data(), Ai.size() * sizeof(double));
-        p += D.progs[i].n_ent();
-    }
-    prog_ent_ptr[D.progs.size()] = (int)p;
-    return AMDG_OK;
-}
-
-// Work list of the warp-specialised streaming kernel (kernels_ws.cu, ws_items.hpp).  Host part (no device needed; exported to the tests by
-// amdg_ws_list_export): items per persistent CTA, balanced by longest-processing-time-first on a cost estimate.
-struct WsHost
-{
-    std::vector<WsItem> items; std::vector<int> cta_ptr, pool, elem_pool, tab_b, tab_c, rows, rows_ptr;
-    std::vector<ShapeProg> progs; std::vector<int> prog_shape; std::vector<long long> prog_piece;
-    bool bulk_ok = true;
-};
-static void build_ws_host(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int lu, int n_cta, WsHost & D)
-{
-    const std::map<int, std::vector<int>> & sf = c->shapes.shape_fibres[t];
-    const DimTables & H = c->grid.dims[t];
-    int cap = ws_stage_doubles();
-    if (const char * e = std::getenv("AMDG_WS_CAP")) cap = std::max(1152, std::min(cap, atoi(e)));       // tests: force column rectangles on small grids
-    const int full = outer * kf * inner;
-    // table sets per rectangle shape (no, ni); set 0 is the whole plane (its B offsets are also global offsets: heavy items)
-    std::map<std::pair<int, int>, std::array<int, 3>> sets;       // -> (first tile, column tiles, vec_ok)
-    auto table_set = [&](int no, int ni) -> std::array<int, 3>
-    {
-        auto it = sets.find({ no, ni });
-        if (it != sets.end()) return it->second;
-        std::vector<int> tb, tc; int nct = 0, nct_pad = 0; bool vec = false;
-        build_ws_tables(no, ni, inner, kf, kt, tb, tc, nct, nct_pad, vec);
-        const int base = (int)D.tab_b.size() / 32;
-        D.tab_b.insert(D.tab_b.end(), tb.begin(), tb.end()); D.tab_c.insert(D.tab_c.end(), tc.begin(), tc.end());
-        return sets.emplace(std::make_pair(no, ni), std::array<int, 3>{ base, nct, vec ? 1 : 0 }).first->second;
-    };
-    const std::array<int, 3> set0 = table_set(outer, inner);
-    const int64_t total = c->grid.n * (int64_t)full;
-    const int item_cap = (int)std::min<int64_t>(cap, std::max<int64_t>(cap / 8, total / std::max(1, n_cta * c->ws_items_per_cta)));
-    std::vector<double> cost;
-    for (auto & kv : sf)
-    {
-        const int shape = kv.first; const std::vector<int> & fibres = kv.second;
-        const int m = (int)c->shapes.ords[shape].size();
-        if (const char * e = std::getenv("AMDG_DIR_MAXM")) { if (m > atoi(e)) continue; }     // timing experiments only (results incomplete)
-        if (const char * e = std::getenv("AMDG_DIR_MINM")) { if (m < atoi(e)) continue; }
-        auto pk = std::make_tuple(shape, kf, kt, rel * 4 + lu);
-        auto pit = c->ws_plans.find(pk);
-        if (pit == c->ws_plans.end())
-        {
-            std::vector<WsPiece> pcs; build_ws_plan(c->pairs, c->shapes.ords[shape], c->nmax, rel, lu, kf, kt, pcs);
-            pit = c->ws_plans.emplace(pk, std::move(pcs)).first;
-        }
-        const std::vector<WsPiece> & pieces = pit->second;
-        const int fib0 = (int)D.elem_pool.size();
-        for (size_t b = 0; b < fibres.size(); ++b) for (int f = 0; f < m; ++f) D.elem_pool.push_back(H.slot_elem[fibres[b] + f]);
-        for (const WsPiece & P : pieces)
-        {
-            const ShapeProg & Q = P.prog;
-            const int prog = (int)D.progs.size();
-            D.progs.push_back(Q); D.prog_shape.push_back(shape); D.prog_piece.push_back(P.hash);
-            const int pofs = (int)D.pool.size();
-            D.pool.insert(D.pool.end(), Q.rt_ptr.begin(), Q.rt_ptr.end());
-            D.pool.insert(D.pool.end(), Q.rt_order.begin(), Q.rt_order.end());
-            D.pool.insert(D.pool.end(), Q.ent_src.begin(), Q.ent_src.end());
-            D.pool.insert(D.pool.end(), P.src.begin(), P.src.end());
-            WsItem x; std::memset(&x, 0, sizeof(x));
-            x.prog = prog; x.pool_ofs = pofs; x.m = m; x.n_rt = Q.n_rt; x.n_src = (int)P.src.size(); x.n_ent = (int)Q.n_ent();
-            if (P.heavy)
-            {
-                x.heavy = 1; x.nfib = 1; x.nct = 1; x.kstride = inner; x.vec = 0;
-                for (size_t f = 0; f < fibres.size(); ++f)
-                    for (int ct = 0; ct < set0[1]; ++ct)
-                    {
-                        x.fib_ofs = fib0 + (int)f * m; x.tab = set0[0] + ct;
-                        D.items.push_back(x); cost.push_back(3.0 * x.n_ent / 8.0 + 60.0);
-                    }
-                continue;
-            }
-            const int n_src = x.n_src;
-            auto emit = [&](int no, int ni, int o0, int i0, int nrun, int run_len, int gstride, int nf_max)
-            {
-                const std::array<int, 3> ts = table_set(no, ni);
-                x.tab = ts[0]; x.nct = ts[1]; x.vec = ts[2];
-                x.src_origin = o0 * kf * inner + i0; x.dst_origin = o0 * kt * inner + i0;
-                x.nrun = nrun; x.run_len = run_len; x.gstride = gstride; x.slot = nrun * run_len; x.kstride = ni;
-                if ((run_len & 1) || (x.src_origin & 1) || (gstride & 1)) D.bulk_ok = false;
-                const int ngroups = (x.nct + 7) / 8;
-                const int nf_per = std::max(1, std::min(nf_max, std::max(1, 32 / std::max(1, x.n_rt * ngroups))));
-                for (size_t f0 = 0; f0 < fibres.size(); f0 += nf_per)
-                {
-                    x.nfib = (int)std::min<size_t>(nf_per, fibres.size() - f0); x.fib_ofs = fib0 + (int)f0 * m;
-                    D.items.push_back(x);
-                    cost.push_back(x.nfib * ((double)x.n_ent * x.nct + (double)n_src * x.slot / 24.0 + 6.0 * x.n_rt * ngroups) + 20.0);
-                }
-            };
-            if (n_src == 0 || (int64_t)n_src * full <= cap)
-                emit(outer, inner, 0, 0, 1, full, 0, n_src == 0 ? 32 : std::max(1, item_cap / (n_src * full)));
-            else if (outer > 1 && (int64_t)n_src * kf * inner <= cap)
-            {
-                const int no = cap / (n_src * kf * inner);
-                for (int o0 = 0; o0 < outer; o0 += no) { const int n = std::min(no, outer - o0); emit(n, inner, o0, 0, 1, n * kf * inner, 0, 1); }
-            }
-            else
-            {
-                const int ni_max = std::max(8, (cap / (n_src * kf)) & ~7);
-                const int n_strip = (inner + ni_max - 1) / ni_max;
-                const int ni = std::min(ni_max, (((inner + n_strip - 1) / n_strip) + 7) & ~7);
-                for (int o = 0; o < outer; ++o)
-                    for (int i0 = 0; i0 < inner; i0 += ni) { const int n = std::min(ni, inner - i0); emit(1, n, o, i0, kf, n, inner, 1); }
-            }
-        }
-    }
-    // longest-processing-time-first over the CTAs
-    const size_t ni = D.items.size();
-    std::vector<int> order(ni); for (size_t i = 0; i < ni; ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-    typedef std::pair<double, int> LB;
-    std::priority_queue<LB, std::vector<LB>, std::greater<LB>> pq;
-    for (int q = 0; q < n_cta; ++q) pq.push({ 0.0, q });
-    std::vector<std::vector<int>> bins(n_cta);
-    for (int i : order) { LB lb = pq.top(); pq.pop(); bins[lb.second].push_back(i); lb.first += cost[i]; pq.push(lb); }
-    std::vector<WsItem> sorted; sorted.reserve(ni);
-    D.cta_ptr.assign(1, 0);
-    for (int q = 0; q < n_cta; ++q) { for (int i : bins[q]) sorted.push_back(D.items[i]); D.cta_ptr.push_back((int)sorted.size()); }
-    D.items.swap(sorted);
-    D.pool.push_back(0);                                           // padding: the kernel fetches one entry ahead
-    // resolved element rows per CTA (the kernel keeps them in shared memory): sources of every slot / entry, targets of every row tile
-    const int tg = 8 / mma_ktp(kt);
-    D.rows.clear(); D.rows_ptr.assign(1, 0);
-    for (int q = 0; q < n_cta; ++q)
-    {
-        const int base = (int)D.rows.size();
-        for (int i = D.cta_ptr[q]; i < D.cta_ptr[q + 1]; ++i)
-        {
-            WsItem & x = D.items[i];
-            x.rows_ofs = (int)D.rows.size() - base;
-            const int * P = D.pool.data() + x.pool_ofs;
-            const int * rt_id = P + x.n_rt + 1, * ent = P + 2 * x.n_rt + 1, * src_local = ent + x.n_ent;
-            if (x.heavy)
-            {
-                for (int p = 0; p < x.n_ent; ++p) D.rows.push_back(D.elem_pool[x.fib_ofs + (ent[p] >> 1)]);
-                for (int g = 0; g < tg; ++g) { const int tl = rt_id[0] * tg + g; D.rows.push_back(tl < x.m ? D.elem_pool[x.fib_ofs + tl] : -1); }
-            }
-            else
-            {
-                for (int b = 0; b < x.nfib; ++b) for (int s2 = 0; s2 < x.n_src; ++s2) D.rows.push_back(D.elem_pool[x.fib_ofs + b * x.m + src_local[s2]]);
-                for (int b = 0; b < x.nfib; ++b) for (int ri = 0; ri < x.n_rt; ++ri) for (int g = 0; g < tg; ++g)
-                { const int tl = rt_id[ri] * tg + g; D.rows.push_back(tl < x.m ? D.elem_pool[x.fib_ofs + b * x.m + tl] : -1); }
-            }
-        }
-        D.rows_ptr.push_back((int)D.rows.size());
-    }
-    if (D.rows.empty()) D.rows.push_back(0);
-}
-
-static amdg_ctx::WsList & get_ws(amdg_ctx * c, int t, int outer, int inner, int kf, int kt, int rel, int lu, int n_cta)
-{
-    auto key = std::make_tuple(t, outer, inner, kf, kt, rel * 4 + lu, n_cta);
-    auto it = c->wss.find(key);
-    if (it != c->wss.end()) return it->second;
-    amdg_ctx::WsList L;
-    WsHost D; build_ws_host(c, t, outer, inner, kf, kt, rel, lu, n_cta, D);
-    if (!D.items.empty())
-    {
-        bool up = meta_upload(c, &L.d_items, D.items.data(), D.items.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.d_cta_ptr, D.cta_ptr.data(), D.cta_ptr.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.d_pool, D.pool.data(), D.pool.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.ml.d_elem_pool, D.elem_pool.data(), D.elem_pool.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.d_tab_b, D.tab_b.data(), D.tab_b.size(), false) == cudaSuccess &&
-                  meta_upload(c, (int **)&L.d_tab_c, D.tab_c.data(), D.tab_c.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.d_rows, D.rows.data(), D.rows.size(), false) == cudaSuccess &&
-                  meta_upload(c, &L.d_rows_ptr, D.rows_ptr.data(), D.rows_ptr.size(), false) == cudaSuccess &&
-                  cudaStreamSynchronize(c->stream) == cudaSuccess;
-        if (up) { L.n_cta = n_cta; L.bulk_ok = D.bulk_ok; L.ml.ok = true; }
-        if (std::getenv("AMDG_VERBOSE"))
-        {
-            int nh = 0; for (auto & x : D.items) nh += x.heavy;
-            fprintf(stderr, "[amdg] ws list t=%d outer=%d inner=%d kf=%d kt=%d rel=%d lu=%d ctas=%d: %d items (%d heavy), %d programs, bulk %d\n",
-                    t, outer, inner, kf, kt, rel, lu, n_cta, (int)D.items.size(), nh, (int)D.progs.size(), (int)D.bulk_ok);
-        }
-        L.ml.progs = std::move(D.progs); L.ml.prog_shape = std::move(D.prog_shape); L.ml.prog_piece = std::move(D.prog_piece);
-    }
-    return c->wss.emplace(key, std::move(L)).first->second;
-}
-
-// Diagnostic export of the streaming kernel's work list (host only): counts[8] = items, CTAs, pool ints, element rows, table tiles, programs,
-// entries, bulk_ok.  Call with items == NULL for the counts.  items[n][20] (WsItem), cta_ptr[CTAs+1], tab_b[tiles][32], tab_c[tiles][32][2].
-int amdg_ws_list_export(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, int n_cta, int64_t * counts, int * items, int * cta_ptr,
-                        int * pool, int * elem_pool, int * tab_b, int * tab_c, int * prog_ent_ptr, double * A, int * rows, int * rows_ptr)
-{
-    if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
-    if (op < 0 || op >= (int)c->ops.size() || t < 0 || t >= c->dim || !sizes_from || !counts || rel < 0 || rel > 1 || lu < 0 || lu > 2 || n_cta < 1) return fail(AMDG_EINVAL, "bad arguments");
-    const Op & O = *c->ops[op];
-    int outer = 1, inner = 1;
-    for (int k = 0; k < t; ++k) outer *= sizes_from[k];
-    for (int k = t + 1; k < c->dim; ++k) inner *= sizes_from[k];
-    WsHost D; build_ws_host(c, t, outer, inner, O.kf, O.kt, rel, lu, n_cta, D);
-    int64_t n_ent = 0; for (auto & P : D.progs) n_ent += P.n_ent();
-    counts[0] = (int64_t)D.items.size(); counts[1] = n_cta; counts[2] = (int64_t)D.pool.size(); counts[3] = (int64_t)D.elem_pool.size();
-    counts[4] = (int64_t)D.tab_b.size() / 32; counts[5] = (int64_t)D.progs.size(); counts[6] = n_ent; counts[7] = (D.bulk_ok ? 1 : 0) + 2 * (int64_t)D.rows.size();
-    if (!items) return AMDG_OK;
-    if (rows) std::memcpy(rows, D.rows.data(), D.rows.size() * sizeof(int));
-    if (rows_ptr) std::memcpy(rows_ptr, D.rows_ptr.data(), D.rows_ptr.size() * sizeof(int));
-    std::memcpy(items, D.items.data(), D.items.size() * sizeof(WsItem));
-    std::memcpy(cta_ptr, D.cta_ptr.data(), D.cta_ptr.size() * sizeof(int));
-    std::memcpy(pool, D.pool.data(), D.pool.size() * sizeof(int));
-    std::memcpy(elem_pool, D.elem_pool.data(), D.elem_pool.size() * sizeof(int));
-    std::memcpy(tab_b, D.tab_b.data(), D.tab_b.size() * sizeof(int));
-    std::memcpy(tab_c, D.tab_c.data(), D.tab_c.size() * sizeof(int));
-    int64_t p = 0;
-    for (size_t i = 0; i < D.progs.size(); ++i)
-    {
-        prog_ent_ptr[i] = (int)p;
-        std::vector<double> Ai; build_shape_A(D.progs[i], O.blocks.data(), O.kf, O.kt, Ai);
-        std::memcpy(A + p * 32, Ai.data(), Ai.size() * sizeof(double));
-        p += D.progs[i].n_ent();
-    }
-    prog_ent_ptr[D.progs.size()] = (int)p;
-    return AMDG_OK;
-}
-
 // device table of operator values (fragment order) for every program of a list, for operator `op`
 static const double * const * get_mma_a_tab(amdg_ctx * c, amdg_ctx::MmaList & L, int op, int rel, int lu)
 {
@@ -1704,7 +1322,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
     // destination maps / accumulate-from exist in the lean, register-direct and streaming kernels only (even map offsets are the caller's contract
     // whenever the block size is even: the kernels keep their 16-byte stores)
     bool mapped = false; for (int i = 0; i < n_job; ++i) mapped = mapped || jobs[i].dst_map || jobs[i].acc_from;
-    const int variant0 = (mapped && c->kernel_variant < 6) ? 5 : c->kernel_variant;
+    const int variant0 = (mapped && c->kernel_variant < 8) ? 5 : c->kernel_variant;
     int done = 0;
     while (done < n_job)
     {
@@ -1729,52 +1347,6 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
             for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
             cudaError_t e = launch_sweep_col(a, O.kf, O.kt, nc, c->stream);
             if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("column sweep launch: ") + cudaGetErrorString(e));
-            c->launches++; done += cnt; continue;
-        }
-        if (variant == 7)
-        {
-            const int n_cta = std::max(1, c->n_sm / std::max(1, cnt * n_comp));
-            amdg_ctx::WsList & WL = get_ws(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, lu, n_cta);
-            const double * const * atab = WL.ml.ok ? get_mma_a_tab(c, WL.ml, op, rel, lu) : nullptr;
-            if (!(WL.ml.ok && atab)) return fail(AMDG_EINVAL, "streaming kernel requested but the work list could not be built");
-            WsArgs a;
-            a.items = WL.d_items; a.cta_ptr = WL.d_cta_ptr; a.rows = WL.d_rows; a.rows_ptr = WL.d_rows_ptr; a.pool = WL.d_pool; a.elem_pool = WL.ml.d_elem_pool; a.a_tab = atab;
-            a.tab_b = WL.d_tab_b; a.tab_c = WL.d_tab_c; a.n_elem = c->grid.n; a.kf = O.kf; a.kt = O.kt; a.inner = inner;
-            const int ktp = mma_ktp(O.kt);
-            a.tg = 8 / ktp; a.tg_shift = ktp == 1 ? 0 : (ktp == 2 ? 1 : (ktp == 4 ? 2 : 3));
-            a.n_comp = n_comp; a.n_job = cnt; a.bulk_jobs = 0; a.vec_jobs = 0;
-            const int64_t s_from = (int64_t)W * O.kf, s_to = (int64_t)W * O.kt;
-            for (int i = 0; i < cnt; ++i)
-            {
-                a.job[i] = jobs[done + i];
-                if (WL.bulk_ok && (s_from & 1) == 0 && (reinterpret_cast<uintptr_t>(a.job[i].src) & 15) == 0) a.bulk_jobs |= 1u << i;
-                if ((s_to & 1) == 0 && (reinterpret_cast<uintptr_t>(a.job[i].dst) & 15) == 0 && !a.job[i].dst_map &&
-                    (!a.job[i].acc_from || (reinterpret_cast<uintptr_t>(a.job[i].acc_from) & 15) == 0)) a.vec_jobs |= 1u << i;
-            }
-            cudaError_t e = launch_sweep_ws(a, WL.n_cta, c->stream);
-            if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("streaming sweep launch: ") + cudaGetErrorString(e));
-            c->launches++; done += cnt; continue;
-        }
-        if (variant == 6)
-        {
-            amdg_ctx::DirList & DL = get_dir(c, t, jobs[done].outer, inner, O.kf, O.kt, rel, lu);
-            const double * const * atab = DL.ml.ok ? get_mma_a_tab(c, DL.ml, op, rel, lu) : nullptr;
-            if (!(DL.ml.ok && atab)) return fail(AMDG_EINVAL, "register-direct kernel requested but the work list could not be built");
-            DirArgs a;
-            a.units = DL.d_units; a.n_unit = DL.n_unit; a.pool = DL.d_pool; a.elem_pool = DL.ml.d_elem_pool; a.a_tab = atab;
-            a.tab_b = DL.d_tab_b; a.tab_c = DL.d_tab_c; a.n_elem = c->grid.n; a.kf = O.kf; a.kt = O.kt; a.inner = inner;
-            const int ktp = mma_ktp(O.kt);
-            a.tg = 8 / ktp; a.tg_shift = ktp == 1 ? 0 : (ktp == 2 ? 1 : (ktp == 4 ? 2 : 3)); a.dkp = 4 * inner;
-            a.n_comp = n_comp; a.n_job = cnt; a.vec_ok = 0;
-            const int64_t s_to = (int64_t)W * O.kt;
-            for (int i = 0; i < cnt; ++i)
-            {
-                a.job[i] = jobs[done + i];
-                // 16-byte accesses: the tables are pairwise aligned, block sizes even, the base aligned and (for mapped destinations) the caller built even offsets
-                if (DL.vec_ok && (s_to & 1) == 0 && (reinterpret_cast<uintptr_t>(a.job[i].dst) & 15) == 0 && !a.job[i].dst_map) a.vec_ok |= 1 << i;
-            }
-            cudaError_t e = launch_sweep_dir(a, c->stream);
-            if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("register-direct sweep launch: ") + cudaGetErrorString(e));
             c->launches++; done += cnt; continue;
         }
         if (variant == 0 || variant == 4 || variant == 5)

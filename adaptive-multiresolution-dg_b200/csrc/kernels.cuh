@@ -33,11 +33,11 @@ struct SweepJob
     int outer;          // prod of block edges of dims < t
     int accumulate;     // dst += result
     double coef;
-    // optional (sweep_dir_kernel only): offset in doubles, relative to dst, of the destination block of every element row; null = row * S_to.
+    // optional (lean and column kernels): offset in doubles, relative to dst, of the destination block of every element row; null = row * S_to.
     // The fibre-partitioned multi-GPU path points these at peer memory: the last sweep before a layout switch stores every element block
     // straight into the buffer of the rank that owns it in the next layout.
     const long long * dst_map = nullptr;
-    // optional (sweep_dir_kernel only, with accumulate): the old values are read from acc_from (plain row * S_to layout) instead of the
+    // optional (lean and column kernels, with accumulate): the old values are read from acc_from (plain row * S_to layout) instead of the
     // destination -- "remote = local partial sum + sweep", the last accumulating sweep before a layout switch
     const double * acc_from = nullptr;
 };
@@ -165,71 +165,6 @@ struct MmaArgs
     SweepJob job[MAX_JOBS];
 };
 
-// register-direct tensor-core sweep kernel (plans built by dir_items.hpp)
-struct __align__(16) DirUnit
-{
-    int pool_ofs;       // ints in `pool`: src code [n_src] | row-tile mask [n_src]
-    int fib_ofs;        // element rows of the unit's fibres: elem_pool[fib_ofs + b*m + local]
-    int nfib, m;
-    int ct0, nct;       // column tiles [ct0, ct0 + nct)
-    int n_src;
-    int prog;           // index into a_tab
-    int variant;        // dir_items.hpp
-    int n_rt;
-    int rt_id[4];
-    int pad[2];
-};
-struct DirArgs
-{
-    const DirUnit * units; int n_unit;
-    const int * pool;
-    const int * elem_pool;
-    const double * const * a_tab;   // per program: operator values in fragment order [entry][32]
-    const int * tab_b;              // [nct_pad][32] source offsets of the B fragments
-    const int2 * tab_c;             // [nct_pad][32] destination offsets of the C fragments (-1: not stored)
-    int64_t n_elem;
-    int kf, kt, inner;
-    int tg_shift;                   // log2(KTP): target slot of C row r is r >> tg_shift
-    int tg;                         // targets per row tile
-    int dkp;                        // inner * 4: source offset of the second k-part (KF > 4)
-    int vec_ok;                     // every stored column pair is an aligned 16-byte pair
-    int n_comp, n_job;
-    SweepJob job[MAX_JOBS];
-};
-
-// warp-specialised streaming sweep kernel (work lists built by ws_items.hpp)
-struct __align__(16) WsItem
-{
-    int prog;                       // index into a_tab (operator values of the piece, entries row tile by row tile)
-    int pool_ofs;                   // ints in `pool`: rt_ptr[n_rt+1] | rt_id[n_rt] | ent[n_ent] (slot*2 + k-part) | src_local[n_src]
-    int fib_ofs, nfib, m;           // element rows of the item's fibres: elem_pool[fib_ofs + b*m + local]
-    int n_rt, n_src, n_ent;
-    int tab, nct;                   // tables of the rectangle shape start at tile `tab`; the rectangle has nct column tiles
-    int src_origin, dst_origin;     // offset of the rectangle's first column in a source / destination block
-    int nrun, run_len, gstride;     // a staged source = nrun runs of run_len doubles, gstride apart in global memory, back to back in the slot
-    int slot;                       // doubles per staged source (nrun * run_len)
-    int kstride;                    // doubles between consecutive source indices k inside a slot (heavy items: in global memory)
-    int heavy;                      // 1: one row tile x one column tile, not staged, the consumer warps split the entry list
-    int vec;                        // the rectangle shape allows aligned 16-byte stores
-    int rows_ofs;                   // element rows of the item in the CTA's part of `rows`: staged: source row of every slot [nfib*n_src], then the target
-                                    // row of every (fibre, row tile, target slot) [nfib*n_rt*tg] (-1: no such target); heavy: source row of every entry
-                                    // [n_ent], then target rows [tg]
-};
-struct WsArgs
-{
-    const WsItem * items; const int * cta_ptr;      // CTA c runs items [cta_ptr[c], cta_ptr[c+1])
-    const int * rows; const int * rows_ptr;         // resolved element rows of CTA c's items: rows[rows_ptr[c] + item.rows_ofs + ...]
-    const int * pool; const int * elem_pool; const double * const * a_tab;
-    const int * tab_b; const int2 * tab_c;
-    int64_t n_elem;
-    int kf, kt, inner, tg, tg_shift;
-    unsigned bulk_jobs, vec_jobs;                   // per job: bulk copies legal (16-byte aligned runs); 16-byte stores legal
-    int n_comp, n_job;
-    SweepJob job[MAX_JOBS];
-};
-int ws_stage_doubles();
-cudaError_t launch_sweep_ws(const WsArgs & a, int n_cta, cudaStream_t st);                                     // kernels_ws.cu
-
 // column-form sweep kernel (kernels_col.cu): one thread per column, no staging
 struct __align__(16) ColUnit { int tgt; int ent0; int n_ent; int g; };     // target element row, first entry, entries, column group (32*NC columns)
 struct ColArgs
@@ -288,7 +223,6 @@ cudaError_t launch_sweep_mma(const MmaArgs & a, int kf, int kt, int smem_doubles
 int mma_smem_capacity_doubles();
 cudaError_t launch_sweep_tc(const MmaArgs & a, int kf, int kt, int smem_doubles, cudaStream_t st);     // kernels_tc.cu
 int tc_smem_capacity_doubles();
-cudaError_t launch_sweep_dir(const DirArgs & a, cudaStream_t st);                                             // kernels_dir.cu
 cudaError_t launch_pointwise(const PointwiseArgs & a, cudaStream_t st);
 cudaError_t launch_pointwise_expr(const PwExprArgs & a, cudaStream_t st);
 // rows of a local array to mapped destinations (peer memory): dst[map[e] + i] = src[e*width + i]

@@ -382,15 +382,40 @@ class DeviceStage:
         n = len(self.rows[bb.layout])
         return _as_tensor(self.local_ptr(key), n * bb.width).view(n, bb.width)
 
-    def run(self):
+    def run(self, profile=None):
+        """executes the plan on the context's stream; `profile` (a dict) collects device time per kind of operation through CUDA events
+        (eager launches only: the caller synchronises and calls profile_summary)"""
         A, plan = self.A, self.plan
         for o in plan.ops:
+            kind = o[0]
+            if profile is not None:
+                import torch
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                key = kind if kind != "sweep" else "sweep:%s" % o[2]
+                profile.setdefault("_events", []).append((key, e0, e1))
+                e0.record()
+                self._run_op(o)
+                e1.record()
+            else:
+                self._run_op(o)
+
+    @staticmethod
+    def profile_summary(profile):
+        """milliseconds per kind of operation from the events of run(profile) (call after a synchronise)"""
+        out = {}
+        for key, e0, e1 in profile.pop("_events", []):
+            out[key] = out.get(key, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    def _run_op(self, o):
+        A, plan = self.A, self.plan
+        if True:
             kind = o[0]
             if kind == "sweep":
                 _, lay, opn, rel, lu, t, jobs = o
                 c = self.ctx[lay]
                 if not len(self.rows[lay]):
-                    continue
+                    return
                 srcs = [self.local_ptr(j["src"]) for j in jobs]
                 dsts = [self.local_ptr(j["dst"]) for j in jobs]
                 coefs = [self.pen_coef if j["coef"] == "pen" else j["coef"] for j in jobs]

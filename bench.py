@@ -189,10 +189,48 @@ def make_stage(A, S, D, dim, nmax, k, m, lev, sup, tables, flux, world, rank, de
         uave = c.op_combine(reg("lagr.ulft_vjp", b, a), 1.0, reg("lagr.urgt_vjp", b, a), 1.0)      # ulft_vjp + urgt_vjp, source/FastMultiplyLU.cpp:1165
         c.points_set(tables["lagr.intep_pt"])
         return {"pt": pt, "uv": uv, "volflx": c.op_combine(uvx, 1.0, uave, 0.5), "pen": reg("alpt.ujp_vjp", a, a), "hier": hier}
-    prog, ptr, consts = vlasov_program(A, dim) if flux == "vlasov" else burgers_program(A, dim)
+    holder = {}                                    # id(context) -> its local element rows (filled in once the stage exists)
+    if flux == "vlasov":
+        # The field E_t(x) lives on the elements with level 0 in the velocity dimensions (the reference's aux-dimension DGSolution).  Every stage
+        # it is evaluated at their interpolation points by one small point-wise launch, and the flux kernel reads it through the element map
+        # DGSolution::copy_up_intp_to_f builds (reference source/DGSolution.cpp:1024-1065) -- the broadcast itself is never materialised.
+        import torch
+        P = A.PW
+        hd = dim // 2
+        frows = np.nonzero((lev[:, hd:] == 0).all(axis=1))[0]
+        fkey = {tuple(lev[i, :hd]) + tuple(sup[i, :hd]): n for n, i in enumerate(frows)}
+        fmap_all = np.array([fkey[tuple(lev[i, :hd]) + tuple(sup[i, :hd])] for i in range(lev.shape[0])], dtype=np.int32)
+        fctx = A.Context(dim, nmax, k, m, device=device)
+        if stream_ptr is not None:
+            fctx.set_stream(stream_ptr)
+        fctx.grid_set(lev[frows], sup[frows])
+        fctx.points_set(tables["lagr.intep_pt"])
+        E = torch.zeros(hd, len(frows), b ** dim, dtype=torch.float64, device="cuda")
+        progE, ptrE, constsE = [], [0], [2.0 * np.pi]
+        for t in range(hd):
+            constsE.append(0.125 * (t + 1))
+            for s_ in range(hd):
+                progE += [(P["X"], s_), (P["CONST"], len(constsE) - 1), (P["ADD"], 0), (P["CONST"], 0), (P["MUL"], 0), (P["SIN"], 0)]
+                if s_:
+                    progE.append((P["ADD"], 0))
+            ptrE.append(len(progE))
+        prog, ptr = [], [0]
+        for t in range(dim):
+            prog += [(P["X"], hd + t), (P["VAR"], 0), (P["MUL"], 0)] if t < hd else [(P["OTHER"], t - hd), (P["VAR"], 0), (P["MUL"], 0)]
+            ptr.append(len(prog))
+        maps = {}
 
-    def pointwise(c, up_ptr, fp_ptrs):
-        c.pointwise_expr([up_ptr], [], None, fp_ptrs, prog, ptr, consts)
+        def pointwise(c, up_ptr, fp_ptrs):
+            if id(c) not in maps:
+                maps[id(c)] = torch.from_numpy(np.ascontiguousarray(fmap_all[holder[id(c)]])).cuda()
+            fctx.pointwise_expr([], [], None, [E[t] for t in range(hd)], progE, ptrE, constsE)
+            c.pointwise_expr([up_ptr], [E[t] for t in range(hd)], maps[id(c)], fp_ptrs, prog, ptr, [])
+        holder["close"] = fctx.close
+    else:
+        prog, ptr, consts = burgers_program(A, dim)
+
+        def pointwise(c, up_ptr, fp_ptrs):
+            c.pointwise_expr([up_ptr], [], None, fp_ptrs, prog, ptr, consts)
 
     def exchange(obj):
         import torch.distributed as dist
@@ -200,6 +238,11 @@ def make_stage(A, S, D, dim, nmax, k, m, lev, sup, tables, flux, world, rank, de
         dist.all_gather_object(out, obj)
         return out
     st = S.DeviceStage(A, plan, lev, sup, nmax, k, m, device, make_ops, pointwise, -LXF_ALPHA / 2.0, rk, exchange=exchange, stream_ptr=stream_ptr, kernel=kernel)
+    for L, c in st.ctx.items():
+        holder[id(c)] = st.rows[L]
+    if "close" in holder:
+        close_stage, close_field = st.close, holder["close"]
+        st.close = lambda: (close_stage(), close_field())
     return st, plan, part
 
 
@@ -278,7 +321,49 @@ def sweep_roofline(A, ctx, stream, op, sizes_of_t, kf, kt, dim, ne, flush, label
             "kernel": label, "bytes_per_launch": bytes_launch, "us_per_launch": t_launch * 1e6, "peak_source": peak_src}
 
 
-KERNEL_NAMES = {0: "sweep_tc_kernel", 5: "sweep_tc_kernel", 4: "sweep_mma_kernel", 6: "sweep_dir_kernel", 7: "sweep_ws_kernel"}
+def stage_sweep_roofline(torch, S, st, plan, stream, kf, kt, kernel_label, kernel_key):
+    """The dominant kernel of the stage in the mix the stage runs it: every kf -> kt sweep launch of the plan (the L sweeps of the down pass, the
+    full sweeps along the last dimension and the accumulating U sweeps of the up pass, batched as in the stage), replayed from a CUDA graph;
+    achieved = sum over jobs of B_sweep = 8 N_e (S_from + S_to) (read once, written once; the re-read of an accumulating sweep is not
+    counted) / device time.  The launches touch far more than L2 (tens of GB per pass)."""
+    peak, peak_src = peaks()
+    ops = [o for o in plan.ops if o[0] == "sweep" and o[2] in ("uv", "volflx")]          # the kf -> kt operators of the right-hand side
+    byts, n_jobs = 0.0, 0
+    for o in ops:
+        ne_loc = len(st.rows[o[1]])
+        for j in o[6]:
+            s_from = int(np.prod(j["sizes"]))
+            byts += 8.0 * ne_loc * (s_from + s_from // kf * kt)
+            n_jobs += 1
+    if not ops or byts == 0:
+        return None
+    l0 = st.launch_count()
+    with torch.cuda.stream(stream):
+        for o in ops:
+            st._run_op(o)
+    stream.synchronize()
+    n_launch = st.launch_count() - l0
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        for o in ops:
+            st._run_op(o)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_replay = 4
+    with torch.cuda.stream(stream):
+        g.replay()
+        e0.record(stream)
+        for _ in range(n_replay):
+            g.replay()
+        e1.record(stream)
+    stream.synchronize()
+    t_pass = e0.elapsed_time(e1) / n_replay * 1e-3
+    achieved = byts / t_pass / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(kernel_key),
+            "kernel": kernel_label, "launches": int(n_launch), "sweep_jobs": int(n_jobs), "bytes_per_launch": byts / max(n_launch, 1),
+            "us_per_launch": t_pass * 1e6 / max(n_launch, 1), "pass_ms": t_pass * 1e3, "peak_source": peak_src}
+
+
+KERNEL_NAMES = {0: "sweep_tc_kernel", 5: "sweep_tc_kernel", 4: "sweep_mma_kernel", 8: "sweep_col_kernel"}
 
 
 def timed_replays(torch, stream, flush, run_step, steps, barrier):
@@ -380,6 +465,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (quick kernel comparisons)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 secondary record at N = 1")
+    ap.add_argument("--breakdown", action="store_true", help="also report device time per kind of operation of the stage (eager launches, CUDA events; max over ranks)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -511,6 +597,22 @@ def main():
     t_e2e = (time.perf_counter() - t0) / n_e2e
     clocks = sampler.finish()
     berr = st.barrier_error()
+    breakdown = None
+    if args.breakdown:
+        acc = {}
+        for _ in range(5):
+            prof = {}
+            barrier()
+            with torch.cuda.stream(stream):
+                st.run(prof)
+            stream.synchronize()
+            for kk, vv in S.DeviceStage.profile_summary(prof).items():
+                acc[kk] = acc.get(kk, 0.0) + vv / 5.0
+        keys = sorted(acc)
+        bt = torch.tensor([acc[kk] for kk in keys], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(bt, op=dist.ReduceOp.MAX)          # the plan (and so the key list) is the same on every rank
+        breakdown = {kk: float(v) for kk, v in zip(keys, bt.cpu().numpy())}
 
     tt = torch.tensor([t_step_ms, t_e2e, float(len(rows)), float(len(part.local["V"]) if part is not None else ne), float(st.sent_bytes), float(berr)], dtype=torch.float64, device="cuda")
     mx, sm = tt.clone(), tt.clone()
@@ -520,22 +622,23 @@ def main():
     t_step_ms, t_e2e = float(mx[0]), float(mx[1])
     value = dof / (t_step_ms * 1e-3)
 
-    roof = None
+    # roofline of the dominant kernel of the stage: the b -> a sweeps of the right-hand-side applications (d of the d+1 tensor applications), in the
+    # mix of L / full / accumulating-U launches the stage runs (every rank replays its own launches; rank 0 reports its GPU)
+    col = args.kernel in (0, 8) and b * a <= 9 and dim >= 3
+    kname = "sweep_col_kernel" if col else KERNEL_NAMES.get(args.kernel, "sweep kernel %d" % args.kernel)
+    roof = stage_sweep_roofline(torch, S, st, plan, stream, b, a,
+                                "%s<%d,%d,*>: all %d -> %d sweep launches of one stage (L sweeps, full sweeps along the last dimension, accumulating U sweeps of the shared-prefix schedule; FP64 %s)"
+                                % (kname, b, a, b, a, "DFMA, one thread per column" if col else "DMMA m8n8k4"), "%s<%d,%d>" % (kname, b, a))
+    barrier()
     if rank == 0:
-        # roofline of the dominant kernel of the stage: the b -> a sweeps of the right-hand-side applications (d of the d+1 tensor applications)
-        rctx = A.Context(dim, nmax, k, m, device=local_rank)
-        rctx.set_stream(stream.cuda_stream); rctx.set_kernel(args.kernel); rctx.grid_set(lev, sup)
-        op_uv = rctx.op_register_compact(tb["lagr.u_v"])
-        kname = KERNEL_NAMES.get(args.kernel, "sweep kernel %d" % args.kernel)
-        roof = sweep_roofline(A, rctx, stream, op_uv, lambda t: [a if q < t else b for q in range(dim)], b, a, dim, ne, flush,
-                              "%s<%d,%d> (one 1D sweep of the right-hand-side chain along each dimension in turn, single job, whole grid on one GPU; FP64 DMMA m8n8k4)" % (kname, b, a),
-                              "%s<%d,%d>" % (kname, b, a))
+        if roof is None:
+            peak, peak_src = peaks()
+            roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "kernel": kname, "peak_source": peak_src}
         C = lambda p, q: sum((p ** (dim - i) * q ** i + p ** (dim - i - 1) * q ** (i + 1)) for i in range(dim))
         n_ch, nf = 2 ** (dim - 1), dim
         b_alg = 8.0 * ne * (n_ch * C(a, b) + (1 + nf) * b ** dim + nf * dim * 2 * b ** dim + 2 * nf * n_ch * C(b, a) + dim * 2 * a ** dim + 4 * a ** dim)
         roof["step"] = {"b_alg_bytes": b_alg, "gbs": b_alg / (t_step_ms * 1e-3) / 1e9, "frac_of_n_gpus": b_alg / (t_step_ms * 1e-3) / 1e9 / (roof["peak"] * world),
                         "note": "reference sweep list bytes / measured stage time / (N x measured HBM peak); every tensor application runs %d instead of %d sweeps (shared-prefix schedule), vol + flx of a dimension are one application" % (3 * n_ch - 2, dim * n_ch)}
-        rctx.close()
         line = {
             "metric": "sparse-grid DoF-stage updates/sec (FP64)", "value": value, "unit": "DoF-stage/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -555,6 +658,8 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roof,
         }
+        if breakdown is not None:
+            line["config"]["breakdown_ms_eager_max_over_ranks"] = breakdown
     st.close()
     if rank == 0:
         if world == 1 and not args.no_cpu:

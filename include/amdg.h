@@ -57,7 +57,9 @@ int amdg_ctx_destroy(amdg_ctx *ctx);
 int amdg_ctx_set_stream(amdg_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: a stream owned by ctx */
 int amdg_ctx_sync(amdg_ctx *ctx);
 int amdg_ctx_set_schedule(amdg_ctx *ctx, int sched);
-int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto (lean tensor-core kernel; whole-fibre tensor-core and staged list kernels as fall-backs), 1 = gather, 2 = fibre-staged list kernel, 3 = pipelined list kernel, 4 = whole-fibre tensor-core (FP64 MMA) kernel, 5 = lean tensor-core kernel, 6 = register-direct tensor-core kernel, 7 = warp-specialised streaming tensor-core kernel */
+int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto: per launch the column kernel (one thread per column, FP64 FMA) for blocks of >= 64 doubles with KF*KT <= 9 and >= 32 columns, the lean tensor-core kernel otherwise, the whole-fibre tensor-core kernel for tiny sweeps;
+                                                                 1 = gather, 2 = fibre-staged list kernel, 3 = pipelined list kernel, 4 = whole-fibre tensor-core (FP64 MMA) kernel, 5 = lean tensor-core kernel, 8 = column kernel
+                                                                 (1-4 are independent implementations kept for the parity tests; 6 and 7 were measured 2.5-6x slower and removed, profiles/r02_sweep_kernels.md) */
 int64_t amdg_ctx_launch_count(amdg_ctx *ctx);                 /* kernels launched so far by this context */
 /* profiling aid: device buffer of n_items*8 int64 that the sweep kernel fills with per-CTA clock64 stamps (NULL = off) */
 int amdg_ctx_set_debug_buffer(amdg_ctx *ctx, void *dev_buf);
@@ -65,17 +67,6 @@ int amdg_ctx_set_debug_buffer(amdg_ctx *ctx, void *dev_buf);
  * (a sweep with source block edges sizes_from[dim] and an operator kf -> kt) and verify their invariants; out[6] = shapes, pieces,
  * streamed (coarse) pieces, tile entries, largest staged row count, largest shared-memory need in doubles */
 int amdg_lean_plan_check(amdg_ctx *ctx, int t, const int *sizes_from, int kf, int kt, int rel, int lu, int64_t *out);
-/* diagnostic, host only: the work list of the register-direct sweep kernel (variant 6) for one sweep, so that the tests can replay it against the
- * oracle without a device.  counts[8] = units, pool ints, element rows, padded column tiles, programs, entries, vec_ok, column tiles; call with
- * units == NULL for the counts.  units[n][16] (DirUnit), tab_b[tiles][32], tab_c[tiles][32][2], prog_ent_ptr[programs+1], A[entries][32]. */
-int amdg_dir_list_export(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, int64_t *counts, int *units, int *pool,
-                         int *elem_pool, int *tab_b, int *tab_c, int *prog_ent_ptr, double *A);
-
-/* the same for the warp-specialised streaming sweep kernel (variant 7): counts[8] = items, CTAs, pool ints, element rows, table tiles, programs,
- * entries, bulk_ok + 2 * resolved rows; items[n][20] (WsItem), cta_ptr[CTAs+1], rows[], rows_ptr[CTAs+1] (resolved element rows per CTA) */
-int amdg_ws_list_export(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, int n_cta, int64_t *counts, int *items, int *cta_ptr,
-                        int *pool, int *elem_pool, int *tab_b, int *tab_c, int *prog_ent_ptr, double *A, int *rows, int *rows_ptr);
-
 /* ---- Hash (source/Hash.cpp:55-114) and 1D element order (source/Element.cpp:388-391), bit exact ---- */
 int amdg_hash_key(int dim, const int *level, const int *suppt);
 int amdg_order_elem(int level, int suppt);

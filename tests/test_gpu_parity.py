@@ -378,7 +378,7 @@ def test_wave_rk4_ode2nd_stages():
     c.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 8])
 @pytest.mark.parametrize("name", ["adapt_d2_k2_n6", "adapt_d3_k1_n4", "cfg3_wave_d3_k2_n3", "cfg5_vlasov_d6_k1_n2", "cfg2_rt_d4_k3_n3", "line_d1_k2_n5"])
 def test_all_kernel_variants(name, kernel):
     """every sweep kernel (gather, fibre-staged list, pipelined list, tensor-core) on regular and adaptive grids:
@@ -424,7 +424,7 @@ def test_full_size_roundtrip_identity_and_kernel_agreement():
     import importlib
     A = importlib.import_module("adaptive-multiresolution-dg_b200")
     outs = {}
-    for kernel in (0, 4, 1, 6, 7):
+    for kernel in (0, 4, 1, 8):
         ctx, lev, tb = _full_size_context(A, kernel)
         dim, ne = 4, lev.shape[0]
         rng = np.random.default_rng(20240901)
@@ -439,12 +439,12 @@ def test_full_size_roundtrip_identity_and_kernel_agreement():
         assert rel(ua.cpu().numpy(), u.cpu().numpy()) < 1e-10
         outs[kernel] = (up.cpu().numpy(), uc.cpu().numpy(), ua.cpu().numpy())
         ctx.close()
-    for kernel in (4, 1, 6, 7):
+    for kernel in (4, 1, 8):
         for x, y in zip(outs[0], outs[kernel]):
             assert rel(x, y) < TOL
 
 
-@pytest.mark.parametrize("kernel", [0, 6, 7])
+@pytest.mark.parametrize("kernel", [0, 5, 8])
 def test_sweep_batch_equals_single_sweeps(kernel):
     """amdg_sweep1d_batch: one launch for several (src, dst) pairs gives exactly what the single sweeps give (bitwise), for every
     L/U/full part, with coef and accumulate, on the d=6 fixture grid"""
@@ -497,7 +497,7 @@ def _random_adaptive_grid(A, dim, nmax, seed, keep=0.55):
 
 
 @pytest.mark.parametrize("dim,nmax,a,b,seed", [(2, 7, 3, 4, 1), (3, 6, 2, 3, 2), (3, 5, 4, 4, 3), (4, 5, 3, 2, 4)])
-@pytest.mark.parametrize("fast", [5, 6, 7, 8])
+@pytest.mark.parametrize("fast", [5, 8])
 def test_random_adaptive_grids_lean_vs_gather(dim, nmax, a, b, seed, fast):
     """irregular fibre shapes that no fixture has: on random downward-closed grids the lean tensor-core kernel (subtree pieces,
     streamed coarse targets, several fibres per item) agrees with the gather kernel -- an independent implementation that walks the
@@ -564,7 +564,7 @@ def live_dump(name, tmp_path_factory):
 
 
 @pytest.mark.parametrize("sched", [0, 1])
-@pytest.mark.parametrize("kernel", [0, 5, 6, 7, 8])
+@pytest.mark.parametrize("kernel", [0, 5, 8])
 def test_live_reference_cfg2_n6(kernel, sched, tmp_path_factory):
     """cfg2 at d=4, k=3, m=3, N=6 (1 520 elements, fibres up to 64 elements): the <4,4> instantiation the benchmark runs, both schedules,
     against the reference run on this machine; the plans must contain the streamed (coarse) pieces / narrow pieces"""
@@ -574,14 +574,7 @@ def test_live_reference_cfg2_n6(kernel, sched, tmp_path_factory):
     if kernel in (0, 5):
         st = c.ctx.lean_plan_check(0, [c.a] * c.dim, c.a, c.b, A.REL_VOL, A.LU_FULL)
         assert st["coarse_pieces"] > 0 and st["pieces"] > st["shapes"]
-    elif kernel == 8:
-        pass                                                               # the column kernel has no plan to inspect: heavy units appear on the 64-element fibres
-    elif kernel == 6:
-        L = c.ctx.dir_list_export(c.op_pt, A.REL_VOL, A.LU_FULL, 0, [c.a] * c.dim)
-        assert (L["units"][:, 8] == 3).any() and (L["units"][:, 8] == 2).any() and L["vec_ok"]
-    else:
-        L = c.ctx.ws_list_export(c.op_pt, A.REL_VOL, A.LU_FULL, 0, [c.a] * c.dim)
-        assert (L["items"][:, 17] == 1).any() and L["bulk_ok"]             # heavy items exist; aligned runs go as bulk copies
+    # (the column kernel has no plan to inspect: its heavy units appear on the 64-element fibres of this grid)
     u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
     up = c.eval_up(u)
     assert rel(c.to_host(up), d["rt.up_intp"][:, 0, :]) < TOL
@@ -592,7 +585,7 @@ def test_live_reference_cfg2_n6(kernel, sched, tmp_path_factory):
     c.close()
 
 
-@pytest.mark.parametrize("kernel", [0, 5, 6, 7, 8])
+@pytest.mark.parametrize("kernel", [0, 5, 8])
 def test_live_reference_cfg5_n4(kernel, tmp_path_factory):
     """cfg5 at d=6, k=1, m=2, N=4 (501 elements): one nonlinear stage (interpolate, Vlasov products, hierarchise, vol + flx + penalty, RK3SSP
     stage 0) against the reference run on this machine -- the <2,3>, <3,3>, <3,2> and <2,2> instantiations of the 6-D benchmark"""
