@@ -47,6 +47,8 @@ class StagePlan:
         self.h = (dim // 2 if n_x_dims is None else n_x_dims) if self.dist else dim      # dims < h are swept in layout X, the rest in layout V
         self.bufs, self.alias, self.ops = {}, {}, []
         self.n_barrier = 0
+        self.n_group = 0
+        self.max_jobs = 32           # jobs per launch (MAX_JOBS of the kernels)
         self.push_bytes = 0          # doubles per element pushed / scattered to the other layout (exchange volume)
         self._build()
 
@@ -100,12 +102,16 @@ class StagePlan:
         X = [{0: ap["src"]} for ap in apps]
 
         def emit(layout, k, lu, jobs_by_app):
+            # the launches of one schedule level are independent of each other (they read and write different buffers): they carry a common
+            # group id, and DeviceStage runs a group on parallel streams
             groups = {}
             for i, jobs in enumerate(jobs_by_app):
                 for j in jobs:
                     groups.setdefault((apps[i]["ops"][k], apps[i]["rels"][k]), []).append(j)
+            self.n_group += 1
             for (opn, rel), jobs in groups.items():
-                self.ops.append(("sweep", layout, opn, rel, lu, k, jobs))
+                for c0 in range(0, len(jobs), self.max_jobs):
+                    self.ops.append(("sweep", layout, opn, rel, lu, k, jobs[c0:c0 + self.max_jobs], self.n_group))
 
         def switch_down(k_next):
             """all live X buffers of the down pass move from layout X to layout V before level k_next"""
@@ -325,6 +331,8 @@ class DeviceStage:
         self.world = part.world if plan.dist else 1
         self.rank = part.rank if plan.dist else 0
         self.pointwise, self.pen_coef, self.rk = pointwise, pen_coef, rk
+        import os
+        self.n_side, self._side = int(os.environ.get("AMDG_STAGE_STREAMS", "2")), None      # parallel streams for the launches of one schedule level
         self.ctx, self.ops, self.rows = {}, {}, {}
         layouts = ("X", "V") if plan.dist else ("X",)
         for L in layouts:
@@ -386,7 +394,41 @@ class DeviceStage:
         """executes the plan on the context's stream; `profile` (a dict) collects device time per kind of operation through CUDA events
         (eager launches only: the caller synchronises and calls profile_summary)"""
         A, plan = self.A, self.plan
-        for o in plan.ops:
+        ops = plan.ops
+        if profile is None and self.n_side > 0:
+            import torch
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = [torch.cuda.Stream() for _ in range(self.n_side)]
+            i = 0
+            while i < len(ops):
+                o = ops[i]
+                j = i + 1
+                if o[0] == "sweep" and len(o) > 7:
+                    while j < len(ops) and ops[j][0] == "sweep" and len(ops[j]) > 7 and ops[j][7] == o[7]:
+                        j += 1
+                if j - i == 1:
+                    self._run_op(o)
+                else:
+                    # fork: the launches of one schedule level on parallel streams; join before the next level
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    used = []
+                    for n, op in enumerate(ops[i:j]):
+                        st = main if n % (self.n_side + 1) == 0 else self._side[n % (self.n_side + 1) - 1]
+                        if st is not main and st not in used:
+                            st.wait_event(fork)
+                            used.append(st)
+                        self.ctx[op[1]].set_stream(st.cuda_stream)
+                        self._run_op(op)
+                        self.ctx[op[1]].set_stream(main.cuda_stream)
+                    for st in used:
+                        e = torch.cuda.Event()
+                        e.record(st)
+                        main.wait_event(e)
+                i = j
+            return
+        for o in ops:
             kind = o[0]
             if profile is not None:
                 import torch
@@ -412,7 +454,7 @@ class DeviceStage:
         if True:
             kind = o[0]
             if kind == "sweep":
-                _, lay, opn, rel, lu, t, jobs = o
+                _, lay, opn, rel, lu, t, jobs = o[:7]
                 c = self.ctx[lay]
                 if not len(self.rows[lay]):
                     return

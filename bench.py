@@ -36,6 +36,8 @@ WORKLOADS = {
     # cpu_nmax: bounded sample for the cpu_baseline leg; ref_nmax: the --impl reference arm (same config where the reference finishes in minutes)
     "cfg2": dict(kind="roundtrip", dim=4, k=3, m=3, nmax=8, cpu_nmax=7, ref_nmax=8, desc="example/01_interp_01_high_dim: Lagrange interpolation round trip d=4 k=3 m=3 NMAX=8 (full sparse grid)"),
     "cfg5": dict(kind="stage", flux="vlasov", dim=6, k=1, m=2, nmax=7, cpu_nmax=5, ref_nmax=6, ref_single=True, desc="example/07_vlasov_maxwell_sparse scaled to 3D3V: d=6 k=1 m=2 NMAX=7 full sparse grid, one nonlinear RK3SSP stage (interpolate, Vlasov products with a prescribed smooth field, hierarchise, vol+flx+penalty, RK)"),
+    "cfg1": dict(kind="linear", op="advection", dim=2, k=2, m=3, nmax=7, cpu_nmax=7, ref_nmax=7, stages=3, desc="example/02_hyperbolic_01_scalar_const_coefficient: 2D linear advection, Alpert k=2, NMAX=7 full sparse grid, one RK3SSP stage (operator as 1D sweeps: u_vx + upwind flux per dimension)"),
+    "cfg3": dict(kind="linear", op="wave", dim=3, k=2, m=3, nmax=7, cpu_nmax=7, ref_nmax=7, stages=4, desc="example/03_wave_01_const_coeff_periodic: 3D second-order wave, k=2, NMAX=7, IPDG (sigma=20), one RK4ODE2nd stage (operator as 1D sweeps: four terms per dimension merged into one operator)"),
     "cfg4": dict(kind="stage", flux="burgers", dim=2, k=2, m=3, nmax=7, cpu_nmax=7, ref_nmax=7, desc="example/02_hyperbolic_05_burgers_adapt (static upper-bound grid NMAX=7, Lagrange flux): one nonlinear RK3SSP stage"),
 }
 LXF_ALPHA, DT = 1.2, 1e-4
@@ -121,6 +123,11 @@ def run_reference(args, w, n_threads=None, as_baseline=False):
         cmd += ["--run", "roundtrip"]
         phases = ("intp", "hier", "init")
         what = "same round trip"
+    elif w["kind"] == "linear":
+        # the shipped path of these examples: assembled SpMV inside ExplicitRK::step_rk (all stages of one step are timed together)
+        cmd += ["--run", w["op"], "--dt", "1e-4"]
+        phases = ("adv_step_rk",) if w["op"] == "advection" else ("wave_step_rk",)
+        what = "one %s::step_rk on the assembled operator (the shipped path), divided by its %d stages" % ("RK3SSP" if w["op"] == "advection" else "RK4ODE2nd", w["stages"])
     else:
         cmd += ["--run", "rhs", "--flux", w["flux"]]
         phases = ("intp", "pointwise", "hier", "rhs_vol", "rhs_flx", "rhs_penalty")
@@ -129,7 +136,7 @@ def run_reference(args, w, n_threads=None, as_baseline=False):
     out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, text=True).stdout.strip().splitlines()[-1]
     wall = time.time() - t0
     r = json.loads(out)
-    t_step = sum(r[p] for p in phases)          # medians over the repetitions
+    t_step = sum(r[p] for p in phases) / (w["stages"] if w["kind"] == "linear" else 1)          # medians over the repetitions
     dof = r["dof"]
     same = nmax == w["nmax"]
     return {"value": dof / t_step, "unit": "DoF-stage/s", "cores": r["threads"], "kind": "reference", "same_config": same,
@@ -453,6 +460,102 @@ def roundtrip_record(args, A, torch, stream, flush, local_rank, w, with_cpu):
     return rec
 
 
+def linear_record(args, A, torch, stream, flush, local_rank, w, with_cpu):
+    """cfg1 / cfg3: one RK stage of a linear operator applied as single 1D sweeps (FastRHS::transform_ucoe_alpt_to_rhs, reference
+    source/FastMultiplyLU.cpp:46-59; the shipped examples assemble the same operator as a sparse matrix, source/BilinearForm.cpp:691-710, 877-929)"""
+    dim, k, nmax = w["dim"], w["k"], w["nmax"]
+    a = k + 1
+    lev, sup = A.sparse_grid(dim, nmax)
+    keys = np.array([A.hash_key(l, s_) for l, s_ in zip(lev, sup)])
+    o = np.argsort(keys, kind="stable")
+    lev, sup = lev[o], sup[o]
+    ne = lev.shape[0]
+    dof = ne * a ** dim
+    ctx = A.Context(dim, nmax, k, w["m"], device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_kernel(args.kernel)
+    ctx.grid_set(lev, sup)
+    tb = load_tables(A, w)
+    reg = lambda nm: ctx.op_register_compact(tb["alpt." + nm])
+    if w["op"] == "advection":
+        op = ctx.op_combine(reg("u_vx"), 1.0, reg("ulft_vjp"), 1.0)                     # volume + upwind flux (c >= 0: left trace), one operator under the flx relation
+    else:
+        sigma_dx = 20.0 * 2 ** nmax
+        op = ctx.op_combine(ctx.op_combine(reg("ux_vx"), -1.0, reg("uxave_vjp"), -1.0), 1.0, ctx.op_combine(reg("ujp_vxave"), -1.0, reg("ujp_vjp"), -sigma_dx), 1.0)
+    host_in = torch.from_numpy(synthetic_field(lev, a ** dim, 1, 20240901)).pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    with torch.cuda.stream(stream):
+        u = host_in.to("cuda", non_blocking=True)
+        u_tn, v, v_tn, rhs = u.clone(), u.clone(), u.clone(), torch.zeros_like(u)
+        ku, kv = torch.zeros(4, *u.shape, dtype=torch.float64, device="cuda"), torch.zeros(4, *u.shape, dtype=torch.float64, device="cuda")
+
+    def step():
+        for t in range(dim):
+            ctx.sweep1d(op, A.REL_FLX, A.LU_FULL, t, [a] * dim, u, rhs, accumulate=t > 0)
+        if w["op"] == "advection":
+            ctx.rk_stage(A.RK_RK3SSP, 1, DT, u_tn, u, rhs)
+        else:
+            ctx.rk4_ode2nd_stage(1, DT, u_tn, v_tn, u, v, rhs, ku, kv)
+    sync = lambda: torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+    sync()
+    l0 = ctx.launch_count
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        step()
+    launches = ctx.launch_count - l0
+    with torch.cuda.stream(stream):
+        graph.replay()
+    sync()
+    t_ms = timed_replays(torch, stream, flush, graph.replay, args.steps, sync)
+
+    def e2e_call():
+        with torch.cuda.stream(stream):
+            u.copy_(host_in, non_blocking=True)
+            graph.replay()
+            host_out.copy_(u, non_blocking=True)
+        stream.synchronize()
+    for _ in range(2):
+        e2e_call()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        e2e_call()
+    t_e2e = (time.perf_counter() - t0) / n_e2e
+    peak, peak_src = peaks()
+    byts = 8.0 * ne * 2 * a ** dim
+    # the sweeps alone (graph of dim launches)
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2, stream=stream):
+        for t in range(dim):
+            ctx.sweep1d(op, A.REL_FLX, A.LU_FULL, t, [a] * dim, u, rhs, accumulate=t > 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        g2.replay(); e0.record(stream)
+        for _ in range(20):
+            g2.replay()
+        e1.record(stream)
+    sync()
+    t_launch = e0.elapsed_time(e1) / (20 * dim) * 1e-3
+    kname = "sweep_mma_kernel" if args.kernel == 0 else KERNEL_NAMES.get(args.kernel, "sweep kernel %d" % args.kernel)
+    roof = {"bound": "hbm", "achieved": byts / t_launch / 1e9, "peak": peak, "unit": "GB/s", "frac": byts / t_launch / 1e9 / peak, "traffic": None,
+            "kernel": "%s<%d,%d> (one 1D sweep, %.2f MB vector: L2 resident, the launch is latency bound -- SURVEY.md 8d caveat)" % (kname, a, a, byts / 2e6),
+            "bytes_per_launch": byts, "us_per_launch": t_launch * 1e6, "peak_source": peak_src}
+    rec = {"metric": "sparse-grid DoF-stage updates/sec (FP64)", "value": dof / (t_ms * 1e-3), "unit": "DoF-stage/s", "ms_per_step": t_ms, "n_elem": int(ne), "dof": int(dof),
+           "gpu_launches": int(launches * args.steps), "launches_per_stage": int(launches),
+           "e2e": {"value": dof / t_e2e, "unit": "DoF-stage/s", "h2d_bytes_per_step": int(host_in.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8), "ms_per_step": t_e2e * 1e3,
+                   "api": "pinned host buffer -> device, the stage's C-ABI calls (CUDA-graph replay), device -> pinned host buffer"},
+           "roofline": roof}
+    if with_cpu:
+        cb = run_reference(args, w, as_baseline=True)
+        if cb:
+            rec["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+    ctx.close()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -511,15 +614,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if w["kind"] == "roundtrip":
+    if w["kind"] in ("roundtrip", "linear"):
         if world > 1:
-            raise SystemExit("the round trip has no exchange step: run it on one GPU (the multi-GPU benchmark is the cfg5 stage)")
-        rec = roundtrip_record(args, A, torch, stream, flush, local_rank, w, with_cpu=not args.no_cpu)
+            raise SystemExit("this workload has no exchange step: run it on one GPU (the multi-GPU benchmark is the cfg5 stage)")
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        rec = (roundtrip_record if w["kind"] == "roundtrip" else linear_record)(args, A, torch, stream, flush, local_rank, w, with_cpu=not args.no_cpu)
+        clocks = sampler.finish()
         line = {"metric": rec["metric"], "value": rec["value"], "unit": rec["unit"], "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rec["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": w["desc"], "n_elem": rec["n_elem"], "dof": rec["dof"], "kernel": args.kernel, "cuda_graph": True,
                            "l2": "flushed (256 MiB write) between timed steps; per-step CUDA event pairs on the launch stream"},
-                "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"]}
+                "clocks": clocks, "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"]}
         if "cpu_baseline" in rec:
             line["cpu_baseline"] = rec["cpu_baseline"]
         emit(line)

@@ -120,7 +120,7 @@ class Emulator:
                 o = self.plans[r].ops[i]
                 assert o[0] == self.plans[0].ops[i][0]
                 if o[0] == "sweep":
-                    _, lay, opn, rel, lu, t, jobs = o
+                    _, lay, opn, rel, lu, t, jobs = o[:7]
                     rows = self.rows[r][lay]
                     if not len(rows):
                         continue
