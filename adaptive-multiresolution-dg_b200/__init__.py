@@ -69,6 +69,7 @@ SYMBOLS = {
     "amdg_rk4_ode2nd_stage": (_i, [_p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _i64]),
     "amdg_axpby": (_i, [_p, _i64, _d, _p, _d, _p]),
     "amdg_lincomb": (_i, [_p, _i64, _i, _dp, _p, _d, _p]),
+    "amdg_moment": (_i, [_p, _i64, _p, _i, _ip, _d, _p, _p]),
     "amdg_sweep1d_batch_mapped": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _dp, _ip, _p, _p, _i]),
     "amdg_points_set": (_i, [_p, _dp]),
     "amdg_pointwise_expr": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _ip, _i, _ip, _dp, _i]),
@@ -327,6 +328,11 @@ class Context:
         cs, csp = _dbls(np.asarray(consts if len(consts) else [0.0]))
         _check(lib.amdg_pointwise_expr(self._h, len(ups), pu, len(others), po, _ptr(other_map) if other_map is not None else None, len(outs), pout,
                                        prp, pr.shape[0], opp, csp, len(consts)))
+
+    def moment(self, field_map, n_vdim, order, weight, f, rhs_field):
+        """amdg_moment: rhs_field[e][x, v = 0] += weight * velocity moment of f at the partner element field_map[e] (int32 device tensor, -1 = none)"""
+        od, odp = _ints(order)
+        _check(lib.amdg_moment(self._h, int(field_map.numel()), _ptr(field_map), n_vdim, odp, weight, _ptr(f), _ptr(rhs_field)))
 
     def scatter_rows(self, src, n_rows, width, dst_base, dst_map):
         _check(lib.amdg_scatter_rows(self._h, _ptr(src), n_rows, width, _ptr(dst_base), _ptr(dst_map)))

@@ -1888,6 +1888,39 @@ int amdg_lincomb(amdg_ctx * c, int64_t n, int k, const double * coefs, const dou
     return AMDG_OK;
 }
 
+int amdg_moment(amdg_ctx * c, int64_t n_field, const int * dev_map, int n_vdim, const int * order, double weight, const double * dev_f, double * dev_rhs_field)
+{
+    int r = need_device(c); if (r) return r;
+    if (n_field < 0 || !dev_map || n_vdim < 1 || n_vdim >= c->dim || n_vdim > 4 || !order || !dev_f || !dev_rhs_field) return fail(AMDG_EINVAL, "bad moment arguments");
+    const int a = c->edge_alpt;
+    MomentArgs m; std::memset(&m, 0, sizeof(m));
+    m.f = dev_f; m.rhs = dev_rhs_field; m.map = dev_map; m.n_field = n_field; m.weight = weight;
+    m.x_block = (int)ipow(a, c->dim - n_vdim); m.v_block = (int)ipow(a, n_vdim);
+    // combinations of velocity degrees: dv_i in 0..order_i; block index of dv = sum dv_i a^(n_vdim-1-i) (last dimension fastest)
+    m.n_combo = 1;
+    for (int i = 0; i < n_vdim; ++i)
+    {
+        if (order[i] < 0 || order[i] > 1 || (order[i] == 1 && a < 2)) return fail(AMDG_EINVAL, "moment order must be 0 or 1 (1 needs polynomial degree >= 1)");
+        m.n_combo *= order[i] + 1;
+    }
+    for (int combo = 0; combo < m.n_combo; ++combo)
+    {
+        int rest = combo, off = 0; double cf = 1.0;
+        for (int i = n_vdim - 1; i >= 0; --i)
+        {
+            const int dv = rest % (order[i] + 1); rest /= order[i] + 1;
+            off += dv * (int)ipow(a, n_vdim - 1 - i);
+            cf *= order[i] == 0 ? 1.0 : (dv == 0 ? 0.5 : 1.0 / (2.0 * std::sqrt(3.0)));
+        }
+        m.offset[combo] = off; m.coef[combo] = cf;
+    }
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_moment(m, c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("moment: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
 // ---- device memory helpers -------------------------------------------------------------------------------------------
 int amdg_dev_alloc(amdg_ctx * c, int64_t n, double ** out)
 {

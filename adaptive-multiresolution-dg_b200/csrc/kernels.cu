@@ -742,6 +742,33 @@ cudaError_t launch_lincomb(const LincombArgs & a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// Velocity moments of f accumulated into the right-hand side of a field solution (DGAdapt::compute_moment_1D2V / _2D2V, reference
+// source/DGAdapt.cpp:243-338): for every field element (level 0 in the n_v trailing dimensions) that has a partner in f (map >= 0) and every index
+// x of the leading dimensions,  rhs_E[e][x, 0..0] += weight * sum_{dv} prod_i c(order_i, dv_i) f[map[e]][x, dv],  dv_i in 0..order_i,
+// c(0,0) = 1, c(1,0) = 1/2, c(1,1) = 1/(2 sqrt 3) (moments of the level-0 Alpert basis on [0,1]; higher levels have vanishing moments).
+__global__ void __launch_bounds__(256) moment_kernel(const MomentArgs a)
+{
+    const int64_t n = a.n_field * a.x_block;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+    {
+        const int64_t e = p / a.x_block; const int x = (int)(p - e * a.x_block);
+        const int fe = a.map[e];
+        if (fe < 0) continue;
+        const double * __restrict__ f = a.f + ((int64_t)fe * a.x_block + x) * a.v_block;
+        double s = 0.0;
+        for (int combo = 0; combo < a.n_combo; ++combo) s += a.coef[combo] * f[a.offset[combo]];
+        a.rhs[((int64_t)e * a.x_block + x) * a.v_block] += a.weight * s;
+    }
+}
+
+cudaError_t launch_moment(const MomentArgs & a, cudaStream_t st)
+{
+    const int64_t nb = (a.n_field * a.x_block + 255) / 256;
+    moment_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st)
 {
     const int64_t nb = (n + 255) / 256;

@@ -235,6 +235,8 @@ cudaError_t launch_rk_stage(int scheme, int stage, double dt, const double * u_t
 cudaError_t launch_rk4_ode2nd_stage(int stage, double dt, const double * u_tn, const double * v_tn, double * u, double * v, const double * rhs,
                                     double * ku, double * kv, int64_t n, cudaStream_t st);
 cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st);
+struct MomentArgs { const double * f; double * rhs; const int * map; int64_t n_field; int x_block, v_block, n_combo; int offset[16]; double coef[16]; double weight; };
+cudaError_t launch_moment(const MomentArgs & a, cudaStream_t st);
 struct LincombArgs { const double * x[16]; double c[16]; double * y; double beta; int64_t n; int k; };
 cudaError_t launch_lincomb(const LincombArgs & a, cudaStream_t st);
 cudaError_t launch_point_coords(const double * pts1d, const int * ord1d, int64_t n_elem, int dim, int edge, double * pts, cudaStream_t st);

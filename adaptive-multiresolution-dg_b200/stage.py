@@ -332,7 +332,7 @@ class DeviceStage:
         self.rank = part.rank if plan.dist else 0
         self.pointwise, self.pen_coef, self.rk = pointwise, pen_coef, rk
         import os
-        self.n_side, self._side = int(os.environ.get("AMDG_STAGE_STREAMS", "2")), None      # parallel streams for the launches of one schedule level
+        self.n_side, self._side = int(os.environ.get("AMDG_STAGE_STREAMS", "3")), None      # parallel streams for the launches of one schedule level
         self.ctx, self.ops, self.rows = {}, {}, {}
         layouts = ("X", "V") if plan.dist else ("X",)
         for L in layouts:

@@ -171,6 +171,13 @@ int amdg_rk4_ode2nd_stage(amdg_ctx *ctx, int stage, double dt, const double *dev
 /* y = alpha*x + beta*y */
 int amdg_axpby(amdg_ctx *ctx, int64_t n, double alpha, const double *dev_x, double beta, double *dev_y);
 /* y = sum_{i<k} coefs[i]*x_i + beta*y (k <= 16): DGSolution rhs accumulated from several FastRHS calls (source/FastMultiplyLU.cpp:69-93) in one pass */
+/* Vlasov coupling: velocity moments of f accumulated into the right-hand side of a field solution that lives on the elements with level 0 in the
+ * n_vdim trailing (velocity) dimensions: DGAdapt::compute_moment_1D2V / _2D2V (source/DGAdapt.cpp:243-338), any number of leading dimensions.
+ * dev_map[n_field] = element row in f of every field element (-1: no partner, skipped, as the reference's `iter_f != f.dg.end()`);
+ * order[n_vdim] in {0, 1} (the reference allows one first-order factor; the product form used here also gives the mixed moment);
+ * dev_f [n_elem of f][a^dim], dev_rhs_field [n_field][a^dim] (only the entries with velocity degree 0 are touched: rhs += weight * moment).
+ * The companion broadcast DGSolution::copy_up_intp_to_f (source/DGSolution.cpp:1024-1065) is the dev_other_map of amdg_pointwise_expr. */
+int amdg_moment(amdg_ctx *ctx, int64_t n_field, const int *dev_map, int n_vdim, const int *order, double weight, const double *dev_f, double *dev_rhs_field);
 int amdg_lincomb(amdg_ctx *ctx, int64_t n, int k, const double *coefs, const double *const *dev_x, double beta, double *dev_y);
 
 /* ---- host-buffer entry points (what the reference-facing classes call; H2D/D2H inside) ---- */

@@ -612,6 +612,36 @@ int main(int argc, char ** argv)
         H.fill_ucoe(a.seed);
     }
 
+    if (has("moment") && (DIM == 3 || DIM == 4))
+    {
+        // Vlasov coupling: moments of f in the two velocity dimensions accumulated into the right-hand side of a field solution E that lives on the
+        // elements with level 0 in the velocity dimensions (DGAdapt::compute_moment_1D2V / _2D2V, source/DGAdapt.cpp:243-338); three calls:
+        // order (0,0) weight 1.25, (1,0) weight -0.5, (0,1) weight 2
+        H.fill_ucoe(a.seed);
+        DGAdapt E(false, a.nmax, a.nmax, 2, all_bas_alpt, all_bas_lagr, all_bas_herm, hash, a.eps, a.eta, false, false);
+        E.set_rhs_zero();
+        const std::vector<std::vector<int>> orders = { {0, 0}, {1, 0}, {0, 1} };
+        const std::vector<double> weights = { 1.25, -0.5, 2.0 };
+        for (size_t q = 0; q < orders.size(); ++q)
+        {
+            if (DIM == 3) E.compute_moment_1D2V(dg, orders[q], weights[q], 0, 0); else E.compute_moment_2D2V(dg, orders[q], weights[q], 0, 0);
+        }
+        std::vector<Element *> es;
+        for (auto & it : E.dg) es.push_back(&it.second);
+        std::sort(es.begin(), es.end(), [](Element * x, Element * y) { return x->hash_key < y->hash_key; });
+        std::vector<int> key, lev, sup; std::vector<double> rhs;
+        for (Element * e : es)
+        {
+            key.push_back(e->hash_key);
+            for (int t = 0; t < DIM; ++t) { lev.push_back(e->level[t]); sup.push_back(e->suppt[t]); }
+            for (int i = 0; i < e->rhs[0].size(); ++i) rhs.push_back(e->rhs[0].at(i));
+        }
+        H.dump.put("moment.hash_key", key);
+        H.dump.put("moment.level", lev, { (int64_t)es.size(), DIM });
+        H.dump.put("moment.suppt", sup, { (int64_t)es.size(), DIM });
+        H.dump.put("moment.rhs", rhs, { (int64_t)es.size(), (int64_t)(es.empty() ? 0 : es[0]->rhs[0].size()) });
+    }
+
     H.dump.close();
 
     if (a.time_reps > 0)

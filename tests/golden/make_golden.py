@@ -30,6 +30,9 @@ CASES = {
     "cfg5_vlasov_d6_k1_n2": "--dim 6 --nmax 2 --pa 1 --pl 2 --run grid,rhs,stage --flux vlasov --dump-tables 1 --dt 0.001",
     # 4D Vlasov 2D2V-like with the shipped degrees (k=3, m=4, mesh case 2), N=2
     "vlasov_d4_k3_m4_n2": "--dim 4 --nmax 2 --pa 3 --pl 4 --msh-lagr 2 --run grid,rhs --flux vlasov --dump-tables 1",
+    # Vlasov coupling: velocity moments of f into the field solution (compute_moment_1D2V / _2D2V); no tables needed
+    "moment_d3_k2_n4": "--dim 3 --nmax 4 --pa 2 --pl 3 --run grid,moment",
+    "moment_d4_k1_n3": "--dim 4 --nmax 3 --pa 1 --pl 2 --run grid,moment",
     # full (non-sparse) grid and a 1D grid: edge cases of the schedule (d=1 is a single full sweep)
     "full_d2_k2_n3": "--dim 2 --nmax 3 --sparse 0 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux linear --dump-tables 1",
     # adaptive (irregular) grids produced by DGAdapt::refine / coarsen: fibres are arbitrary subsets of the 1D tree

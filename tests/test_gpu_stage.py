@@ -169,3 +169,30 @@ def test_live_reference_dropin_burgers_adapt():
         pytest.skip("examples/live_burgers_adapt is built only where the reference sources exist (__graft_entry__.build())")
     r = subprocess.run([exe, "-NM", "6", "-N0", "2", "-steps", "10"], capture_output=True, text=True, timeout=900)
     assert "LIVE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["moment_d3_k2_n4", "moment_d4_k1_n3"])
+def test_velocity_moments_device(name):
+    """amdg_moment against DGAdapt::compute_moment_1D2V / _2D2V of the compiled reference (three accumulated calls), and the mixed first-order
+    moment (product form, not offered by the reference) against the numpy restatement"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import amdg_oracle as O
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    d = load_golden(name)
+    dim, nmax, n0, sparse, pa, pl = [int(x) for x in d["config"][:6]]
+    a = pa + 1
+    ctx = A.Context(dim, nmax, pa, pl, device=0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.grid_set(d["level"], d["suppt"])
+    f = torch.from_numpy(np.ascontiguousarray(d["ucoe_alpt.in"][:, 0, :])).cuda()
+    partner = O.field_partner(d["level"], d["suppt"], d["moment.level"], d["moment.suppt"])
+    pmap = torch.from_numpy(partner).cuda()
+    rhs = torch.zeros(d["moment.rhs"].shape, dtype=torch.float64, device="cuda")
+    for order, w in (((0, 0), 1.25), ((1, 0), -0.5), ((0, 1), 2.0)):
+        ctx.moment(pmap, 2, order, w, f, rhs)
+    assert rel(rhs.cpu().numpy(), d["moment.rhs"]) < TOL
+    mixed = torch.zeros_like(rhs)
+    ctx.moment(pmap, 2, (1, 1), 3.0, f, mixed)
+    ref = O.moments(d["ucoe_alpt.in"][:, 0, :], partner, a, dim, 2, (1, 1), 3.0, np.zeros_like(d["moment.rhs"]))
+    assert rel(mixed.cpu().numpy(), ref) < TOL
+    ctx.close()

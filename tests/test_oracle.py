@@ -235,3 +235,17 @@ def test_hierarchisation_stencil_restated():
             assert [list(x) for x in anc] == d["lagr.pw_anc"][row].tolist()
             assert np.allclose(wt, d["lagr.pw_wt"][row], atol=1e-13)
             row += 1
+
+
+@pytest.mark.parametrize("name", ["moment_d3_k2_n4", "moment_d4_k1_n3"])
+def test_velocity_moments(name):
+    """DGAdapt::compute_moment_1D2V / _2D2V (reference source/DGAdapt.cpp:243-338): three accumulated calls, as the harness made them"""
+    c = Case(name)
+    d = c.d
+    partner = O.field_partner(c.lev, c.sup, d["moment.level"], d["moment.suppt"])
+    assert (partner >= 0).any()
+    rhs = np.zeros_like(d["moment.rhs"])
+    for order, w in (((0, 0), 1.25), ((1, 0), -0.5), ((0, 1), 2.0)):
+        O.moments(d["ucoe_alpt.in"][:, 0, :], partner, c.a, c.dim, 2, order, w, rhs)
+    assert rel(rhs, d["moment.rhs"]) < TOL
+    assert np.array_equal(rhs != 0, d["moment.rhs"] != 0)
