@@ -12,7 +12,7 @@
 // against the exact Burgers solution is evaluated by the reference's own error routine on both coefficient sets.
 // Built only where the reference sources exist (examples/Makefile.live, run by __graft_entry__.build()); the binary travels to the GPU box.
 //
-// Usage: live_burgers_adapt [-NM 6] [-N0 2] [-steps 10] [-r 1e-2] [-timing 1]
+// Usage: live_burgers_adapt [-NM 6] [-N0 2] [-steps 10] [-r 1e-2] [-timing 1] [-static 1 -tf 0.05]   (static: sparse grid of level N0 = NM, no adaptivity -- convergence study)
 #include <iostream>
 #include <iomanip>
 #include <fstream>
@@ -82,13 +82,16 @@ static void download_ucoe(DGSolution & dg, amdg::DGSolution & dev)
 int main(int argc, char ** argv)
 {
     int NMAX = 6, N_init = 2, n_steps = 10, timing = 0;
-    double refine_eps = 1e-2;
+    bool is_static = false;
+    double refine_eps = 1e-2, final_time = -1.;
     for (int i = 1; i + 1 < argc; i += 2)
     {
         std::string k = argv[i];
         if (k == "-NM") NMAX = std::atoi(argv[i + 1]); else if (k == "-N0") N_init = std::atoi(argv[i + 1]);
         else if (k == "-steps") n_steps = std::atoi(argv[i + 1]); else if (k == "-r") refine_eps = std::atof(argv[i + 1]);
         else if (k == "-timing") timing = std::atoi(argv[i + 1]);
+        else if (k == "-static") is_static = std::atoi(argv[i + 1]) != 0;      // no predictor / refine / coarsen: the sparse grid of level N0 for the whole run (convergence study)
+        else if (k == "-tf") final_time = std::atof(argv[i + 1]);              // run to this time (the last step is shortened), overrides -steps
     }
     const double coarsen_eta = refine_eps / 10.;
     // ---- statics exactly as example/02_hyperbolic_05_burgers_adapt.cpp:34-63
@@ -165,15 +168,20 @@ int main(int argc, char ** argv)
         const std::vector<int> flux_id(DIM, AMDG_FLUX_BURGERS);
 
         double curr_time = 0., worst = 0., t_ref = 0., t_dev = 0., t_grid = 0., t_copy = 0., t_adapt = 0.;
-        for (int step = 0; step < n_steps; ++step)
+        int n_done = 0;
+        for (int step = 0; final_time > 0. ? curr_time < final_time * (1. - 1e-14) : step < n_steps; ++step)
         {
             // ---- part 1: dt (both arms must agree)
             auto dt_of = [&](DGAdapt & dg) { const std::vector<int> & mm = dg.max_mesh_level_vec(); double s = 0.; for (int d = 0; d < DIM; ++d) s += std::abs(wave_speed[d]) * std::pow(2., mm[d]); return cfl_hyper / s; };
-            const double dt = dt_of(dg_ref);
+            double dt = dt_of(dg_ref);
             if (dt != dt_of(dg_dev)) { std::printf("FAIL: the arms disagree on dt at step %d\n", step); return 1; }
+
+            if (final_time > 0. && curr_time + dt > final_time) dt = final_time - curr_time;
+            n_done = step + 1;
 
             // =============================== reference arm (stock code of the example)
             double t0 = now();
+            if (!is_static)
             {
                 dg_ref.copy_ucoe_to_predict();
                 HyperbolicAlpt linear(dg_ref, oper_matx_alpt);
@@ -187,8 +195,7 @@ int main(int argc, char ** argv)
                 odeSolver.set_rhs_zero(); odeSolver.add_rhs_to_eigenvec(); odeSolver.add_rhs_matrix(linear);
                 odeSolver.step_stage(0); odeSolver.final();
             }
-            dg_ref.refine();
-            dg_ref.copy_predict_to_ucoe();
+            if (!is_static) { dg_ref.refine(); dg_ref.copy_predict_to_ucoe(); }
             {
                 HyperbolicAlpt linear(dg_ref, oper_matx_alpt);
                 linear.assemble_matrix_flx_scalar(0, -1, lxf_alpha[0] / 2); linear.assemble_matrix_flx_scalar(0, 1, -lxf_alpha[0] / 2);
@@ -204,11 +211,14 @@ int main(int argc, char ** argv)
                     odeSolver.step_stage(stage); odeSolver.final();
                 }
             }
-            dg_ref.coarsen();
+            if (!is_static) dg_ref.coarsen();
             t_ref += now() - t0;
 
             // =============================== device arm (mirror classes; DGAdapt on the host)
             t0 = now();
+            double t1 = now();
+            if (!is_static)
+            {
             dg_dev.copy_ucoe_to_predict();
             {
                 amdg::ForwardEuler odeSolver(dev, dt);
@@ -220,7 +230,7 @@ int main(int argc, char ** argv)
                 odeSolver.set_rhs_zero(); odeSolver.add_rhs_to_eigenvec();
                 odeSolver.step_stage(0); odeSolver.final();
             }
-            double t1 = now();
+            t1 = now();
             download_ucoe(dg_dev, dev);                                         // DGAdapt::refine reads the predicted coefficients on the host
             t_copy += now() - t1; t1 = now();
             dg_dev.refine();
@@ -230,6 +240,7 @@ int main(int argc, char ** argv)
             t_grid += now() - t1; t1 = now();
             upload_ucoe(dg_dev, dev);
             t_copy += now() - t1;
+            }
             {
                 amdg::RK3SSP odeSolver(dev, dt);
                 odeSolver.init();
@@ -246,12 +257,15 @@ int main(int argc, char ** argv)
             t1 = now();
             download_ucoe(dg_dev, dev);
             t_copy += now() - t1; t1 = now();
-            dg_dev.coarsen();
-            t_adapt += now() - t1; t1 = now();
-            export_elements(dg_dev, dev);
-            t_grid += now() - t1; t1 = now();
-            upload_ucoe(dg_dev, dev);
-            t_copy += now() - t1;
+            if (!is_static)
+            {
+                dg_dev.coarsen();
+                t_adapt += now() - t1; t1 = now();
+                export_elements(dg_dev, dev);
+                t_grid += now() - t1; t1 = now();
+                upload_ucoe(dg_dev, dev);
+                t_copy += now() - t1;
+            }
             t_dev += now() - t0;
 
             // =============================== compare
@@ -281,10 +295,10 @@ int main(int argc, char ** argv)
         std::printf("L1 / L2 / Linf error vs exact Burgers at t = %.4f: reference %.6e %.6e %.6e | device %.6e %.6e %.6e\n", curr_time,
                     err_ref[0], err_ref[1], err_ref[2], err_dev[0], err_dev[1], err_dev[2]);
         std::printf("wall per step: reference arm %.2f ms (host cores: %d) | device arm %.2f ms = kernels+launch %.2f + amdg_grid_set/realloc %.2f + coefficient copies %.2f + DGAdapt refine/coarsen %.2f\n",
-                    1e3 * t_ref / n_steps, omp_get_max_threads(), 1e3 * t_dev / n_steps, 1e3 * (t_dev - t_grid - t_copy - t_adapt) / n_steps, 1e3 * t_grid / n_steps,
-                    1e3 * t_copy / n_steps, 1e3 * t_adapt / n_steps);
+                    1e3 * t_ref / n_done, omp_get_max_threads(), 1e3 * t_dev / n_done, 1e3 * (t_dev - t_grid - t_copy - t_adapt) / n_done, 1e3 * t_grid / n_done,
+                    1e3 * t_copy / n_done, 1e3 * t_adapt / n_done);
         if (!(worst < 1e-10) || std::abs(err_ref[1] - err_dev[1]) > 1e-10 * std::max(1., err_ref[1])) { std::printf("LIVE FAIL worst %.3e\n", worst); return 1; }
-        std::printf("LIVE OK worst rel-L2 %.3e over %d adaptive steps (NMAX %d)\n", worst, n_steps, NMAX);
+        std::printf("LIVE OK worst rel-L2 %.3e over %d %s steps (NMAX %d)\n", worst, n_done, is_static ? "static-grid" : "adaptive", NMAX);
     }
     catch (const std::exception & e) { std::cerr << e.what() << std::endl; return 1; }
     return 0;

@@ -171,6 +171,39 @@ def test_live_reference_dropin_burgers_adapt():
     assert "LIVE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_live_reference_full_runs_static_burgers():
+    """full runs to t = 0.05 on static sparse grids of level 3..6 (2-D Burgers, k = 2, Hermite flux interpolation, RK3SSP, the time step of the
+    example: 4 .. 32 steps): after every step the device coefficients stay within 1e-10 of the stock reference run (north_star's full-run bound) and the
+    L1 / L2 / Linf errors against ExactSolution are the same for both arms"""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "live_burgers_adapt")
+    if not os.path.exists(exe):
+        pytest.skip("examples/live_burgers_adapt is built only where the reference sources exist (__graft_entry__.build())")
+    for n in (3, 4, 5, 6):
+        r = subprocess.run([exe, "-NM", str(n), "-N0", str(n), "-static", "1", "-tf", "0.05"], capture_output=True, text=True, timeout=900)
+        assert "LIVE OK" in r.stdout and "static-grid" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+        m = re.search(r"reference (\S+) (\S+) (\S+) \| device (\S+) (\S+) (\S+)", r.stdout)
+        assert abs(float(m.group(2)) - float(m.group(5))) <= 1e-10 * max(1.0, float(m.group(2)))
+
+
+def test_live_reference_advection_convergence_orders():
+    """examples/live_advection_convergence: the reference's linear advection example (example/02_hyperbolic_01_scalar_const_coefficient.cpp, k = 2,
+    sparse grids N = 3..6, RK3SSP to t = 0.1) run to the end by the stock assembled-matrix path and by the device sweeps: coefficients within 1e-10 after
+    the full run, identical L2 errors against the exact solution, and so identical observed orders of convergence (about k + 1/2 .. k + 1 on sparse grids)"""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "live_advection_convergence")
+    if not os.path.exists(exe):
+        pytest.skip("examples/live_advection_convergence is built only where the reference sources exist (__graft_entry__.build())")
+    r = subprocess.run([exe, "-Nmin", "3", "-Nmax", "6"], capture_output=True, text=True, timeout=1500)
+    assert "CONVERGENCE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    rows = re.findall(r"^\| (\d) \| (\S+) \| (\S+) \| (\S+) \| (\S+) \|$", r.stdout, flags=re.M)
+    orders = [float(x[4]) for x in rows if x[4] != "-"]
+    print(r.stdout[-900:])
+    assert len(orders) == 3 and min(orders) > 2.0          # third order scheme on sparse grids (log factors): observed 2.3 .. 3.1 in the reference as well
+
+
 @pytest.mark.parametrize("name", ["moment_d3_k2_n4", "moment_d4_k1_n3"])
 def test_velocity_moments_device(name):
     """amdg_moment against DGAdapt::compute_moment_1D2V / _2D2V of the compiled reference (three accumulated calls), and the mixed first-order
