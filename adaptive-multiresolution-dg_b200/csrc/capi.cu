@@ -50,6 +50,9 @@ struct amdg_ctx
     cudaStream_t stream = nullptr; bool own_stream = false;
     Pairs1D pairs;
     Grid grid; bool have_grid = false;
+    Grid grid_spare;                                 // the previous grid's tables: amdg_grid_set builds into their storage (no fresh pages)
+    std::vector<NbrCache> nbr_caches;                // neighbour lists per fibre shape, kept across grid changes (grid.hpp)
+    char * meta_stage = nullptr; size_t meta_stage_cap = 0;   // pinned staging of the grid tables: one copy per amdg_grid_set
     std::vector<DevDim> ddims;
     int * d_ord1d = nullptr;
     std::vector<std::unique_ptr<Op>> ops;
@@ -302,6 +305,7 @@ int amdg_ctx_destroy(amdg_ctx * c)
         cudaFree(c->arena);
         for (double * p : c->scratch) cudaFree(p);
         cudaFree(c->h2d); cudaFree(c->d2h); cudaFree(c->d_pts1d);
+        if (c->meta_stage) cudaFreeHost(c->meta_stage);
         if (c->own_stream) cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -341,11 +345,11 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
 {
     if (!c || n < 1 || !level || !suppt) return fail(AMDG_EINVAL, "bad arguments to amdg_grid_set");
     if (n > 0x7fffffff) return fail(AMDG_EINVAL, "too many elements");
-    Grid g;
     const auto t0 = std::chrono::steady_clock::now();
-    if (g.build(c->dim, c->nmax, n, level, suppt, c->pairs) != 0) return fail(AMDG_EINVAL, "invalid or duplicate element index");
+    // level / suppt may alias the current grid's own arrays: the spare is built first, then swapped in
+    if (c->grid_spare.build(c->dim, c->nmax, n, level, suppt, c->pairs, &c->nbr_caches) != 0) return fail(AMDG_EINVAL, "invalid or duplicate element index");
     const auto t1 = std::chrono::steady_clock::now();
-    c->grid = std::move(g); c->have_grid = true;
+    std::swap(c->grid, c->grid_spare); c->have_grid = true;
     c->shapes.build(c->grid);
     evict_shape_caches(c);
     if (std::getenv("AMDG_VERBOSE"))
@@ -357,8 +361,57 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
     CU(cudaStreamSynchronize(c->stream));
     free_dev_grid(c);
     // the device tables are committed as a whole: a failed upload leaves the context without a grid (host tables included), never with partial tables
+    // fast path: every table into one pinned staging buffer at the offsets it will have in the arena, one copy.  The staging buffer is
+    // reused by the next amdg_grid_set only, which synchronises the stream first.
+    auto up_packed = [&]() -> bool
+    {
+        if (!c->arena || std::getenv("AMDG_GRID_UPLOAD_SPLIT")) return false;
+        struct Part { const void * src; size_t bytes; void ** dst; };
+        std::vector<Part> parts;
+        std::vector<std::vector<int>> fbase(c->dim);
+        c->ddims.assign(c->dim, DevDim());
+        parts.push_back({ c->grid.ord1d.data(), c->grid.ord1d.size() * sizeof(int), (void **)&c->d_ord1d });
+        for (int t = 0; t < c->dim; ++t)
+        {
+            const DimTables & H = c->grid.dims[t]; DevDim & D = c->ddims[t];
+            fbase[t].resize(n);
+            for (int64_t s = 0; s < n; ++s) fbase[t][s] = (int)H.fibre_ptr[H.slot_fibre[s]];
+            parts.push_back({ H.slot_elem.data(), (size_t)n * sizeof(int), (void **)&D.slot_elem });
+            parts.push_back({ fbase[t].data(), (size_t)n * sizeof(int), (void **)&D.slot_fbase });
+            parts.push_back({ H.fibre_ptr.data(), H.fibre_ptr.size() * sizeof(int64_t), (void **)&D.fibre_ptr });
+            for (int k = 0; k < 2; ++k)
+            {
+                parts.push_back({ H.nbr_ptr[k].data(), H.nbr_ptr[k].size() * sizeof(int64_t), (void **)&D.nbr_ptr[k] });
+                parts.push_back({ H.nbr_split[k].data(), H.nbr_split[k].size() * sizeof(int), (void **)&D.nbr_split[k] });
+                parts.push_back({ H.nbr[k].data(), H.nbr[k].size() * sizeof(Nbr), (void **)&D.nbr[k] });
+            }
+        }
+        size_t total = 0;
+        for (const Part & p : parts) total += (std::max<size_t>(p.bytes, 1) + 255) & ~(size_t)255;
+        if (c->arena_lo + total + (c->arena_cap - c->arena_hi) > c->arena_cap) { c->ddims.clear(); c->d_ord1d = nullptr; return false; }
+        if (c->meta_stage_cap < total)
+        {
+            if (c->meta_stage) cudaFreeHost(c->meta_stage);
+            c->meta_stage = nullptr; c->meta_stage_cap = 0;
+            const size_t cap = total + total / 2;
+            if (cudaMallocHost((void **)&c->meta_stage, cap) != cudaSuccess) { cudaGetLastError(); c->ddims.clear(); c->d_ord1d = nullptr; return false; }
+            c->meta_stage_cap = cap;
+        }
+        size_t ofs = 0;
+        char * base = c->arena + c->arena_lo;
+        for (const Part & p : parts)
+        {
+            if (p.bytes) std::memcpy(c->meta_stage + ofs, p.src, p.bytes);
+            *p.dst = base + ofs;
+            ofs += (std::max<size_t>(p.bytes, 1) + 255) & ~(size_t)255;
+        }
+        if (cudaMemcpyAsync(base, c->meta_stage, total, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { cudaGetLastError(); c->ddims.clear(); c->d_ord1d = nullptr; return false; }
+        c->arena_lo += total;
+        return true;
+    };
     auto up_all = [&]() -> cudaError_t
     {
+        if (up_packed()) return cudaSuccess;
         cudaError_t e;
         c->ddims.resize(c->dim);
         if ((e = meta_upload(c, &c->d_ord1d, c->grid.ord1d.data(), c->grid.ord1d.size(), false)) != cudaSuccess) return e;

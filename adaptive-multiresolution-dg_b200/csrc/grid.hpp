@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <numeric>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace amdg {
@@ -127,6 +128,27 @@ struct Pairs1D
 
 struct Nbr { int local; int pair; };
 
+// Neighbour lists of a fibre depend only on its SHAPE (the ascending 1D orders of its elements): a refine / coarsen step
+// (source/DGAdapt.cpp:1073-1248) changes a few fibres per dimension and leaves the shape of almost all others as it was, so the lists are
+// kept per shape across amdg_grid_set calls and a rebuild only renumbers rows and copies templates (the reference re-scans all element
+// pairs, source/DGSolution.cpp:675-728, or walks every element per added one, source/DGAdapt.cpp:1108-1136).  One cache per dimension
+// (the dimensions are built on parallel host threads).
+struct NbrTemplate
+{
+    std::vector<int> sig;            // 1D orders, ascending
+    std::vector<Nbr> nbr[2];         // vol / flx entries of all targets, target after target
+    std::vector<int> cnt[2], nu[2];  // per target: entries, leading "U" entries
+    mutable int shape_id = -1;       // memo of ShapeTable (mma_items.hpp), valid while shape_epoch equals the table's epoch
+    mutable uint64_t shape_epoch = 0;
+};
+struct NbrCache
+{
+    std::unordered_multimap<uint64_t, NbrTemplate> map;
+    size_t entries = 0;
+    int64_t hits = 0, misses = 0;
+    void clear() { map.clear(); entries = 0; }
+};
+
 struct DimTables
 {
     int64_t n_fibre = 0;
@@ -139,6 +161,7 @@ struct DimTables
     std::vector<int> nbr_split[2];      // [n] number of leading "U" entries
     std::vector<Nbr> nbr[2];
     int max_fibre_len = 0;
+    std::vector<const NbrTemplate *> fibre_tmpl;   // [n_fibre] template of every fibre when built with a cache (valid until that cache is cleared)
 };
 
 struct Grid
@@ -149,8 +172,11 @@ struct Grid
     std::vector<DimTables> dims;
 
     // returns 0, or -1 for an invalid element / duplicate
-    int build(int dim_, int nmax_, int64_t n_, const int * level_, const int * suppt_, const Pairs1D & P)
+    int build(int dim_, int nmax_, int64_t n_, const int * level_, const int * suppt_, const Pairs1D & P, std::vector<NbrCache> * caches = nullptr)
     {
+        if (caches && (int)caches->size() != dim_) caches->assign(dim_, NbrCache());
+        std::vector<uint8_t> lev_of(P.T);
+        for (int o = 0; o < P.T; ++o) lev_of[o] = (uint8_t)level_of_order(o);
         dim = dim_; nmax = nmax_; n = n_;
         level.assign(level_, level_ + n * dim); suppt.assign(suppt_, suppt_ + n * dim);
         ord1d.resize(n * dim); hash.resize(n);
@@ -164,12 +190,14 @@ struct Grid
             }
             hash[e] = hash_key(dim, &level[e * dim], &suppt[e * dim]);
         }
-        dims.assign(dim, DimTables());
+        dims.resize(dim);   // a Grid object that is built again keeps the capacity of its tables (no fresh pages to fault in)
         // the tables of the dimensions are independent: one host thread per dimension
         auto build_dim = [&](int t) -> int
         {
-            std::vector<int> perm(n), pos_of_ord(P.T, -1);
+            std::vector<int> pos_of_ord(P.T, -1);
             DimTables & D = dims[t];
+            std::vector<int> & perm = D.slot_elem;
+            perm.resize(n);
             std::iota(perm.begin(), perm.end(), 0);
             const int * o = ord1d.data();
             const int d = dim;
@@ -198,7 +226,7 @@ struct Grid
                 for (int k = 0; k < d; ++k) if (k != t) { const int x = o[(int64_t)a * d + k], y = o[(int64_t)b * d + k]; if (x != y) return x < y; }
                 return o[(int64_t)a * d + t] < o[(int64_t)b * d + t];
             });
-            D.slot_elem = perm; D.elem_slot.resize(n); D.slot_fibre.resize(n);
+            D.elem_slot.resize(n); D.slot_fibre.resize(n);
             D.fibre_ptr.clear(); D.fibre_ptr.push_back(0);
             for (int64_t s = 0; s < n; ++s)
             {
@@ -209,44 +237,91 @@ struct Grid
             }
             D.fibre_ptr.push_back(n);
             D.n_fibre = (int64_t)D.fibre_ptr.size() - 1;
-            for (int k = 0; k < 2; ++k) { D.nbr_ptr[k].assign(1, 0); D.nbr_split[k].clear(); D.nbr[k].clear(); }
+            for (int k = 0; k < 2; ++k) { D.nbr_ptr[k].assign(1, 0); D.nbr_ptr[k].reserve(n + 1); D.nbr_split[k].clear(); D.nbr_split[k].reserve(n); D.nbr[k].clear(); }
             D.max_fibre_len = 0;
+            NbrCache * cache = caches ? &(*caches)[t] : nullptr;
+            if (cache && cache->entries > ((size_t)1 << 24)) cache->clear();   // bound: 16 M entries (128 MB) per dimension
+            NbrTemplate scratch;
+            std::vector<int> sig;
+            std::vector<const NbrTemplate *> & fibre_tmpl = D.fibre_tmpl;
+            fibre_tmpl.assign(D.n_fibre, nullptr);
+            auto append = [&D](const NbrTemplate * T, int m)
+            {
+                for (int k = 0; k < 2; ++k)
+                {
+                    D.nbr[k].insert(D.nbr[k].end(), T->nbr[k].begin(), T->nbr[k].end());
+                    int64_t p = D.nbr_ptr[k].back();
+                    for (int i = 0; i < m; ++i) { p += T->cnt[k][i]; D.nbr_ptr[k].push_back(p); }
+                    D.nbr_split[k].insert(D.nbr_split[k].end(), T->nu[k].begin(), T->nu[k].end());
+                }
+            };
             for (int64_t f = 0; f < D.n_fibre; ++f)
             {
                 const int64_t s0 = D.fibre_ptr[f], s1 = D.fibre_ptr[f + 1];
                 const int m = (int)(s1 - s0);
                 D.max_fibre_len = std::max(D.max_fibre_len, m);
-                for (int64_t s = s0; s < s1; ++s) pos_of_ord[o[(int64_t)perm[s] * d + t]] = (int)(s - s0);
-                for (int64_t s = s0; s < s1; ++s)
+                sig.resize(m);
+                uint64_t h = 1469598103934665603ull;
+                for (int i = 0; i < m; ++i) { sig[i] = o[(int64_t)perm[s0 + i] * d + t]; h = (h ^ (uint64_t)sig[i]) * 1099511628211ull; }
+                const NbrTemplate * T = nullptr;
+                if (cache)
                 {
-                    const int oe = o[(int64_t)perm[s] * d + t];
-                    const int le = level_of_order(oe);
-                    int nu[2] = { 0, 0 };
-                    auto visit = [&](int of, int pair)
-                    {
-                        const int local = pos_of_ord[of];
-                        const bool is_u = level_of_order(of) <= le;
-                        D.nbr[1].push_back({ local, pair }); if (is_u) nu[1]++;
-                        if (P.vol[pair]) { D.nbr[0].push_back({ local, pair }); if (is_u) nu[0]++; }
-                    };
-                    const int c0 = P.tgt_ptr[oe], c1 = P.tgt_ptr[oe + 1];
-                    if (c1 - c0 <= m)
-                    {
-                        for (int c = c0; c < c1; ++c) if (pos_of_ord[P.src[c]] >= 0) visit(P.src[c], c);
-                    }
-                    else
-                    {
-                        for (int64_t r = s0; r < s1; ++r)
-                        {
-                            const int of = o[(int64_t)perm[r] * d + t];
-                            const int pair = P.id[(size_t)of * P.T + oe];
-                            if (pair >= 0) visit(of, pair);
-                        }
-                    }
-                    // sources were visited in ascending 1D order, and order grows with level: U entries lead
-                    for (int k = 0; k < 2; ++k) { D.nbr_ptr[k].push_back((int64_t)D.nbr[k].size()); D.nbr_split[k].push_back(nu[k]); }
+                    auto range = cache->map.equal_range(h);
+                    for (auto it = range.first; it != range.second; ++it) if (it->second.sig == sig) { T = &it->second; break; }
+                    if (T) cache->hits++; else cache->misses++;
                 }
-                for (int64_t s = s0; s < s1; ++s) pos_of_ord[o[(int64_t)perm[s] * d + t]] = -1;
+                if (!T)
+                {
+                    NbrTemplate & N = scratch;
+                    N.sig = sig;
+                    for (int k = 0; k < 2; ++k) { N.nbr[k].clear(); N.cnt[k].assign(m, 0); N.nu[k].assign(m, 0); }
+                    for (int i = 0; i < m; ++i) pos_of_ord[sig[i]] = i;
+                    for (int i = 0; i < m; ++i)
+                    {
+                        const int oe = sig[i];
+                        const int le = lev_of[oe];
+                        auto visit = [&](int of, int pair)
+                        {
+                            const int local = pos_of_ord[of];
+                            const bool is_u = lev_of[of] <= le;
+                            N.nbr[1].push_back({ local, pair }); N.cnt[1][i]++; if (is_u) N.nu[1][i]++;
+                            if (P.vol[pair]) { N.nbr[0].push_back({ local, pair }); N.cnt[0][i]++; if (is_u) N.nu[0][i]++; }
+                        };
+                        const int c0 = P.tgt_ptr[oe], c1 = P.tgt_ptr[oe + 1];
+                        if (c1 - c0 <= m)
+                        {
+                            for (int c = c0; c < c1; ++c) if (pos_of_ord[P.src[c]] >= 0) visit(P.src[c], c);
+                        }
+                        else
+                        {
+                            for (int r = 0; r < m; ++r)
+                            {
+                                const int pair = P.id[(size_t)sig[r] * P.T + oe];
+                                if (pair >= 0) visit(sig[r], pair);
+                            }
+                        }
+                        // sources were visited in ascending 1D order, and order grows with level: U entries lead
+                    }
+                    for (int i = 0; i < m; ++i) pos_of_ord[sig[i]] = -1;
+                    if (cache)
+                    {
+                        cache->entries += N.nbr[0].size() + N.nbr[1].size() + (size_t)m;
+                        T = &cache->map.emplace(h, std::move(N))->second;
+                        scratch = NbrTemplate();
+                    }
+                    else T = &N;
+                }
+                fibre_tmpl[f] = T;
+                if (!cache) append(T, m);
+            }
+            if (!cache) fibre_tmpl.clear();
+            if (cache)
+            {
+                // unordered_multimap never moves its nodes: the pointers collected above are still valid
+                size_t tot[2] = { 0, 0 };
+                for (int64_t f = 0; f < D.n_fibre; ++f) for (int k = 0; k < 2; ++k) tot[k] += fibre_tmpl[f]->nbr[k].size();
+                for (int k = 0; k < 2; ++k) D.nbr[k].reserve(tot[k]);
+                for (int64_t f = 0; f < D.n_fibre; ++f) append(fibre_tmpl[f], (int)(D.fibre_ptr[f + 1] - D.fibre_ptr[f]));
             }
                     return 0;
         };

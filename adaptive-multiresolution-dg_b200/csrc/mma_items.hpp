@@ -40,8 +40,10 @@ struct ShapeTable
         return live;
     }
     size_t n_known() const { return id_of.size(); }
+    uint64_t epoch = 1;   // memoised ids in the neighbour templates (grid.hpp) are valid for this epoch only
     void retire(const std::vector<char> & live)
     {
+        ++epoch;
         for (auto it = id_of.begin(); it != id_of.end();)
         {
             if (!live[it->second]) { std::vector<int>().swap(ords[it->second]); it = id_of.erase(it); } else ++it;
@@ -56,11 +58,17 @@ struct ShapeTable
             fibre_shape[t].resize(H.n_fibre);
             for (int64_t f = 0; f < H.n_fibre; ++f)
             {
-                std::vector<int> sig;
-                for (int64_t s = H.fibre_ptr[f]; s < H.fibre_ptr[f + 1]; ++s) sig.push_back(G.ord1d[(int64_t)H.slot_elem[s] * G.dim + t]);
-                auto it = id_of.find(sig);
+                const NbrTemplate * T = H.fibre_tmpl.empty() ? nullptr : H.fibre_tmpl[f];
                 int id;
-                if (it == id_of.end()) { id = (int)ords.size(); id_of.emplace(sig, id); ords.push_back(sig); } else id = it->second;
+                if (T && T->shape_epoch == epoch && T->shape_id >= 0) id = T->shape_id;
+                else
+                {
+                    std::vector<int> sig;
+                    for (int64_t s = H.fibre_ptr[f]; s < H.fibre_ptr[f + 1]; ++s) sig.push_back(G.ord1d[(int64_t)H.slot_elem[s] * G.dim + t]);
+                    auto it = id_of.find(sig);
+                    if (it == id_of.end()) { id = (int)ords.size(); id_of.emplace(sig, id); ords.push_back(sig); } else id = it->second;
+                    if (T) { T->shape_id = id; T->shape_epoch = epoch; }
+                }
                 fibre_shape[t][f] = id;
                 shape_fibres[t][id].push_back((int)H.fibre_ptr[f]);
             }

@@ -93,3 +93,58 @@ def test_tables_in_permuted_element_order(amdg):
             got = sorted(perm[idx[ptr[e_new]:ptr[e_new + 1]]].tolist())
             assert got == ridx[rptr[e_old]:rptr[e_old + 1]].tolist()
     ctx.close()
+
+
+def _brute_relation(lev, sup, t, flx):
+    """Element::is_vol_alpt / is_flx_alpt (source/Element.cpp:265-299, 337-386) by the O(N^2) scan of source/DGSolution.cpp:675-728"""
+    n, dim = lev.shape
+    def supp(l, j):
+        return (0.0, 1.0) if l <= 1 else (2.0 ** (1 - l) * (j - 1) / 2, 2.0 ** (1 - l) * (j + 1) / 2)
+    rows = []
+    others = [k for k in range(dim) if k != t]
+    for e in range(n):
+        same = np.all(lev[:, others] == lev[e, others], axis=1) & np.all(sup[:, others] == sup[e, others], axis=1)
+        u0, u1 = supp(lev[e, t], sup[e, t])
+        out = []
+        for f in np.nonzero(same)[0]:
+            v0, v1 = supp(lev[f, t], sup[f, t])
+            hit = not (u0 >= v1 or u1 <= v0)
+            if flx:
+                hit = hit or abs(u0 - v1) < 1e-13 or abs(u1 - v0) < 1e-13 or (abs(u0) < 1e-13 and abs(v1 - 1) < 1e-13) or (abs(v0) < 1e-13 and abs(u1 - 1) < 1e-13)
+            if hit:
+                out.append(int(f))
+        rows.append(out)
+    return rows
+
+
+@pytest.mark.parametrize("dim,nmax", [(2, 6), (3, 4)])
+def test_grid_change_sequence_matches_fresh_build(amdg, dim, nmax):
+    """a context that goes through a sequence of refine / coarsen-like grid changes (neighbour lists of known fibre shapes come from its
+    per-shape cache, tables are rebuilt into the previous grid's storage) has exactly the tables of a fresh context, in any row order,
+    and they are the brute-force relations of the reference"""
+    from test_lean_plans import random_adaptive_grid
+    ctx = amdg.Context(dim, nmax, 1, 2, device=-1)
+    rng = np.random.default_rng(7)
+    for step, keep in enumerate([1.0, 0.7, 0.5, 0.8, 0.35, 1.0]):
+        if keep == 1.0:
+            lev, sup = amdg.sparse_grid(dim, nmax)
+        else:
+            lev, sup = random_adaptive_grid(dim, nmax, seed=step, keep=keep)
+        o = rng.permutation(lev.shape[0])                     # DGSolution::dg iteration order changes with every rehash
+        lev, sup = np.ascontiguousarray(lev[o]), np.ascontiguousarray(sup[o])
+        ctx.grid_set(lev, sup)
+        fresh = amdg.Context(dim, nmax, 1, 2, device=-1)
+        fresh.grid_set(lev, sup)
+        assert np.array_equal(ctx.grid_keys()[0], fresh.grid_keys()[0]) and np.array_equal(ctx.grid_keys()[1], fresh.grid_keys()[1])
+        for t in range(dim):
+            pa, ea = ctx.grid_fibres(t); pb, eb = fresh.grid_fibres(t)
+            assert np.array_equal(pa, pb) and np.array_equal(ea, eb)
+            for rel in (amdg.REL_VOL, amdg.REL_FLX):
+                p1, i1 = ctx.grid_relation(t, rel); p2, i2 = fresh.grid_relation(t, rel)
+                assert np.array_equal(p1, p2) and np.array_equal(i1, i2)
+                if step in (1, 4):
+                    brute = _brute_relation(lev, sup, t, rel == amdg.REL_FLX)
+                    for e in range(lev.shape[0]):
+                        assert sorted(i1[p1[e]:p1[e + 1]].tolist()) == brute[e]
+        fresh.close()
+    ctx.close()
