@@ -61,6 +61,7 @@ SYMBOLS = {
     "amdg_sweep1d": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _i, _d, _i]),
     "amdg_sweep1d_batch": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _dp, _ip, _i, _i]),
     "amdg_apply_tensor": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i]),
+    "amdg_apply_tensor_coarse": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i, _i]),
     "amdg_hierarchize": (_i, [_p, _i, _p, _p, _i]),
     "amdg_pointwise": (_i, [_p, _i, _ip, _dp, _p, _p, _p]),
     "amdg_pointwise_hermite2d": (_i, [_p, _i, _ip, _dp, _p, _p]),
@@ -70,6 +71,7 @@ SYMBOLS = {
     "amdg_axpby": (_i, [_p, _i64, _d, _p, _d, _p]),
     "amdg_lincomb": (_i, [_p, _i64, _i, _dp, _p, _d, _p]),
     "amdg_moment": (_i, [_p, _i64, _p, _i, _ip, _d, _p, _p]),
+    "amdg_indicator_norm": (_i, [_p, _i, _p, _p]),
     "amdg_sweep1d_batch_mapped": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _dp, _ip, _p, _p, _i]),
     "amdg_points_set": (_i, [_p, _dp]),
     "amdg_pointwise_expr": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _ip, _i, _ip, _dp, _i]),
@@ -271,6 +273,12 @@ class Context:
         r, rp = _ints(rels)
         _check(lib.amdg_apply_tensor(self._h, op, rp, _ptr(src), _ptr(dst), n_comp, coef, int(accumulate)))
 
+    def apply_tensor_coarse(self, ops, rels, src, dst, mesh_nmax, n_comp=1, coef=1.0, accumulate=False):
+        """the *_coarse_grid transforms: only elements with sum of levels <= mesh_nmax take part"""
+        o, op = _ints(ops)
+        r, rp = _ints(rels)
+        _check(lib.amdg_apply_tensor_coarse(self._h, op, rp, _ptr(src), _ptr(dst), n_comp, coef, int(accumulate), int(mesh_nmax)))
+
     def hierarchize(self, hier_op, src, dst, n_comp=1):
         _check(lib.amdg_hierarchize(self._h, hier_op, _ptr(src), _ptr(dst), n_comp))
 
@@ -333,6 +341,11 @@ class Context:
         """amdg_moment: rhs_field[e][x, v = 0] += weight * velocity moment of f at the partner element field_map[e] (int32 device tensor, -1 = none)"""
         od, odp = _ints(order)
         _check(lib.amdg_moment(self._h, int(field_map.numel()), _ptr(field_map), n_vdim, odp, weight, _ptr(f), _ptr(rhs_field)))
+
+    def indicator_norm(self, us, norm):
+        """amdg_indicator_norm: norm[e] = sum_v ||us[v][e]||_2 (DGAdapt::indicator_norm)"""
+        pu = (ctypes.c_void_p * len(us))(*[_ptr(x) for x in us])
+        _check(lib.amdg_indicator_norm(self._h, len(us), pu, _ptr(norm)))
 
     def scatter_rows(self, src, n_rows, width, dst_base, dst_map):
         _check(lib.amdg_scatter_rows(self._h, _ptr(src), n_rows, width, _ptr(dst_base), _ptr(dst_map)))

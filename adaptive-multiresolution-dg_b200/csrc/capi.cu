@@ -21,6 +21,7 @@ using namespace amdg;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string & msg) { g_err = msg; return code; }
+static thread_local int g_arena_mb_override = -1;   // sub-contexts (coarse views) take a small metadata arena
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(AMDG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct Op
@@ -52,6 +53,9 @@ struct amdg_ctx
     Grid grid; bool have_grid = false;
     Grid grid_spare;                                 // the previous grid's tables: amdg_grid_set builds into their storage (no fresh pages)
     std::vector<NbrCache> nbr_caches;                // neighbour lists per fibre shape, kept across grid changes (grid.hpp)
+    // *_coarse_grid transforms (amdg_apply_tensor_coarse): the elements with sum of levels <= mesh_nmax as a grid of their own
+    struct CoarseView { amdg_ctx * sub = nullptr; int * d_rows = nullptr; int64_t n = 0; std::vector<int> op_map; double * buf[2] = { nullptr, nullptr }; int64_t cap[2] = { 0, 0 }; };
+    std::map<int, CoarseView> coarse;
     char * meta_stage = nullptr; size_t meta_stage_cap = 0;   // pinned staging of the grid tables: one copy per amdg_grid_set
     std::vector<DevDim> ddims;
     int * d_ord1d = nullptr;
@@ -117,8 +121,18 @@ static int need_device(amdg_ctx * c)
 }
 
 static void meta_free(amdg_ctx * c, void * p);
+static void free_coarse_views(amdg_ctx * c)
+{
+    for (auto & kv : c->coarse)
+    {
+        if (kv.second.sub) amdg_ctx_destroy(kv.second.sub);
+        cudaFree(kv.second.d_rows); cudaFree(kv.second.buf[0]); cudaFree(kv.second.buf[1]);
+    }
+    c->coarse.clear();
+}
 static void free_dev_grid(amdg_ctx * c)
 {
+    free_coarse_views(c);
     for (auto & D : c->ddims)
     {
         meta_free(c, D.slot_elem); meta_free(c, D.slot_fbase); meta_free(c, D.fibre_ptr);
@@ -268,6 +282,7 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
         size_t arena_mb = 96; if (const char * e2 = std::getenv("AMDG_ARENA_MB")) arena_mb = (size_t)std::max(0, atoi(e2));
+        if (g_arena_mb_override >= 0) arena_mb = (size_t)g_arena_mb_override;
         cudaDeviceProp prop;
         { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) c->n_sm = v; }
         if (arena_mb > 0 && cudaGetDeviceProperties(&prop, device) == cudaSuccess)
@@ -1681,6 +1696,88 @@ int amdg_apply_tensor(amdg_ctx * c, const int * ops, const int * rels, const dou
     return apply_tensor_shared(c, ops, rels, src, dst, n_comp, coef, accumulate);
 }
 
+// The *_coarse_grid forms (FastMultiplyLU::transform_1D_coarse_grid, reference source/FastMultiplyLU.cpp:514-594, and the drivers
+// :18-30, 144-165, 760-779, 926-946): every sweep skips targets and sources whose levels sum to more than mesh_nmax and leaves the skipped
+// targets at zero.  The kept elements are a downward-closed grid and relations are pairwise, so this is the plain transform on that
+// sub-grid: rows are gathered, transformed by a sub-context that owns the sub-grid's tables, and added back into their rows.
+int amdg_apply_tensor_coarse(amdg_ctx * c, const int * ops, const int * rels, const double * src, double * dst, int n_comp, double coef, int accumulate, int mesh_nmax)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (!ops || !rels || !src || !dst || n_comp < 1) return fail(AMDG_EINVAL, "bad arguments");
+    for (int t = 0; t < c->dim; ++t)
+    {
+        if ((r = check_op(c, ops[t]))) return r;
+        if (c->ops[ops[t]]->kf != c->ops[ops[0]]->kf || c->ops[ops[t]]->kt != c->ops[ops[0]]->kt) return fail(AMDG_EINVAL, "operators of one tensor product must share block edges");
+    }
+    CU(cudaSetDevice(c->device));
+    const int64_t n = c->grid.n;
+    auto it = c->coarse.find(mesh_nmax);
+    if (it == c->coarse.end())
+    {
+        amdg_ctx::CoarseView V;
+        std::vector<int> rows, lev, sup;
+        for (int64_t e = 0; e < n; ++e)
+        {
+            int sum = 0; for (int t = 0; t < c->dim; ++t) sum += c->grid.level[e * c->dim + t];
+            if (sum > mesh_nmax) continue;
+            rows.push_back((int)e);
+            for (int t = 0; t < c->dim; ++t) { lev.push_back(c->grid.level[e * c->dim + t]); sup.push_back(c->grid.suppt[e * c->dim + t]); }
+        }
+        V.n = (int64_t)rows.size();
+        if (V.n > 0 && V.n < n)
+        {
+            g_arena_mb_override = 8;
+            r = amdg_ctx_create(c->dim, c->nmax, c->edge_alpt - 1, c->edge_intp - 1, c->device, &V.sub);
+            g_arena_mb_override = -1;
+            if (r) return r;
+            if ((r = amdg_grid_set(V.sub, V.n, lev.data(), sup.data()))) { amdg_ctx_destroy(V.sub); return r; }
+            cudaError_t e = upload(&V.d_rows, rows.data(), rows.size(), c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);     // rows is a local
+            if (e != cudaSuccess) { amdg_ctx_destroy(V.sub); cudaFree(V.d_rows); return fail(AMDG_ECUDA, std::string("coarse view: ") + cudaGetErrorString(e)); }
+        }
+        it = c->coarse.emplace(mesh_nmax, std::move(V)).first;
+    }
+    amdg_ctx::CoarseView & V = it->second;
+    const int kf = c->ops[ops[0]]->kf, kt = c->ops[ops[0]]->kt;
+    const int64_t s_from = ipow(kf, c->dim), s_to = ipow(kt, c->dim);
+    if (V.n == n) return amdg_apply_tensor(c, ops, rels, src, dst, n_comp, coef, accumulate);
+    if (!accumulate) CU(cudaMemsetAsync(dst, 0, (size_t)n_comp * n * s_to * sizeof(double), c->stream));
+    if (V.n == 0) return AMDG_OK;
+    amdg_ctx * sub = V.sub;
+    if (sub->stream != c->stream) { if ((r = amdg_ctx_set_stream(sub, (void *)c->stream))) return r; }
+    sub->sched = c->sched; sub->kernel_variant = c->kernel_variant;
+    V.op_map.resize(c->ops.size(), -1);
+    std::vector<int> sub_ops(c->dim);
+    for (int t = 0; t < c->dim; ++t)
+    {
+        int & m = V.op_map[ops[t]];
+        if (m < 0)
+        {
+            const Op & O = *c->ops[ops[t]];
+            if ((r = amdg_op_register_compact(sub, O.blocks.data(), c->pairs.n_pairs, O.kf, O.kt, O.hier ? 1 : 0, &m))) return r;
+        }
+        sub_ops[t] = m;
+    }
+    const int64_t need[2] = { (int64_t)n_comp * V.n * s_from, (int64_t)n_comp * V.n * s_to };
+    for (int k = 0; k < 2; ++k)
+    {
+        if (V.cap[k] >= need[k]) continue;
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(V.buf[k]); V.buf[k] = nullptr; V.cap[k] = 0;
+        if (cudaMalloc((void **)&V.buf[k], (size_t)need[k] * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(AMDG_ENOMEM, "coarse view buffers"); }
+        V.cap[k] = need[k];
+    }
+    for (int v = 0; v < n_comp; ++v)
+        CU(launch_rows_gather(src + (int64_t)v * n * s_from, V.d_rows, V.n, (int)s_from, V.buf[0] + (int64_t)v * V.n * s_from, c->stream));
+    const int64_t l0 = sub->launches;
+    if ((r = amdg_apply_tensor(sub, sub_ops.data(), rels, V.buf[0], V.buf[1], n_comp, coef, 0))) return r;
+    for (int v = 0; v < n_comp; ++v)
+        CU(launch_rows_scatter_add(V.buf[1] + (int64_t)v * V.n * s_to, V.d_rows, V.n, (int)s_to, dst + (int64_t)v * n * s_to, c->stream));
+    c->launches += (sub->launches - l0) + 2 * n_comp;
+    return AMDG_OK;
+}
+
 int amdg_hierarchize(amdg_ctx * c, int hop, const double * src, double * dst, int n_comp)
 {
     int r = need_device(c); if (r) return r;
@@ -1970,6 +2067,21 @@ int amdg_moment(amdg_ctx * c, int64_t n_field, const int * dev_map, int n_vdim, 
     CU(cudaSetDevice(c->device));
     cudaError_t e = launch_moment(m, c->stream);
     if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("moment: ") + cudaGetErrorString(e));
+    c->launches++;
+    return AMDG_OK;
+}
+
+int amdg_indicator_norm(amdg_ctx * c, int n_var, const double * const * dev_u, double * dev_norm)
+{
+    int r = need_device(c); if (r) return r;
+    if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
+    if (n_var < 1 || n_var > 16 || !dev_u || !dev_norm) return fail(AMDG_EINVAL, "bad indicator arguments");
+    IndicatorArgs a; std::memset(&a, 0, sizeof(a));
+    for (int v = 0; v < n_var; ++v) { if (!dev_u[v]) return fail(AMDG_EINVAL, "null coefficient array"); a.u[v] = dev_u[v]; }
+    a.norm = dev_norm; a.n_elem = c->grid.n; a.block = (int)ipow(c->edge_alpt, c->dim); a.n_var = n_var;
+    CU(cudaSetDevice(c->device));
+    cudaError_t e = launch_indicator_norm(a, c->stream);
+    if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("indicator norm: ") + cudaGetErrorString(e));
     c->launches++;
     return AMDG_OK;
 }

@@ -539,6 +539,39 @@ cudaError_t launch_scatter_rows(const double * src, int64_t n_rows, int width, d
     return cudaGetLastError();
 }
 
+// element rows of an array into a compact array and back (the sub-grid of the *_coarse_grid transforms, capi.cu: amdg_apply_tensor_coarse):
+// gather: dst[e][i] = src[rows[e]][i];  scatter-add: dst[rows[e]][i] += src[e][i]
+__global__ void __launch_bounds__(256) rows_gather_kernel(const double * __restrict__ src, const int * __restrict__ rows, int64_t n_rows, int width, double * __restrict__ dst)
+{
+    const int64_t total = n_rows * width, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride)
+    {
+        const int64_t e = g / width; const int i = (int)(g - e * width);
+        dst[g] = src[(int64_t)__ldg(rows + e) * width + i];
+    }
+}
+__global__ void __launch_bounds__(256) rows_scatter_add_kernel(const double * __restrict__ src, const int * __restrict__ rows, int64_t n_rows, int width, double * __restrict__ dst)
+{
+    const int64_t total = n_rows * width, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride)
+    {
+        const int64_t e = g / width; const int i = (int)(g - e * width);
+        dst[(int64_t)__ldg(rows + e) * width + i] += src[g];
+    }
+}
+cudaError_t launch_rows_gather(const double * src, const int * rows, int64_t n_rows, int width, double * dst, cudaStream_t st)
+{
+    const int64_t nb = (n_rows * width + 255) / 256;
+    rows_gather_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(src, rows, n_rows, width, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_rows_scatter_add(const double * src, const int * rows, int64_t n_rows, int width, double * dst, cudaStream_t st)
+{
+    const int64_t nb = (n_rows * width + 255) / 256;
+    rows_scatter_add_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(src, rows, n_rows, width, dst);
+    return cudaGetLastError();
+}
+
 // Cross-GPU barrier over peer-mapped flags (one process per GPU, flags in IPC-shared device memory).  Thread r < world: publish this rank's
 // new epoch in rank r's flag array (system-scope release: everything earlier kernels of this stream stored to peers is visible first), then wait
 // until rank r's epoch has arrived here (acquire).  The epoch lives on the device so that the kernel can be replayed from a CUDA graph.  A peer
@@ -766,6 +799,34 @@ cudaError_t launch_moment(const MomentArgs & a, cudaStream_t st)
 {
     const int64_t nb = (a.n_field * a.x_block + 255) / 256;
     moment_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// Refinement / coarsening indicator of DGAdapt (reference source/DGAdapt.cpp:1018-1030): norm[e] = sum over the indicator variables of the l2
+// norm of the element's Alpert coefficients.  One warp per element row, lanes over the block, fixed-order shuffle reduction (deterministic).
+__global__ void __launch_bounds__(256) indicator_norm_kernel(const IndicatorArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < a.n_elem; e += warps)
+    {
+        double norm = 0.0;
+        for (int v = 0; v < a.n_var; ++v)
+        {
+            const double * __restrict__ u = a.u[v] + e * a.block;
+            double s = 0.0;
+            for (int i = lane; i < a.block; i += 32) { const double x = u[i]; s += x * x; }
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            norm += sqrt(s);
+        }
+        if (lane == 0) a.norm[e] = norm;
+    }
+}
+
+cudaError_t launch_indicator_norm(const IndicatorArgs & a, cudaStream_t st)
+{
+    const int64_t nb = (a.n_elem + 7) / 8;
+    indicator_norm_kernel<<<(unsigned)(nb < 148 * 16 ? (nb > 0 ? nb : 1) : 148 * 16), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

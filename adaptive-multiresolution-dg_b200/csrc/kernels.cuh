@@ -237,6 +237,10 @@ cudaError_t launch_rk4_ode2nd_stage(int stage, double dt, const double * u_tn, c
 cudaError_t launch_axpby(int64_t n, double alpha, const double * x, double beta, double * y, cudaStream_t st);
 struct MomentArgs { const double * f; double * rhs; const int * map; int64_t n_field; int x_block, v_block, n_combo; int offset[16]; double coef[16]; double weight; };
 cudaError_t launch_moment(const MomentArgs & a, cudaStream_t st);
+cudaError_t launch_rows_gather(const double * src, const int * rows, int64_t n_rows, int width, double * dst, cudaStream_t st);
+cudaError_t launch_rows_scatter_add(const double * src, const int * rows, int64_t n_rows, int width, double * dst, cudaStream_t st);
+struct IndicatorArgs { const double * u[16]; double * norm; int64_t n_elem; int block, n_var; };
+cudaError_t launch_indicator_norm(const IndicatorArgs & a, cudaStream_t st);
 struct LincombArgs { const double * x[16]; double c[16]; double * y; double beta; int64_t n; int k; };
 cudaError_t launch_lincomb(const LincombArgs & a, cudaStream_t st);
 cudaError_t launch_point_coords(const double * pts1d, const int * ord1d, int64_t n_elem, int dim, int edge, double * pts, cudaStream_t st);

@@ -118,7 +118,18 @@ struct OperatorMatrix1D
         check(amdg_op_register(dg.ctx, t_urgt_vjp, rows, cols, edge_from, edge_to, &urgt_vjp));
         check(amdg_op_combine(dg.ctx, ulft_vjp, 1.0, urgt_vjp, 1.0, &uave2_vjp));
         if (t_ujp_vjp) check(amdg_op_register(dg.ctx, t_ujp_vjp, rows, cols, edge_from, edge_to, &ujp_vjp));
+        // uave_vjp = (urgt_vjp + ulft_vjp) / 2 (include/OperatorMatrix1D.h:199)
+        check(amdg_op_combine(dg.ctx, ulft_vjp, 0.5, urgt_vjp, 0.5, &uave_vjp));
     }
+    // the [u] * v_x^-, [u] * v_x^+ tables of DiffusionRHS (include/OperatorMatrix1D.h:209-214)
+    void set_ujp_vx(DGSolution & dg, const double * t_ujp_vxlft, const double * t_ujp_vxrgt)
+    {
+        const int T = 1 << dg.NMAX, rows = T * edge_from, cols = T * edge_to;
+        check(amdg_op_register(dg.ctx, t_ujp_vxlft, rows, cols, edge_from, edge_to, &ujp_vxlft));
+        check(amdg_op_register(dg.ctx, t_ujp_vxrgt, rows, cols, edge_from, edge_to, &ujp_vxrgt));
+        check(amdg_op_combine(dg.ctx, ujp_vxlft, 1.0, ujp_vxrgt, 1.0, &ujp_vxave2));
+    }
+    int uave_vjp = -1, ujp_vxlft = -1, ujp_vxrgt = -1, ujp_vxave2 = -1;   // ujp_vxave2 = ujp_vxlft + ujp_vxrgt (source/FastMultiplyLU.cpp:1742)
 };
 
 // FastLagrIntp / FastHermIntp (source/FastMultiplyLU.cpp:1316-1390): the constructor takes the point table in the
@@ -129,6 +140,13 @@ public:
     FastLagrIntp(DGSolution & dg, const std::vector<std::vector<double>> & Lag_pt_Alpt_1D, const std::vector<std::vector<double>> & Lag_pt_Alpt_1D_d1)
         : dg_(&dg) { op_pt_ = reg(Lag_pt_Alpt_1D); if (!Lag_pt_Alpt_1D_d1.empty()) op_d1_ = reg(Lag_pt_Alpt_1D_d1); }
     void eval_up_Lagr() { for (int v = 0; v < dg_->VEC_NUM; ++v) eval_up_Lagr(v); }
+    // FastLagrIntp::eval_up_Lagr_coarse_grid (source/FastMultiplyLU.cpp:1367-1370): elements above the cut are skipped and left at zero
+    void eval_up_Lagr_coarse_grid(int mesh_nmax)
+    {
+        const int d = dg_->DIM; std::vector<int> ops(d, op_pt_), rels(d, AMDG_REL_VOL);
+        for (int v = 0; v < dg_->VEC_NUM; ++v)
+            check(amdg_apply_tensor_coarse(dg_->ctx, ops.data(), rels.data(), dg_->ucoe(v), dg_->up(v), 1, 1.0, 0, mesh_nmax));
+    }
     void eval_up_Lagr(int vec_index)
     {
         std::vector<int> ops(dg_->DIM, op_pt_), rels(dg_->DIM, AMDG_REL_VOL);
@@ -246,6 +264,25 @@ public:
             check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, t), dg_->rhs_v(0), 1, 0.5, 1));
         }
     }
+    // rhs_vol_scalar_coarse_grid / rhs_flx_intp_scalar_coarse_grid (source/FastMultiplyLU.cpp:1143-1158, 1191-1219)
+    void rhs_vol_scalar_coarse_grid(int mesh_nmax)
+    {
+        const int d = dg_->DIM; std::vector<int> rels(d, AMDG_REL_VOL);
+        for (int t = 0; t < d; ++t)
+        {
+            std::vector<int> ops(d, m_->u_v); ops[t] = m_->u_vx;
+            check(amdg_apply_tensor_coarse(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, t), dg_->rhs_v(0), 1, 1.0, 1, mesh_nmax));
+        }
+    }
+    void rhs_flx_intp_scalar_coarse_grid(int mesh_nmax)
+    {
+        const int d = dg_->DIM;
+        for (int t = 0; t < d; ++t)
+        {
+            std::vector<int> ops(d, m_->u_v), rels(d, AMDG_REL_VOL); ops[t] = m_->uave2_vjp; rels[t] = AMDG_REL_FLX;
+            check(amdg_apply_tensor_coarse(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, t), dg_->rhs_v(0), 1, 0.5, 1, mesh_nmax));
+        }
+    }
 private:
     DGSolution * dg_; OperatorMatrix1D * m_;
 };
@@ -288,6 +325,41 @@ public:
         const int d = dg_->DIM; std::vector<int> rels(d, AMDG_REL_VOL), ops(d, m_->u_v);
         for (int v = 0; v < dg_->VEC_NUM; ++v)
             check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(v, 0), dg_->rhs_v(v), 1, 1.0, 1));
+    }
+private:
+    DGSolution * dg_; OperatorMatrix1D * m_;
+};
+
+// DiffusionRHS (source/FastMultiplyLU.cpp:1691-1821): the interior-penalty terms of a nonlinear diffusion flux interpolated in the Lagrange basis.
+// rhs_vol and rhs_flx_gradu read one flux component per direction (fucoe_intp[0][t]); the three [u]-terms read fucoe_intp[0][0].
+class DiffusionRHS
+{
+public:
+    DiffusionRHS(DGSolution & dg, OperatorMatrix1D & oper) : dg_(&dg), m_(&oper) {}
+    void rhs_vol() { for (int t = 0; t < dg_->DIM; ++t) term(m_->u_vx, AMDG_REL_VOL, t, t, -1.0); }
+    void rhs_flx_gradu() { for (int t = 0; t < dg_->DIM; ++t) term(m_->uave_vjp, AMDG_REL_FLX, t, t, -1.0); }
+    void rhs_flx_u() { for (int t = 0; t < dg_->DIM; ++t) term(m_->ujp_vxave2, AMDG_REL_FLX, t, 0, -0.5); }
+    void rhs_flx_k_minus_u() { for (int t = 0; t < dg_->DIM; ++t) term(m_->ujp_vxlft, AMDG_REL_FLX, t, 0, -0.5); }
+    void rhs_flx_k_plus_u() { for (int t = 0; t < dg_->DIM; ++t) term(m_->ujp_vxrgt, AMDG_REL_FLX, t, 0, -0.5); }
+private:
+    void term(int op_t, int rel_t, int t, int dim_interp, double coef)
+    {
+        if (op_t < 0) throw Error("DiffusionRHS: table not registered (OperatorMatrix1D::set_ujp_vx)");
+        const int d = dg_->DIM; std::vector<int> ops(d, m_->u_v), rels(d, AMDG_REL_VOL); ops[t] = op_t; rels[t] = rel_t;
+        check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, dim_interp), dg_->rhs_v(0), 1, coef, 1));
+    }
+    DGSolution * dg_; OperatorMatrix1D * m_;
+};
+
+// FastRHSHamiltonJacobi::rhs_nonlinear (source/FastMultiplyLU.cpp:426-434): rhs += (u_v x ... x u_v) fucoe_intp[0][0]
+class FastRHSHamiltonJacobi
+{
+public:
+    FastRHSHamiltonJacobi(DGSolution & dg, OperatorMatrix1D & oper) : dg_(&dg), m_(&oper) {}
+    void rhs_nonlinear()
+    {
+        const int d = dg_->DIM; std::vector<int> rels(d, AMDG_REL_VOL), ops(d, m_->u_v);
+        check(amdg_apply_tensor(dg_->ctx, ops.data(), rels.data(), dg_->fucoe(0, 0), dg_->rhs_v(0), 1, 1.0, 1));
     }
 private:
     DGSolution * dg_; OperatorMatrix1D * m_;

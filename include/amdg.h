@@ -130,6 +130,12 @@ int amdg_sweep1d_batch_mapped(amdg_ctx *ctx, int op, int rel, int lu, int t, con
 int amdg_apply_tensor(amdg_ctx *ctx, const int *ops, const int *rels, const double *dev_src, double *dev_dst,
                       int n_comp, double coef, int accumulate);
 
+/* the *_coarse_grid forms of the same transforms: FastRHS::transform_fucoe_to_rhs_coarse_grid (source/FastMultiplyLU.cpp:18-30),
+ * FastInterpolation::transform_ucoealpt_to_upintp_coarse_grid (:760-779) over FastMultiplyLU::transform_1D_coarse_grid (:514-594): elements whose
+ * levels sum to more than mesh_nmax are skipped as sources and as targets in every sweep (their part of dst is 0, or untouched if accumulate). */
+int amdg_apply_tensor_coarse(amdg_ctx *ctx, const int *ops, const int *rels, const double *dev_src, double *dev_dst,
+                             int n_comp, double coef, int accumulate, int mesh_nmax);
+
 /* ---- hierarchisation: LagrInterpolation::eval_fp_to_coe_D_Lag / eval_up_to_coe_D_Lag
  * (source/Interplation.cpp:1222-1430, 891-1048) and the Hermite twins (:3651-3849, 3319-3479); in place allowed ---- */
 int amdg_hierarchize(amdg_ctx *ctx, int hier_op, const double *dev_src, double *dev_dst, int n_comp);
@@ -178,6 +184,10 @@ int amdg_axpby(amdg_ctx *ctx, int64_t n, double alpha, const double *dev_x, doub
  * dev_f [n_elem of f][a^dim], dev_rhs_field [n_field][a^dim] (only the entries with velocity degree 0 are touched: rhs += weight * moment).
  * The companion broadcast DGSolution::copy_up_intp_to_f (source/DGSolution.cpp:1024-1065) is the dev_other_map of amdg_pointwise_expr. */
 int amdg_moment(amdg_ctx *ctx, int64_t n_field, const int *dev_map, int n_vdim, const int *order, double weight, const double *dev_f, double *dev_rhs_field);
+/* refinement / coarsening indicator of DGAdapt::indicator_norm (source/DGAdapt.cpp:1018-1030): dev_norm[e] = sum_{v < n_var} || dev_u[v][e][.] ||_2 over
+ * the Alpert coefficient blocks (a^dim doubles) of the indicator variables (for "wave" problems the caller lists ucoe_ut as further variables);
+ * the adapt decision then needs n_elem doubles from the device instead of every coefficient */
+int amdg_indicator_norm(amdg_ctx *ctx, int n_var, const double *const *dev_u, double *dev_norm);
 int amdg_lincomb(amdg_ctx *ctx, int64_t n, int k, const double *coefs, const double *const *dev_x, double beta, double *dev_y);
 
 /* ---- host-buffer entry points (what the reference-facing classes call; H2D/D2H inside) ---- */

@@ -300,6 +300,15 @@ int main(int argc, char ** argv)
         dump_matrix(H.dump, "alpt.uxave_vjp", oper_alpt.uxave_vjp); dump_matrix(H.dump, "alpt.ujp_vxave", oper_alpt.ujp_vxave);
         dump_matrix(H.dump, "lagr.u_v", oper_lagr.u_v); dump_matrix(H.dump, "lagr.u_vx", oper_lagr.u_vx);
         dump_matrix(H.dump, "lagr.ulft_vjp", oper_lagr.ulft_vjp); dump_matrix(H.dump, "lagr.urgt_vjp", oper_lagr.urgt_vjp);
+        if (a.dump_tables > 1)   // the tables DiffusionRHS uses, and the remaining Alpert x Alpert tables (table-generation parity)
+        {
+            dump_matrix(H.dump, "lagr.uave_vjp", oper_lagr.uave_vjp); dump_matrix(H.dump, "lagr.ujp_vxlft", oper_lagr.ujp_vxlft);
+            dump_matrix(H.dump, "lagr.ujp_vxrgt", oper_lagr.ujp_vxrgt); dump_matrix(H.dump, "lagr.ujp_vjp", oper_lagr.ujp_vjp);
+            dump_matrix(H.dump, "alpt.uave_vjp", oper_alpt.uave_vjp); dump_matrix(H.dump, "alpt.ujp_vxlft", oper_alpt.ujp_vxlft);
+            dump_matrix(H.dump, "alpt.ujp_vxrgt", oper_alpt.ujp_vxrgt); dump_matrix(H.dump, "alpt.ux_v", oper_alpt.ux_v);
+            dump_matrix(H.dump, "alpt.uxrgt_vjp", oper_alpt.uxrgt_vjp); dump_matrix(H.dump, "alpt.uxlft_vjp", oper_alpt.uxlft_vjp);
+            dump_matrix(H.dump, "herm.uave_vjp", oper_herm.uave_vjp); dump_matrix(H.dump, "herm.ujp_vjp", oper_herm.ujp_vjp);
+        }
         dump_matrix(H.dump, "herm.u_v", oper_herm.u_v); dump_matrix(H.dump, "herm.u_vx", oper_herm.u_vx);
         dump_matrix(H.dump, "herm.ulft_vjp", oper_herm.ulft_vjp); dump_matrix(H.dump, "herm.urgt_vjp", oper_herm.urgt_vjp);
         dump_matrix(H.dump, "Lag_pt_Alpt_1D", interp_lagr.Lag_pt_Alpt_1D);
@@ -519,6 +528,35 @@ int main(int argc, char ** argv)
         dg.set_rhs_zero();
         HyperbolicDiffFluxHermRHS diff(dg, oper_herm); diff.rhs_vol_scalar(); diff.rhs_flx_intp_scalar();
         H.dump_field("var.rhs_diffflux", Harness::RHS);
+    }
+    if (has("f4") && !herm)   // DiffusionRHS, FastRHSHamiltonJacobi, the *_coarse_grid transforms, the adapt indicator
+    {
+        nonlinear_rhs(false, "");
+        H.dump_flux_field("f4.fucoe_intp", true);
+        DiffusionRHS diff(dg, oper_lagr);
+        dg.set_rhs_zero(); diff.rhs_vol(); H.dump_field("f4.diff_vol", Harness::RHS);
+        dg.set_rhs_zero(); diff.rhs_flx_gradu(); H.dump_field("f4.diff_flx_gradu", Harness::RHS);
+        dg.set_rhs_zero(); diff.rhs_flx_u(); H.dump_field("f4.diff_flx_u", Harness::RHS);
+        dg.set_rhs_zero(); diff.rhs_flx_k_minus_u(); H.dump_field("f4.diff_flx_k_minus_u", Harness::RHS);
+        dg.set_rhs_zero(); diff.rhs_flx_k_plus_u(); H.dump_field("f4.diff_flx_k_plus_u", Harness::RHS);
+        FastRHSHamiltonJacobi hj(dg, oper_lagr);
+        dg.set_rhs_zero(); hj.rhs_nonlinear(); H.dump_field("f4.hj", Harness::RHS);
+        for (int cut = 1; cut <= 2 && a.nmax - cut >= 0; ++cut)
+        {
+            const int M = a.nmax - cut;
+            const std::string tag = "f4.cg" + std::to_string(cut);
+            H.dump.put(tag + ".mesh_nmax", std::vector<int>{ M });
+            fast_lagr_intp.eval_up_Lagr_coarse_grid(M);
+            H.dump_field(tag + ".up_intp", Harness::UP_INTP);
+            dg.set_rhs_zero(); rhs_lagr.rhs_vol_scalar_coarse_grid(M); H.dump_field(tag + ".rhs_vol", Harness::RHS);
+            rhs_lagr.rhs_flx_intp_scalar_coarse_grid(M); H.dump_field(tag + ".rhs_vol_flx", Harness::RHS);
+        }
+        {
+            std::vector<double> norms;
+            for (Element * e : H.sorted) norms.push_back(dg.indicator_norm(*e));
+            H.dump.put("f4.indicator_norm", norms);
+        }
+        dg.set_rhs_zero();
     }
     if (has("stage"))        // full RK3SSP step with the nonlinear right-hand side, a.steps steps
     {

@@ -42,6 +42,9 @@ CASES = {
     "variants_lagr_d2_k2_n4": "--dim 2 --nmax 4 --pa 2 --pl 3 --run grid,variants --flux kpp --dump-tables 1",
     "variants_herm_d2_k2_n4": "--dim 2 --nmax 4 --pa 2 --ph 3 --intp herm --run grid,variants --flux burgers --dump-tables 1",
     "variants_lagr_d3_k1_n3": "--dim 3 --nmax 3 --pa 1 --pl 2 --vecnum 2 --run grid,variants --flux kpp --dump-tables 1",
+    # DiffusionRHS, FastRHSHamiltonJacobi, the *_coarse_grid transforms (mesh_nmax = N-1, N-2) and DGAdapt::indicator_norm
+    "f4_lagr_d2_k2_n4": "--dim 2 --nmax 4 --pa 2 --pl 3 --run grid,f4 --flux kpp --dump-tables 2",
+    "f4_lagr_d3_k1_n3": "--dim 3 --nmax 3 --pa 1 --pl 2 --run grid,f4 --flux burgers --dump-tables 2",
     "line_d1_k2_n5": "--dim 1 --nmax 5 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux burgers --dump-tables 1",
 }
 

@@ -331,6 +331,52 @@ def test_rhs_variants(name):
     c.close()
 
 
+@pytest.mark.parametrize("name", ["f4_lagr_d2_k2_n4", "f4_lagr_d3_k1_n3"])
+@pytest.mark.parametrize("schedule", [0, 1])
+def test_f4_compositions(name, schedule):
+    """SURVEY 8(f4) against the reference's own classes: DiffusionRHS::rhs_vol / rhs_flx_gradu / rhs_flx_u / rhs_flx_k_minus_u / rhs_flx_k_plus_u
+    (source/FastMultiplyLU.cpp:1691-1821), FastRHSHamiltonJacobi::rhs_nonlinear (:426-434), FastLagrIntp::eval_up_Lagr_coarse_grid and
+    HyperbolicLagrRHS::rhs_{vol,flx_intp}_scalar_coarse_grid (:1143-1219, 1367-1370) through amdg_apply_tensor_coarse, DGAdapt::indicator_norm"""
+    from test_oracle import f4_terms
+    d = load_golden(name)
+    c = DevCase(d, schedule=schedule)
+    A = c.amdg
+    fuc = d["f4.fucoe_intp"]
+    reg = {}
+    def op_of(table):
+        if id(table) not in reg:
+            reg[id(table)] = c.ctx.op_register(table, c.b, c.a)
+        return reg[id(table)]
+    kind = {"vol": A.REL_VOL, "flx": A.REL_FLX}
+    for key, terms in f4_terms(d, c.dim).items():
+        rhs = c.zeros(c.a)
+        for comp, mats, kinds, coef in terms:
+            c.ctx.apply_tensor([op_of(m) for m in mats], [kind[k] for k in kinds], c.to_dev(fuc[:, 0, comp, :]), rhs, coef=coef, accumulate=True)
+        assert rel(c.to_host(rhs), d[key][:, 0, :]) < TOL, key
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    for cut in (1, 2):
+        tag = "f4.cg%d" % cut
+        M = int(d[tag + ".mesh_nmax"][0])
+        up = torch.full((c.ne, c.b ** c.dim), 7.0, dtype=torch.float64, device="cuda")     # overwritten, rows above the cut zeroed
+        c.ctx.apply_tensor_coarse([c.op_pt] * c.dim, [A.REL_VOL] * c.dim, u, up, M)
+        assert rel(c.to_host(up), d[tag + ".up_intp"][:, 0, :]) < TOL
+        rhs = c.zeros(c.a)
+        for t in range(c.dim):
+            c.ctx.apply_tensor_coarse([c.op_uvx if s == t else c.op_uv for s in range(c.dim)], [A.REL_VOL] * c.dim, c.to_dev(fuc[:, 0, t, :]), rhs, M, accumulate=True)
+        assert rel(c.to_host(rhs), d[tag + ".rhs_vol"][:, 0, :]) < TOL
+        for t in range(c.dim):
+            c.ctx.apply_tensor_coarse([c.op_uave if s == t else c.op_uv for s in range(c.dim)], [A.REL_FLX if s == t else A.REL_VOL for s in range(c.dim)],
+                                      c.to_dev(fuc[:, 0, t, :]), rhs, M, coef=0.5, accumulate=True)
+        assert rel(c.to_host(rhs), d[tag + ".rhs_vol_flx"][:, 0, :]) < TOL
+    # mesh_nmax at or above the grid's level: the plain transform
+    up_all = c.zeros(c.b); c.ctx.apply_tensor_coarse([c.op_pt] * c.dim, [A.REL_VOL] * c.dim, u, up_all, c.nmax)
+    assert rel(c.to_host(up_all), c.to_host(c.eval_up(u))) < 1e-14
+    norm = torch.zeros(c.ne, dtype=torch.float64, device="cuda")
+    c.ctx.indicator_norm([u], norm)
+    assert rel(c.to_host(norm), d["f4.indicator_norm"]) < 1e-14
+    c.close()
+
+
 def test_rk_schemes():
     """amdg_rk_stage for ForwardEuler / RK2SSP / RK2Midpoint / RK3SSP / RK3HeunLinear (source/ODESolver.cpp:209-330)"""
     import amdg_oracle as O

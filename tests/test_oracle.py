@@ -209,6 +209,54 @@ def test_rhs_variants(name):
             assert rel(out, d["var.rhs_source"][:, v, :]) < TOL
 
 
+def f4_terms(d, dim):
+    """the compositions of SURVEY 8(f4) as (dump key, [(flux component, table per dim, relation per dim, coef)], mesh_nmax):
+    DiffusionRHS (source/FastMultiplyLU.cpp:1691-1821), FastRHSHamiltonJacobi::rhs_nonlinear (:426-434)"""
+    uv, uvx = d["lagr.u_v"], d["lagr.u_vx"]
+    jx = d["lagr.ujp_vxlft"] + d["lagr.ujp_vxrgt"]
+    def per_dim(table, kind, coef, comp):
+        return [(comp(t), [table if s == t else uv for s in range(dim)], [kind if s == t else "vol" for s in range(dim)], coef) for t in range(dim)]
+    return {
+        "f4.diff_vol": per_dim(uvx, "vol", -1.0, lambda t: t),
+        "f4.diff_flx_gradu": per_dim(d["lagr.uave_vjp"], "flx", -1.0, lambda t: t),
+        "f4.diff_flx_u": per_dim(jx, "flx", -0.5, lambda t: 0),
+        "f4.diff_flx_k_minus_u": per_dim(d["lagr.ujp_vxlft"], "flx", -0.5, lambda t: 0),
+        "f4.diff_flx_k_plus_u": per_dim(d["lagr.ujp_vxrgt"], "flx", -0.5, lambda t: 0),
+        "f4.hj": [(0, [uv] * dim, ["vol"] * dim, 1.0)],
+    }
+
+
+@pytest.mark.parametrize("name", ["f4_lagr_d2_k2_n4", "f4_lagr_d3_k1_n3"])
+def test_f4_compositions(name):
+    """DiffusionRHS, FastRHSHamiltonJacobi, the *_coarse_grid transforms and DGAdapt::indicator_norm restated over the oracle's tensor application"""
+    c = Case(name)
+    d = c.d
+    pt, u_v, u_vx, uave, anc, wt = _tables(c)
+    rels = c.relations()
+    fuc = d["f4.fucoe_intp"]
+    for key, terms in f4_terms(d, c.dim).items():
+        rhs = np.zeros((c.ne, c.a ** c.dim))
+        for comp, mats, kinds, coef in terms:
+            rhs += O.apply_tensor(fuc[:, 0, comp, :], c.b, c.a, mats, kinds, rels, c.lev, c.ord1d, coef)
+        assert rel(rhs, d[key][:, 0, :]) < TOL, key
+    u = d["ucoe_alpt.in"][:, 0, :]
+    for cut in (1, 2):
+        tag = "f4.cg%d" % cut
+        M = int(d[tag + ".mesh_nmax"][0])
+        up = O.apply_tensor(u, c.a, c.b, [pt] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d, mesh_nmax=M)
+        assert rel(up, d[tag + ".up_intp"][:, 0, :]) < TOL
+        assert np.all(up[c.lev.sum(axis=1) > M] == 0) and np.any(c.lev.sum(axis=1) > M)
+        rhs = np.zeros((c.ne, c.a ** c.dim))
+        for t in range(c.dim):
+            rhs += O.apply_tensor(fuc[:, 0, t, :], c.b, c.a, [u_vx if s == t else u_v for s in range(c.dim)], ["vol"] * c.dim, rels, c.lev, c.ord1d, mesh_nmax=M)
+        assert rel(rhs, d[tag + ".rhs_vol"][:, 0, :]) < TOL
+        for t in range(c.dim):
+            rhs += O.apply_tensor(fuc[:, 0, t, :], c.b, c.a, [uave if s == t else u_v for s in range(c.dim)], ["flx" if s == t else "vol" for s in range(c.dim)],
+                                  rels, c.lev, c.ord1d, 0.5, mesh_nmax=M)
+        assert rel(rhs, d[tag + ".rhs_vol_flx"][:, 0, :]) < TOL
+    assert rel(np.linalg.norm(u, axis=1), d["f4.indicator_norm"]) < 1e-14
+
+
 def test_hierarchisation_stencil_restated():
     """set_pts_wts_1d_ada_Lag restated from point coordinates and level-0 basis values (Lagrange)"""
     c = Case("cfg4_burgers_lagr_d2_k2_n4")
