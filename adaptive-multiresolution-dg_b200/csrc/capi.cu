@@ -21,7 +21,7 @@ using namespace amdg;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string & msg) { g_err = msg; return code; }
-static thread_local int g_arena_mb_override = -1;   // sub-contexts (coarse views) take a small metadata arena
+static thread_local int g_arena_mb_override = -1;   // sub-contexts (coarse views) take a small metadata arena and no L2 access-policy window (they run on the parent's stream)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(AMDG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct Op
@@ -293,7 +293,7 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
             {
                 c->arena_cap = cap; c->arena_lo = 0; c->arena_hi = cap;
                 const char * w = std::getenv("AMDG_L2_PERSIST");
-                if (!(w && w[0] == '0') && prop.persistingL2CacheMaxSize > 0)
+                if (!(w && w[0] == '0') && prop.persistingL2CacheMaxSize > 0 && g_arena_mb_override < 0)
                 {
                     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)(32u << 20)));
                     c->l2_window = true; apply_l2_window(c.get());
@@ -408,7 +408,8 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
         {
             if (c->meta_stage) cudaFreeHost(c->meta_stage);
             c->meta_stage = nullptr; c->meta_stage_cap = 0;
-            const size_t cap = total + total / 2;
+            // pinned allocations cost milliseconds: grow geometrically from 1 MiB so that an adaptive run reallocates a handful of times at most
+            size_t cap = (size_t)1 << 20; while (cap < total) cap <<= 1;
             if (cudaMallocHost((void **)&c->meta_stage, cap) != cudaSuccess) { cudaGetLastError(); c->ddims.clear(); c->d_ord1d = nullptr; return false; }
             c->meta_stage_cap = cap;
         }
