@@ -20,6 +20,9 @@ if not os.path.exists(LIB_PATH):
 lib = ctypes.CDLL(LIB_PATH)
 
 REL_VOL, REL_FLX = 0, 1
+BASIS_ALPERT, BASIS_LAGRANGE, BASIS_HERMITE = 0, 1, 2
+TABLES = {"u_v": 0, "u_vx": 1, "ulft_vjp": 2, "urgt_vjp": 3, "ujp_vjp": 4, "uave_vjp": 5, "ujp_vxlft": 6, "ujp_vxrgt": 7, "ux_vx": 8, "uxave_vjp": 9,
+          "ujp_vxave": 10, "ux_v": 11}
 LU_L, LU_U, LU_FULL = 0, 1, 2
 SCHED_LITERAL, SCHED_SHARED = 0, 1
 PW = dict(VAR=1, X=2, OTHER=3, CONST=4, ADD=5, SUB=6, MUL=7, DIV=8, NEG=9, SIN=10, COS=11, SQR=12, EXP=13, SQRT=14, ABS=15, POW=16, TANH=17, MIN=18, MAX=19)
@@ -60,6 +63,11 @@ SYMBOLS = {
     "amdg_op_combine": (_i, [_p, _i, _d, _i, _d, _ip]),
     "amdg_sweep1d": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _i, _d, _i]),
     "amdg_sweep1d_batch": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _dp, _ip, _i, _i]),
+    "amdg_ctx_info": (_i, [_p, _p]),
+    "amdg_op_generate": (_i, [_p, _i, _i, _i, _i, _p]),
+    "amdg_op_generate_points": (_i, [_p, _i, _i, _i, _i, _p]),
+    "amdg_op_generate_hier": (_i, [_p, _i, _i, _i, _p]),
+    "amdg_points_generate": (_i, [_p, _i, _i, _i, _p]),
     "amdg_apply_tensor": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i]),
     "amdg_apply_tensor_coarse": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i, _i]),
     "amdg_hierarchize": (_i, [_p, _i, _p, _p, _i]),
@@ -222,6 +230,27 @@ class Context:
         out = _i()
         _check(lib.amdg_op_register_hier(self._h, ap, wp, w.shape[-1], ctypes.byref(out)))
         return out.value
+
+    # ---- tables generated by the library (no reference run): compact blocks per related 1D pair
+    def op_generate(self, basis_u, pmax_u, table, msh_case=1):
+        out = _i()
+        _check(lib.amdg_op_generate(self._h, basis_u, pmax_u, msh_case, TABLES[table] if isinstance(table, str) else table, ctypes.byref(out)))
+        return out.value
+
+    def op_generate_points(self, basis, pmax, msh_case=1, derivative=0):
+        out = _i()
+        _check(lib.amdg_op_generate_points(self._h, basis, pmax, msh_case, derivative, ctypes.byref(out)))
+        return out.value
+
+    def op_generate_hier(self, basis, pmax, msh_case=1):
+        out = _i()
+        _check(lib.amdg_op_generate_hier(self._h, basis, pmax, msh_case, ctypes.byref(out)))
+        return out.value
+
+    def points_generate(self, basis, pmax, msh_case=1):
+        pts = np.zeros((1 << self.nmax) * (pmax + 1), dtype=np.float64)
+        _check(lib.amdg_points_generate(self._h, basis, pmax, msh_case, pts.ctypes.data_as(ctypes.c_void_p)))
+        return pts
 
     def pairs(self):
         n = _check(lib.amdg_pairs(self._h, None, None, None))
@@ -411,3 +440,23 @@ class Context:
             out = np.empty_like(s)
         _check(lib.amdg_host_roundtrip(self._h, op_fwd, hier_op, op_inv, sp, out.ctypes.data_as(_dp), n_comp))
         return out
+
+
+def generate_tables(nmax, k, m, msh_case=1):
+    """Every 1D table the path uses for Alpert degree k and Lagrange interpolation degree m, generated by the library in compact form
+    (blocks per related 1D pair, amdg_pairs order) -- the replacement of a run of the reference's OperatorMatrix1D / LagrInterpolation
+    constructors.  Keys as in the reference: "alpt.<table>", "lagr.<table>", "pt" / "pt_d1" (transposed Lag_pt_Alpt_1D / _d1), "hier"
+    (I + W of the hierarchisation stencils), "lagr.intep_pt"."""
+    ctx = Context(1, nmax, k, m, device=-1)
+    a, b = k + 1, m + 1
+    out = {}
+    for t in ("u_v", "u_vx", "ulft_vjp", "urgt_vjp", "ujp_vjp", "ux_vx", "uxave_vjp", "ujp_vxave"):
+        out["alpt." + t] = ctx.op_blocks(ctx.op_generate(BASIS_ALPERT, k, t), a, a)
+    for t in ("u_v", "u_vx", "ulft_vjp", "urgt_vjp", "uave_vjp", "ujp_vxlft", "ujp_vxrgt"):
+        out["lagr." + t] = ctx.op_blocks(ctx.op_generate(BASIS_LAGRANGE, m, t, msh_case), b, a)
+    out["pt"] = ctx.op_blocks(ctx.op_generate_points(BASIS_LAGRANGE, m, msh_case, 0), a, b)
+    out["pt_d1"] = ctx.op_blocks(ctx.op_generate_points(BASIS_LAGRANGE, m, msh_case, 1), a, b)
+    out["hier"] = ctx.op_blocks(ctx.op_generate_hier(BASIS_LAGRANGE, m, msh_case), b, b)
+    out["lagr.intep_pt"] = ctx.points_generate(BASIS_LAGRANGE, m, msh_case)
+    ctx.close()
+    return out

@@ -590,6 +590,15 @@ int amdg_op_combine(amdg_ctx * c, int a, double alpha, int b, double beta, int *
     return push_op(c, std::move(op), out);
 }
 
+int amdg_internal_fail(int code, const char * msg) { return fail(code, msg ? msg : ""); }     // for the library's other translation units (tables.cu)
+
+int amdg_ctx_info(amdg_ctx * c, int * out)
+{
+    if (!c || !out) return fail(AMDG_EINVAL, "null argument");
+    out[0] = c->dim; out[1] = c->nmax; out[2] = c->edge_alpt - 1; out[3] = c->edge_intp - 1; out[4] = c->device;
+    return AMDG_OK;
+}
+
 // ---- sweeps ------------------------------------------------------------------------------------------------------
 static int check_op(amdg_ctx * c, int op) { return (op >= 0 && op < (int)c->ops.size()) ? AMDG_OK : fail(AMDG_EINVAL, "bad operator handle"); }
 

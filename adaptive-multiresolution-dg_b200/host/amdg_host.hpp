@@ -121,6 +121,21 @@ struct OperatorMatrix1D
         // uave_vjp = (urgt_vjp + ulft_vjp) / 2 (include/OperatorMatrix1D.h:199)
         check(amdg_op_combine(dg.ctx, ulft_vjp, 0.5, urgt_vjp, 0.5, &uave_vjp));
     }
+    // the same tables without any table of the reference: the library generates them in compact form (amdg_op_generate, csrc/tables.hpp).
+    // basis = AMDG_BASIS_ALPERT / _LAGRANGE / _HERMITE of degree pmax (U, the row basis); V is the Alpert basis of the context.
+    OperatorMatrix1D(DGSolution & dg, int basis, int pmax, int msh_case = 1) : edge_from(pmax + 1), edge_to(dg.PMAX_alpt + 1)
+    {
+        check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_U_V, &u_v));
+        check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_U_VX, &u_vx));
+        check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_ULFT_VJP, &ulft_vjp));
+        check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_URGT_VJP, &urgt_vjp));
+        check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_UJP_VJP, &ujp_vjp));
+        check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_UJP_VXLFT, &ujp_vxlft));
+        check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_UJP_VXRGT, &ujp_vxrgt));
+        check(amdg_op_combine(dg.ctx, ulft_vjp, 1.0, urgt_vjp, 1.0, &uave2_vjp));
+        check(amdg_op_combine(dg.ctx, ulft_vjp, 0.5, urgt_vjp, 0.5, &uave_vjp));
+        check(amdg_op_combine(dg.ctx, ujp_vxlft, 1.0, ujp_vxrgt, 1.0, &ujp_vxave2));
+    }
     // the [u] * v_x^-, [u] * v_x^+ tables of DiffusionRHS (include/OperatorMatrix1D.h:209-214)
     void set_ujp_vx(DGSolution & dg, const double * t_ujp_vxlft, const double * t_ujp_vxrgt)
     {
@@ -139,6 +154,13 @@ class FastLagrIntp
 public:
     FastLagrIntp(DGSolution & dg, const std::vector<std::vector<double>> & Lag_pt_Alpt_1D, const std::vector<std::vector<double>> & Lag_pt_Alpt_1D_d1)
         : dg_(&dg) { op_pt_ = reg(Lag_pt_Alpt_1D); if (!Lag_pt_Alpt_1D_d1.empty()) op_d1_ = reg(Lag_pt_Alpt_1D_d1); }
+    // point tables generated by the library (amdg_op_generate_points); also installs the point coordinates (amdg_points_generate)
+    FastLagrIntp(DGSolution & dg, int basis, int msh_case = 1) : dg_(&dg)
+    {
+        check(amdg_op_generate_points(dg.ctx, basis, dg.PMAX_intp, msh_case, 0, &op_pt_));
+        if (basis == AMDG_BASIS_LAGRANGE) check(amdg_op_generate_points(dg.ctx, basis, dg.PMAX_intp, msh_case, 1, &op_d1_));
+        check(amdg_points_generate(dg.ctx, basis, dg.PMAX_intp, msh_case, nullptr));
+    }
     void eval_up_Lagr() { for (int v = 0; v < dg_->VEC_NUM; ++v) eval_up_Lagr(v); }
     // FastLagrIntp::eval_up_Lagr_coarse_grid (source/FastMultiplyLU.cpp:1367-1370): elements above the cut are skipped and left at zero
     void eval_up_Lagr_coarse_grid(int mesh_nmax)
@@ -171,6 +193,7 @@ class FastHermIntp : public FastLagrIntp
 {
 public:
     FastHermIntp(DGSolution & dg, const std::vector<std::vector<double>> & Her_pt_Alpt_1D) : FastLagrIntp(dg, Her_pt_Alpt_1D, {}) {}
+    explicit FastHermIntp(DGSolution & dg) : FastLagrIntp(dg, AMDG_BASIS_HERMITE) {}     // Her_pt_Alpt_1D generated by the library
     void eval_up_Herm() { eval_up_Lagr(); }
 };
 
@@ -198,6 +221,9 @@ public:
     // pw_anc / pw_wt: the pwts stencils of every 1D element (include/Interpolation.h:5-11) in amdg_op_register_hier layout
     LagrInterpolation(DGSolution & dg, const int * pw_anc, const double * pw_wt) : dg_(&dg)
     { check(amdg_op_register_hier(dg.ctx, pw_anc, pw_wt, dg.PMAX_intp + 1, &op_hier_)); }
+    // stencils generated by the library (amdg_op_generate_hier)
+    explicit LagrInterpolation(DGSolution & dg, int msh_case = 1) : dg_(&dg)
+    { check(amdg_op_generate_hier(dg.ctx, AMDG_BASIS_LAGRANGE, dg.PMAX_intp, msh_case, &op_hier_)); }
     // nonlinear_Lagr_fast: fastLagr.eval_up_Lagr(); eval_fp_Lag(func, is_intp); eval_fp_to_coe_D_Lag(is_intp)
     void nonlinear_Lagr_fast(const std::vector<int> & flux_id, const std::vector<double> & params, const std::vector<std::vector<bool>> & is_intp, FastLagrIntp & fastLagr)
     {
@@ -225,6 +251,8 @@ class HermInterpolation
 public:
     HermInterpolation(DGSolution & dg, const int * pw_anc, const double * pw_wt) : dg_(&dg)
     { check(amdg_op_register_hier(dg.ctx, pw_anc, pw_wt, dg.PMAX_intp + 1, &op_hier_)); }
+    explicit HermInterpolation(DGSolution & dg) : dg_(&dg)
+    { check(amdg_op_generate_hier(dg.ctx, AMDG_BASIS_HERMITE, dg.PMAX_intp, 1, &op_hier_)); }
     void nonlinear_Herm_2D_fast(const std::vector<int> & flux_id, const std::vector<std::vector<bool>> & is_intp, FastLagrIntp & fastHerm, const std::vector<double> & params = {})
     {
         fastHerm.eval_up_Lagr();

@@ -41,7 +41,10 @@ static double rel_l2(const std::vector<double> & x, const double * y)
 
 int main(int argc, char ** argv)
 {
-    if (argc < 2) { std::cerr << "usage: burgers_stage <dump>" << std::endl; return 2; }
+    if (argc < 2) { std::cerr << "usage: burgers_stage <dump> [--generated]" << std::endl; return 2; }
+    // --generated: every 1D table comes from the library's own generator (amdg_op_generate*); the dump then only supplies the grid, the
+    // initial coefficients and the reference's stage results
+    const bool generated = argc > 2 && std::string(argv[2]) == "--generated";
     auto D = load_dump(argv[1]);
     const int * cfg = D["config"].i();
     const int DIM = cfg[0], NMAX = cfg[1], PA = cfg[4], PL = cfg[5];
@@ -50,10 +53,13 @@ int main(int argc, char ** argv)
     {
         amdg::DGSolution dg_solu(DIM, NMAX, PA, PL, 1, 0);
         dg_solu.set_elements(ne, D["level"].i(), D["suppt"].i());
-        amdg::OperatorMatrix1D oper_matx_lagr(dg_solu, PL + 1, PA + 1, D["lagr.u_v"].d(), D["lagr.u_vx"].d(), D["lagr.ulft_vjp"].d(), D["lagr.urgt_vjp"].d());
-        amdg::OperatorMatrix1D oper_matx_alpt(dg_solu, PA + 1, PA + 1, D["alpt.u_v"].d(), D["alpt.u_vx"].d(), D["alpt.ulft_vjp"].d(), D["alpt.urgt_vjp"].d(), D["alpt.ujp_vjp"].d());
-        amdg::LagrInterpolation interp_lagr(dg_solu, D["lagr.pw_anc"].i(), D["lagr.pw_wt"].d());
-        amdg::FastLagrIntp fast_lagr_intp(dg_solu, rows_of(D["Lag_pt_Alpt_1D"]), rows_of(D["Lag_pt_Alpt_1D_d1"]));
+        amdg::OperatorMatrix1D oper_matx_lagr = generated ? amdg::OperatorMatrix1D(dg_solu, AMDG_BASIS_LAGRANGE, PL)
+            : amdg::OperatorMatrix1D(dg_solu, PL + 1, PA + 1, D["lagr.u_v"].d(), D["lagr.u_vx"].d(), D["lagr.ulft_vjp"].d(), D["lagr.urgt_vjp"].d());
+        amdg::OperatorMatrix1D oper_matx_alpt = generated ? amdg::OperatorMatrix1D(dg_solu, AMDG_BASIS_ALPERT, PA)
+            : amdg::OperatorMatrix1D(dg_solu, PA + 1, PA + 1, D["alpt.u_v"].d(), D["alpt.u_vx"].d(), D["alpt.ulft_vjp"].d(), D["alpt.urgt_vjp"].d(), D["alpt.ujp_vjp"].d());
+        amdg::LagrInterpolation interp_lagr = generated ? amdg::LagrInterpolation(dg_solu) : amdg::LagrInterpolation(dg_solu, D["lagr.pw_anc"].i(), D["lagr.pw_wt"].d());
+        amdg::FastLagrIntp fast_lagr_intp = generated ? amdg::FastLagrIntp(dg_solu, AMDG_BASIS_LAGRANGE)
+            : amdg::FastLagrIntp(dg_solu, rows_of(D["Lag_pt_Alpt_1D"]), rows_of(D["Lag_pt_Alpt_1D_d1"]));
         amdg::HyperbolicLagrRHS fast_rhs_lagr(dg_solu, oper_matx_lagr);
         amdg::HyperbolicAlptRHS fast_rhs_alpt(dg_solu, oper_matx_alpt);
         dg_solu.ucoe_alpt.upload(D["ucoe_alpt.in"].d());

@@ -83,6 +83,7 @@ int main(int argc, char ** argv)
 {
     int NMAX = 6, N_init = 2, n_steps = 10, timing = 0;
     bool is_static = false;
+    bool gen_tables = false;         // -gen 1: the device arm takes no table from the reference objects, the library generates them (amdg_op_generate*)
     double refine_eps = 1e-2, final_time = -1.;
     for (int i = 1; i + 1 < argc; i += 2)
     {
@@ -90,6 +91,7 @@ int main(int argc, char ** argv)
         if (k == "-NM") NMAX = std::atoi(argv[i + 1]); else if (k == "-N0") N_init = std::atoi(argv[i + 1]);
         else if (k == "-steps") n_steps = std::atoi(argv[i + 1]); else if (k == "-r") refine_eps = std::atof(argv[i + 1]);
         else if (k == "-timing") timing = std::atoi(argv[i + 1]);
+        else if (k == "-gen") gen_tables = std::atoi(argv[i + 1]) != 0;
         else if (k == "-static") is_static = std::atoi(argv[i + 1]) != 0;      // no predictor / refine / coarsen: the sparse grid of level N0 for the whole run (convergence study)
         else if (k == "-tf") final_time = std::atof(argv[i + 1]);              // run to this time (the last step is shortened), overrides -steps
     }
@@ -142,12 +144,15 @@ int main(int argc, char ** argv)
     {
         amdg::DGSolution dev(DIM, NMAX, AlptBasis::PMAX, HermBasis::PMAX, 1, 0);
         export_elements(dg_dev, dev);
-        amdg::OperatorMatrix1D d_oper_herm(dev, HermBasis::PMAX + 1, AlptBasis::PMAX + 1, dense(oper_matx_herm.u_v).data(), dense(oper_matx_herm.u_vx).data(),
-                                           dense(oper_matx_herm.ulft_vjp).data(), dense(oper_matx_herm.urgt_vjp).data());
-        amdg::OperatorMatrix1D d_oper_alpt(dev, AlptBasis::PMAX + 1, AlptBasis::PMAX + 1, dense(oper_matx_alpt.u_v).data(), dense(oper_matx_alpt.u_vx).data(),
-                                           dense(oper_matx_alpt.ulft_vjp).data(), dense(oper_matx_alpt.urgt_vjp).data(), dense(oper_matx_alpt.ujp_vjp).data());
-        // glue (c): pwts stencils of every 1D element with level > 0 (include/Interpolation.h:5-11)
+        amdg::OperatorMatrix1D d_oper_herm = gen_tables ? amdg::OperatorMatrix1D(dev, AMDG_BASIS_HERMITE, HermBasis::PMAX)
+            : amdg::OperatorMatrix1D(dev, HermBasis::PMAX + 1, AlptBasis::PMAX + 1, dense(oper_matx_herm.u_v).data(), dense(oper_matx_herm.u_vx).data(),
+                                     dense(oper_matx_herm.ulft_vjp).data(), dense(oper_matx_herm.urgt_vjp).data());
+        amdg::OperatorMatrix1D d_oper_alpt = gen_tables ? amdg::OperatorMatrix1D(dev, AMDG_BASIS_ALPERT, AlptBasis::PMAX)
+            : amdg::OperatorMatrix1D(dev, AlptBasis::PMAX + 1, AlptBasis::PMAX + 1, dense(oper_matx_alpt.u_v).data(), dense(oper_matx_alpt.u_vx).data(),
+                                     dense(oper_matx_alpt.ulft_vjp).data(), dense(oper_matx_alpt.urgt_vjp).data(), dense(oper_matx_alpt.ujp_vjp).data());
+        // glue (c): pwts stencils of every 1D element with level > 0 (include/Interpolation.h:5-11); not needed with -gen 1
         std::vector<int> anc; std::vector<double> wt;
+        if (!gen_tables)
         {
             HermInterpolation tmp(dg_dev);
             for (int n = 1; n <= NMAX; ++n)
@@ -159,9 +164,9 @@ int main(int argc, char ** argv)
                     for (size_t p0 = 0; p0 < p.wt.size(); ++p0) for (size_t ic = 0; ic < p.wt[p0].size(); ++ic) wt.push_back(p.wt[p0][ic]);
                 }
         }
-        amdg::HermInterpolation d_interp_herm(dev, anc.data(), wt.data());
+        amdg::HermInterpolation d_interp_herm = gen_tables ? amdg::HermInterpolation(dev) : amdg::HermInterpolation(dev, anc.data(), wt.data());
         std::vector<std::vector<double>> her_pt(interp_herm.Her_pt_Alpt_1D);
-        amdg::FastHermIntp d_fast_herm_intp(dev, her_pt);
+        amdg::FastHermIntp d_fast_herm_intp = gen_tables ? amdg::FastHermIntp(dev) : amdg::FastHermIntp(dev, her_pt);
         amdg::HyperbolicSameFluxHermRHS d_fast_rhs_herm(dev, d_oper_herm);
         amdg::HyperbolicAlptRHS d_fast_rhs_alpt(dev, d_oper_alpt);
         upload_ucoe(dg_dev, dev);

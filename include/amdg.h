@@ -56,6 +56,7 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
 int amdg_ctx_destroy(amdg_ctx *ctx);
 int amdg_ctx_set_stream(amdg_ctx *ctx, void *cuda_stream);   /* cudaStream_t; default: a stream owned by ctx */
 int amdg_ctx_sync(amdg_ctx *ctx);
+int amdg_ctx_info(amdg_ctx *ctx, int *out5);                 /* out5 = dim, nmax, pmax_alpt, pmax_intp, device */
 int amdg_ctx_set_schedule(amdg_ctx *ctx, int sched);
 int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto: per launch the column kernel (one thread per column, FP64 FMA) for blocks of >= 64 doubles with KF*KT <= 9 and >= 32 columns, the lean tensor-core kernel otherwise, the whole-fibre tensor-core kernel for tiny sweeps;
                                                                  1 = gather, 2 = fibre-staged list kernel, 3 = pipelined list kernel, 4 = whole-fibre tensor-core (FP64 MMA) kernel, 5 = lean tensor-core kernel, 8 = column kernel
@@ -102,6 +103,24 @@ int amdg_op_blocks(amdg_ctx *ctx, int op, double *host_blocks);
 int amdg_op_register_hier(amdg_ctx *ctx, const int *anc, const double *wt, int p1, int *op_out);
 /* op = alpha*op_a + beta*op_b (e.g. ulft_vjp + urgt_vjp, source/FastMultiplyLU.cpp:1165) */
 int amdg_op_combine(amdg_ctx *ctx, int op_a, double alpha, int op_b, double beta, int *op_out);
+
+/* ---- the same tables generated by the library itself, straight into the compact form (no dense table, no reference run): one block per related 1D
+ * element pair, O(2^nmax * nmax) blocks instead of the O(4^nmax) basis pairs the reference's constructors evaluate.
+ * amdg_op_generate: table `table` of OperatorMatrix1D<U, AlptBasis>(.., "period") (include/OperatorMatrix1D.h:124-264 over Basis::product_volume /
+ *   product_edge_dis_v / product_edge_dis_u, source/Basis.cpp:62-235); U = basis_u of degree pmax_u (mesh case msh_case_u of LagrBasis::set_interp_msh01,
+ *   source/LagrBasis.cpp:33-154; ignored for Alpert / Hermite), V = Alpert of the context's degree.  The UX_* / *_VXAVE / UX_V tables exist for U = Alpert only.
+ * amdg_op_generate_points: the transposed point table of FastLagrIntp / FastHermIntp (source/FastMultiplyLU.cpp:1316-1360): Alpert coefficients -> values
+ *   (derivative 0: Lag_pt_Alpt_1D / Her_pt_Alpt_1D, source/Interplation.cpp:16-99, 1886-1965) or first derivatives (1: Lag_pt_Alpt_1D_d1) at the points.
+ * amdg_op_generate_hier: the stencils of set_pts_wts_1d_ada_Lag / _Her (source/Interplation.cpp:775-887, 3166-3315) as the operator I + W.
+ * amdg_points_generate: the 1D point coordinate table (LagrBasis::intep_pt / HermBasis::intep_pt); copied to host_pts1d[2^nmax * (pmax+1)] if not NULL and
+ *   installed like amdg_points_set on a device context whose pmax_intp equals pmax. ---- */
+enum { AMDG_BASIS_ALPERT = 0, AMDG_BASIS_LAGRANGE = 1, AMDG_BASIS_HERMITE = 2 };
+enum { AMDG_TAB_U_V = 0, AMDG_TAB_U_VX = 1, AMDG_TAB_ULFT_VJP = 2, AMDG_TAB_URGT_VJP = 3, AMDG_TAB_UJP_VJP = 4, AMDG_TAB_UAVE_VJP = 5, AMDG_TAB_UJP_VXLFT = 6,
+       AMDG_TAB_UJP_VXRGT = 7, AMDG_TAB_UX_VX = 8, AMDG_TAB_UXAVE_VJP = 9, AMDG_TAB_UJP_VXAVE = 10, AMDG_TAB_UX_V = 11 };
+int amdg_op_generate(amdg_ctx *ctx, int basis_u, int pmax_u, int msh_case_u, int table, int *op_out);
+int amdg_op_generate_points(amdg_ctx *ctx, int basis, int pmax, int msh_case, int derivative, int *op_out);
+int amdg_op_generate_hier(amdg_ctx *ctx, int basis, int pmax, int msh_case, int *op_out);
+int amdg_points_generate(amdg_ctx *ctx, int basis, int pmax, int msh_case, double *host_pts1d);
 
 /* ---- K1: one 1D sweep, FastMultiplyLU::transform_1D (source/FastMultiplyLU.cpp:436-512).
  * sizes_from[dim] = block edges of src; dst has the same edges except edge_to(op) in dim t.

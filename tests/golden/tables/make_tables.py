@@ -1,12 +1,11 @@
-"""Build the 1D operator-table bundles the benchmarks and examples feed to the path.
+"""TEST FIXTURE generator: the reference's 1D tables at the benchmark sizes, for tests/test_tables.py.
 
-The dense OperatorMatrix1D / Lag_pt_Alpt_1D tables are INPUTS of the hot path (the drop-in receives them from
-the reference's own host code); re-deriving them is outside the path.  For stand-alone
-runs (bench.py on a box without the reference) they are produced once, here, by the compiled reference
-(oracle/_ref/ref_harness --dump-tables) and stored in the compact per-pair block form of include/amdg.h
-(amdg_pairs order).  Run in the build container:
+The dense OperatorMatrix1D / Lag_pt_Alpt_1D tables are produced by the compiled reference (oracle/_ref/ref_harness --dump-tables) and
+stored in the compact per-pair block form of include/amdg.h (amdg_pairs order).  Rounds 1-2 shipped these bundles as inputs of bench.py;
+the library now generates the tables itself (csrc/tables.hpp, amdg_op_generate*) and the bundles only pin that generator.  Run in the
+build container:
 
-    python adaptive-multiresolution-dg_b200/data/make_tables.py K M N [msh_case]
+    python tests/golden/tables/make_tables.py K M N [msh_case]
 """
 import importlib
 import os
@@ -16,7 +15,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -11,7 +11,7 @@ def rel(a, b):
 
 
 class DevCase:
-    def __init__(self, d, schedule=None, kernel=None, perm=None):
+    def __init__(self, d, schedule=None, kernel=None, perm=None, generated=False, msh_case=1):
         amdg = self.amdg = importlib.import_module("adaptive-multiresolution-dg_b200")
         self.d = d
         (self.dim, self.nmax, self.n0, self.sparse, self.pa, self.pl, self.ph, self.vecnum, self.herm, self.ne) = [int(x) for x in d["config"]]
@@ -27,6 +27,18 @@ class DevCase:
         self.ctx.grid_set(d["level"][self.perm], d["suppt"][self.perm])
         pre = "herm" if self.herm else "lagr"
         c = self.ctx
+        if generated:
+            # every table from the library's own generator (amdg_op_generate*): nothing but the grid and the coefficients comes from the dump
+            basis, P = (amdg.BASIS_HERMITE, self.ph) if self.herm else (amdg.BASIS_LAGRANGE, self.pl)
+            self.op_pt = c.op_generate_points(basis, P, msh_case)
+            self.op_uv, self.op_uvx = c.op_generate(basis, P, "u_v", msh_case), c.op_generate(basis, P, "u_vx", msh_case)
+            self.op_ul, self.op_ur = c.op_generate(basis, P, "ulft_vjp", msh_case), c.op_generate(basis, P, "urgt_vjp", msh_case)
+            self.op_uave = c.op_combine(self.op_ul, 1.0, self.op_ur, 1.0)
+            self.op_hier = c.op_generate_hier(basis, P, msh_case)
+            self.alpt = {k: c.op_generate(amdg.BASIS_ALPERT, self.pa, k) for k in ("u_v", "u_vx", "ulft_vjp", "urgt_vjp", "ujp_vjp", "ux_vx", "uxave_vjp", "ujp_vxave")}
+            if not self.herm:
+                self.op_pt_d1 = c.op_generate_points(basis, P, msh_case, 1)
+            return
         pt = (d["Her_pt_Alpt_1D"] if self.herm else d["Lag_pt_Alpt_1D"]).T.copy()     # FastLagrIntp ctor transpose
         self.op_pt = c.op_register(pt, self.a, self.b)
         self.op_uv = c.op_register(d[pre + ".u_v"], self.b, self.a)

@@ -208,6 +208,9 @@ def test_cpp_host_mirror_example(tmp_path):
         dump.write_bytes(f.read())
     r = subprocess.run([exe, str(dump)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+    # the same three stages with every table generated by the library (no table of the reference is read)
+    r = subprocess.run([exe, str(dump), "--generated"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout
 
 
 def test_multi_gpu_fibre_partition():
@@ -377,6 +380,33 @@ def test_f4_compositions(name, schedule):
     c.close()
 
 
+@pytest.mark.parametrize("name", ["cfg4_burgers_lagr_d2_k2_n4", "cfg4_burgers_herm_d2_k2_n4", "cfg5_vlasov_d6_k1_n2", "cfg2_rt_d4_k3_n3", "vlasov_d4_k3_m4_n2"])
+def test_phases_with_generated_tables(name):
+    """the path with the library's OWN tables (amdg_op_generate / _points / _hier; no table of the reference is read): round trip and the
+    right-hand side phases still meet the reference's dumps"""
+    d = load_golden(name)
+    c = DevCase(d, generated=True, msh_case=2 if name == "vlasov_d4_k3_m4_n2" else 1)
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    if "rt.up_intp" in d:
+        up = c.eval_up(u)
+        assert rel(c.to_host(up), d["rt.up_intp"][:, 0, :]) < TOL
+        ci = c.hier(up)
+        assert rel(c.to_host(ci), d["rt.ucoe_intp"][:, 0, :]) < TOL
+        assert rel(c.to_host(c.to_alpt(ci)), d["rt.ucoe_alpt"][:, 0, :]) < TOL
+    if "fucoe_intp" in d:
+        assert rel(c.to_host(c.eval_up(u)), d["up_intp"][:, 0, :]) < TOL
+        nf = d["fp_intp"].shape[2]
+        for t in range(nf):
+            assert rel(c.to_host(c.hier(c.to_dev(d["fp_intp"][:, 0, t, :]))), d["fucoe_intp"][:, 0, t, :]) < TOL
+        if nf == c.dim:
+            rhs = c.zeros(c.a)
+            vol = c.rhs_vol_flx([c.to_dev(d["fucoe_intp"][:, 0, t, :]) for t in range(c.dim)], rhs)
+            assert rel(c.to_host(vol), d["rhs_vol"][:, 0, :]) < TOL and rel(c.to_host(rhs), d["rhs_vol_flx"][:, 0, :]) < TOL
+            c.penalty(u, rhs, 1.2)
+            assert rel(c.to_host(rhs), d["rhs_all"][:, 0, :]) < TOL
+    c.close()
+
+
 def test_rk_schemes():
     """amdg_rk_stage for ForwardEuler / RK2SSP / RK2Midpoint / RK3SSP / RK3HeunLinear (source/ODESolver.cpp:209-330)"""
     import amdg_oracle as O
@@ -459,7 +489,7 @@ def _full_size_context(A, kernel):
     ctx.set_kernel(kernel)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.grid_set(lev, sup)
-    tb = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "adaptive-multiresolution-dg_b200", "data", "tables_k3_m3_n8.npz"))
+    tb = A.generate_tables(8, 3, 3)
     return ctx, lev, tb
 
 

@@ -169,6 +169,10 @@ def test_live_reference_dropin_burgers_adapt():
         pytest.skip("examples/live_burgers_adapt is built only where the reference sources exist (__graft_entry__.build())")
     r = subprocess.run([exe, "-NM", "6", "-N0", "2", "-steps", "10"], capture_output=True, text=True, timeout=900)
     assert "LIVE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    # -gen 1: the device arm takes no table from the reference objects (library-generated Hermite / Alpert tables, point table, stencils): the
+    # adaptive run must still make the same refine / coarsen decisions and stay within the full-run bound
+    r = subprocess.run([exe, "-NM", "6", "-N0", "2", "-steps", "10", "-gen", "1"], capture_output=True, text=True, timeout=900)
+    assert "LIVE OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_live_reference_full_runs_static_burgers():

@@ -1,0 +1,95 @@
+"""The library's own 1D tables (csrc/tables.hpp through amdg_op_generate / _points / _hier / amdg_points_generate) against the
+reference's: every OperatorMatrix1D table, the point tables Lag_pt_Alpt_1D / _d1 / Her_pt_Alpt_1D, the interpolation point coordinates
+(bit exact) and the hierarchisation stencils dumped by the compiled reference (tests/golden/*.dump.xz and the benchmark-size bundles
+tests/golden/tables/*.npz).  Host only: no GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden
+
+TOL = 1e-12          # relative to the largest entry of the table; observed <= 2e-13 (quintic Hermite), typically 1e-15
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _msh_case(name):
+    return 2 if name == "vlasov_d4_k3_m4_n2" else 1     # tests/golden/make_golden.py: --msh-lagr 2
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "alpt.u_v" in load_golden(n)])
+def test_generated_tables_match_reference_dump(amdg, name):
+    d = load_golden(name)
+    dim, nmax, n0, sparse, pa, pl, ph, vecnum, herm, ne = [int(x) for x in d["config"]]
+    a, msh = pa + 1, _msh_case(name)
+    ctx = amdg.Context(1, nmax, pa, pl, device=-1)
+    fam = {"alpt": (amdg.BASIS_ALPERT, pa, 1), "lagr": (amdg.BASIS_LAGRANGE, pl, msh), "herm": (amdg.BASIS_HERMITE, ph, 1)}
+    checked = 0
+    for key in d:
+        pre, _, tab = key.partition(".")
+        if pre in fam and tab in amdg.TABLES:
+            basis, p, m = fam[pre]
+            if pre == "herm" and p not in (3, 5):
+                continue
+            gen = ctx.op_blocks(ctx.op_generate(basis, p, tab, m), p + 1, a)
+            ref = ctx.op_blocks(ctx.op_register(d[key], p + 1, a), p + 1, a)
+            assert _rel(gen, ref) < TOL, key
+            checked += 1
+    assert checked >= 12
+    for der, key in ((0, "Lag_pt_Alpt_1D"), (1, "Lag_pt_Alpt_1D_d1")):
+        gen = ctx.op_blocks(ctx.op_generate_points(amdg.BASIS_LAGRANGE, pl, msh, der), a, pl + 1)
+        ref = ctx.op_blocks(ctx.op_register(d[key].T.copy(), a, pl + 1), a, pl + 1)
+        assert _rel(gen, ref) < TOL, key
+    assert np.array_equal(ctx.points_generate(amdg.BASIS_LAGRANGE, pl, msh), d["lagr.intep_pt"])            # same floating-point expressions
+    gen = ctx.op_blocks(ctx.op_generate_hier(amdg.BASIS_LAGRANGE, pl, msh), pl + 1, pl + 1)
+    ref = ctx.op_blocks(ctx.op_register_hier(d["lagr.pw_anc"], d["lagr.pw_wt"]), pl + 1, pl + 1)
+    assert _rel(gen, ref) < TOL
+    if ph in (3, 5):
+        gen = ctx.op_blocks(ctx.op_generate_points(amdg.BASIS_HERMITE, ph), a, ph + 1)
+        ref = ctx.op_blocks(ctx.op_register(d["Her_pt_Alpt_1D"].T.copy(), a, ph + 1), a, ph + 1)
+        assert _rel(gen, ref) < TOL
+        assert np.array_equal(ctx.points_generate(amdg.BASIS_HERMITE, ph), d["herm.intep_pt"])
+        gen = ctx.op_blocks(ctx.op_generate_hier(amdg.BASIS_HERMITE, ph), ph + 1, ph + 1)
+        ref = ctx.op_blocks(ctx.op_register_hier(d["herm.pw_anc"], d["herm.pw_wt"]), ph + 1, ph + 1)
+        assert _rel(gen, ref) < TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("k,m,nmax", [(1, 2, 7), (2, 3, 7), (3, 3, 8)])
+def test_generated_tables_match_reference_bundles(amdg, k, m, nmax):
+    """the benchmark sizes: bundles made from the compiled reference by tests/golden/tables/make_tables.py"""
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "tables", "tables_k%d_m%d_n%d.npz" % (k, m, nmax)))
+    gen = amdg.generate_tables(nmax, k, m)
+    keys = [key for key in ref if key in gen]
+    assert len(keys) >= 14
+    for key in keys:
+        assert _rel(gen[key], ref[key]) < TOL, key
+
+
+@pytest.mark.parametrize("P", [0, 1, 2, 3, 4, 5])
+def test_alpert_construction_is_orthonormal(amdg, P):
+    """the multiwavelets are constructed from their defining properties (the reference hard-codes P <= 4): the mass matrix of the whole
+    hierarchical basis is the identity, for every degree the context accepts"""
+    ctx = amdg.Context(1, 5, P, max(P, 1), device=-1)
+    src, tgt, vol = ctx.pairs()
+    uv = ctx.op_blocks(ctx.op_generate(amdg.BASIS_ALPERT, P, "u_v"), P + 1, P + 1)
+    expect = np.zeros_like(uv)
+    expect[src == tgt] = np.eye(P + 1)
+    assert np.abs(uv - expect).max() < 1e-13
+    ctx.close()
+
+
+def test_table_generator_rejects_bad_requests(amdg):
+    ctx = amdg.Context(1, 3, 2, 3, device=-1)
+    with pytest.raises(amdg.AmdgError, match="Alpert x Alpert only"):
+        ctx.op_generate(amdg.BASIS_LAGRANGE, 3, "ux_vx")
+    with pytest.raises(amdg.AmdgError, match="no Lagrange point set"):
+        ctx.op_generate(amdg.BASIS_LAGRANGE, 3, "u_v", 7)
+    with pytest.raises(amdg.AmdgError, match="pmax 3 or 5"):
+        ctx.op_generate_points(amdg.BASIS_HERMITE, 4)
+    with pytest.raises(amdg.AmdgError):
+        ctx.op_generate(amdg.BASIS_ALPERT, 2, 99)
+    ctx.close()

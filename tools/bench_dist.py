@@ -21,7 +21,7 @@ def main():
     D = importlib.import_module("adaptive-multiresolution-dg_b200.dist")
     a, b = k + 1, m + 1
     lev, sup = A.sparse_grid(dim, nmax)
-    tb = np.load(os.path.join(ROOT, "adaptive-multiresolution-dg_b200", "data", "tables_k%d_m%d_n%d.npz" % (k, m, nmax)))
+    tb = A.generate_tables(nmax, k, m)
     part = D.FibrePartition(lev, sup, world, rank)
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):

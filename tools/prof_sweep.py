@@ -16,7 +16,7 @@ lev, sup = A.sparse_grid(dim, nmax)
 ctx = A.Context(dim, nmax, k, m, device=0)
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 ctx.grid_set(lev, sup)
-tb = np.load(os.path.join(ROOT, "adaptive-multiresolution-dg_b200", "data", "tables_k3_m3_n8.npz"))
+tb = A.generate_tables(8, 3, 3)
 assert nmax == 8
 op_pt = ctx.op_register_compact(tb["pt"])
 op_uv = ctx.op_register_compact(tb["lagr.u_v"])
