@@ -40,8 +40,12 @@ class Buf:
 class StagePlan:
     """ops for one rank; `part` is a dist.FibrePartition (or None for a single GPU)"""
 
-    def __init__(self, dim, a, b, n_flux, part=None, n_x_dims=None):
+    def __init__(self, dim, a, b, n_flux, part=None, n_x_dims=None, fuse_rk=False):
         self.dim, self.a, self.b, self.nf = dim, a, b, n_flux
+        # fuse_rk: the Runge-Kutta combination u_new = a u_tn + b u + c dt rhs (ExplicitRK::step_stage, source/ODESolver.cpp:209-301) rides in the
+        # epilogues of the sweeps that produce the right-hand side: the accumulator starts as a u_tn + b u, every right-hand-side chain carries the
+        # factor c dt and its last sweeps accumulate straight into it -- no rhs array, no per-application sums, no separate RK pass
+        self.fuse_rk = fuse_rk
         self.dist = part is not None and part.world > 1
         self.part = part
         self.h = (dim // 2 if n_x_dims is None else n_x_dims) if self.dist else dim      # dims < h are swept in layout X, the rest in layout V
@@ -86,17 +90,22 @@ class StagePlan:
         return d
 
     # ---- batched tensor applications (shared-prefix schedule)
-    def apply_batch(self, tag, apps, kf, kt, final_layout="X"):
+    def apply_batch(self, tag, apps, kf, kt, final_layout="X", acc_into=None):
         """apps: list of dict(src=buffer in layout X, ops=[name per dim], rels=[per dim], coef).  Returns the result buffer of every application,
-        living in `final_layout` (X: the natural end of the schedule; V: the last sweeps push it)."""
+        living in `final_layout` (X: the natural end of the schedule; V: the last sweeps push it).  acc_into (single GPU): an existing buffer the
+        result is ADDED to -- the chain of accumulating sweeps of the up pass ends in the output of the full sweep of the all-L chain, so that one
+        job accumulates into acc_into instead of writing a scratch buffer and the sum over applications needs no extra pass."""
         d, h = self.dim, self.h
+        assert acc_into is None or not self.dist
         edge = lambda S, k: kt if (S >> k) & 1 else kf
         width = lambda sizes: int(np.prod(sizes))
         if d == 1:
             outs = []
             for i, ap in enumerate(apps):
                 o = self.buf("%s.res%d" % (tag, i), "X", kt)
-                self.ops.append(("sweep", "X", ap["ops"][0], ap["rels"][0], LU_FULL, 0, [dict(sizes=[kf], src=ap["src"], dst=o, coef=ap.get("coef", 1.0), acc=False)]))
+                if acc_into is not None:
+                    o = acc_into
+                self.ops.append(("sweep", "X", ap["ops"][0], ap["rels"][0], LU_FULL, 0, [dict(sizes=[kf], src=ap["src"], dst=o, coef=ap.get("coef", 1.0), acc=acc_into is not None)]))
                 outs.append(o)
             return outs
         X = [{0: ap["src"]} for ap in apps]
@@ -155,8 +164,9 @@ class StagePlan:
                 sizes = [edge(S, q) for q in range(d - 1)] + [kf]
                 osz = sizes[:-1] + [kt]
                 dl = "X" if to_x_after_full else lay
-                dst = self.buf("%s.y%d.%d%s" % (tag, i, S, "@V" if dl == "V" and self.dist else ""), dl, width(osz))
-                jobs.append(dict(sizes=sizes, src=X[i][S], dst=dst, coef=ap.get("coef", 1.0), acc=False, push=to_x_after_full))
+                into = acc_into is not None and S == (1 << (d - 1)) - 1
+                dst = acc_into if into else self.buf("%s.y%d.%d%s" % (tag, i, S, "@V" if dl == "V" and self.dist else ""), dl, width(osz))
+                jobs.append(dict(sizes=sizes, src=X[i][S], dst=dst, coef=ap.get("coef", 1.0), acc=into, push=to_x_after_full))
                 if to_x_after_full:
                     self.push_bytes += width(osz)
                 R[i][S] = dst
@@ -198,6 +208,11 @@ class StagePlan:
         A, B = a ** d, b ** d
         u = self.buf("u", "X", A)
         self.buf("u_tn", "X", A)
+        fuse = self.fuse_rk
+        acc = None
+        if fuse and not self.dist:
+            acc = self.buf("u_new", "X", A)
+            self.ops.append(("lincomb", acc, ["u_tn", u], 0.0, ["rk_a", "rk_b"]))
         # penalty in the V dims needs u in layout V (rides on the first barrier of the interpolation)
         u_v = self.move(u, "u@V", "V") if self.dist else u
         # 1. Alpert coefficients -> point values; the last sweeps deliver them in layout V (where the point-wise products and the V-dim
@@ -240,6 +255,15 @@ class StagePlan:
         fuc = cur
         # 4. right-hand side: rhs_vol + rhs_flx of dimension t as one application (u_vx + (ulft_vjp + urgt_vjp)/2 under the flx relation in dim t)
         apps = [dict(src=fuc[t], ops=["volflx" if s == t else "uv" for s in range(d)], rels=[REL_FLX if s == t else REL_VOL for s in range(d)]) for t in range(nf)]
+        if acc is not None:
+            # single GPU, fused: every application accumulates into the RK accumulator, the penalty sweeps as well; nothing is left to combine
+            for t in range(nf):
+                self.apply_batch("rhs", [dict(apps[t], coef="rk_c")], b, a, final_layout="X", acc_into=acc)
+            if d > 1:
+                for t in x_dims:
+                    self.ops.append(("sweep", "X", "pen", REL_FLX, LU_FULL, t, [dict(sizes=[a] * d, src=u, dst=acc, coef="pen*rk_c", acc=True, push=False)]))
+            self.result, self.rhs, self.up, self.fuc = acc, None, up, fuc
+            return
         rhs = self.buf("rhs", "X", A)
         first = True
         if self.dist:
@@ -260,6 +284,12 @@ class StagePlan:
                 self.ops.append(("sweep", "X", "pen", REL_FLX, LU_FULL, t, [dict(sizes=[a] * d, src=u, dst=px2, coef="pen", acc=n_ > 0, push=False)]))
             if x_dims:
                 pen_parts.append(px2)
+        if fuse:
+            # partitioned, fused: the pushed partial results, the penalty parts and the RK combination in ONE pass (in place: element-wise)
+            parts = res + pen_parts
+            self.ops.append(("lincomb", u, ["u_tn", u] + parts, 0.0, ["rk_a", "rk_b"] + ["rk_c"] * len(parts)))
+            self.result, self.rhs, self.up, self.fuc = u, None, up, fuc
+            return
         if res + pen_parts:
             self.ops.append(("lincomb", rhs, res + pen_parts, 0.0 if first else 1.0))
         self.ops.append(("rk", "u_tn", u, rhs))
@@ -460,7 +490,7 @@ class DeviceStage:
                     return
                 srcs = [self.local_ptr(j["src"]) for j in jobs]
                 dsts = [self.local_ptr(j["dst"]) for j in jobs]
-                coefs = [self.pen_coef if j["coef"] == "pen" else j["coef"] for j in jobs]
+                coefs = [self.coef(j["coef"]) for j in jobs]
                 maps = [self.maps[(j["dst"], lay)] if (plan.dist and j.get("push")) else None for j in jobs]
                 accf = [self.local_ptr(j["acc_from"]) if j.get("acc_from") else None for j in jobs]
                 c.sweep1d_batch_mapped(self.ops[lay][opn], rel, lu, t, [j["sizes"] for j in jobs], srcs, dsts, coefs=coefs,
@@ -478,11 +508,11 @@ class DeviceStage:
                 if len(self.rows[lay]):
                     self.pointwise(self.ctx[lay], self.local_ptr(up), [self.local_ptr(f) for f in fps])
             elif kind == "lincomb":
-                _, dst, parts, beta = o
-                n = len(self.rows["X"]) * plan.bufs[dst].width
+                _, dst, parts, beta = o[:4]
+                n = len(self.rows["X"]) * plan.bufs[plan.alias.get(dst, dst)].width
                 if n:
                     c = self.ctx["X"]
-                    cf = np.ones(len(parts))
+                    cf = np.ones(len(parts)) if len(o) < 5 else np.array([self.coef(x) for x in o[4]], dtype=np.float64)
                     px = (ctypes.c_void_p * len(parts))(*[ctypes.c_void_p(self.local_ptr(p)) for p in parts])
                     A._check(A.lib.amdg_lincomb(c._h, n, len(parts), cf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), px, beta, ctypes.c_void_p(self.local_ptr(dst))))
             elif kind == "rk":
@@ -493,6 +523,18 @@ class DeviceStage:
                     A._check(A.lib.amdg_rk_stage(self.ctx["X"]._h, scheme, stage, dt, ctypes.c_void_p(self.local_ptr(u_tn)), ctypes.c_void_p(self.local_ptr(u)),
                                                  ctypes.c_void_p(self.local_ptr(rhs)), n))
 
+    def coef(self, c):
+        """numbers, or the symbols of the plan: "pen" (penalty coefficient), "rk_a" / "rk_b" / "rk_c" (u_new = rk_a u_tn + rk_b u + rk_c rhs), products "x*y"""
+        if isinstance(c, str):
+            v = 1.0
+            for f in c.split("*"):
+                v *= self.pen_coef if f == "pen" else self._rk_abc()[("rk_a", "rk_b", "rk_c").index(f)]
+            return v
+        return c
+
+    def _rk_abc(self):
+        return rk_coefficients(*self.rk)
+
     def launch_count(self):
         return sum(c.launch_count for c in self.ctx.values())
 
@@ -502,6 +544,23 @@ class DeviceStage:
         c = self.ctx["X"]
         self.A._check(self.A.lib.amdg_dev_download(c._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_void_p(self.error), 1))
         return int(out.view(np.uint32)[0])
+
+
+def rk_coefficients(scheme, stage, dt):
+    """(a, b, c) of u_new = a u_tn + b u + c rhs for ExplicitRK::step_stage (source/ODESolver.cpp:209-330), as amdg_rk_stage applies it
+    (csrc/kernels.cu: launch_rk_stage).  Schemes: 0 ForwardEuler, 1 RK2SSP, 2 RK2Midpoint, 3 RK3SSP, 4 RK3HeunLinear."""
+    c_tn, c_u, c_rhs = 1.0, 0.0, dt
+    if scheme == 1 and stage == 1:
+        c_tn, c_u = 0.5, 0.5
+    elif scheme == 2 and stage == 0:
+        c_rhs = 0.5 * dt
+    elif scheme == 3 and stage == 1:
+        c_tn, c_u = 3.0 / 4.0, 1.0 / 4.0
+    elif scheme == 3 and stage == 2:
+        c_tn, c_u = 1.0 / 3.0, 2.0 / 3.0
+    elif scheme == 4 and stage in (0, 1):
+        c_rhs = (1.0 / 3.0 if stage == 0 else 1.0 / 2.0) * dt
+    return (c_tn, c_u, c_u * c_rhs) if c_u != 0.0 else (c_tn, 0.0, c_rhs)
 
 
 def _as_tensor(ptr, n_doubles):

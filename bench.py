@@ -178,11 +178,12 @@ def burgers_program(A, dim):
     return prog, ptr, [0.5]
 
 
-def make_stage(A, S, D, dim, nmax, k, m, lev, sup, tables, flux, world, rank, device, stream_ptr, kernel, rk, dense=False):
-    """DeviceStage of one rank for the grid (lev, sup); tables: compact bundles (bench) or dense dump tables (fixture)"""
+def make_stage(A, S, D, dim, nmax, k, m, lev, sup, tables, flux, world, rank, device, stream_ptr, kernel, rk, dense=False, fuse_rk=False):
+    """DeviceStage of one rank for the grid (lev, sup); tables: compact bundles (bench) or dense dump tables (fixture).  fuse_rk: the RK combination
+    rides in the epilogues of the right-hand-side sweeps (stage.StagePlan)"""
     a, b = k + 1, m + 1
     part = D.FibrePartition(lev, sup, world, rank) if world > 1 else None
-    plan = S.StagePlan(dim, a, b, dim, part=part)
+    plan = S.StagePlan(dim, a, b, dim, part=part, fuse_rk=fuse_rk)
 
     def make_ops(c):
         if dense:
@@ -255,43 +256,46 @@ def make_stage(A, S, D, dim, nmax, k, m, lev, sup, tables, flux, world, rank, de
 
 
 def parity_check(A, S, D, world, rank, device, stream, kernel):
-    """the stage program at this N on the reference's d=6 fixture: max over (rhs, stage update) of the relative L2 error against the dump"""
+    """the stage program at this N on the reference's d=6 fixture, as the unfused plan (rhs array + RK kernel) and as the fused plan bench.py times
+    (RK combination in the sweep epilogues): max over (rhs, stage update unfused, stage update fused) of the relative L2 error against the dump"""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refdump
     d = refdump.load(os.path.join(ROOT, "tests", "golden", "cfg5_vlasov_d6_k1_n2.dump.xz"))
     dim, nmax, n0, sparse, pa, pl = [int(x) for x in d["config"][:6]]
     tables = d
-    with torch.cuda.stream(stream):
-        st, plan, part = make_stage(A, S, D, dim, nmax, pa, pl, d["level"], d["suppt"], tables, "vlasov", world, rank, device, stream.cuda_stream, kernel,
-                                    (A.RK_RK3SSP, 0, 0.001), dense=True)
-        rows = part.local["X"] if part is not None else np.arange(d["level"].shape[0])
-        u0 = torch.from_numpy(np.ascontiguousarray(d["ucoe_alpt.in"][:, 0, :][rows])).cuda()
-        if len(rows):
-            st.view("u").copy_(u0); st.view("u_tn").copy_(u0)
+    num = np.zeros(3)
+    berr = 0
+    for fuse in (False, True):
+        with torch.cuda.stream(stream):
+            st, plan, part = make_stage(A, S, D, dim, nmax, pa, pl, d["level"], d["suppt"], tables, "vlasov", world, rank, device, stream.cuda_stream, kernel,
+                                        (A.RK_RK3SSP, 0, 0.001), dense=True, fuse_rk=fuse)
+            rows = part.local["X"] if part is not None else np.arange(d["level"].shape[0])
+            u0 = torch.from_numpy(np.ascontiguousarray(d["ucoe_alpt.in"][:, 0, :][rows])).cuda()
+            if len(rows):
+                st.view("u").copy_(u0); st.view("u_tn").copy_(u0)
+            stream.synchronize()
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()
+            st.run()
         stream.synchronize()
+        if len(rows):
+            if not fuse:
+                num[0] = np.linalg.norm(st.view("rhs").cpu().numpy() - d["rhs_all"][:, 0, :][rows]) ** 2
+            num[2 if fuse else 1] = np.linalg.norm(st.view(plan.result).cpu().numpy() - d["stage0.ucoe_alpt"][:, 0, :][rows]) ** 2
+        berr = max(berr, st.barrier_error())
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
-        st.run()
-    stream.synchronize()
-    err = 0.0
-    if len(rows):
-        rel = lambda x, y: float(np.linalg.norm(x - y) / max(np.linalg.norm(y), 1e-300))
-        num = np.array([np.linalg.norm(st.view("rhs").cpu().numpy() - d["rhs_all"][:, 0, :][rows]) ** 2, np.linalg.norm(st.view("u").cpu().numpy() - d["stage0.ucoe_alpt"][:, 0, :][rows]) ** 2])
-    else:
-        num = np.zeros(2)
+        st.close()
     t = torch.from_numpy(num).cuda()
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t)
     num = t.cpu().numpy()
-    err = max(float(np.sqrt(num[0]) / np.linalg.norm(d["rhs_all"][:, 0, :])), float(np.sqrt(num[1]) / np.linalg.norm(d["stage0.ucoe_alpt"][:, 0, :])))
-    berr = st.barrier_error()
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    st.close()
+    nu = np.linalg.norm(d["stage0.ucoe_alpt"][:, 0, :])
+    err = max(float(np.sqrt(num[0]) / np.linalg.norm(d["rhs_all"][:, 0, :])), float(np.sqrt(num[1]) / nu), float(np.sqrt(num[2]) / nu))
     return err, berr
 
 
@@ -567,6 +571,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--schedule", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-fuse-rk", action="store_true", help="separate rhs array, per-application sums and RK kernel instead of the RK combination in the sweep epilogues")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (quick kernel comparisons)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 secondary record at N = 1")
     ap.add_argument("--breakdown", action="store_true", help="also report device time per kind of operation of the stage (eager launches, CUDA events; max over ranks)")
@@ -644,13 +649,15 @@ def main():
     dof = ne * a ** dim
     tb = load_tables(A, w)
     with torch.cuda.stream(stream):
-        st, plan, part = make_stage(A, S, D, dim, nmax, k, m, lev, sup, tb, w["flux"], world, rank, local_rank, stream.cuda_stream, args.kernel, (A.RK_RK3SSP, 1, DT))
+        st, plan, part = make_stage(A, S, D, dim, nmax, k, m, lev, sup, tb, w["flux"], world, rank, local_rank, stream.cuda_stream, args.kernel, (A.RK_RK3SSP, 1, DT),
+                                    fuse_rk=not args.no_fuse_rk)
     rows = part.local["X"] if part is not None else np.arange(ne)
     u_all = synthetic_field(lev, a ** dim, 1, 20240901)[0]
     host_in = torch.from_numpy(np.ascontiguousarray(u_all[rows])).pin_memory()
     host_out = torch.empty_like(host_in).pin_memory()
     hin, hout = host_in.numpy(), host_out.numpy()
     d_u = ctypes.c_void_p(st.local_ptr("u"))
+    d_res = ctypes.c_void_p(st.local_ptr(plan.result))          # the stage's result: "u" (in place) or the RK accumulator of the fused plan
     c0 = st.ctx["X"]
     dp = ctypes.POINTER(ctypes.c_double)
     with torch.cuda.stream(stream):
@@ -691,7 +698,7 @@ def main():
         with torch.cuda.stream(stream):
             run_step()
         if len(rows):
-            A.lib.amdg_dev_download(c0._h, hout.ctypes.data_as(dp), d_u, hout.size)
+            A.lib.amdg_dev_download(c0._h, hout.ctypes.data_as(dp), d_res, hout.size)
         c0.sync()
     for _ in range(2):
         e2e_call()
@@ -755,9 +762,10 @@ def main():
                        "multi_gpu": ("fibre-partitioned: %d ranks, layout switches = stores into IPC-mapped peer memory from the sweep epilogues + row scatters, %d device-side barriers per stage"
                                      % (world, plan.n_barrier)) if world > 1 else "single GPU (same batched program, one layout)",
                        "launches_per_stage": int(launches_per_step), "barriers_per_stage": int(plan.n_barrier),
+                       "rk_update": "in the epilogues of the right-hand-side sweeps (no rhs array, no RK kernel)" if plan.fuse_rk else "separate kernel",
                        "exchange_bytes_per_stage_all_ranks": float(sm[4]), "exchange_doubles_per_element": int(plan.push_bytes) if world > 1 else 0,
                        "max_local_elements": [int(mx[2]), int(mx[3])], "ideal_local_elements": ne / world,
-                       "parity_rel_l2": (parity[0] if parity else None), "parity_fixture": "tests/golden/cfg5_vlasov_d6_k1_n2 (reference dump): rhs and RK stage after one stage at this N" if parity else None,
+                       "parity_rel_l2": (parity[0] if parity else None), "parity_fixture": "tests/golden/cfg5_vlasov_d6_k1_n2 (reference dump): rhs and RK stage after one stage at this N, unfused and fused plan" if parity else None,
                        "barrier_timeouts": int(mx[5]) + (parity[1] if parity else 0)},
             "clocks": clocks,
             "e2e": {"value": dof / t_e2e, "unit": "DoF-stage/s", "h2d_bytes_per_step": int(dof * 8), "d2h_bytes_per_step": int(dof * 8), "ms_per_step": t_e2e * 1e3,

@@ -143,7 +143,21 @@ def test_stage_program_burgers_2d_vs_reference():
     torch.cuda.synchronize()
     assert rel(st.view("rhs").cpu().numpy(), d["rhs_all"][:, 0, :]) < TOL
     assert rel(st.view("u").cpu().numpy(), d["stage0.ucoe_alpt"][:, 0, :]) < TOL
+    n_unfused = plan.launches()
     st.close()
+    # the fused plan: all three RK3SSP stages in a row (the accumulator of one stage is the input of the next), each against the reference's stage dump
+    u_tn = u0.clone()
+    cur = u0
+    for stage in range(3):
+        st, plan, part = bench.make_stage(A, S, D, dim, nmax, pa, pl, d["level"], d["suppt"], d, "burgers", 1, 0, 0, stream.cuda_stream, 0, (A.RK_RK3SSP, stage, 0.002),
+                                          dense=True, fuse_rk=True)
+        assert plan.launches() < n_unfused and plan.rhs is None
+        st.view("u").copy_(cur); st.view("u_tn").copy_(u_tn)
+        st.run()
+        torch.cuda.synchronize()
+        cur = st.view(plan.result).clone()
+        assert rel(cur.cpu().numpy(), d["stage%d.ucoe_alpt" % stage][:, 0, :]) < TOL
+        st.close()
 
 
 def _n_gpus():
