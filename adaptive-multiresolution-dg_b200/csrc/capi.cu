@@ -51,6 +51,10 @@ struct amdg_ctx
     cudaStream_t stream = nullptr; bool own_stream = false;
     Pairs1D pairs;
     Grid grid; bool have_grid = false;
+    // adaptive runs (DGAdapt::refine / coarsen every step) change the grid every few dozen sweeps: building per-grid work lists for the fast kernels then
+    // costs more than the sweeps they serve.  A grid that replaces one which lived fewer than adaptive_life sweeps puts the context in adaptive mode:
+    // sweeps below tc_min_doubles run the gather kernel, which needs nothing beyond the tables amdg_grid_set uploads, until the grid has lived that long.
+    int64_t sweeps_on_grid = 0, adaptive_life = 512; bool adaptive_mode = false;
     Grid grid_spare;                                 // the previous grid's tables: amdg_grid_set builds into their storage (no fresh pages)
     std::vector<NbrCache> nbr_caches;                // neighbour lists per fibre shape, kept across grid changes (grid.hpp)
     // *_coarse_grid transforms (amdg_apply_tensor_coarse): the elements with sum of levels <= mesh_nmax as a grid of their own
@@ -267,6 +271,7 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_TC_ENT")) c->tc_ent_target = std::max(16, atoi(e));
     if (const char * e = std::getenv("AMDG_TC_STAGE_A")) c->tc_stage_a_max = std::max(0, atoi(e));
     if (const char * e = std::getenv("AMDG_TC_MIN_DOUBLES")) c->tc_min_doubles = atoll(e);
+    if (const char * e = std::getenv("AMDG_ADAPTIVE_LIFE")) c->adaptive_life = atoll(e);
     if (const char * e = std::getenv("AMDG_TC_FORCE_STAGE")) c->tc_force_stage = atoi(e) != 0;
     if (const char * e = std::getenv("AMDG_TC_COARSE_ENT")) c->tc_coarse_ent = std::max(16, atoi(e));
     if (const char * e = std::getenv("AMDG_PIPE_CAP")) c->pipe_cap_doubles = std::max(256, atoi(e)) & ~1;
@@ -364,6 +369,8 @@ int amdg_grid_set(amdg_ctx * c, int64_t n, const int * level, const int * suppt)
     // level / suppt may alias the current grid's own arrays: the spare is built first, then swapped in
     if (c->grid_spare.build(c->dim, c->nmax, n, level, suppt, c->pairs, &c->nbr_caches) != 0) return fail(AMDG_EINVAL, "invalid or duplicate element index");
     const auto t1 = std::chrono::steady_clock::now();
+    if (c->have_grid) c->adaptive_mode = c->sweeps_on_grid < c->adaptive_life;
+    c->sweeps_on_grid = 0;
     std::swap(c->grid, c->grid_spare); c->have_grid = true;
     c->shapes.build(c->grid);
     evict_shape_caches(c);
@@ -1401,6 +1408,8 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
     // whenever the block size is even: the kernels keep their 16-byte stores)
     bool mapped = false; for (int i = 0; i < n_job; ++i) mapped = mapped || jobs[i].dst_map || jobs[i].acc_from;
     const int variant0 = (mapped && c->kernel_variant < 8) ? 5 : c->kernel_variant;
+    c->sweeps_on_grid++;
+    const bool young = c->kernel_variant == 0 && !mapped && c->adaptive_mode && c->sweeps_on_grid <= c->adaptive_life;
     int done = 0;
     while (done < n_job)
     {
@@ -1411,6 +1420,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         // (the 6-D shapes), the lean tensor-core kernel otherwise
         int variant = variant0;
         if (c->kernel_variant == 0 && W >= 32 && (int64_t)W * O.kf >= c->col_min_block && O.kf * O.kt <= c->col_max_kk) variant = 8;
+        if (young && (int64_t)c->grid.n * W * O.kf < c->tc_min_doubles) variant = 1;        // adaptive mode: no work list is built for a grid that will be replaced soon
         const bool lean = variant == 0 || variant == 5;
         if (variant == 8)
         {

@@ -407,6 +407,30 @@ def test_phases_with_generated_tables(name):
     c.close()
 
 
+def test_adaptive_mode_needs_no_work_lists(monkeypatch, capfd):
+    """a grid that replaces a short-lived one (DGAdapt::refine / coarsen every step) is swept by the list-free gather kernel in auto mode: no work
+    list is built for it (AMDG_VERBOSE would print one line per list), results stay those of the reference; a long-lived grid gets its lists"""
+    monkeypatch.setenv("AMDG_VERBOSE", "1")
+    monkeypatch.setenv("AMDG_ADAPTIVE_LIFE", "40")
+    d = load_golden("adapt_d2_k2_n6")
+    c = DevCase(d)                                          # first grid of the context: not adaptive yet
+    u = c.to_dev(d["ucoe_alpt.in"][:, 0, :])
+    assert rel(c.to_host(c.eval_up(u)), d["rt.up_intp"][:, 0, :]) < TOL
+    assert " list " in capfd.readouterr().err
+    c.ctx.grid_set(d["level"][c.perm], d["suppt"][c.perm])       # the first grid lived 4 sweeps: adaptive mode
+    capfd.readouterr()
+    up = c.eval_up(u)
+    ci = c.hier(up)
+    assert rel(c.to_host(up), d["rt.up_intp"][:, 0, :]) < TOL and rel(c.to_host(ci), d["rt.ucoe_intp"][:, 0, :]) < TOL
+    assert rel(c.to_host(c.to_alpt(ci)), d["rt.ucoe_alpt"][:, 0, :]) < TOL
+    assert " list " not in capfd.readouterr().err
+    for _ in range(12):                                          # past the configured life: the grid is treated as static, lists are built
+        up = c.eval_up(u)
+    assert " list " in capfd.readouterr().err
+    assert rel(c.to_host(up), d["rt.up_intp"][:, 0, :]) < TOL
+    c.close()
+
+
 def test_rk_schemes():
     """amdg_rk_stage for ForwardEuler / RK2SSP / RK2Midpoint / RK3SSP / RK3HeunLinear (source/ODESolver.cpp:209-330)"""
     import amdg_oracle as O
