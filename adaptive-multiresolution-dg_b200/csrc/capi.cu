@@ -212,9 +212,11 @@ static int ensure_scratch(amdg_ctx * c, size_t idx, int64_t n)
     if (c->scratch.size() <= idx) { c->scratch.resize(idx + 1, nullptr); c->scratch_cap.resize(idx + 1, 0); }
     if (c->scratch_cap[idx] >= n) return AMDG_OK;
     if (c->scratch[idx]) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch[idx])); c->scratch[idx] = nullptr; c->scratch_cap[idx] = 0; }
-    cudaError_t e = cudaMalloc((void **)&c->scratch[idx], (size_t)n * sizeof(double));
+    // small buffers grow geometrically: an adaptive run whose grid grows a little every step does not reallocate (and synchronise) every step
+    const int64_t want = n < ((int64_t)1 << 24) ? std::max<int64_t>(n + n / 2, 4096) : n;
+    cudaError_t e = cudaMalloc((void **)&c->scratch[idx], (size_t)want * sizeof(double));
     if (e != cudaSuccess) return fail(AMDG_ENOMEM, std::string("scratch cudaMalloc: ") + cudaGetErrorString(e));
-    c->scratch_cap[idx] = n;
+    c->scratch_cap[idx] = want;
     return AMDG_OK;
 }
 
