@@ -3,10 +3,11 @@
 //
 // Why a second form: on the named grids most fibres are short (cfg2: 58 % of the elements sit on fibres of 1-4
 // elements), so an item is a handful of element blocks and a warp owns one or two row tiles of it.  ncu of
-// sweep_mma_kernel (profiles/r01_sweep_mma_ncu.md) shows ~1 360 warp instructions per warp of which ~100 are MMA
-// work: the kernel is its own prologue, at 24 resident warps per SM.  Here:
-//   * 128 threads per CTA, <= 64 registers, <= 27 KiB of shared memory -> 8 CTAs (32 warps) per SM, so that the
-//     load phase of some CTAs always overlaps the compute/store phase of others (one-shot CTAs, no pipeline state);
+// sweep_mma_kernel (round 1) showed ~1 360 warp instructions per warp of which ~100 are MMA work: the kernel is its own
+// prologue, at 24 resident warps per SM.  Here:
+//   * 128 threads per CTA, 80 registers (ncu: profiles/r02_roofline_kernels_ncu.md), <= 36 KiB of shared memory -> 6 CTAs
+//     (24 warps) per SM (registers and shared memory both cap there), so that the load phase of some CTAs overlaps the
+//     compute/store phase of others (one-shot CTAs, no pipeline state);
 //   * units are (row tile, fibre, 32-column group): 4 accumulator tiles instead of 8, one code path for the MMA
 //     loop (operator fragments from shared memory or straight from L1/L2), unit decode by two multiplications;
 //   * copy offsets of a row are computed once per lane (4 slots) and the rest of a long row incrementally.

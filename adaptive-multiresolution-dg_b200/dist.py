@@ -119,9 +119,12 @@ class DistTensorApply:
             rows = part.local[k]
             c = amdg.Context(dim, nmax, pmax_alpt, pmax_intp, device=device)
             c.set_stream(torch.cuda.current_stream().cuda_stream)
-            c.grid_set(part.level[rows], part.suppt[rows])
+            # a layout with fewer ownership groups than ranks leaves some rank without elements: it keeps the context for the plumbing only
+            # (amdg_grid_set rejects an empty grid) and still takes part in every all-to-all with zero rows
+            if len(rows):
+                c.grid_set(part.level[rows], part.suppt[rows])
             self.ctx[k] = c
-            self.ops[k] = register(c)
+            self.ops[k] = register(c) if len(rows) else {}
         self.switches = 0
         self.switch_bytes = 0
 
