@@ -38,7 +38,7 @@ WORKLOADS = {
     "cfg5": dict(kind="stage", flux="vlasov", dim=6, k=1, m=2, nmax=7, cpu_nmax=5, ref_nmax=6, ref_single=True, desc="example/07_vlasov_maxwell_sparse scaled to 3D3V: d=6 k=1 m=2 NMAX=7 full sparse grid, one nonlinear RK3SSP stage (interpolate, Vlasov products with a prescribed smooth field, hierarchise, vol+flx+penalty, RK)"),
     "cfg1": dict(kind="linear", op="advection", dim=2, k=2, m=3, nmax=7, cpu_nmax=7, ref_nmax=7, stages=3, desc="example/02_hyperbolic_01_scalar_const_coefficient: 2D linear advection, Alpert k=2, NMAX=7 full sparse grid, one RK3SSP stage (operator as 1D sweeps: u_vx + upwind flux per dimension)"),
     "cfg3": dict(kind="linear", op="wave", dim=3, k=2, m=3, nmax=7, cpu_nmax=7, ref_nmax=7, stages=4, desc="example/03_wave_01_const_coeff_periodic: 3D second-order wave, k=2, NMAX=7, IPDG (sigma=20), one RK4ODE2nd stage (operator as 1D sweeps: four terms per dimension merged into one operator)"),
-    "cfg4": dict(kind="stage", flux="burgers", dim=2, k=2, m=3, nmax=7, cpu_nmax=7, ref_nmax=7, desc="example/02_hyperbolic_05_burgers_adapt (static upper-bound grid NMAX=7, Lagrange flux): one nonlinear RK3SSP stage"),
+    "cfg4": dict(kind="stage", flux="burgers", dim=2, k=2, m=3, nmax=9, cpu_nmax=9, ref_nmax=9, desc="example/02_hyperbolic_05_burgers_adapt at BASELINE's NMAX=9 on the static upper-bound grid (full sparse grid, 2 816 elements; Lagrange flux): one nonlinear RK3SSP stage.  The adaptive run itself (refine + coarsen every step, live reference DGAdapt) is examples/live_burgers_adapt"),
 }
 LXF_ALPHA, DT = 1.2, 1e-4
 

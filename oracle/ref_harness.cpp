@@ -558,6 +558,67 @@ int main(int argc, char ** argv)
         }
         dg.set_rhs_zero();
     }
+    if (has("pw") && !herm)   // the point-wise kernels of the reference beyond a scalar flux
+    {
+        H.fill_ucoe(a.seed);
+        // (A) system flux: LagrInterpolation::eval_fp_Lag passes all VEC_NUM unknowns to the flux (source/Interplation.cpp:256-295)
+        if (a.vecnum >= 2)
+        {
+            auto sys_flux = [&](std::vector<double> u, int i, int d) -> double
+            {
+                return i == 0 ? (d + 1.) * u[0] * u[1] : 0.5 * u[1] * u[1] - (d + 1.) * u[0];
+            };
+            std::vector<std::vector<bool>> all_intp(a.vecnum, std::vector<bool>(DIM, true));
+            interp_lagr.pw1d.clear();
+            interp_lagr.nonlinear_Lagr_fast(sys_flux, all_intp, fast_lagr_intp);
+            H.dump_field("pw.sys.up_intp", Harness::UP_INTP);
+            H.dump_flux_field("pw.sys.fp_intp", false);
+            H.dump_flux_field("pw.sys.fucoe_intp", true);
+        }
+        // (B) coefficient of position: LagrInterpolation::var_coeff_u_Lagr_fast -> eval_coe_u_Lag (:648-698, 4199-4213)
+        {
+            auto coe = [&](std::vector<double> x, int d) -> double
+            {
+                double s = 0.3 * (d + 1.);
+                for (int t = 0; t < DIM; ++t) s += std::sin(2. * Const::PI * (x[t] + 0.1 * t)) * (t == d ? 1. : 0.25);
+                return s;
+            };
+            std::vector<std::vector<bool>> all_intp(a.vecnum, std::vector<bool>(DIM, true));
+            interp_lagr.pw1d.clear();
+            interp_lagr.var_coeff_u_Lagr_fast(coe, all_intp, fast_lagr_intp);
+            H.dump_flux_field("pw.coe.fp_intp", false);
+            H.dump_flux_field("pw.coe.fucoe_intp", true);
+        }
+        // (C) the 2D2V Vlasov body with the field values of a second solution broadcast by DGSolution::copy_up_intp_to_f
+        //     (LagrInterpolation::interp_Vlasov_2D2V, :4508-4580; source/DGSolution.cpp:1024-1065)
+        if (DIM == 4 && a.vecnum == 2)
+        {
+            DGAdapt E(false, a.nmax, a.nmax, 2, all_bas_alpt, all_bas_lagr, all_bas_herm, hash, a.eps, a.eta, true, false);   // swept: needs its Alpert neighbour sets
+            std::vector<Element *> es;
+            for (auto & it : E.dg) es.push_back(&it.second);
+            std::sort(es.begin(), es.end(), [](Element * x, Element * y) { return x->hash_key < y->hash_key; });
+            std::vector<int> key, lev, sup; std::vector<double> ue;
+            for (Element * e : es)
+            {
+                int sl = 0; for (int t = 0; t < DIM; ++t) sl += e->level[t];
+                key.push_back(e->hash_key);
+                for (int t = 0; t < DIM; ++t) { lev.push_back(e->level[t]); sup.push_back(e->suppt[t]); }
+                for (int v = 0; v < a.vecnum; ++v)
+                    for (int i = 0; i < e->ucoe_alpt[v].size(); ++i) { e->ucoe_alpt[v].at(i) = field_value(a.seed + 7, e->hash_key, v, i, sl); ue.push_back(e->ucoe_alpt[v].at(i)); }
+            }
+            H.dump.put("pw.vl.E.hash_key", key);
+            H.dump.put("pw.vl.E.level", lev, { (int64_t)es.size(), DIM });
+            H.dump.put("pw.vl.E.suppt", sup, { (int64_t)es.size(), DIM });
+            H.dump.put("pw.vl.E.ucoe_alpt", ue, { (int64_t)es.size(), a.vecnum, (int64_t)es[0]->ucoe_alpt[0].size() });
+            FastLagrIntp fast_lagr_E(E, interp_lagr.Lag_pt_Alpt_1D, interp_lagr.Lag_pt_Alpt_1D_d1);
+            interp_lagr.pw1d.clear();
+            interp_lagr.interp_Vlasov_2D2V(E, fast_lagr_intp, fast_lagr_E);
+            H.dump_field("pw.vl.up_intp", Harness::UP_INTP);
+            H.dump_flux_field("pw.vl.fp_intp", false);
+            H.dump_flux_field("pw.vl.fucoe_intp", true);
+        }
+        H.fill_ucoe(a.seed);
+    }
     if (has("stage"))        // full RK3SSP step with the nonlinear right-hand side, a.steps steps
     {
         for (int step = 0; step < a.steps; ++step)

@@ -45,6 +45,10 @@ CASES = {
     # DiffusionRHS, FastRHSHamiltonJacobi, the *_coarse_grid transforms (mesh_nmax = N-1, N-2) and DGAdapt::indicator_norm
     "f4_lagr_d2_k2_n4": "--dim 2 --nmax 4 --pa 2 --pl 3 --run grid,f4 --flux kpp --dump-tables 2",
     "f4_lagr_d3_k1_n3": "--dim 3 --nmax 3 --pa 1 --pl 2 --run grid,f4 --flux burgers --dump-tables 2",
+    # point-wise kernels beyond a scalar flux: a coupled two-variable flux through eval_fp_Lag, a coefficient of position through
+    # var_coeff_u_Lagr_fast, the 2D2V Vlasov body with a second solution's field values broadcast by copy_up_intp_to_f
+    "pw_d2_k2_n4_v2": "--dim 2 --nmax 4 --pa 2 --pl 3 --vecnum 2 --run grid,pw --dump-tables 1",
+    "pw_vlasov_d4_k1_n3_v2": "--dim 4 --nmax 3 --pa 1 --pl 2 --vecnum 2 --run grid,pw --dump-tables 1",
     "line_d1_k2_n5": "--dim 1 --nmax 5 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux burgers --dump-tables 1",
 }
 

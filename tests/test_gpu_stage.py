@@ -114,6 +114,83 @@ def test_pointwise_expressions_match_enumerated_and_oracle():
     c.close()
 
 
+@pytest.mark.parametrize("name", ["pw_d2_k2_n4_v2", "pw_vlasov_d4_k1_n3_v2"])
+def test_pointwise_bodies_vs_reference(name):
+    """amdg_pointwise_expr against the reference's own point-wise kernels (fixtures from the compiled reference, run "pw" of oracle/ref_harness.cpp):
+    a coupled two-variable flux through LagrInterpolation::eval_fp_Lag (all VEC_NUM unknowns reach the flux, source/Interplation.cpp:271-286), a
+    coefficient of position through var_coeff_u_Lagr_fast / eval_coe_u_Lag (:648-698, 4199-4213), and interp_Vlasov_2D2V (:4508-4580) with the
+    field values of a second solution reaching f through the element map of DGSolution::copy_up_intp_to_f (source/DGSolution.cpp:1024-1065)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import amdg_oracle as O
+    d = load_golden(name)
+    c = DevCase(d)
+    A = c.amdg
+    P = A.PW
+    dim, B = c.dim, c.b ** c.dim
+    c.ctx.points_set(d["lagr.intep_pt"])
+    up = [c.eval_up(c.to_dev(d["ucoe_alpt.in"][:, v, :])) for v in range(2)]
+    for v in range(2):
+        assert rel(c.to_host(up[v]), d["pw.sys.up_intp"][:, v, :]) < TOL
+    new = lambda n: [torch.zeros(c.ne, B, dtype=torch.float64, device="cuda") for _ in range(n)]
+    # (A) f_{0,t} = (t+1) u0 u1, f_{1,t} = u1^2 / 2 - (t+1) u0; then hierarchisation of every component
+    consts = [0.5] + [t + 1.0 for t in range(dim)]
+    for i in range(2):
+        prog, ptr = [], [0]
+        for t in range(dim):
+            if i == 0:
+                prog += [(P["CONST"], 1 + t), (P["VAR"], 0), (P["MUL"], 0), (P["VAR"], 1), (P["MUL"], 0)]
+            else:
+                prog += [(P["CONST"], 0), (P["VAR"], 1), (P["SQR"], 0), (P["MUL"], 0), (P["CONST"], 1 + t), (P["VAR"], 0), (P["MUL"], 0), (P["SUB"], 0)]
+            ptr.append(len(prog))
+        outs = new(dim)
+        c.ctx.pointwise_expr(up, [], None, outs, prog, ptr, consts)
+        for t in range(dim):
+            assert rel(c.to_host(outs[t]), d["pw.sys.fp_intp"][:, i, t, :]) < 1e-14
+            assert rel(c.to_host(c.hier(outs[t])), d["pw.sys.fucoe_intp"][:, i, t, :]) < TOL
+    # (B) coe(x, t) u_v with coe(x, t) = 0.3 (t+1) + sum_q w_q sin(2 pi (x_q + q/10)), w_t = 1, else 1/4: coordinates from the 1D point table
+    consts = [2.0 * np.pi, 0.25] + [0.3 * (t + 1.0) for t in range(dim)] + [0.1 * q for q in range(dim)]
+    for v in range(2):
+        prog, ptr = [], [0]
+        for t in range(dim):
+            prog += [(P["CONST"], 2 + t)]
+            for q in range(dim):
+                prog += [(P["X"], q), (P["CONST"], 2 + dim + q), (P["ADD"], 0), (P["CONST"], 0), (P["MUL"], 0), (P["SIN"], 0)]
+                if q != t:
+                    prog += [(P["CONST"], 1), (P["MUL"], 0)]
+                prog += [(P["ADD"], 0)]
+            prog += [(P["VAR"], v), (P["MUL"], 0)]
+            ptr.append(len(prog))
+        outs = new(dim)
+        c.ctx.pointwise_expr(up, [], None, outs, prog, ptr, consts)
+        for t in range(dim):
+            assert rel(c.to_host(outs[t]), d["pw.coe.fp_intp"][:, v, t, :]) < 1e-13
+            assert rel(c.to_host(c.hier(outs[t])), d["pw.coe.fucoe_intp"][:, v, t, :]) < TOL
+    # (C) interp_Vlasov_2D2V: E = (E1, E2) lives on its own grid (full in x, level 0 in v); its point values reach f through the element map
+    if "pw.vl.fp_intp" in d:
+        le, se = d["pw.vl.E.level"], d["pw.vl.E.suppt"]
+        cE = A.Context(dim, c.nmax, c.pa, c.pl, device=0)
+        cE.set_stream(torch.cuda.current_stream().cuda_stream)
+        cE.grid_set(le, se)
+        op_pt = cE.op_generate_points(A.BASIS_LAGRANGE, c.pl)
+        Eup = []
+        for v in range(2):
+            uE = torch.from_numpy(np.ascontiguousarray(d["pw.vl.E.ucoe_alpt"][:, v, :])).cuda()
+            o = torch.zeros(le.shape[0], B, dtype=torch.float64, device="cuda")
+            cE.apply_tensor([op_pt] * dim, [A.REL_VOL] * dim, uE, o)
+            Eup.append(o)
+        rows = O.field_rows_of(d["level"][c.perm], d["suppt"][c.perm], le, se, (2, 3))
+        emap = torch.from_numpy(rows).cuda()
+        prog = [(P["X"], 2), (P["VAR"], 0), (P["MUL"], 0), (P["X"], 3), (P["VAR"], 0), (P["MUL"], 0),
+                (P["OTHER"], 0), (P["VAR"], 0), (P["MUL"], 0), (P["OTHER"], 1), (P["VAR"], 0), (P["MUL"], 0)]
+        outs = new(4)
+        c.ctx.pointwise_expr([up[0]], Eup, emap, outs, prog, [0, 3, 6, 9, 12])
+        for t in range(4):
+            assert rel(c.to_host(outs[t]), d["pw.vl.fp_intp"][:, 0, t, :]) < TOL
+            assert rel(c.to_host(c.hier(outs[t])), d["pw.vl.fucoe_intp"][:, 0, t, :]) < TOL
+        cE.close()
+    c.close()
+
+
 @pytest.mark.parametrize("kernel", [0, 5, 8])
 def test_stage_program_single_gpu_vs_reference(kernel):
     """the whole batched stage program (stage.py) on one GPU: right-hand side and RK stage 0 of the d=6 Vlasov fixture against the reference"""

@@ -257,6 +257,38 @@ def test_f4_compositions(name):
     assert rel(np.linalg.norm(u, axis=1), d["f4.indicator_norm"]) < 1e-14
 
 
+@pytest.mark.parametrize("name", ["pw_d2_k2_n4_v2", "pw_vlasov_d4_k1_n3_v2"])
+def test_pointwise_bodies_beyond_scalar_flux(name):
+    """the reference's point-wise kernels with several unknowns, a coefficient of position and a broadcast field (eval_fp_Lag with VEC_NUM = 2,
+    var_coeff_u_Lagr_fast / eval_coe_u_Lag, interp_Vlasov_2D2V over copy_up_intp_to_f) restated; also pins what the GPU test feeds amdg_pointwise_expr"""
+    c = Case(name)
+    d = c.d
+    pt, u_v, u_vx, uave, anc, wt = _tables(c)
+    rels = c.relations()
+    up = np.stack([O.apply_tensor(d["ucoe_alpt.in"][:, v, :], c.a, c.b, [pt] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d) for v in range(2)], axis=1)
+    assert rel(up, d["pw.sys.up_intp"]) < TOL
+    f = O.system_flux(up)
+    for i in range(2):
+        for t in range(c.dim):
+            assert rel(f(i, t), d["pw.sys.fp_intp"][:, i, t, :]) < 1e-14
+    assert rel(O.hierarchize(f(1, 0), c.b, c.lev, c.sup, c.ord1d, anc, wt), d["pw.sys.fucoe_intp"][:, 1, 0, :]) < TOL
+    X = O.point_coordinates(c.ord1d, d["lagr.intep_pt"], c.b)
+    for v in range(2):
+        for t in range(c.dim):
+            assert rel(O.position_coefficient(X, t) * up[:, v], d["pw.coe.fp_intp"][:, v, t, :]) < 1e-13
+    if "pw.vl.fp_intp" in d:
+        le, se = d["pw.vl.E.level"], d["pw.vl.E.suppt"]
+        orde = np.array([[O.order_elem(int(n), int(j)) for n, j in zip(l, s)] for l, s in zip(le, se)])
+        rels_e = {"vol": [O.relations(le, se, t, "vol") for t in range(c.dim)]}
+        Eup = np.stack([O.apply_tensor(d["pw.vl.E.ucoe_alpt"][:, v, :], c.a, c.b, [pt] * c.dim, ["vol"] * c.dim, rels_e, le, orde) for v in range(2)], axis=1)
+        rows = O.field_rows_of(c.lev, c.sup, le, se, (2, 3))
+        fpt = d["pw.vl.up_intp"][:, 0, :]
+        assert rel(fpt, up[:, 0]) < TOL
+        want = [X[..., 2] * fpt, X[..., 3] * fpt, Eup[rows, 0] * fpt, Eup[rows, 1] * fpt]
+        for t in range(4):
+            assert rel(want[t], d["pw.vl.fp_intp"][:, 0, t, :]) < TOL, t
+
+
 def test_hierarchisation_stencil_restated():
     """set_pts_wts_1d_ada_Lag restated from point coordinates and level-0 basis values (Lagrange)"""
     c = Case("cfg4_burgers_lagr_d2_k2_n4")
