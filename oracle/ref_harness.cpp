@@ -619,6 +619,57 @@ int main(int argc, char ** argv)
         }
         H.fill_ucoe(a.seed);
     }
+    if (has("vlasov_ampere") && !herm && DIM == 4 && a.vecnum == 2)
+    {
+        // one RK3SSP step of the coupled 2D2V Vlasov-Ampere system on static grids, stage by stage as example/07_vlasov_ampere_02_2D2V_accuracy.cpp:255-318
+        // (without its manufactured source): f through interp_Vlasov_2D2V + HyperbolicLagrRHS + penalty, E_t = -J through compute_moment_2D2V
+        H.fill_ucoe(a.seed);
+        DGAdapt E(false, a.nmax, a.nmax, 2, all_bas_alpt, all_bas_lagr, all_bas_herm, hash, a.eps, a.eta, true, false);
+        std::vector<Element *> es;
+        for (auto & it : E.dg) es.push_back(&it.second);
+        std::sort(es.begin(), es.end(), [](Element * x, Element * y) { return x->hash_key < y->hash_key; });
+        auto dump_E = [&](const std::string & name)
+        {
+            std::vector<double> ue;
+            for (Element * e : es) for (int v = 0; v < a.vecnum; ++v) for (int i = 0; i < e->ucoe_alpt[v].size(); ++i) ue.push_back(e->ucoe_alpt[v].at(i));
+            H.dump.put(name, ue, { (int64_t)es.size(), a.vecnum, (int64_t)es[0]->ucoe_alpt[0].size() });
+        };
+        {
+            std::vector<int> key, lev, sup;
+            for (Element * e : es)
+            {
+                int sl = 0; for (int t = 0; t < DIM; ++t) sl += e->level[t];
+                key.push_back(e->hash_key);
+                for (int t = 0; t < DIM; ++t) { lev.push_back(e->level[t]); sup.push_back(e->suppt[t]); }
+                for (int v = 0; v < a.vecnum; ++v)
+                    for (int i = 0; i < e->ucoe_alpt[v].size(); ++i) e->ucoe_alpt[v].at(i) = field_value(a.seed + 7, e->hash_key, v, i, sl);
+            }
+            H.dump.put("va.E.hash_key", key);
+            H.dump.put("va.E.level", lev, { (int64_t)es.size(), DIM });
+            H.dump.put("va.E.suppt", sup, { (int64_t)es.size(), DIM });
+            dump_E("va.E.ucoe_alpt.in");
+        }
+        FastLagrIntp fast_lagr_E(E, interp_lagr.Lag_pt_Alpt_1D, interp_lagr.Lag_pt_Alpt_1D_d1);
+        RK3SSP ode_f(dg, a.dt); ode_f.init();
+        RK3SSP ode_E(E, a.dt); ode_E.init();
+        for (int stage = 0; stage < ode_f.num_stage; ++stage)
+        {
+            interp_lagr.pw1d.clear();
+            interp_lagr.interp_Vlasov_2D2V(E, fast_lagr_intp, fast_lagr_E);
+            dg.set_rhs_zero();
+            rhs_lagr.rhs_vol_scalar(); rhs_lagr.rhs_flx_intp_scalar(); rhs_alpt.rhs_flx_penalty_scalar(lax_alpha);
+            if (stage == 0) H.dump_field("va.stage0.rhs_f", Harness::RHS);
+            ode_f.set_rhs_zero(); ode_f.add_rhs_to_eigenvec(); ode_f.step_stage(stage);
+            E.set_rhs_zero();
+            E.compute_moment_2D2V(dg, { 1, 0 }, -1.0, 0, 0);      // - int f v1 dv -> rhs of E1
+            E.compute_moment_2D2V(dg, { 0, 1 }, -1.0, 1, 0);      // - int f v2 dv -> rhs of E2
+            ode_E.set_rhs_zero(); ode_E.add_rhs_to_eigenvec(); ode_E.step_stage(stage);
+            ode_f.final(); ode_E.final();
+            H.dump_field("va.stage" + std::to_string(stage) + ".f", Harness::UCOE_ALPT);
+            dump_E("va.stage" + std::to_string(stage) + ".E");
+        }
+        H.fill_ucoe(a.seed);
+    }
     if (has("stage"))        // full RK3SSP step with the nonlinear right-hand side, a.steps steps
     {
         for (int step = 0; step < a.steps; ++step)

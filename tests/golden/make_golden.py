@@ -49,6 +49,8 @@ CASES = {
     # var_coeff_u_Lagr_fast, the 2D2V Vlasov body with a second solution's field values broadcast by copy_up_intp_to_f
     "pw_d2_k2_n4_v2": "--dim 2 --nmax 4 --pa 2 --pl 3 --vecnum 2 --run grid,pw --dump-tables 1",
     "pw_vlasov_d4_k1_n3_v2": "--dim 4 --nmax 3 --pa 1 --pl 2 --vecnum 2 --run grid,pw --dump-tables 1",
+    # one RK3SSP step of the coupled 2D2V Vlasov-Ampere system (f: interp_Vlasov_2D2V + rhs + penalty; E_t = -J by compute_moment_2D2V), per stage
+    "vlasov_ampere_d4_k1_n3_v2": "--dim 4 --nmax 3 --pa 1 --pl 2 --vecnum 2 --run grid,vlasov_ampere --dump-tables 1 --dt 0.002",
     "line_d1_k2_n5": "--dim 1 --nmax 5 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux burgers --dump-tables 1",
 }
 

@@ -191,6 +191,61 @@ def test_pointwise_bodies_vs_reference(name):
     c.close()
 
 
+@pytest.mark.parametrize("generated", [False, True])
+def test_vlasov_ampere_2d2v_rk3_step_on_device(generated):
+    """one complete RK3SSP step of the coupled 2D2V Vlasov-Ampere system on the device, no host round trip between the stages: f by the field broadcast
+    through the element map (DGSolution::copy_up_intp_to_f), the Vlasov products (interp_Vlasov_2D2V), hierarchisation, vol + flx + penalty sweeps;
+    E_t = -J by the velocity moments (compute_moment_2D2V); both by amdg_rk_stage.  Every stage against the compiled reference running
+    example/07_vlasov_ampere_02_2D2V_accuracy.cpp:255-318 on the same grids (fixture vlasov_ampere_d4_k1_n3_v2); with `generated` no table of the
+    reference is used either"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import amdg_oracle as O
+    d = load_golden("vlasov_ampere_d4_k1_n3_v2")
+    c = DevCase(d, generated=generated)
+    A = c.amdg
+    P = A.PW
+    dim, B, dt = 4, c.b ** 4, 0.002
+    if generated:
+        c.ctx.points_generate(A.BASIS_LAGRANGE, c.pl)
+    else:
+        c.ctx.points_set(d["lagr.intep_pt"])
+    le, se = d["va.E.level"], d["va.E.suppt"]
+    nE = le.shape[0]
+    cE = A.Context(dim, c.nmax, c.pa, c.pl, device=0)
+    cE.set_stream(torch.cuda.current_stream().cuda_stream)
+    cE.grid_set(le, se)
+    op_pt_E = cE.op_generate_points(A.BASIS_LAGRANGE, c.pl) if generated else cE.op_register(d["Lag_pt_Alpt_1D"].T.copy(), c.a, c.b)
+    lev_f, sup_f = d["level"][c.perm], d["suppt"][c.perm]
+    emap = torch.from_numpy(O.field_rows_of(lev_f, sup_f, le, se, (2, 3))).cuda()                 # f element -> field element (broadcast)
+    pmap = torch.from_numpy(O.field_partner(lev_f, sup_f, le, se)).cuda()                          # field element -> f element (moments)
+    f = c.to_dev(d["ucoe_alpt.in"][:, 0, :]); f_tn = f.clone()
+    E = torch.from_numpy(np.ascontiguousarray(d["va.E.ucoe_alpt.in"].transpose(1, 0, 2))).cuda(); E_tn = E.clone()      # [2][nE][a^4]
+    prog = [(P["X"], 2), (P["VAR"], 0), (P["MUL"], 0), (P["X"], 3), (P["VAR"], 0), (P["MUL"], 0),
+            (P["OTHER"], 0), (P["VAR"], 0), (P["MUL"], 0), (P["OTHER"], 1), (P["VAR"], 0), (P["MUL"], 0)]
+    launches0 = c.ctx.launch_count + cE.launch_count
+    for stage in range(3):
+        up = c.eval_up(f)
+        Eup = torch.zeros(2, nE, B, dtype=torch.float64, device="cuda")
+        cE.apply_tensor([op_pt_E] * dim, [A.REL_VOL] * dim, E, Eup, n_comp=2)
+        fp = [torch.zeros(c.ne, B, dtype=torch.float64, device="cuda") for _ in range(4)]
+        c.ctx.pointwise_expr([up], [Eup[0], Eup[1]], emap, fp, prog, [0, 3, 6, 9, 12])
+        rhs = c.zeros(c.a)
+        c.rhs_vol_flx([c.hier(x) for x in fp], rhs)
+        c.penalty(f, rhs, 1.2)
+        if stage == 0:
+            assert rel(c.to_host(rhs), d["va.stage0.rhs_f"][:, 0, :]) < TOL
+        rhs_E = torch.zeros_like(E)
+        c.ctx.moment(pmap, 2, (1, 0), -1.0, f, rhs_E[0])                # the moments read f at the start of the stage, as the reference does
+        c.ctx.moment(pmap, 2, (0, 1), -1.0, f, rhs_E[1])
+        c.ctx.rk_stage(A.RK_RK3SSP, stage, dt, f_tn, f, rhs)
+        cE.rk_stage(A.RK_RK3SSP, stage, dt, E_tn, E, rhs_E)
+        assert rel(c.to_host(f), d["va.stage%d.f" % stage][:, 0, :]) < TOL
+        assert rel(E.cpu().numpy().transpose(1, 0, 2), d["va.stage%d.E" % stage]) < TOL
+    assert c.ctx.launch_count + cE.launch_count > launches0
+    cE.close()
+    c.close()
+
+
 @pytest.mark.parametrize("kernel", [0, 5, 8])
 def test_stage_program_single_gpu_vs_reference(kernel):
     """the whole batched stage program (stage.py) on one GPU: right-hand side and RK stage 0 of the d=6 Vlasov fixture against the reference"""

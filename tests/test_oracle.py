@@ -289,6 +289,44 @@ def test_pointwise_bodies_beyond_scalar_flux(name):
             assert rel(want[t], d["pw.vl.fp_intp"][:, 0, t, :]) < TOL, t
 
 
+def test_vlasov_ampere_2d2v_step_restated():
+    """one RK3SSP step of the coupled 2D2V Vlasov-Ampere system, stage by stage (example/07_vlasov_ampere_02_2D2V_accuracy.cpp:255-318 without its
+    manufactured source): f through interp_Vlasov_2D2V (field broadcast by copy_up_intp_to_f), HyperbolicLagrRHS vol + flx, penalty; E_t = -J through
+    compute_moment_2D2V; both advanced by ExplicitRK::step_stage"""
+    c = Case("vlasov_ampere_d4_k1_n3_v2")
+    d = c.d
+    dt, alpha = 0.002, 1.2
+    pt, u_v, u_vx, uave, anc, wt = _tables(c)
+    rels = c.relations()
+    le, se = d["va.E.level"], d["va.E.suppt"]
+    orde = np.array([[O.order_elem(int(n), int(j)) for n, j in zip(l, s)] for l, s in zip(le, se)])
+    rels_e = {"vol": [O.relations(le, se, t, "vol") for t in range(4)]}
+    rows = O.field_rows_of(c.lev, c.sup, le, se, (2, 3))
+    partner = O.field_partner(c.lev, c.sup, le, se)
+    X = O.point_coordinates(c.ord1d, d["lagr.intep_pt"], c.b)
+    f = d["ucoe_alpt.in"][:, 0, :].copy(); f_tn = f.copy()
+    E = d["va.E.ucoe_alpt.in"].copy(); E_tn = E.copy()
+    for stage in range(3):
+        up = O.apply_tensor(f, c.a, c.b, [pt] * 4, ["vol"] * 4, rels, c.lev, c.ord1d)
+        Eup = [O.apply_tensor(E[:, v, :], c.a, c.b, [pt] * 4, ["vol"] * 4, rels_e, le, orde) for v in range(2)]
+        fp = [X[..., 2] * up, X[..., 3] * up, Eup[0][rows] * up, Eup[1][rows] * up]
+        rhs = np.zeros_like(f)
+        for t in range(4):
+            fuc = O.hierarchize(fp[t], c.b, c.lev, c.sup, c.ord1d, anc, wt)
+            rhs += O.apply_tensor(fuc, c.b, c.a, [u_vx if s == t else u_v for s in range(4)], ["vol"] * 4, rels, c.lev, c.ord1d)
+            rhs += O.apply_tensor(fuc, c.b, c.a, [uave if s == t else u_v for s in range(4)], ["flx" if s == t else "vol" for s in range(4)], rels, c.lev, c.ord1d, 0.5)
+        for t in range(4):
+            rhs += O.single_sweep(f, c.a, d["alpt.ujp_vjp"], "flx", rels, c.lev, c.ord1d, t, -alpha / 2.0)
+        if stage == 0:
+            assert rel(rhs, d["va.stage0.rhs_f"][:, 0, :]) < TOL
+        rhs_e = np.zeros_like(E)
+        rhs_e[:, 0, :] = O.moments(f, partner, c.a, 4, 2, (1, 0), -1.0, np.zeros_like(E[:, 0, :]))
+        rhs_e[:, 1, :] = O.moments(f, partner, c.a, 4, 2, (0, 1), -1.0, np.zeros_like(E[:, 1, :]))
+        f = O.rk3ssp_stage(stage, f_tn, f, rhs, dt)
+        E = O.rk3ssp_stage(stage, E_tn, E, rhs_e, dt)
+        assert rel(f, d["va.stage%d.f" % stage][:, 0, :]) < TOL and rel(E, d["va.stage%d.E" % stage]) < TOL
+
+
 def test_hierarchisation_stencil_restated():
     """set_pts_wts_1d_ada_Lag restated from point coordinates and level-0 basis values (Lagrange)"""
     c = Case("cfg4_burgers_lagr_d2_k2_n4")
