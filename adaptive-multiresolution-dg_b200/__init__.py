@@ -68,6 +68,7 @@ SYMBOLS = {
     "amdg_op_generate_points": (_i, [_p, _i, _i, _i, _i, _p]),
     "amdg_op_generate_hier": (_i, [_p, _i, _i, _i, _p]),
     "amdg_points_generate": (_i, [_p, _i, _i, _i, _p]),
+    "amdg_sweep1d_batch_dual": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _dp, _ip, _p, _p, _p, _p, _i]),
     "amdg_apply_tensor": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i]),
     "amdg_apply_tensor_coarse": (_i, [_p, _ip, _ip, _p, _p, _i, _d, _i, _i]),
     "amdg_hierarchize": (_i, [_p, _i, _p, _p, _i]),
@@ -339,9 +340,17 @@ class Context:
         n = y.numel() if hasattr(y, "numel") else None
         _check(lib.amdg_lincomb(self._h, n, len(xs), cp, px, beta, _ptr(y)))
 
-    def sweep1d_batch_mapped(self, op, rel, lu, t, sizes_from, srcs, dsts, coefs=None, accumulates=None, dst_maps=None, acc_froms=None):
-        """amdg_sweep1d_batch_mapped; srcs/dsts/dst_maps/acc_froms are raw device addresses (ints) or torch tensors, None entries allowed in the last two"""
+    def sweep1d_batch_mapped(self, op, rel, lu, t, sizes_from, srcs, dsts, coefs=None, accumulates=None, dst_maps=None, acc_froms=None, dst2s=None, dst2_maps=None):
+        """amdg_sweep1d_batch_mapped / _dual; srcs/dsts/dst_maps/acc_froms/dst2s/dst2_maps are raw device addresses (ints) or torch tensors, None entries
+        allowed in the optional ones"""
         n = len(srcs)
+        if dst2s is not None and any(x is not None for x in dst2s):
+            s, sp = _ints(np.asarray(sizes_from).reshape(n, self.dim))
+            arr = lambda xs: (ctypes.c_void_p * n)(*[(_ptr(x) if x is not None else None) for x in (xs or [None] * n)])
+            cf, cp = _dbls(np.ones(n) if coefs is None else coefs)
+            ac, ap = _ints(np.zeros(n) if accumulates is None else accumulates)
+            _check(lib.amdg_sweep1d_batch_dual(self._h, op, rel, lu, t, sp, arr(srcs), arr(dsts), cp, ap, arr(dst_maps), arr(acc_froms), arr(dst2s), arr(dst2_maps), n))
+            return
         s, sp = _ints(np.asarray(sizes_from).reshape(n, self.dim))
         ps = (ctypes.c_void_p * n)(*[_ptr(x) for x in srcs])
         pd = (ctypes.c_void_p * n)(*[_ptr(x) for x in dsts])

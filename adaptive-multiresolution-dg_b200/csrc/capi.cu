@@ -1408,7 +1408,21 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
     const DevDim & D = c->ddims[t];
     // destination maps / accumulate-from exist in the lean, register-direct and streaming kernels only (even map offsets are the caller's contract
     // whenever the block size is even: the kernels keep their 16-byte stores)
-    bool mapped = false; for (int i = 0; i < n_job; ++i) mapped = mapped || jobs[i].dst_map || jobs[i].acc_from;
+    bool mapped = false; for (int i = 0; i < n_job; ++i) mapped = mapped || jobs[i].dst_map || jobs[i].acc_from || jobs[i].dst2;
+    // second destinations are written by the column kernel's epilogue; after any other kernel the blocks are copied by a row scatter (same result)
+    auto scatter_second = [&](int first, int cnt) -> int
+    {
+        for (int i = first; i < first + cnt; ++i)
+        {
+            if (!jobs[i].dst2) continue;
+            if (jobs[i].dst_map) return fail(AMDG_EINVAL, "a second destination needs a plain first destination outside the column kernel");
+            const int64_t s_to = (int64_t)jobs[i].outer * inner * O.kt;
+            cudaError_t e = launch_scatter_rows(jobs[i].dst, c->grid.n, (int)s_to, jobs[i].dst2, jobs[i].dst2_map, c->stream);
+            if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("second-destination scatter: ") + cudaGetErrorString(e));
+            c->launches++;
+        }
+        return AMDG_OK;
+    };
     const int variant0 = (mapped && c->kernel_variant < 8) ? 5 : c->kernel_variant;
     c->sweeps_on_grid++;
     const bool young = c->kernel_variant == 0 && !mapped && c->adaptive_mode && c->sweeps_on_grid <= c->adaptive_life;
@@ -1458,7 +1472,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
                 if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("tensor-core sweep launch: ") + cudaGetErrorString(e));
                 launched = true;
             }
-            if (launched) { c->launches++; done += cnt; continue; }
+            if (launched) { c->launches++; int r2 = scatter_second(done, cnt); if (r2) return r2; done += cnt; continue; }
             if (variant == 4 || variant == 5) return fail(AMDG_EINVAL, "tensor-core kernel requested but the work list could not be built");
         }
         if (variant == 3)
@@ -1483,6 +1497,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
                 cudaError_t e = launch_sweep_pipe(a, O.kf, O.kt, PL.ct, c->n_sm, c->stream);
                 if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("pipelined sweep launch: ") + cudaGetErrorString(e));
                 c->launches++;
+                { int r2 = scatter_second(done, cnt); if (r2) return r2; }
                 done += cnt;
                 continue;
             }
@@ -1512,6 +1527,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
         }
         if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
         c->launches++;
+        { int r2 = scatter_second(done, cnt); if (r2) return r2; }
         done += cnt;
     }
     return AMDG_OK;
@@ -1536,7 +1552,8 @@ int amdg_sweep1d(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes
 }
 
 static int sweep1d_batch_impl(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * const * src, double * const * dst,
-                             const double * coef, const int * accumulate, const long long * const * dst_map, const double * const * acc_from, int n_job, int n_comp)
+                             const double * coef, const int * accumulate, const long long * const * dst_map, const double * const * acc_from, int n_job, int n_comp,
+                             double * const * dst2 = nullptr, const long long * const * dst2_map = nullptr)
 {
     int r = need_device(c); if (r) return r;
     if (!c->have_grid) return fail(AMDG_ESTATE, "no grid");
@@ -1556,7 +1573,8 @@ static int sweep1d_batch_impl(amdg_ctx * c, int op, int rel, int lu, int t, cons
         if (inner0 < 0) inner0 = inner; else if (inner != inner0) return fail(AMDG_EINVAL, "the jobs of a batch must agree in the edges of the dims after t");
         jobs[i].src = src[i]; jobs[i].dst = dst[i]; jobs[i].outer = outer; jobs[i].accumulate = accumulate ? accumulate[i] : 0; jobs[i].coef = coef ? coef[i] : 1.0;
         jobs[i].dst_map = dst_map ? dst_map[i] : nullptr; jobs[i].acc_from = acc_from ? acc_from[i] : nullptr;
-        if ((jobs[i].dst_map || jobs[i].acc_from) && n_comp != 1) return fail(AMDG_EINVAL, "mapped destinations take one component per job");
+        if (dst2 && dst2[i]) { if (!dst2_map || !dst2_map[i]) return fail(AMDG_EINVAL, "a second destination needs its map"); jobs[i].dst2 = dst2[i]; jobs[i].dst2_map = dst2_map[i]; }
+        if ((jobs[i].dst_map || jobs[i].acc_from || jobs[i].dst2) && n_comp != 1) return fail(AMDG_EINVAL, "mapped destinations take one component per job");
         if (jobs[i].acc_from && !jobs[i].accumulate) return fail(AMDG_EINVAL, "acc_from needs accumulate");
     }
     std::stable_sort(jobs.begin(), jobs.end(), [](const SweepJob & a, const SweepJob & b) { return a.outer < b.outer; });
@@ -1574,6 +1592,14 @@ int amdg_sweep1d_batch_mapped(amdg_ctx * c, int op, int rel, int lu, int t, cons
                               const double * coef, const int * accumulate, const int64_t * const * dst_map, const double * const * acc_from, int n_job)
 {
     return sweep1d_batch_impl(c, op, rel, lu, t, sizes_from, src, dst, coef, accumulate, reinterpret_cast<const long long * const *>(dst_map), acc_from, n_job, 1);
+}
+
+int amdg_sweep1d_batch_dual(amdg_ctx * c, int op, int rel, int lu, int t, const int * sizes_from, const double * const * src, double * const * dst,
+                            const double * coef, const int * accumulate, const int64_t * const * dst_map, const double * const * acc_from,
+                            double * const * dst2, const int64_t * const * dst2_map, int n_job)
+{
+    return sweep1d_batch_impl(c, op, rel, lu, t, sizes_from, src, dst, coef, accumulate, reinterpret_cast<const long long * const *>(dst_map), acc_from, n_job, 1,
+                              dst2, reinterpret_cast<const long long * const *>(dst2_map));
 }
 
 static int64_t ipow(int b, int e) { int64_t r = 1; while (e-- > 0) r *= b; return r; }

@@ -40,6 +40,11 @@ struct SweepJob
     // optional (lean and column kernels, with accumulate): the old values are read from acc_from (plain row * S_to layout) instead of the
     // destination -- "remote = local partial sum + sweep", the last accumulating sweep before a layout switch
     const double * acc_from = nullptr;
+    // optional (column kernel; the other kernels are followed by a row scatter, capi.cu: launch_sweep): a SECOND copy of every output block at
+    // dst2 + dst2_map[row] -- a buffer that is consumed locally in this layout AND in the other layout after the next switch is stored to both
+    // places from the same epilogue instead of being moved by a separate pass
+    double * dst2 = nullptr;
+    const long long * dst2_map = nullptr;
 };
 
 static const int MAX_JOBS = 32;

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(COL_THREADS) sweep_col_kernel(const ColArgs a)
     double * __restrict__ dst = J.dst + (int64_t)comp * a.n_elem * s_to;
     const long long * __restrict__ dmap = J.dst_map;
     const double * __restrict__ accf = J.acc_from ? J.acc_from + (int64_t)comp * a.n_elem * s_to : nullptr;
+    const long long * __restrict__ dmap2 = J.dst2_map;            // second copy of the output (one component per job), see SweepJob::dst2
     const bool accumulate = J.accumulate != 0;
     const double coef = J.coef;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -203,12 +204,18 @@ __global__ void __launch_bounds__(COL_THREADS) sweep_col_kernel(const ColArgs a)
         for (int j = 0; j < NC; ++j)
 #pragma unroll
             for (int q = 0; q < KT; ++q) old[j][q] = (accumulate && offt[j] >= 0) ? yr[offt[j] + (int64_t)q * inner] : 0.0;
+        double * y2 = dmap2 ? J.dst2 + __ldg(dmap2 + U.x) : nullptr;
 #pragma unroll
         for (int j = 0; j < NC; ++j)
             if (offt[j] >= 0)
             {
 #pragma unroll
-                for (int q = 0; q < KT; ++q) y[offt[j] + (int64_t)q * inner] = fma(coef, acc[j][q], old[j][q]);
+                for (int q = 0; q < KT; ++q)
+                {
+                    const double v = fma(coef, acc[j][q], old[j][q]);
+                    y[offt[j] + (int64_t)q * inner] = v;
+                    if (y2) y2[offt[j] + (int64_t)q * inner] = v;
+                }
             }
     }
 #ifdef AMDG_COL_TOUCH

@@ -40,8 +40,13 @@ class Buf:
 class StagePlan:
     """ops for one rank; `part` is a dist.FibrePartition (or None for a single GPU)"""
 
-    def __init__(self, dim, a, b, n_flux, part=None, n_x_dims=None, fuse_rk=False):
+    def __init__(self, dim, a, b, n_flux, part=None, n_x_dims=None, fuse_rk=False, dual_store=True):
         self.dim, self.a, self.b, self.nf = dim, a, b, n_flux
+        # dual_store (partitioned plans): a buffer that is consumed locally in layout X and, after the switch, in layout V (the outputs of the early
+        # down-pass levels, the hierarchised fluxes) is stored to both places by the sweep that produces it (SweepJob::dst2) instead of being moved by a
+        # row scatter before the switch; twin[x buffer] = its copy in layout V
+        self.dual_store = dual_store
+        self.twin = {}
         # fuse_rk: the Runge-Kutta combination u_new = a u_tn + b u + c dt rhs (ExplicitRK::step_stage, source/ODESolver.cpp:209-301) rides in the
         # epilogues of the sweeps that produce the right-hand side: the accumulator starts as a u_tn + b u, every right-hand-side chain carries the
         # factor c dt and its last sweeps accumulate straight into it -- no rhs array, no per-application sums, no separate RK pass
@@ -128,7 +133,7 @@ class StagePlan:
                 for S in sorted(X[i]):
                     name = "%s.x%d.%d@V" % (tag, i, S)
                     if self.bufs[X[i][S]].layout == "X" and self.dist:
-                        X[i][S] = self.move(X[i][S], name, "V")
+                        X[i][S] = self.twin[X[i][S]] if X[i][S] in self.twin else self.move(X[i][S], name, "V")
             self.barrier()
 
         # down pass: L_k applied to X_S for every S subset of {0..k-1}
@@ -145,7 +150,13 @@ class StagePlan:
                     osz = list(sizes); osz[k] = kt
                     dl = self.other(lay) if push else lay
                     dst = self.buf("%s.x%d.%d%s" % (tag, i, S | (1 << k), "@V" if (push or lay == "V") and self.dist else ""), dl, width(osz))
-                    jobs.append(dict(sizes=sizes, src=X[i][S], dst=dst, coef=1.0, acc=False, push=push))
+                    job = dict(sizes=sizes, src=X[i][S], dst=dst, coef=1.0, acc=False, push=push)
+                    if self.dist and self.dual_store and lay == "X" and not push and k < h:
+                        # consumed by the later X levels here and by the V levels after the switch: stored to both places
+                        job["dst2"] = self.buf("%s.x%d.%d@V" % (tag, i, S | (1 << k)), "V", width(osz))
+                        self.twin[dst] = job["dst2"]
+                        self.push_bytes += width(osz)
+                    jobs.append(job)
                     if push:
                         self.push_bytes += width(osz)
                     X[i][S | (1 << k)] = dst
@@ -215,6 +226,8 @@ class StagePlan:
             self.ops.append(("lincomb", acc, ["u_tn", u], 0.0, ["rk_a", "rk_b"]))
         # penalty in the V dims needs u in layout V (rides on the first barrier of the interpolation)
         u_v = self.move(u, "u@V", "V") if self.dist else u
+        if self.dist and self.dual_store:
+            self.twin[u] = u_v                      # the interpolation's X_0 in layout V is this copy: no second scatter
         # 1. Alpert coefficients -> point values; the last sweeps deliver them in layout V (where the point-wise products and the V-dim
         #    hierarchisation run)
         pw_layout = "V" if self.dist else "X"
@@ -247,7 +260,14 @@ class StagePlan:
             dl = "X" if push else lay
             nxt = [self.buf("h%d.%d%s" % (n_ % 2, c, "@X" if dl == "X" and self.dist else ""), dl, B) for c in range(nf)]
             sizes = [b] * d
-            self.ops.append(("sweep", lay, "hier", REL_VOL, LU_U, t, [dict(sizes=sizes, src=cur[c], dst=nxt[c], coef=1.0, acc=False, push=push) for c in range(nf)]))
+            hjobs = [dict(sizes=sizes, src=cur[c], dst=nxt[c], coef=1.0, acc=False, push=push) for c in range(nf)]
+            if self.dist and self.dual_store and n_ + 1 == len(order) and dl == "X" and self.h < d:
+                # the hierarchised fluxes are the X_0 of the right-hand-side applications: needed in layout X (first L sweeps) and in layout V (full sweep)
+                for c in range(nf):
+                    hjobs[c]["dst2"] = self.buf("rhs.x%d.0@V" % c, "V", B)
+                    self.twin[nxt[c]] = hjobs[c]["dst2"]
+                    self.push_bytes += B
+            self.ops.append(("sweep", lay, "hier", REL_VOL, LU_U, t, hjobs))
             if push:
                 self.push_bytes += nf * B
                 self.barrier()
@@ -336,6 +356,8 @@ class SlabLayout:
                 for j in o[6]:
                     if j.get("push"):
                         need.add((j["dst"], o[1]))
+                    if j.get("dst2"):
+                        need.add((j["dst2"], o[1]))
             elif o[0] == "scatter":
                 need.add((o[2], plan.bufs[o[1]].layout))
         out, sent = {}, 0
@@ -493,8 +515,10 @@ class DeviceStage:
                 coefs = [self.coef(j["coef"]) for j in jobs]
                 maps = [self.maps[(j["dst"], lay)] if (plan.dist and j.get("push")) else None for j in jobs]
                 accf = [self.local_ptr(j["acc_from"]) if j.get("acc_from") else None for j in jobs]
+                d2 = [self.local_ptr(j["dst2"]) if j.get("dst2") else None for j in jobs]
+                m2 = [self.maps[(j["dst2"], lay)] if j.get("dst2") else None for j in jobs]
                 c.sweep1d_batch_mapped(self.ops[lay][opn], rel, lu, t, [j["sizes"] for j in jobs], srcs, dsts, coefs=coefs,
-                                       accumulates=[int(j["acc"]) for j in jobs], dst_maps=maps, acc_froms=accf)
+                                       accumulates=[int(j["acc"]) for j in jobs], dst_maps=maps, acc_froms=accf, dst2s=d2, dst2_maps=m2)
             elif kind == "scatter":
                 _, src, dst = o
                 lay = plan.bufs[src].layout

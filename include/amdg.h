@@ -143,6 +143,13 @@ int amdg_sweep1d_batch_mapped(amdg_ctx *ctx, int op, int rel, int lu, int t, con
                               double *const *dev_dst, const double *coef, const int *accumulate, const int64_t *const *dev_dst_map,
                               const double *const *dev_acc_from, int n_job);
 
+/* the same with a SECOND destination per job (or NULL): every output block is also stored at dev_dst2[j] + dev_dst2_map[j][row] (peer memory) -- a buffer that
+ * is consumed in this layout and, after the next layout switch, in the other one leaves the producing sweep for both places (the column kernel stores twice
+ * from its epilogue; after the other kernels the library copies the rows) */
+int amdg_sweep1d_batch_dual(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, const double *const *dev_src,
+                            double *const *dev_dst, const double *coef, const int *accumulate, const int64_t *const *dev_dst_map,
+                            const double *const *dev_acc_from, double *const *dev_dst2, const int64_t *const *dev_dst2_map, int n_job);
+
 /* ---- sum over all orderings of the chain of sweeps: FastRHS::transform_fucoe_to_rhs (source/FastMultiplyLU.cpp:4-16),
  * FastInterpolation::transform_ucoealpt_to_upintp (:740-819), FastInitial::transform_ucoeintp_to_ucoealpt (:1418-1445).
  * ops[dim], rels[dim]; src blocks edge_from^dim, dst blocks edge_to^dim; dst = coef*(...) (+ dst if accumulate). ---- */

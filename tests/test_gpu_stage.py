@@ -49,6 +49,17 @@ def test_mapped_destination_and_accumulate_from(name, kernel):
             c.ctx.sweep1d_batch_mapped(c.op_pt, A.REL_VOL, lu, t, [sizes], [x], [out], dst_maps=[dmap])
             c.ctx.sync()
             assert torch.equal(out[perm][:, :s_to], plain2) or torch.allclose(out[perm][:, :s_to], plain2, rtol=0, atol=1e-14 * float(plain2.abs().max()))
+            # second destination (amdg_sweep1d_batch_dual): the plain local result AND a mapped copy from the same launch (column kernel: two stores in
+            # the epilogue; other kernels: a row scatter issued by the library), with and without accumulation
+            for acc in (0, 1):
+                loc = base.clone()
+                out.fill_(-7.0)
+                c.ctx.sweep1d_batch_mapped(c.op_pt, A.REL_VOL, lu, t, [sizes], [x], [loc], coefs=[0.5], accumulates=[acc], dst2s=[out], dst2_maps=[dmap])
+                c.ctx.sync()
+                want = plain if acc else 0.5 * plain2
+                assert torch.allclose(loc, want, rtol=0, atol=1e-14 * float(plain.abs().max()))
+                assert torch.equal(out[perm][:, :s_to], loc)
+                assert float(out[:, s_to:].min()) == -7.0 and float(out[:, s_to:].max()) == -7.0
     c.close()
 
 

@@ -82,11 +82,11 @@ class Emulator:
             return v
         return c
 
-    def __init__(self, d, dim, a, b, mats, world, fuse_rk=False):
+    def __init__(self, d, dim, a, b, mats, world, fuse_rk=False, dual_store=True):
         self.d, self.dim, self.a, self.b, self.mats, self.world = d, dim, a, b, mats, world
         lev, sup = d["level"], d["suppt"]
         self.parts = [D.FibrePartition(lev, sup, world, r) if world > 1 else None for r in range(world)]
-        self.plans = [S.StagePlan(dim, a, b, dim, part=self.parts[r], fuse_rk=fuse_rk) for r in range(world)]
+        self.plans = [S.StagePlan(dim, a, b, dim, part=self.parts[r], fuse_rk=fuse_rk, dual_store=dual_store) for r in range(world)]
         self.lay = [S.SlabLayout(self.plans[r], lev.shape[0]) for r in range(world)]
         self.base = [(r + 1) << 44 for r in range(world)]                     # fake byte addresses, far apart
         self.slab = [np.zeros(int(self.lay[r].total[r])) for r in range(world)]
@@ -146,6 +146,8 @@ class Emulator:
                             self.store_mapped(r, j["dst"], lay, out)
                         else:
                             self.view(r, j["dst"])[:] = out
+                        if j.get("dst2"):
+                            self.store_mapped(r, j["dst2"], lay, out)
                 elif o[0] == "scatter":
                     _, src, dst = o
                     lay = self.plans[r].bufs[src].layout
@@ -181,7 +183,7 @@ def test_partitioned_stage_equals_single_grid(name, worlds):
     up_ref, fuc_ref, rhs_ref, u_ref = reference(d, dim, a, b, mats, u)
     rel = lambda x, y: np.linalg.norm(x - y) / np.linalg.norm(y)
     for world, fuse in [(w, f) for w in worlds for f in (False, True)]:
-        E = Emulator(d, dim, a, b, mats, world, fuse_rk=fuse)
+        E = Emulator(d, dim, a, b, mats, world, fuse_rk=fuse, dual_store=fuse)          # the older form (row scatters) rides with the unfused plan
         for r in range(world):
             E.view(r, "u")[:] = u[E.rows[r]["X"]]
             E.view(r, "u_tn")[:] = u[E.rows[r]["X"]]
@@ -193,7 +195,11 @@ def test_partitioned_stage_equals_single_grid(name, worlds):
         if fuse:
             # the RK combination rides in the sweep epilogues: no rhs array, no "rk" operation, fewer launches than the unfused plan
             assert p.rhs is None and not any(o[0] == "rk" for o in p.ops)
-            assert p.launches() < S.StagePlan(dim, a, b, dim, part=E.parts[0]).launches()
+            assert p.launches() < S.StagePlan(dim, a, b, dim, part=E.parts[0], dual_store=False).launches()
+            if world > 1 and dim > 2:
+                # second destinations replace the row scatters of the down-pass buffers and of the hierarchised fluxes
+                n_sc = lambda q: sum(1 for o in q.ops if o[0] == "scatter")
+                assert n_sc(p) < n_sc(S.StagePlan(dim, a, b, dim, part=E.parts[0], fuse_rk=True, dual_store=False))
         else:
             assert rel(E.gather(p.rhs), rhs_ref) < 1e-12
         assert rel(E.gather(p.result), u_ref) < 1e-13
@@ -215,4 +221,8 @@ def test_plan_summary_cfg5():
     assert p1.n_barrier == 0 and p8.n_barrier == 6
     assert sum(1 for o in p8.ops if o[0] == "sweep") < 70
     # exchange volume per element and stage: interpolation 1000 + 3375 + u 64 + pen 64 + up 729 + hierarchisation 6*729 + rhs 6*(3375 + 1000)
-    assert p8.push_bytes == 64 + 1000 + 3375 + 64 + 729 + 6 * 729 + 6 * (3375 + 1000)
+    vol = 64 + 1000 + 3375 + 64 + 729 + 6 * 729 + 6 * (3375 + 1000)
+    assert S.StagePlan(6, 2, 3, 6, part=part, dual_store=False).push_bytes == vol
+    # second destinations move the same blocks from the epilogues of their producers; u@V serves the interpolation as well (one scatter of u less)
+    assert p8.push_bytes == vol - 64
+    assert sum(1 for o in p8.ops if o[0] == "scatter") == 1 and sum(1 for o in S.StagePlan(6, 2, 3, 6, part=part, dual_store=False).ops if o[0] == "scatter") == 29
