@@ -1448,10 +1448,13 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
             ColArgs a;
             a.units = CL.d_units; a.n_unit = CL.n_unit; a.n_heavy = CL.n_heavy; a.upc = c->col_upc; a.ent = ent; a.blocks = O.d_blocks;
             a.n_elem = c->grid.n; a.inner = inner; a.n_comp = n_comp; a.n_job = cnt;
-            for (int i = 0; i < cnt; ++i) a.job[i] = jobs[done + i];
+            const bool dual_ok = O.kf <= 4 && O.kt <= 4;          // the column kernel's two-store epilogue is instantiated for these edges
+            for (int i = 0; i < cnt; ++i) { a.job[i] = jobs[done + i]; if (!dual_ok) { a.job[i].dst2 = nullptr; a.job[i].dst2_map = nullptr; } }
             cudaError_t e = launch_sweep_col(a, O.kf, O.kt, nc, c->stream);
             if (e != cudaSuccess) return fail(AMDG_ECUDA, std::string("column sweep launch: ") + cudaGetErrorString(e));
-            c->launches++; done += cnt; continue;
+            c->launches++;
+            if (!dual_ok) { int r2 = scatter_second(done, cnt); if (r2) return r2; }
+            done += cnt; continue;
         }
         if (variant == 0 || variant == 4 || variant == 5)
         {

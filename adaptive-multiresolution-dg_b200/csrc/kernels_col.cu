@@ -103,7 +103,9 @@ __device__ __forceinline__ void col_entries(double (&acc)[NC][KT], const int2 * 
     }
 }
 
-template <int KF, int KT, int NC>
+// DUAL: some job of the launch has a second destination (SweepJob::dst2).  A template parameter because the kernel's register allocation is fragile:
+// the extra pointer and branch in the epilogue of the plain form cost 10 % of the cfg5 stage (17.1 -> 18.85 ms, gpurun call AK)
+template <int KF, int KT, int NC, bool DUAL>
 __global__ void __launch_bounds__(COL_THREADS) sweep_col_kernel(const ColArgs a)
 {
     __shared__ double s_red[(COL_NW - 1) * NC * KT * 32];
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(COL_THREADS) sweep_col_kernel(const ColArgs a)
     double * __restrict__ dst = J.dst + (int64_t)comp * a.n_elem * s_to;
     const long long * __restrict__ dmap = J.dst_map;
     const double * __restrict__ accf = J.acc_from ? J.acc_from + (int64_t)comp * a.n_elem * s_to : nullptr;
-    const long long * __restrict__ dmap2 = J.dst2_map;            // second copy of the output (one component per job), see SweepJob::dst2
+    const long long * __restrict__ dmap2 = DUAL ? J.dst2_map : nullptr;            // second copy of the output (one component per job), see SweepJob::dst2
     const bool accumulate = J.accumulate != 0;
     const double coef = J.coef;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(COL_THREADS) sweep_col_kernel(const ColArgs a)
         for (int j = 0; j < NC; ++j)
 #pragma unroll
             for (int q = 0; q < KT; ++q) old[j][q] = (accumulate && offt[j] >= 0) ? yr[offt[j] + (int64_t)q * inner] : 0.0;
-        double * y2 = dmap2 ? J.dst2 + __ldg(dmap2 + U.x) : nullptr;
+        double * y2 = (DUAL && dmap2) ? J.dst2 + __ldg(dmap2 + U.x) : nullptr;
 #pragma unroll
         for (int j = 0; j < NC; ++j)
             if (offt[j] >= 0)
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(COL_THREADS) sweep_col_kernel(const ColArgs a)
                 {
                     const double v = fma(coef, acc[j][q], old[j][q]);
                     y[offt[j] + (int64_t)q * inner] = v;
-                    if (y2) y2[offt[j] + (int64_t)q * inner] = v;
+                    if (DUAL && y2) y2[offt[j] + (int64_t)q * inner] = v;
                 }
             }
     }
@@ -225,8 +227,9 @@ __global__ void __launch_bounds__(COL_THREADS) sweep_col_kernel(const ColArgs a)
 
 #ifdef AMDG_COL_PROBE
 // SASS inspection builds (nvcc -DAMDG_COL_PROBE -cubin): two instantiations only
-template __global__ void sweep_col_kernel<4, 4, 2>(const ColArgs);
-template __global__ void sweep_col_kernel<3, 2, 4>(const ColArgs);
+template __global__ void sweep_col_kernel<4, 4, 2, false>(const ColArgs);
+template __global__ void sweep_col_kernel<3, 2, 4, false>(const ColArgs);
+template __global__ void sweep_col_kernel<3, 2, 4, true>(const ColArgs);
 #else
 template <int KF, int KT, int NC>
 static cudaError_t launch_col_t(const ColArgs & a, cudaStream_t st)
@@ -243,7 +246,14 @@ static cudaError_t launch_col_t(const ColArgs & a, cudaStream_t st)
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, sweep_col_kernel<KF, KT, NC>, a);
+    bool dual = false;
+    for (int i = 0; i < a.n_job; ++i) dual = dual || a.job[i].dst2 != nullptr;
+    if constexpr (KF <= 4 && KT <= 4)
+    {
+        if (dual) return cudaLaunchKernelEx(&cfg, sweep_col_kernel<KF, KT, NC, true>, a);
+    }
+    else if (dual) return cudaErrorInvalidValue;                 // capi.cu routes such launches through the scatter fall-back
+    return cudaLaunchKernelEx(&cfg, sweep_col_kernel<KF, KT, NC, false>, a);
 }
 
 int col_max_nc(int kf, int kt) { return (kf <= 4 && kt <= 4) ? 4 : 2; }

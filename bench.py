@@ -178,12 +178,12 @@ def burgers_program(A, dim):
     return prog, ptr, [0.5]
 
 
-def make_stage(A, S, D, dim, nmax, k, m, lev, sup, tables, flux, world, rank, device, stream_ptr, kernel, rk, dense=False, fuse_rk=False):
+def make_stage(A, S, D, dim, nmax, k, m, lev, sup, tables, flux, world, rank, device, stream_ptr, kernel, rk, dense=False, fuse_rk=False, dual_store=True):
     """DeviceStage of one rank for the grid (lev, sup); tables: compact bundles (bench) or dense dump tables (fixture).  fuse_rk: the RK combination
     rides in the epilogues of the right-hand-side sweeps (stage.StagePlan)"""
     a, b = k + 1, m + 1
     part = D.FibrePartition(lev, sup, world, rank) if world > 1 else None
-    plan = S.StagePlan(dim, a, b, dim, part=part, fuse_rk=fuse_rk)
+    plan = S.StagePlan(dim, a, b, dim, part=part, fuse_rk=fuse_rk, dual_store=dual_store)
 
     def make_ops(c):
         if dense:
@@ -269,7 +269,7 @@ def parity_check(A, S, D, world, rank, device, stream, kernel):
     for fuse in (False, True):
         with torch.cuda.stream(stream):
             st, plan, part = make_stage(A, S, D, dim, nmax, pa, pl, d["level"], d["suppt"], tables, "vlasov", world, rank, device, stream.cuda_stream, kernel,
-                                        (A.RK_RK3SSP, 0, 0.001), dense=True, fuse_rk=fuse)
+                                        (A.RK_RK3SSP, 0, 0.001), dense=True, fuse_rk=fuse, dual_store=fuse)
             rows = part.local["X"] if part is not None else np.arange(d["level"].shape[0])
             u0 = torch.from_numpy(np.ascontiguousarray(d["ucoe_alpt.in"][:, 0, :][rows])).cuda()
             if len(rows):
@@ -571,6 +571,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--schedule", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-dual-store", action="store_true", help="partitioned runs: move the buffers that both layouts consume by row scatters instead of second destinations of their producing sweeps")
     ap.add_argument("--no-fuse-rk", action="store_true", help="separate rhs array, per-application sums and RK kernel instead of the RK combination in the sweep epilogues")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (quick kernel comparisons)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 secondary record at N = 1")
@@ -650,7 +651,7 @@ def main():
     tb = load_tables(A, w)
     with torch.cuda.stream(stream):
         st, plan, part = make_stage(A, S, D, dim, nmax, k, m, lev, sup, tb, w["flux"], world, rank, local_rank, stream.cuda_stream, args.kernel, (A.RK_RK3SSP, 1, DT),
-                                    fuse_rk=not args.no_fuse_rk)
+                                    fuse_rk=not args.no_fuse_rk, dual_store=not args.no_dual_store)
     rows = part.local["X"] if part is not None else np.arange(ne)
     u_all = synthetic_field(lev, a ** dim, 1, 20240901)[0]
     host_in = torch.from_numpy(np.ascontiguousarray(u_all[rows])).pin_memory()
@@ -762,6 +763,7 @@ def main():
                        "multi_gpu": ("fibre-partitioned: %d ranks, layout switches = stores into IPC-mapped peer memory from the sweep epilogues + row scatters, %d device-side barriers per stage"
                                      % (world, plan.n_barrier)) if world > 1 else "single GPU (same batched program, one layout)",
                        "launches_per_stage": int(launches_per_step), "barriers_per_stage": int(plan.n_barrier),
+                       "row_scatters_per_stage": int(sum(1 for o in plan.ops if o[0] == "scatter")),
                        "rk_update": "in the epilogues of the right-hand-side sweeps (no rhs array, no RK kernel)" if plan.fuse_rk else "separate kernel",
                        "exchange_bytes_per_stage_all_ranks": float(sm[4]), "exchange_doubles_per_element": int(plan.push_bytes) if world > 1 else 0,
                        "max_local_elements": [int(mx[2]), int(mx[3])], "ideal_local_elements": ne / world,
