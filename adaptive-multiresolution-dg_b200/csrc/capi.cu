@@ -472,7 +472,7 @@ int64_t amdg_grid_size(amdg_ctx * c) { return (c && c->have_grid) ? c->grid.n : 
 int amdg_grid_keys(amdg_ctx * c, int * hash, int * ord1d)
 {
     if (!c || !c->have_grid) return fail(AMDG_ESTATE, "no grid");
-    if (hash) std::memcpy(hash, c->grid.hash.data(), c->grid.hash.size() * sizeof(int));
+    if (hash) { const std::vector<int> & k = c->grid.keys(); std::memcpy(hash, k.data(), k.size() * sizeof(int)); }
     if (ord1d) std::memcpy(ord1d, c->grid.ord1d.data(), c->grid.ord1d.size() * sizeof(int));
     return AMDG_OK;
 }

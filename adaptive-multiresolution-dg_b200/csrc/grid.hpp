@@ -171,6 +171,17 @@ struct Grid
     std::vector<int> level, suppt, ord1d, hash;   // [n*dim] x3, [n]
     std::vector<DimTables> dims;
 
+    // Hash::hash_key of every element (the parity export amdg_grid_keys), computed on first use
+    const std::vector<int> & keys()
+    {
+        if ((int64_t)hash.size() != n)
+        {
+            hash.resize(n);
+            for (int64_t e = 0; e < n; ++e) hash[e] = hash_key(dim, &level[e * dim], &suppt[e * dim]);
+        }
+        return hash;
+    }
+
     // returns 0, or -1 for an invalid element / duplicate
     int build(int dim_, int nmax_, int64_t n_, const int * level_, const int * suppt_, const Pairs1D & P, std::vector<NbrCache> * caches = nullptr)
     {
@@ -179,7 +190,7 @@ struct Grid
         for (int o = 0; o < P.T; ++o) lev_of[o] = (uint8_t)level_of_order(o);
         dim = dim_; nmax = nmax_; n = n_;
         level.assign(level_, level_ + n * dim); suppt.assign(suppt_, suppt_ + n * dim);
-        ord1d.resize(n * dim); hash.resize(n);
+        ord1d.resize(n * dim); hash.clear();          // hash keys are computed on demand (keys()): only the parity export reads them
         for (int64_t e = 0; e < n; ++e)
         {
             for (int t = 0; t < dim; ++t)
@@ -188,7 +199,6 @@ struct Grid
                 if (l < 0 || l > nmax || j < 1 || (j % 2) == 0 || (l == 0 && j != 1) || (l >= 1 && (j - 1) / 2 > (1 << (l - 1)) - 1)) return -1;
                 ord1d[e * dim + t] = order_elem(l, j);
             }
-            hash[e] = hash_key(dim, &level[e * dim], &suppt[e * dim]);
         }
         dims.resize(dim);   // a Grid object that is built again keeps the capacity of its tables (no fresh pages to fault in)
         // the tables of the dimensions are independent: one host thread per dimension
@@ -209,7 +219,7 @@ struct Grid
             if (d * nmax <= 64)
             {
                 // the lexicographic key (1D orders of the other dims, then of dim t; each below 2^nmax) fits one 64-bit word
-                std::vector<std::pair<uint64_t, int>> keyed(n);
+                std::vector<std::pair<uint64_t, int>> keyed(n), tmp;
                 for (int64_t e = 0; e < n; ++e)
                 {
                     uint64_t key = 0;
@@ -217,7 +227,22 @@ struct Grid
                     key = (key << nmax) | (uint64_t)o[e * d + t];
                     keyed[e] = { key, (int)e };
                 }
-                std::sort(keyed.begin(), keyed.end());
+                // least-significant-digit radix sort, 11 bits per pass over the d * nmax key bits (stable; 2 passes for the 2-D NMAX = 9 grid, 4 for
+                // the 6-D NMAX = 7 grid): a grid change is on the critical path of an adaptive run
+                const int bits = d * nmax;
+                if (n >= 256)
+                {
+                    tmp.resize(n);
+                    for (int shift = 0; shift < bits; shift += 11)
+                    {
+                        uint32_t count[2049] = { 0 };
+                        for (int64_t e = 0; e < n; ++e) count[((keyed[e].first >> shift) & 2047u) + 1]++;
+                        for (int b = 0; b < 2048; ++b) count[b + 1] += count[b];
+                        for (int64_t e = 0; e < n; ++e) tmp[count[(keyed[e].first >> shift) & 2047u]++] = keyed[e];
+                        keyed.swap(tmp);
+                    }
+                }
+                else std::sort(keyed.begin(), keyed.end());
                 for (int64_t s = 0; s < n; ++s) perm[s] = keyed[s].second;
             }
             else
@@ -326,7 +351,7 @@ struct Grid
                     return 0;
         };
         std::vector<int> rc(dim, 0);
-        if (dim > 1 && n >= 8192)
+        if (dim > 1 && n >= 2048)
         {
             std::vector<std::thread> th;
             for (int t = 0; t < dim; ++t) th.emplace_back([&, t]() { rc[t] = build_dim(t); });
