@@ -34,20 +34,33 @@ class DeviceArray
 {
 public:
     DeviceArray() {}
-    DeviceArray(amdg_ctx * c, int64_t n) : ctx_(c), n_(n) { check(amdg_dev_alloc(c, n, &p_)); check(amdg_dev_zero(c, p_, n)); }
+    DeviceArray(amdg_ctx * c, int64_t n) : ctx_(c), n_(n), cap_(n) { check(amdg_dev_alloc(c, n, &p_)); check(amdg_dev_zero(c, p_, n)); }
     DeviceArray(const DeviceArray &) = delete;
     DeviceArray & operator=(const DeviceArray &) = delete;
     DeviceArray(DeviceArray && o) noexcept { *this = std::move(o); }
-    DeviceArray & operator=(DeviceArray && o) noexcept { release(); ctx_ = o.ctx_; p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; return *this; }
+    DeviceArray & operator=(DeviceArray && o) noexcept { release(); ctx_ = o.ctx_; p_ = o.p_; n_ = o.n_; cap_ = o.cap_; o.p_ = nullptr; o.n_ = 0; o.cap_ = 0; return *this; }
     ~DeviceArray() { release(); }
     double * data() const { return p_; }
     int64_t size() const { return n_; }
     void upload(const double * h) { check(amdg_dev_upload(ctx_, p_, h, n_)); }
     void download(double * h) const { check(amdg_dev_download(ctx_, h, p_, n_)); }
     void set_zero() { check(amdg_dev_zero(ctx_, p_, n_)); }
+    // n zeroed doubles in place: the allocation is kept while it is large enough and grows geometrically, so an adaptive run whose grid changes
+    // every step (DGAdapt::refine / coarsen) does not pay a cudaFree (which synchronises) and a cudaMalloc per array and step
+    void resize(amdg_ctx * c, int64_t n)
+    {
+        if (c != ctx_ || n > cap_)
+        {
+            release();
+            ctx_ = c; cap_ = n + n / 2 + 1024;
+            check(amdg_dev_alloc(c, cap_, &p_));
+        }
+        n_ = n;
+        check(amdg_dev_zero(ctx_, p_, n_));
+    }
 private:
-    void release() { if (p_) amdg_dev_free(ctx_, p_); p_ = nullptr; }
-    amdg_ctx * ctx_ = nullptr; double * p_ = nullptr; int64_t n_ = 0;
+    void release() { if (p_) amdg_dev_free(ctx_, p_); p_ = nullptr; cap_ = 0; }
+    amdg_ctx * ctx_ = nullptr; double * p_ = nullptr; int64_t n_ = 0, cap_ = 0;
 };
 
 // The device-side stand-in of DGSolution: the statics Element::DIM / PMAX_alpt / PMAX_intp / VEC_NUM
@@ -68,12 +81,12 @@ public:
     {
         check(amdg_grid_set(ctx, n, level, suppt));
         n_elem = n;
-        ucoe_alpt = DeviceArray(ctx, VEC_NUM * n * size_alpt());
-        rhs = DeviceArray(ctx, VEC_NUM * n * size_alpt());
-        up_intp = DeviceArray(ctx, VEC_NUM * n * size_intp());
-        ucoe_intp = DeviceArray(ctx, VEC_NUM * n * size_intp());
-        fp_intp = DeviceArray(ctx, (int64_t)VEC_NUM * DIM * n * size_intp());
-        fucoe_intp = DeviceArray(ctx, (int64_t)VEC_NUM * DIM * n * size_intp());
+        ucoe_alpt.resize(ctx, VEC_NUM * n * size_alpt());
+        rhs.resize(ctx, VEC_NUM * n * size_alpt());
+        up_intp.resize(ctx, VEC_NUM * n * size_intp());
+        ucoe_intp.resize(ctx, VEC_NUM * n * size_intp());
+        fp_intp.resize(ctx, (int64_t)VEC_NUM * DIM * n * size_intp());
+        fucoe_intp.resize(ctx, (int64_t)VEC_NUM * DIM * n * size_intp());
     }
     // DGSolution(sparse, level_init, ...) initial grid (source/DGSolution.cpp:10-57)
     void init_sparse_grid(int level_init, bool sparse = true)
@@ -99,6 +112,7 @@ public:
     amdg_ctx * ctx = nullptr;
     int64_t n_elem = 0;
     DeviceArray ucoe_alpt, up_intp, ucoe_intp, fp_intp, fucoe_intp, rhs;
+    DeviceArray rk_u_tn;                 // the u^n snapshot of ExplicitRK (ODESolver::ucoe_tn): lives with the solution, not with the short-lived solver objects
 };
 
 // Handles of the registered 1D tables of one (U,V) basis pair: the members the path uses
@@ -416,17 +430,17 @@ private:
 class ExplicitRK
 {
 public:
-    ExplicitRK(DGSolution & dg, double dt_, int scheme, int stages) : num_stage(stages), dt(dt_), dg_(&dg), scheme_(scheme), u_tn_(dg.ctx, dg.get_dof()) {}
+    ExplicitRK(DGSolution & dg, double dt_, int scheme, int stages) : num_stage(stages), dt(dt_), dg_(&dg), scheme_(scheme) { dg.rk_u_tn.resize(dg.ctx, dg.get_dof()); }
     virtual ~ExplicitRK() {}
-    virtual void init() { check(amdg_axpby(dg_->ctx, dg_->get_dof(), 1.0, dg_->ucoe_alpt.data(), 0.0, u_tn_.data())); }
+    virtual void init() { check(amdg_axpby(dg_->ctx, dg_->get_dof(), 1.0, dg_->ucoe_alpt.data(), 0.0, dg_->rk_u_tn.data())); }
     void set_rhs_zero() {}
     void add_rhs_to_eigenvec() {}
-    virtual void step_stage(int stage) { check(amdg_rk_stage(dg_->ctx, scheme_, stage, dt, u_tn_.data(), dg_->ucoe_alpt.data(), dg_->rhs.data(), dg_->get_dof())); }
+    virtual void step_stage(int stage) { check(amdg_rk_stage(dg_->ctx, scheme_, stage, dt, dg_->rk_u_tn.data(), dg_->ucoe_alpt.data(), dg_->rhs.data(), dg_->get_dof())); }
     virtual void final() {}
     const int num_stage;
     const double dt;
 protected:
-    DGSolution * dg_; int scheme_; DeviceArray u_tn_;
+    DGSolution * dg_; int scheme_;
 };
 struct ForwardEuler : ExplicitRK { ForwardEuler(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_EULER, 1) {} };
 struct RK2SSP : ExplicitRK { RK2SSP(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK2SSP, 2) {} };
