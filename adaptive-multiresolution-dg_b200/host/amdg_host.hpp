@@ -72,7 +72,7 @@ public:
     DGSolution(int dim, int nmax, int pmax_alpt, int pmax_intp, int vec_num, int device = 0)
         : DIM(dim), NMAX(nmax), PMAX_alpt(pmax_alpt), PMAX_intp(pmax_intp), VEC_NUM(vec_num)
     { check(amdg_ctx_create(dim, nmax, pmax_alpt, pmax_intp, device, &ctx)); }
-    ~DGSolution() { ucoe_alpt = DeviceArray(); up_intp = DeviceArray(); ucoe_intp = DeviceArray(); fp_intp = DeviceArray(); fucoe_intp = DeviceArray(); rhs = DeviceArray(); amdg_ctx_destroy(ctx); }
+    ~DGSolution() { ucoe_alpt = DeviceArray(); up_intp = DeviceArray(); ucoe_intp = DeviceArray(); fp_intp = DeviceArray(); fucoe_intp = DeviceArray(); rhs = DeviceArray(); rk_u_tn = DeviceArray(); amdg_ctx_destroy(ctx); }
     DGSolution(const DGSolution &) = delete;
 
     // (re)build the index tables from the element list (call after construction / DGAdapt::refine / coarsen);
