@@ -65,6 +65,7 @@ SYMBOLS = {
     "amdg_sweep1d_batch": (_i, [_p, _i, _i, _i, _i, _ip, _p, _p, _dp, _ip, _i, _i]),
     "amdg_ctx_info": (_i, [_p, _p]),
     "amdg_op_generate": (_i, [_p, _i, _i, _i, _i, _p]),
+    "amdg_op_generate_bc": (_i, [_p, _i, _i, _i, _i, _i, _p]),
     "amdg_op_generate_points": (_i, [_p, _i, _i, _i, _i, _p]),
     "amdg_op_generate_hier": (_i, [_p, _i, _i, _i, _p]),
     "amdg_points_generate": (_i, [_p, _i, _i, _i, _p]),
@@ -233,9 +234,10 @@ class Context:
         return out.value
 
     # ---- tables generated by the library (no reference run): compact blocks per related 1D pair
-    def op_generate(self, basis_u, pmax_u, table, msh_case=1):
+    def op_generate(self, basis_u, pmax_u, table, msh_case=1, boundary="period"):
         out = _i()
-        _check(lib.amdg_op_generate(self._h, basis_u, pmax_u, msh_case, TABLES[table] if isinstance(table, str) else table, ctypes.byref(out)))
+        bc = {"period": 0, "zero": 1, "inside": 2}[boundary]
+        _check(lib.amdg_op_generate_bc(self._h, basis_u, pmax_u, msh_case, TABLES[table] if isinstance(table, str) else table, bc, ctypes.byref(out)))
         return out.value
 
     def op_generate_points(self, basis, pmax, msh_case=1, derivative=0):

@@ -46,11 +46,18 @@ static int make_intp_basis(int basis, int pmax, int msh_case, std::unique_ptr<ta
 
 extern "C" {
 
-int amdg_op_generate(amdg_ctx * c, int basis_u, int pmax_u, int msh_case_u, int table, int * out)
+static int op_generate_impl(amdg_ctx * c, int basis_u, int pmax_u, int msh_case_u, int table, int boundary, int * out);
+int amdg_op_generate(amdg_ctx * c, int basis_u, int pmax_u, int msh_case_u, int table, int * out) { return op_generate_impl(c, basis_u, pmax_u, msh_case_u, table, AMDG_BC_PERIOD, out); }
+int amdg_op_generate_bc(amdg_ctx * c, int basis_u, int pmax_u, int msh_case_u, int table, int boundary, int * out) { return op_generate_impl(c, basis_u, pmax_u, msh_case_u, table, boundary, out); }
+
+}  // extern "C"
+
+static int op_generate_impl(amdg_ctx * c, int basis_u, int pmax_u, int msh_case_u, int table, int boundary, int * out)
 {
     if (!c || !out) return fail(AMDG_EINVAL, "null argument");
     CTX_INFO();
     if (table < 0 || table >= tab::N_TABLE) return fail(AMDG_EINVAL, "unknown table");
+    if (boundary < 0 || boundary > 2) return fail(AMDG_EINVAL, "boundary must be AMDG_BC_PERIOD, _ZERO or _INSIDE");
     if (pmax_u < 0 || pmax_u > 5) return fail(AMDG_EINVAL, "pmax must be in 0..5");
     const tab::AlpertBasis V(pmax_alpt);
     std::unique_ptr<tab::Basis1D> U;
@@ -63,9 +70,11 @@ int amdg_op_generate(amdg_ctx * c, int basis_u, int pmax_u, int msh_case_u, int 
     }
     if ((table == tab::UX_V || table == tab::UJP_VXAVE) && (basis_u != AMDG_BASIS_ALPERT || pmax_u != pmax_alpt)) return fail(AMDG_EINVAL, "transposed tables need U == V");
     std::vector<double> blocks;
-    tab::operator_blocks(pairs, *U, V, table, blocks);
+    tab::operator_blocks(pairs, *U, V, table, blocks, boundary);
     return amdg_op_register_compact(c, blocks.data(), pairs.n_pairs, pmax_u + 1, (pmax_alpt + 1), 0, out);
 }
+
+extern "C" {
 
 int amdg_op_generate_points(amdg_ctx * c, int basis, int pmax, int msh_case, int derivative, int * out)
 {

@@ -16,7 +16,7 @@
 //   * the hierarchical Hermite basis is the two-point Hermite polynomial of degree 3 / 5 on a half interval (source/HermBasis.cpp:347-1150).
 //   * inner products use the reference's rule (two 10-point Gauss panels over the finer support, source/Basis.cpp:62-83) and one-sided
 //     limits are taken at x -/+ 1e-13 exactly like Basis::val (source/AlptBasis.cpp:16-29), so tables agree to ~1e-15, not just to O(1e-13).
-//   * periodic boundary ("period", source/Basis.cpp:145-173, 207-235) -- the only boundary type the examples of the path use.
+//   * boundary types "period" (the examples of the path; source/Basis.cpp:145-173, 207-235), "zero" and "inside" (:131-147, 193-205).
 // Host code only; no device needed.
 #pragma once
 #include <algorithm>
@@ -372,11 +372,12 @@ inline Elem1D elem_of_order(int o)
 }
 
 // ---- inner products of Basis (source/Basis.cpp) ------------------------------------------------------------------------
+enum Boundary { PERIOD = 0, ZERO = 1, INSIDE = 2 };     // boundary_type "period" / "zero" / "inside" of Basis::product_edge_dis_v / _u
 struct Products
 {
-    const Basis1D & U; const Basis1D & V; Gauss g;
+    const Basis1D & U; const Basis1D & V; Gauss g; int boundary = PERIOD;
     // the reference uses 10 points per panel; any rule exact for degree P_u + P_v gives the same integrals up to rounding
-    Products(const Basis1D & u, const Basis1D & v) : U(u), V(v), g(10) {}
+    Products(const Basis1D & u, const Basis1D & v, int boundary_ = PERIOD) : U(u), V(v), g(10), boundary(boundary_) {}
     double gl(const Elem1D & eu, int pu, int du, const Elem1D & ev, int pv, int dv, double tl, double tr) const
     {
         double s = 0;
@@ -403,8 +404,15 @@ struct Products
         double s = 0;
         for (int i = 0; i < 3; ++i)
         {
-            if (e.n <= 1 && i == 2) continue;
             const double pt = e.dis[i];
+            if (boundary == ZERO) { s += U.val(pt, eu.n, eu.j, pu, du, su) * V.val(pt, ev.n, ev.j, pv, dv, sv); continue; }                     // :131-137
+            if (boundary == INSIDE)                                                                                                                     // :139-147
+            {
+                if (std::abs(pt - 0.) < RO || std::abs(pt - 1.) < RO) continue;
+                s += U.val(pt, eu.n, eu.j, pu, du, su) * V.val(pt, ev.n, ev.j, pv, dv, sv);
+                continue;
+            }
+            if (e.n <= 1 && i == 2) continue;
             double vu = U.val(pt, eu.n, eu.j, pu, du, su), vv = V.val(pt, ev.n, ev.j, pv, dv, sv);
             if (std::abs(pt - 0.) < RO)
             {
@@ -454,14 +462,14 @@ inline void parallel_pairs(int n, F body)
 }
 
 // blocks[n_pairs][ku][kv] of one table of OperatorMatrix1D<U, V>, pairs in the canonical order (source element carries U, target element V)
-inline void operator_blocks(const Pairs1D & P1, const Basis1D & U, const Basis1D & V, int table, std::vector<double> & blocks)
+inline void operator_blocks(const Pairs1D & P1, const Basis1D & U, const Basis1D & V, int table, std::vector<double> & blocks, int boundary = PERIOD)
 {
     const int ku = U.P + 1, kv = V.P + 1;
     blocks.assign((size_t)P1.n_pairs * ku * kv, 0.0);
     // transposed tables: ux_v.at(v, u) = u_vx.at(u, v), ujp_vxave.at(v, u) = uxave_vjp.at(u, v) (both square, U == V)
     const bool transposed = (table == UX_V || table == UJP_VXAVE);
     const int base = table == UX_V ? (int)U_VX : (table == UJP_VXAVE ? (int)UXAVE_VJP : table);
-    const Products pr(U, V);
+    const Products pr(U, V, boundary);
     std::vector<Elem1D> el(P1.T);
     for (int o = 0; o < P1.T; ++o) el[o] = elem_of_order(o);
     parallel_pairs(P1.n_pairs, [&](int p)

@@ -118,6 +118,10 @@ enum { AMDG_BASIS_ALPERT = 0, AMDG_BASIS_LAGRANGE = 1, AMDG_BASIS_HERMITE = 2 };
 enum { AMDG_TAB_U_V = 0, AMDG_TAB_U_VX = 1, AMDG_TAB_ULFT_VJP = 2, AMDG_TAB_URGT_VJP = 3, AMDG_TAB_UJP_VJP = 4, AMDG_TAB_UAVE_VJP = 5, AMDG_TAB_UJP_VXLFT = 6,
        AMDG_TAB_UJP_VXRGT = 7, AMDG_TAB_UX_VX = 8, AMDG_TAB_UXAVE_VJP = 9, AMDG_TAB_UJP_VXAVE = 10, AMDG_TAB_UX_V = 11 };
 int amdg_op_generate(amdg_ctx *ctx, int basis_u, int pmax_u, int msh_case_u, int table, int *op_out);
+/* the same for the other boundary types of Basis::product_edge_dis_v / _u (source/Basis.cpp:127-235): "zero" (all discontinuity points, no wrap) and
+ * "inside" (points on x = 0, 1 skipped); the volume tables do not depend on it */
+enum { AMDG_BC_PERIOD = 0, AMDG_BC_ZERO = 1, AMDG_BC_INSIDE = 2 };
+int amdg_op_generate_bc(amdg_ctx *ctx, int basis_u, int pmax_u, int msh_case_u, int table, int boundary, int *op_out);
 int amdg_op_generate_points(amdg_ctx *ctx, int basis, int pmax, int msh_case, int derivative, int *op_out);
 int amdg_op_generate_hier(amdg_ctx *ctx, int basis, int pmax, int msh_case, int *op_out);
 int amdg_points_generate(amdg_ctx *ctx, int basis, int pmax, int msh_case, double *host_pts1d);

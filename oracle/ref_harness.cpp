@@ -100,7 +100,7 @@ struct Args
     double eps = 1e10, eta = -1.0;
     uint64_t seed = 20240901ULL;
     double dt = 1e-3;
-    std::string intp = "lagr", flux = "burgers", run = "grid", out = "";
+    std::string intp = "lagr", flux = "burgers", run = "grid", out = "", boundary = "period";
 };
 
 static Args parse(int argc, char ** argv)
@@ -119,6 +119,7 @@ static Args parse(int argc, char ** argv)
         else if (k == "--dump-tables") a.dump_tables = std::stoi(v); else if (k == "--dt") a.dt = std::stod(v);
         else if (k == "--msh-lagr") a.msh_lagr = std::stoi(v); else if (k == "--msh-herm") a.msh_herm = std::stoi(v);
         else if (k == "--steps") a.steps = std::stoi(v);
+        else if (k == "--boundary") a.boundary = v;
         else if (k == "--adapt-eps") a.eps = std::stod(v); else if (k == "--adapt-eta") a.eta = std::stod(v);
         else if (k == "--adapt-rounds") a.rounds = std::stoi(v);
         else { std::cerr << "unknown option " << k << std::endl; exit(2); }
@@ -254,7 +255,7 @@ int main(int argc, char ** argv)
     Element::is_intp.resize(a.vecnum);
     for (int v = 0; v < a.vecnum; ++v) Element::is_intp[v] = std::vector<bool>(DIM, true);
     if (a.threads > 0) omp_set_num_threads(a.threads);
-    const std::string boundary_type = "period";
+    const std::string boundary_type = a.boundary;
 
     std::set<std::string> run; { std::stringstream ss(a.run); std::string tok; while (std::getline(ss, tok, ',')) run.insert(tok); }
     auto has = [&](const char * s) { return run.count(s) > 0; };

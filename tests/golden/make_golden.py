@@ -51,6 +51,9 @@ CASES = {
     "pw_vlasov_d4_k1_n3_v2": "--dim 4 --nmax 3 --pa 1 --pl 2 --vecnum 2 --run grid,pw --dump-tables 1",
     # one RK3SSP step of the coupled 2D2V Vlasov-Ampere system (f: interp_Vlasov_2D2V + rhs + penalty; E_t = -J by compute_moment_2D2V), per stage
     "vlasov_ampere_d4_k1_n3_v2": "--dim 4 --nmax 3 --pa 1 --pl 2 --vecnum 2 --run grid,vlasov_ampere --dump-tables 1 --dt 0.002",
+    # 1D tables under the other boundary types of Basis::product_edge_dis_v / _u (table-generation parity only)
+    "tables_bc_zero_k2_n4": "--dim 1 --nmax 4 --pa 2 --pl 3 --ph 3 --boundary zero --run grid --dump-tables 2",
+    "tables_bc_inside_k2_n4": "--dim 1 --nmax 4 --pa 2 --pl 3 --ph 3 --boundary inside --run grid --dump-tables 2",
     "line_d1_k2_n5": "--dim 1 --nmax 5 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux burgers --dump-tables 1",
 }
 

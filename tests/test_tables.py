@@ -20,11 +20,15 @@ def _msh_case(name):
     return 2 if name == "vlasov_d4_k3_m4_n2" else 1     # tests/golden/make_golden.py: --msh-lagr 2
 
 
+def _boundary(name):
+    return "zero" if "_bc_zero_" in name else ("inside" if "_bc_inside_" in name else "period")
+
+
 @pytest.mark.parametrize("name", [n for n in golden_names() if "alpt.u_v" in load_golden(n)])
 def test_generated_tables_match_reference_dump(amdg, name):
     d = load_golden(name)
     dim, nmax, n0, sparse, pa, pl, ph, vecnum, herm, ne = [int(x) for x in d["config"]]
-    a, msh = pa + 1, _msh_case(name)
+    a, msh, bc = pa + 1, _msh_case(name), _boundary(name)
     ctx = amdg.Context(1, nmax, pa, pl, device=-1)
     fam = {"alpt": (amdg.BASIS_ALPERT, pa, 1), "lagr": (amdg.BASIS_LAGRANGE, pl, msh), "herm": (amdg.BASIS_HERMITE, ph, 1)}
     checked = 0
@@ -34,7 +38,7 @@ def test_generated_tables_match_reference_dump(amdg, name):
             basis, p, m = fam[pre]
             if pre == "herm" and p not in (3, 5):
                 continue
-            gen = ctx.op_blocks(ctx.op_generate(basis, p, tab, m), p + 1, a)
+            gen = ctx.op_blocks(ctx.op_generate(basis, p, tab, m, bc), p + 1, a)
             ref = ctx.op_blocks(ctx.op_register(d[key], p + 1, a), p + 1, a)
             assert _rel(gen, ref) < TOL, key
             checked += 1
