@@ -82,3 +82,22 @@ def test_partition_and_switch_world2(dim, nmax):
         p.join(timeout=60)
     for r, msg in res:
         assert msg == "ok", msg
+
+
+def test_partition_with_more_ranks_than_groups():
+    """a layout with fewer ownership groups than ranks (coarse grid, many GPUs) leaves ranks without elements; the partition still covers every
+    element exactly once in both layouts, empty ranks get empty row lists, and the stage plan of an empty rank has the same operation list as the
+    others (it must take part in every barrier)"""
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    D = importlib.import_module("adaptive-multiresolution-dg_b200.dist")
+    S = importlib.import_module("adaptive-multiresolution-dg_b200.stage")
+    lev, sup = A.sparse_grid(4, 1)                    # 4-D level 1: 5 elements, at most 3 ownership groups per layout
+    world = 8
+    parts = [D.FibrePartition(lev, sup, world, r) for r in range(world)]
+    for k in ("X", "V"):
+        rows = np.concatenate([p.local[k] for p in parts])
+        assert sorted(rows.tolist()) == list(range(lev.shape[0]))
+        assert sum(1 for p in parts if len(p.local[k]) == 0) >= world - lev.shape[0]
+    plans = [S.StagePlan(4, 2, 3, 4, part=p, fuse_rk=True) for p in parts]
+    kinds = [[o[0] for o in pl.ops] for pl in plans]
+    assert all(k == kinds[0] for k in kinds) and all(pl.n_barrier == plans[0].n_barrier for pl in plans)
