@@ -424,6 +424,16 @@ class DeviceStage:
     def local_ptr(self, name):
         return self.slab + 8 * self.layout.offset(name)
 
+    def swap_result(self):
+        """single-GPU fused plans leave the stage's result in the RK accumulator ("u_new"), not in "u": exchange the slab offsets of the two buffers so
+        that the next run() of the same (eager) program reads the new state -- a pointer swap, no copy.  CUDA graphs bake addresses in: a time
+        loop that replays graphs captures one graph per parity instead."""
+        r = self.plan.alias.get(self.plan.result, self.plan.result)
+        if r == "u":
+            return
+        i, j = self.layout.index["u"], self.layout.index[r]
+        self.layout.off[:, [i, j]] = self.layout.off[:, [j, i]]
+
     def close(self):
         c0 = self.ctx["X"]
         c0.sync()

@@ -300,6 +300,8 @@ def test_stage_program_burgers_2d_vs_reference():
         torch.cuda.synchronize()
         cur = st.view(plan.result).clone()
         assert rel(cur.cpu().numpy(), d["stage%d.ucoe_alpt" % stage][:, 0, :]) < TOL
+        st.swap_result()                                         # the accumulator becomes "u" of the next run of this program (pointer swap)
+        assert torch.equal(st.view("u"), cur)
         st.close()
 
 
