@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <cmath>
 #include <vector>
 
 #include "../../include/amdg.h"
@@ -81,6 +82,8 @@ public:
     {
         check(amdg_grid_set(ctx, n, level, suppt));
         n_elem = n;
+        max_mesh = 0;                                                    // DGSolution::max_mesh_level (source/DGSolution.cpp): largest 1D level of any element
+        for (int64_t i = 0; i < n * DIM; ++i) max_mesh = std::max(max_mesh, level[i]);
         ucoe_alpt.resize(ctx, VEC_NUM * n * size_alpt());
         rhs.resize(ctx, VEC_NUM * n * size_alpt());
         up_intp.resize(ctx, VEC_NUM * n * size_intp());
@@ -111,6 +114,8 @@ public:
     const int DIM, NMAX, PMAX_alpt, PMAX_intp, VEC_NUM;
     amdg_ctx * ctx = nullptr;
     int64_t n_elem = 0;
+    int max_mesh = 0;
+    int max_mesh_level() const { return max_mesh; }
     DeviceArray ucoe_alpt, up_intp, ucoe_intp, fp_intp, fucoe_intp, rhs;
     DeviceArray rk_u_tn;                 // the u^n snapshot of ExplicitRK (ODESolver::ucoe_tn): lives with the solution, not with the short-lived solver objects
 };
@@ -149,7 +154,23 @@ struct OperatorMatrix1D
         check(amdg_op_combine(dg.ctx, ulft_vjp, 1.0, urgt_vjp, 1.0, &uave2_vjp));
         check(amdg_op_combine(dg.ctx, ulft_vjp, 0.5, urgt_vjp, 0.5, &uave_vjp));
         check(amdg_op_combine(dg.ctx, ujp_vxlft, 1.0, ujp_vxrgt, 1.0, &ujp_vxave2));
+        if (basis == AMDG_BASIS_ALPERT && pmax == dg.PMAX_alpt)
+        {
+            // the tables of the interior-penalty diffusion operator (include/OperatorMatrix1D.h:216-226), Alpert x Alpert only
+            check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_UX_VX, &ux_vx));
+            check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_UXAVE_VJP, &uxave_vjp));
+            check(amdg_op_generate(dg.ctx, basis, pmax, msh_case, AMDG_TAB_UJP_VXAVE, &ujp_vxave));
+        }
     }
+    // the same three tables from the reference's dense ones
+    void set_diffusion_tables(DGSolution & dg, const double * t_ux_vx, const double * t_uxave_vjp, const double * t_ujp_vxave)
+    {
+        const int T = 1 << dg.NMAX, rows = T * edge_from, cols = T * edge_to;
+        check(amdg_op_register(dg.ctx, t_ux_vx, rows, cols, edge_from, edge_to, &ux_vx));
+        check(amdg_op_register(dg.ctx, t_uxave_vjp, rows, cols, edge_from, edge_to, &uxave_vjp));
+        check(amdg_op_register(dg.ctx, t_ujp_vxave, rows, cols, edge_from, edge_to, &ujp_vxave));
+    }
+    int ux_vx = -1, uxave_vjp = -1, ujp_vxave = -1;
     // the [u] * v_x^-, [u] * v_x^+ tables of DiffusionRHS (include/OperatorMatrix1D.h:209-214)
     void set_ujp_vx(DGSolution & dg, const double * t_ujp_vxlft, const double * t_ujp_vxrgt)
     {
@@ -424,6 +445,73 @@ private:
     DGSolution * dg_; OperatorMatrix1D * m_;
 };
 
+// BilinearFormAlpt / HyperbolicAlpt / DiffusionAlpt (include/BilinearForm.h; source/BilinearForm.cpp:25-87, 691-779, 877-929).  The reference assembles an
+// Eigen sparse matrix from the 1D tables (assemble_matrix_alpt: the 1D operator along `dim`, the mass matrix elsewhere, "vol" or "flx" relation) and
+// ExplicitRK::add_rhs_matrix / step_rk multiply it.  Here every assemble call adds its scaled 1D table to ONE pre-merged operator per dimension
+// (amdg_op_combine; a volume table has zero blocks on the pairs that are only flux-related, so the merged operator runs under the flx relation, and
+// the Alpert mass matrix is the identity) and the product is one full sweep per dimension -- no matrix is ever assembled.
+class BilinearFormAlpt
+{
+public:
+    BilinearFormAlpt(DGSolution & dg, OperatorMatrix1D & oper_alpt) : dg_(&dg), m_(&oper_alpt), merged_(dg.DIM, -1) {}
+    // mat += coef * (table along dim (x) identity elsewhere)
+    void assemble_matrix_alpt(double coef, int dim, int table)
+    {
+        if (table < 0) throw Error("BilinearFormAlpt: table not registered");
+        int out = -1;
+        if (merged_[dim] < 0) check(amdg_op_combine(dg_->ctx, table, coef, table, 0.0, &out));
+        else check(amdg_op_combine(dg_->ctx, merged_[dim], 1.0, table, coef, &out));
+        merged_[dim] = out;
+    }
+    // rhs += mat * ucoe_alpt (ODESolver::add_rhs_matrix, source/ODESolver.cpp:129-137)
+    void add_to_rhs(int vec_index = 0) const
+    {
+        std::vector<int> sizes(dg_->DIM, dg_->PMAX_alpt + 1);
+        for (int t = 0; t < dg_->DIM; ++t)
+            if (merged_[t] >= 0)
+                check(amdg_sweep1d(dg_->ctx, merged_[t], AMDG_REL_FLX, AMDG_LU_FULL, t, sizes.data(), dg_->ucoe(vec_index), dg_->rhs_v(vec_index), 1, 1.0, 1));
+    }
+    DGSolution & solution() const { return *dg_; }
+protected:
+    DGSolution * dg_; OperatorMatrix1D * m_; std::vector<int> merged_;
+};
+
+class HyperbolicAlpt : public BilinearFormAlpt
+{
+public:
+    using BilinearFormAlpt::BilinearFormAlpt;
+    // u_t + sum_d c_d u_{x_d} = 0 with upwind fluxes (source/BilinearForm.cpp:691-710)
+    void assemble_matrix_scalar(const std::vector<double> & eqnCoefficient)
+    {
+        for (int dim = 0; dim < dg_->DIM; ++dim)
+        {
+            assemble_matrix_alpt(eqnCoefficient[dim], dim, m_->u_vx);
+            assemble_matrix_alpt(eqnCoefficient[dim], dim, eqnCoefficient[dim] >= 0 ? m_->ulft_vjp : m_->urgt_vjp);
+        }
+    }
+    // one-sided flux term (source/BilinearForm.cpp:760-769): sign -1 takes the left limit, +1 the right limit
+    void assemble_matrix_flx_scalar(int dim, int sign, double coefficient = 1.) { assemble_matrix_alpt(coefficient, dim, sign == -1 ? m_->ulft_vjp : m_->urgt_vjp); }
+};
+
+class DiffusionAlpt : public BilinearFormAlpt
+{
+public:
+    DiffusionAlpt(DGSolution & dg, OperatorMatrix1D & oper_alpt, double sigma_ipdg_) : BilinearFormAlpt(dg, oper_alpt), sigma_ipdg(sigma_ipdg_) {}
+    // interior-penalty Laplacian (source/BilinearForm.cpp:877-929): -(u_x, v_x) - {u_x}[v] - [u]{v_x} - sigma / dx [u][v], dx = 2^-max_mesh_level
+    void assemble_matrix_scalar(const std::vector<double> & eqnCoefficient)
+    {
+        const double dx = 1. / std::pow(2., dg_->max_mesh_level());
+        for (int dim = 0; dim < dg_->DIM; ++dim)
+        {
+            assemble_matrix_alpt(-eqnCoefficient[dim], dim, m_->ux_vx);
+            assemble_matrix_alpt(-eqnCoefficient[dim], dim, m_->uxave_vjp);
+            assemble_matrix_alpt(-eqnCoefficient[dim], dim, m_->ujp_vxave);
+            assemble_matrix_alpt(-sigma_ipdg / dx, dim, m_->ujp_vjp);
+        }
+    }
+    const double sigma_ipdg;
+};
+
 // ExplicitRK (include/ODESolver.h:76-112).  The reference packs Element arrays into Eigen vectors
 // (source/ODESolver.cpp:25-127); here ucoe_alpt / rhs already are the flat vectors, so init() only snapshots u_tn
 // and add_rhs_to_eigenvec()/final() are no-ops kept for call-order compatibility.
@@ -431,6 +519,17 @@ class ExplicitRK
 {
 public:
     ExplicitRK(DGSolution & dg, double dt_, int scheme, int stages) : num_stage(stages), dt(dt_), dg_(&dg), scheme_(scheme) { dg.rk_u_tn.resize(dg.ctx, dg.get_dof()); }
+    // the reference's ODESolver(BilinearForm &) constructor (include/ODESolver.h:14): the solver keeps the linear operator for step_rk
+    ExplicitRK(BilinearFormAlpt & linear, double dt_, int scheme, int stages) : ExplicitRK(linear.solution(), dt_, scheme, stages) { linear_ = &linear; }
+    // rhs += mat * ucoe (ODESolver::add_rhs_matrix): here d sweeps with the operator's pre-merged 1D tables
+    void add_rhs_matrix(const BilinearFormAlpt & linear) { linear.add_to_rhs(); }
+    // one whole step of a linear problem (ExplicitRK::step_rk, e.g. RK3SSP::step_rk source/ODESolver.cpp:261-271): every stage evaluates rhs = mat * u
+    void step_rk()
+    {
+        if (!linear_) throw Error("step_rk needs the solver to be constructed from a linear operator");
+        check(amdg_axpby(dg_->ctx, dg_->get_dof(), 1.0, dg_->ucoe_alpt.data(), 0.0, dg_->rk_u_tn.data()));
+        for (int stage = 0; stage < num_stage; ++stage) { dg_->set_rhs_zero(); linear_->add_to_rhs(); step_stage(stage); }
+    }
     virtual ~ExplicitRK() {}
     virtual void init() { check(amdg_axpby(dg_->ctx, dg_->get_dof(), 1.0, dg_->ucoe_alpt.data(), 0.0, dg_->rk_u_tn.data())); }
     void set_rhs_zero() {}
@@ -440,13 +539,16 @@ public:
     const int num_stage;
     const double dt;
 protected:
-    DGSolution * dg_; int scheme_;
+    DGSolution * dg_; int scheme_; BilinearFormAlpt * linear_ = nullptr;
 };
-struct ForwardEuler : ExplicitRK { ForwardEuler(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_EULER, 1) {} };
-struct RK2SSP : ExplicitRK { RK2SSP(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK2SSP, 2) {} };
-struct RK2Midpoint : ExplicitRK { RK2Midpoint(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK2MID, 2) {} };
-struct RK3SSP : ExplicitRK { RK3SSP(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK3SSP, 3) {} };
-struct RK3HeunLinear : ExplicitRK { RK3HeunLinear(DGSolution & dg, double dt) : ExplicitRK(dg, dt, AMDG_RK_RK3HEUN, 3) {} };
+#define AMDG_RK_SCHEME(NAME, ID, STAGES) struct NAME : ExplicitRK { NAME(DGSolution & dg, double dt) : ExplicitRK(dg, dt, ID, STAGES) {} \
+                                                                    NAME(BilinearFormAlpt & linear, double dt) : ExplicitRK(linear, dt, ID, STAGES) {} };
+AMDG_RK_SCHEME(ForwardEuler, AMDG_RK_EULER, 1)
+AMDG_RK_SCHEME(RK2SSP, AMDG_RK_RK2SSP, 2)
+AMDG_RK_SCHEME(RK2Midpoint, AMDG_RK_RK2MID, 2)
+AMDG_RK_SCHEME(RK3SSP, AMDG_RK_RK3SSP, 3)
+AMDG_RK_SCHEME(RK3HeunLinear, AMDG_RK_RK3HEUN, 3)
+#undef AMDG_RK_SCHEME
 
 // RK4ODE2nd (include/ODESolver.h, source/ODESolver.cpp:543-615): u_tt = L u as the pair (ucoe_alpt, ucoe_ut); the caller
 // evaluates rhs = L u before every step_stage, exactly as with the reference's stage interface.

@@ -3,7 +3,7 @@
 // run to t = 0.1) executed twice for every N:
 //   reference arm: the UNMODIFIED reference classes (oracle/_ref/libsgdg_ref.a): HyperbolicAlpt::assemble_matrix_scalar + RK3SSP::step_rk on the
 //                  assembled sparse matrix (:154-166), the shipped path;
-//   device arm:    the same operator as 1D sweeps over the C ABI (libamdg_b200.so): per stage d sweeps with u_vx + ulft_vjp (upwind flux, c >= 0:
+//   device arm:    amdg::HyperbolicAlpt + amdg::RK3SSP::step_rk of the mirror (library-generated tables): per stage d sweeps with u_vx + ulft_vjp (upwind flux, c >= 0:
 //                  source/BilinearForm.cpp:700-703) merged into one operator, then ExplicitRK::step_stage on the device.
 // After the last step the coefficients must agree to 1e-10 (relative L2; north_star's full-run bound) and the L2 errors against the exact solution
 // (the reference's own error routine, DGSolution::get_error_no_separable_scalar, on both coefficient sets) must coincide; the table of errors and
@@ -114,29 +114,21 @@ int main(int argc, char ** argv)
                 for (auto & it : dg_dev.dg) for (int d = 0; d < DIM; ++d) { level.push_back(it.second.level[d]); suppt.push_back(it.second.suppt[d]); }
                 dev.set_elements((int64_t)dg_dev.dg.size(), level.data(), suppt.data());
             }
-            const int a = AlptBasis::PMAX + 1, rows = (int)oper.u_vx.vec_size()[0];
-            int op_vol = -1, op_flx = -1, op_adv = -1;
-            amdg::check(amdg_op_register(dev.ctx, dense(oper.u_vx).data(), rows, rows, a, a, &op_vol));
-            amdg::check(amdg_op_register(dev.ctx, dense(oper.ulft_vjp).data(), rows, rows, a, a, &op_flx));
-            amdg::check(amdg_op_combine(dev.ctx, op_vol, 1.0, op_flx, 1.0, &op_adv));
+            // the device arm reads like the stock example: tables, the linear operator, RK3SSP(operator, dt), step_rk -- only the namespace differs.
+            // The tables are generated by the library (no table of the reference is read); the operator is one pre-merged 1D table per dimension
+            amdg::OperatorMatrix1D d_oper(dev, AMDG_BASIS_ALPERT, AlptBasis::PMAX);
+            amdg::HyperbolicAlpt d_op(dev, d_oper);
+            d_op.assemble_matrix_scalar(c);
             {
                 std::vector<double> h; h.reserve(dev.get_dof());
                 for (auto & it : dg_dev.dg) for (int i = 0; i < it.second.ucoe_alpt[0].size(); ++i) h.push_back(it.second.ucoe_alpt[0].at(i));
                 dev.ucoe_alpt.upload(h.data());
             }
-            const std::vector<int> sizes(DIM, a);
             {
-                amdg::RK3SSP ode(dev, dt);
-                for (int s = 0; s < n_steps; ++s)
-                {
-                    ode.init();
-                    for (int stage = 0; stage < ode.num_stage; ++stage)
-                    {
-                        for (int t = 0; t < DIM; ++t)
-                            amdg::check(amdg_sweep1d(dev.ctx, op_adv, AMDG_REL_FLX, AMDG_LU_FULL, t, sizes.data(), dev.ucoe(0), dev.rhs_v(0), 1, c[t], t > 0));
-                        ode.step_stage(stage);
-                    }
-                }
+                amdg::RK3SSP ode(d_op, dt);
+                ode.init();
+                for (int s = 0; s < n_steps; ++s) ode.step_rk();
+                ode.final();
             }
             {
                 std::vector<double> h(dev.get_dof());
