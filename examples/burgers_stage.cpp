@@ -45,6 +45,42 @@ int main(int argc, char ** argv)
     // --generated: every 1D table comes from the library's own generator (amdg_op_generate*); the dump then only supplies the grid, the
     // initial coefficients and the reference's stage results
     const bool generated = argc > 2 && std::string(argv[2]) == "--generated";
+    // --wave / --wave-generated: the dump is a wave fixture (cfg3): the interior-penalty Laplacian of amdg::DiffusionAlpt (one pre-merged 1D operator per
+    // dimension, no assembled matrix) applied to the dumped coefficients against the reference's assembled SpMV (wave.rhs_spmv)
+    const bool wave = argc > 2 && std::string(argv[2]).rfind("--wave", 0) == 0;
+    if (wave)
+    {
+        auto D = load_dump(argv[1]);
+        const int * cfg = D["config"].i();
+        const int DIM = cfg[0], NMAX = cfg[1], PA = cfg[4], PL = cfg[5];
+        try
+        {
+            amdg::DGSolution dg_solu(DIM, NMAX, PA, PL, 1, 0);
+            dg_solu.set_elements(cfg[9], D["level"].i(), D["suppt"].i());
+            amdg::OperatorMatrix1D oper_matx_alpt;
+            if (std::string(argv[2]) == "--wave-generated") oper_matx_alpt = amdg::OperatorMatrix1D(dg_solu, AMDG_BASIS_ALPERT, PA);
+            else
+            {
+                oper_matx_alpt = amdg::OperatorMatrix1D(dg_solu, PA + 1, PA + 1, D["alpt.u_v"].d(), D["alpt.u_vx"].d(), D["alpt.ulft_vjp"].d(), D["alpt.urgt_vjp"].d(), D["alpt.ujp_vjp"].d());
+                oper_matx_alpt.set_diffusion_tables(dg_solu, D["alpt.ux_vx"].d(), D["alpt.uxave_vjp"].d(), D["alpt.ujp_vxave"].d());
+            }
+            const double sigma = DIM == 2 ? 10. : 20.;                           // example/03_wave_01_const_coeff_periodic.cpp:64
+            amdg::DiffusionAlpt linear(dg_solu, oper_matx_alpt, sigma);
+            linear.assemble_matrix_scalar(std::vector<double>(DIM, 1.));
+            dg_solu.ucoe_alpt.upload(D["ucoe_alpt.in"].d());
+            dg_solu.set_rhs_zero();
+            amdg::RK3SSP ode(linear, 1e-3);
+            ode.add_rhs_matrix(linear);
+            std::vector<double> host(dg_solu.get_dof());
+            dg_solu.rhs.download(host.data());
+            const double e = rel_l2(host, D["wave.rhs_spmv"].d());
+            std::printf("DiffusionAlpt (max mesh level %d): rel-L2 vs the reference's assembled operator %.3e\n", dg_solu.max_mesh_level(), e);
+            if (!(e < 1e-12)) { std::printf("FAIL\n"); return 1; }
+            std::printf("OK\n");
+        }
+        catch (const std::exception & e) { std::cerr << e.what() << std::endl; return 1; }
+        return 0;
+    }
     auto D = load_dump(argv[1]);
     const int * cfg = D["config"].i();
     const int DIM = cfg[0], NMAX = cfg[1], PA = cfg[4], PL = cfg[5];

@@ -211,6 +211,13 @@ def test_cpp_host_mirror_example(tmp_path):
     # the same three stages with every table generated by the library (no table of the reference is read)
     r = subprocess.run([exe, str(dump), "--generated"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+    # the mirror's DiffusionAlpt (interior-penalty Laplacian as one pre-merged 1D operator per dimension) against the reference's assembled SpMV
+    wave = tmp_path / "wave.dump"
+    with lzma.open(os.path.join(GOLDEN, "cfg3_wave_d3_k2_n3.dump.xz"), "rb") as f:
+        wave.write_bytes(f.read())
+    for flag in ("--wave", "--wave-generated"):
+        r = subprocess.run([exe, str(wave), flag], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout
 
 
 def test_multi_gpu_fibre_partition():
