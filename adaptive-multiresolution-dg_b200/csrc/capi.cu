@@ -55,6 +55,8 @@ struct amdg_ctx
     // costs more than the sweeps they serve.  A grid that replaces one which lived fewer than adaptive_life sweeps puts the context in adaptive mode:
     // sweeps below tc_min_doubles run the gather kernel, which needs nothing beyond the tables amdg_grid_set uploads, until the grid has lived that long.
     int64_t sweeps_on_grid = 0, adaptive_life = 512; bool adaptive_mode = false;
+    int adaptive_max_fibre = 128;      // ... and only along dimensions whose longest fibre is short: a gather thread walks its target's whole entry list (measured:
+                                       // 12-14 us per sweep on fibres of a few dozen elements, ~200 us on the 512-element fibres of the full 2-D NMAX = 9 grid)
     Grid grid_spare;                                 // the previous grid's tables: amdg_grid_set builds into their storage (no fresh pages)
     std::vector<NbrCache> nbr_caches;                // neighbour lists per fibre shape, kept across grid changes (grid.hpp)
     // *_coarse_grid transforms (amdg_apply_tensor_coarse): the elements with sum of levels <= mesh_nmax as a grid of their own
@@ -274,6 +276,7 @@ int amdg_ctx_create(int dim, int nmax, int pmax_alpt, int pmax_intp, int device,
     if (const char * e = std::getenv("AMDG_TC_STAGE_A")) c->tc_stage_a_max = std::max(0, atoi(e));
     if (const char * e = std::getenv("AMDG_TC_MIN_DOUBLES")) c->tc_min_doubles = atoll(e);
     if (const char * e = std::getenv("AMDG_ADAPTIVE_LIFE")) c->adaptive_life = atoll(e);
+    if (const char * e = std::getenv("AMDG_ADAPTIVE_FIBRE")) c->adaptive_max_fibre = std::max(1, atoi(e));
     if (const char * e = std::getenv("AMDG_TC_FORCE_STAGE")) c->tc_force_stage = atoi(e) != 0;
     if (const char * e = std::getenv("AMDG_TC_COARSE_ENT")) c->tc_coarse_ent = std::max(16, atoi(e));
     if (const char * e = std::getenv("AMDG_PIPE_CAP")) c->pipe_cap_doubles = std::max(256, atoi(e)) & ~1;
@@ -1425,7 +1428,7 @@ static int launch_sweep(amdg_ctx * c, int op, int rel, int lu, int t, int inner,
     };
     const int variant0 = (mapped && c->kernel_variant < 8) ? 5 : c->kernel_variant;
     c->sweeps_on_grid++;
-    const bool young = c->kernel_variant == 0 && !mapped && c->adaptive_mode && c->sweeps_on_grid <= c->adaptive_life;
+    const bool young = c->kernel_variant == 0 && !mapped && c->adaptive_mode && c->sweeps_on_grid <= c->adaptive_life && c->grid.dims[t].max_fibre_len <= c->adaptive_max_fibre;
     int done = 0;
     while (done < n_job)
     {

@@ -319,6 +319,18 @@ int main(int argc, char ** argv)
             worst = std::max(worst, e);
             curr_time += dt;
             std::printf("step %2d  dt %.3e  elements %5zu  DoF %6d  rel-L2(device, reference) %.3e\n", step, dt, dg_ref.dg.size(), dg_ref.size_basis_alpt(), e);
+            if (trace)
+            {
+                // longest fibre of the current grid per dimension (what decides the list-free kernel in the context's adaptive mode)
+                for (int t = 0; t < DIM; ++t)
+                {
+                    const int64_t nf = amdg_grid_fibres(dev.ctx, t, nullptr, nullptr);
+                    std::vector<int64_t> ptr(nf + 1); std::vector<int> el(dev.n_elem);
+                    amdg_grid_fibres(dev.ctx, t, ptr.data(), el.data());
+                    int64_t longest = 0; for (int64_t f = 0; f < nf; ++f) longest = std::max(longest, ptr[f + 1] - ptr[f]);
+                    std::printf("trace step %d: dimension %d: %lld fibres, longest %lld elements\n", step, t, (long long)nf, (long long)longest);
+                }
+            }
         }
         // ---- L2 error against the exact solution (the reference's own routine on both coefficient sets)
         BurgersExact burgers(0., 1., 0.);
