@@ -86,6 +86,29 @@ def test_alpert_construction_is_orthonormal(amdg, P):
     ctx.close()
 
 
+@pytest.mark.parametrize("P", [0, 1, 2, 3, 4, 5])
+def test_alpert_tables_satisfy_integration_by_parts(amdg, P):
+    """a check that does not involve the reference (whose hard-coded multiwavelets stop at P = 4): on the periodic interval
+        (u, v_x) + (u_x, v) = - sum over all discontinuity points of [[u v]],   [[u v]] = u+ [[v]] + [[u]] v-,
+    i.e. for every related pair (f, e) and its transposed partner (e, f):  u_vx[f,e] + u_vx[e,f]^T + urgt_vjp[f,e] + ulft_vjp[e,f]^T = 0.
+    The residual is the reference's own convention of taking one-sided limits 1e-13 away from the point (Basis::val), amplified by the derivative
+    scale of the fine levels: <= 2e-8 of the largest entry at NMAX = 5, exact for P = 0"""
+    ctx = amdg.Context(1, 5, P, max(P, 1), device=-1)
+    src, tgt, vol = ctx.pairs()
+    gen = lambda t: ctx.op_blocks(ctx.op_generate(amdg.BASIS_ALPERT, P, t), P + 1, P + 1)
+    uvx, ur, ul = gen("u_vx"), gen("urgt_vjp"), gen("ulft_vjp")
+    pid = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(src, tgt))}
+    worst = 0.0
+    for i, (a, b) in enumerate(zip(src, tgt)):
+        j = pid[(int(b), int(a))]                                     # the relation is symmetric: the transposed pair exists
+        r = uvx[i] + uvx[j].T + ur[i] + ul[j].T
+        worst = max(worst, float(np.abs(r).max() / max(np.abs(uvx[i]).max(), np.abs(ur[i]).max(), 1.0)))
+    assert worst < 1e-7
+    if P == 0:
+        assert worst == 0.0
+    ctx.close()
+
+
 def test_table_generator_rejects_bad_requests(amdg):
     ctx = amdg.Context(1, 3, 2, 3, device=-1)
     with pytest.raises(amdg.AmdgError, match="Alpert x Alpert only"):
