@@ -109,6 +109,32 @@ def test_alpert_tables_satisfy_integration_by_parts(amdg, P):
     ctx.close()
 
 
+@pytest.mark.parametrize("basis,P,msh", [("lagr", 1, 1), ("lagr", 1, 2), ("lagr", 2, 1), ("lagr", 2, 2), ("lagr", 3, 1), ("lagr", 3, 2), ("lagr", 3, 3),
+                                         ("lagr", 4, 1), ("lagr", 4, 2), ("lagr", 5, 1), ("lagr", 5, 2), ("herm", 3, 1), ("herm", 5, 1)])
+def test_generated_stencils_annihilate_polynomials(amdg, basis, P, msh):
+    """independent of the reference, for every point set the generator knows: a polynomial of degree <= P is reproduced by the level-0 interpolant,
+    so its hierarchical surplus (I + W applied to its point values; for Hermite dofs the point values of its derivatives) vanishes on every 1D element of
+    level >= 1 and equals the point values on level 0"""
+    nmax = 5
+    b = amdg.BASIS_LAGRANGE if basis == "lagr" else amdg.BASIS_HERMITE
+    ctx = amdg.Context(1, nmax, 1, P, device=-1)
+    src, tgt, vol = ctx.pairs()
+    pts = ctx.points_generate(b, P, msh).reshape(-1, P + 1)
+    B = ctx.op_blocks(ctx.op_generate_hier(b, P, msh), P + 1, P + 1)
+    poly = np.polynomial.Polynomial(np.random.default_rng(P * 10 + msh).standard_normal(P + 1))
+    v = poly(pts)
+    if basis == "herm":                                          # dof p: derivative of order p // 2 at point p % 2 (HermBasis::deg_pt_deri_1d)
+        for p in range(2, P + 1):
+            v[:, p] = poly.deriv(p // 2)(pts[:, p])
+    c = np.zeros_like(v)
+    for i in range(len(src)):
+        c[tgt[i]] += v[src[i]] @ B[i]
+    level = np.array([0 if o == 0 else int(np.floor(np.log2(o))) + 1 for o in range(1 << nmax)])
+    assert np.abs(c[level >= 1]).max() < 1e-11 * np.abs(v).max()
+    assert np.array_equal(c[0], v[0])
+    ctx.close()
+
+
 def test_table_generator_rejects_bad_requests(amdg):
     ctx = amdg.Context(1, 3, 2, 3, device=-1)
     with pytest.raises(amdg.AmdgError, match="Alpert x Alpert only"):
