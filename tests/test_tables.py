@@ -135,6 +135,36 @@ def test_generated_stencils_annihilate_polynomials(amdg, basis, P, msh):
     ctx.close()
 
 
+@pytest.mark.parametrize("k,basis,m,msh", [(1, "lagr", 1, 1), (1, "lagr", 1, 2), (1, "lagr", 2, 1), (2, "lagr", 2, 2), (2, "lagr", 3, 1), (2, "lagr", 3, 2),
+                                           (3, "lagr", 3, 3), (2, "lagr", 4, 1), (3, "lagr", 4, 2), (3, "lagr", 5, 1), (4, "lagr", 5, 2), (5, "lagr", 5, 1),
+                                           (1, "herm", 3, 1), (3, "herm", 3, 1), (2, "herm", 5, 1), (5, "herm", 5, 1)])
+def test_generated_tables_round_trip_in_1d(amdg, k, basis, m, msh):
+    """the three generated table families together, independent of the reference and for combinations it never dumped (Alpert degree 5 included):
+    Alpert coefficients -> values at the interpolation points (point table) -> hierarchical interpolation coefficients (stencils) -> L2 projection
+    back (u_v of the interpolation basis against the Alpert basis) is the identity on the full 1D grid whenever m >= k.  The residual comes from the
+    interface points sitting 1e-13 off the cell boundaries (the reference's convention), amplified on the fine levels"""
+    nmax = 4
+    b_id = amdg.BASIS_LAGRANGE if basis == "lagr" else amdg.BASIS_HERMITE
+    ctx = amdg.Context(1, nmax, k, m, device=-1)
+    src, tgt, vol = ctx.pairs()
+    a, b = k + 1, m + 1
+    PT = ctx.op_blocks(ctx.op_generate_points(b_id, m, msh), a, b)
+    H = ctx.op_blocks(ctx.op_generate_hier(b_id, m, msh), b, b)
+    UV = ctx.op_blocks(ctx.op_generate(b_id, m, "u_v", msh), b, a)
+    T = 1 << nmax
+
+    def apply(x, B, kt):
+        y = np.zeros((T, kt))
+        for i in range(len(src)):
+            if vol[i]:
+                y[tgt[i]] += x[src[i]] @ B[i]
+        return y
+    u = np.random.default_rng(3).standard_normal((T, a))
+    u2 = apply(apply(apply(u, PT, b), H, b), UV, a)
+    assert np.abs(u2 - u).max() < 1e-9 * np.abs(u).max()
+    ctx.close()
+
+
 def test_table_generator_rejects_bad_requests(amdg):
     ctx = amdg.Context(1, 3, 2, 3, device=-1)
     with pytest.raises(amdg.AmdgError, match="Alpert x Alpert only"):
