@@ -257,6 +257,31 @@ def test_f4_compositions(name):
     assert rel(np.linalg.norm(u, axis=1), d["f4.indicator_norm"]) < 1e-14
 
 
+@pytest.mark.parametrize("name", ["f4_lagr_d2_k2_n4", "adapt_d3_k1_n4"])
+def test_coarse_grid_transform_is_the_transform_on_the_sub_grid(name):
+    """the argument behind amdg_apply_tensor_coarse: skipping, in every sweep, the targets and sources whose levels sum to more than mesh_nmax
+    (FastMultiplyLU::transform_1D_coarse_grid, source/FastMultiplyLU.cpp:514-594) is the plain transform on the sub-grid of the kept elements --
+    relations are pairwise and the kept set is closed under taking coarser elements -- with the skipped rows left at zero.  Sparse and adaptive grid"""
+    c = Case(name)
+    d = c.d
+    pt, u_v, u_vx, uave, anc, wt = _tables(c)
+    rels = c.relations()
+    u = d["ucoe_alpt.in"][:, 0, :]
+    for M in (c.nmax - 1, c.nmax - 2):
+        keep = np.nonzero(c.lev.sum(axis=1) <= M)[0]
+        assert 0 < len(keep) < c.ne
+        masked = O.apply_tensor(u, c.a, c.b, [pt] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d, mesh_nmax=M)
+        sub_rels = {"vol": [O.relations(c.lev[keep], c.sup[keep], t, "vol") for t in range(c.dim)]}
+        sub = O.apply_tensor(u[keep], c.a, c.b, [pt] * c.dim, ["vol"] * c.dim, sub_rels, c.lev[keep], c.ord1d[keep])
+        full = np.zeros_like(masked)
+        full[keep] = sub
+        assert rel(full, masked) < 1e-14
+        # and it is NOT the plain transform with the result masked afterwards: values of skipped elements feed kept ones in later sweeps
+        plain = O.apply_tensor(u, c.a, c.b, [pt] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d)
+        plain[c.lev.sum(axis=1) > M] = 0.0
+        assert rel(plain, masked) > 1e-6
+
+
 @pytest.mark.parametrize("name", ["pw_d2_k2_n4_v2", "pw_vlasov_d4_k1_n3_v2"])
 def test_pointwise_bodies_beyond_scalar_flux(name):
     """the reference's point-wise kernels with several unknowns, a coefficient of position and a broadcast field (eval_fp_Lag with VEC_NUM = 2,
