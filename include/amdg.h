@@ -58,7 +58,8 @@ int amdg_ctx_set_stream(amdg_ctx *ctx, void *cuda_stream);   /* cudaStream_t; de
 int amdg_ctx_sync(amdg_ctx *ctx);
 int amdg_ctx_info(amdg_ctx *ctx, int *out5);                 /* out5 = dim, nmax, pmax_alpt, pmax_intp, device */
 int amdg_ctx_set_schedule(amdg_ctx *ctx, int sched);
-int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto: per launch the column kernel (one thread per column, FP64 FMA) for blocks of >= 64 doubles with KF*KT <= 9 and >= 32 columns, the lean tensor-core kernel otherwise, the whole-fibre tensor-core kernel for tiny sweeps;
+int amdg_ctx_set_kernel(amdg_ctx *ctx, int variant);          /* 0 = auto: per launch the column kernel (one thread per column, FP64 FMA) for blocks of >= 64 doubles with KF*KT <= 9 and >= 32 columns, the lean tensor-core kernel otherwise, the whole-fibre tensor-core kernel for tiny sweeps,
+                                                                 and -- adaptive mode -- the list-free gather kernel for tiny sweeps on a grid that replaced a short-lived one (DGAdapt::refine / coarsen every step);
                                                                  1 = gather, 2 = fibre-staged list kernel, 3 = pipelined list kernel, 4 = whole-fibre tensor-core (FP64 MMA) kernel, 5 = lean tensor-core kernel, 8 = column kernel
                                                                  (1-4 are independent implementations kept for the parity tests; 6 and 7 were measured 2.5-6x slower and removed, profiles/r02_sweep_kernels.md) */
 int64_t amdg_ctx_launch_count(amdg_ctx *ctx);                 /* kernels launched so far by this context */
@@ -139,7 +140,7 @@ int amdg_sweep1d(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes
 int amdg_sweep1d_batch(amdg_ctx *ctx, int op, int rel, int lu, int t, const int *sizes_from, const double *const *dev_src,
                        double *const *dev_dst, const double *coef, const int *accumulate, int n_job, int n_comp);
 
-/* the same with mapped destinations (register-direct / streaming kernels only, one component per job): dev_dst_map[j] (or NULL) = per element row the
+/* the same with mapped destinations (lean tensor-core and column kernels, one component per job): dev_dst_map[j] (or NULL) = per element row the
  * offset in doubles, relative to dev_dst[j], of the element's destination block -- possibly in peer memory: the last sweep before a layout
  * switch of the fibre-partitioned multi-GPU path stores every block straight into the rank that owns it next; dev_acc_from[j] (or NULL, needs
  * accumulate[j]) = array in the plain row layout whose values are added instead of the destination's ("remote = local partial sum + sweep") */
