@@ -620,6 +620,68 @@ int main(int argc, char ** argv)
         }
         H.fill_ucoe(a.seed);
     }
+    if (has("pw2") && !herm)   // more of the reference's point-wise wrappers: coefficient times gradient, source terms, the shipped 1D2V Vlasov-Maxwell body
+    {
+        H.fill_ucoe(a.seed);
+        std::vector<std::vector<bool>> all_intp(a.vecnum, std::vector<bool>(DIM, true));
+        auto coe = [&](std::vector<double> x, int d) -> double
+        {
+            double s = 0.3 * (d + 1.);
+            for (int t = 0; t < DIM; ++t) s += std::sin(2. * Const::PI * (x[t] + 0.1 * t)) * (t == d ? 1. : 0.25);
+            return s;
+        };
+        // (D) LagrInterpolation::var_coeff_gradu_Lagr_fast (source/Interplation.cpp:4159-4175): fp[v][d] = coe(x, d) * d/dx_d u_v, then hierarchisation
+        interp_lagr.pw1d.clear();
+        interp_lagr.var_coeff_gradu_Lagr_fast(coe, all_intp, fast_lagr_intp);
+        H.dump_flux_field("pw2.gradu.fp_intp", false);
+        H.dump_flux_field("pw2.gradu.fucoe_intp", true);
+        // (E) LagrInterpolation::source_from_lagr_to_rhs (:4102-4123): a source function sampled at the points, hierarchised, projected, added to rhs
+        {
+            auto src = [&](std::vector<double> x, int i) -> double
+            {
+                double s = 1. + 0.5 * i;
+                for (int t = 0; t < DIM; ++t) s *= std::cos(2. * Const::PI * (x[t] - 0.05 * (t + 1)));
+                return s;
+            };
+            dg.set_rhs_zero();
+            interp_lagr.pw1d.clear();
+            interp_lagr.source_from_lagr_to_rhs(src, fast_lagr_init);
+            H.dump_field("pw2.source.rhs", Harness::RHS);
+            H.dump_field("pw2.source.ucoe_after", Harness::UCOE_ALPT);      // must be the coefficients from before the call
+        }
+        // (F) the body of the shipped example/07_vlasov_maxwell_sparse.cpp: LagrInterpolation::interp_Vlasov_1D2V with the Maxwell coefficient functions
+        //     (:4435-4505; coe_x2 = v2, coe_v1 = E1 + v2 B3, coe_v2 = E2 - v1 B3, example lines 236-239), fields (B3, E1, E2) broadcast from a second solution
+        if (DIM == 3 && a.vecnum == 3)
+        {
+            DGAdapt BE(false, a.nmax, a.nmax, 2, all_bas_alpt, all_bas_lagr, all_bas_herm, hash, a.eps, a.eta, true, false);
+            std::vector<Element *> es;
+            for (auto & it : BE.dg) es.push_back(&it.second);
+            std::sort(es.begin(), es.end(), [](Element * x, Element * y) { return x->hash_key < y->hash_key; });
+            std::vector<int> key, lev, sup; std::vector<double> ue;
+            for (Element * e : es)
+            {
+                int sl = 0; for (int t = 0; t < DIM; ++t) sl += e->level[t];
+                key.push_back(e->hash_key);
+                for (int t = 0; t < DIM; ++t) { lev.push_back(e->level[t]); sup.push_back(e->suppt[t]); }
+                for (int v = 0; v < a.vecnum; ++v)
+                    for (int i = 0; i < e->ucoe_alpt[v].size(); ++i) { e->ucoe_alpt[v].at(i) = field_value(a.seed + 7, e->hash_key, v, i, sl); ue.push_back(e->ucoe_alpt[v].at(i)); }
+            }
+            H.dump.put("pw2.vm.BE.hash_key", key);
+            H.dump.put("pw2.vm.BE.level", lev, { (int64_t)es.size(), DIM });
+            H.dump.put("pw2.vm.BE.suppt", sup, { (int64_t)es.size(), DIM });
+            H.dump.put("pw2.vm.BE.ucoe_alpt", ue, { (int64_t)es.size(), a.vecnum, (int64_t)es[0]->ucoe_alpt[0].size() });
+            FastLagrIntp fast_lagr_BE(BE, interp_lagr.Lag_pt_Alpt_1D, interp_lagr.Lag_pt_Alpt_1D_d1);
+            auto coe_x2 = [](double v2) -> double { return v2; };
+            auto coe_v1 = [](double v2, double E1, double B3) -> double { return E1 + v2 * B3; };
+            auto coe_v2 = [](double v1, double E2, double B3) -> double { return E2 - v1 * B3; };
+            interp_lagr.pw1d.clear();
+            interp_lagr.interp_Vlasov_1D2V(BE, coe_x2, coe_v1, coe_v2, fast_lagr_intp, fast_lagr_BE);
+            H.dump_field("pw2.vm.up_intp", Harness::UP_INTP);
+            H.dump_flux_field("pw2.vm.fp_intp", false);
+            H.dump_flux_field("pw2.vm.fucoe_intp", true);
+        }
+        H.fill_ucoe(a.seed);
+    }
     if (has("vlasov_ampere") && !herm && DIM == 4 && a.vecnum == 2)
     {
         // one RK3SSP step of the coupled 2D2V Vlasov-Ampere system on static grids, stage by stage as example/07_vlasov_ampere_02_2D2V_accuracy.cpp:255-318

@@ -54,6 +54,9 @@ CASES = {
     # 1D tables under the other boundary types of Basis::product_edge_dis_v / _u (table-generation parity only)
     "tables_bc_zero_k2_n4": "--dim 1 --nmax 4 --pa 2 --pl 3 --ph 3 --boundary zero --run grid --dump-tables 2",
     "tables_bc_inside_k2_n4": "--dim 1 --nmax 4 --pa 2 --pl 3 --ph 3 --boundary inside --run grid --dump-tables 2",
+    # coefficient x gradient (var_coeff_gradu_Lagr_fast), source terms (source_from_lagr_to_rhs), the 1D2V Vlasov-Maxwell body of the shipped
+    # example/07_vlasov_maxwell_sparse.cpp (interp_Vlasov_1D2V with B3, E1, E2 broadcast from a second solution); k = 2, m = 3 as shipped
+    "pw2_vm_d3_k2_n3_v3": "--dim 3 --nmax 3 --pa 2 --pl 3 --vecnum 3 --run grid,pw2 --dump-tables 1",
     "line_d1_k2_n5": "--dim 1 --nmax 5 --pa 2 --pl 3 --run grid,rhs,roundtrip --flux burgers --dump-tables 1",
 }
 

@@ -314,6 +314,49 @@ def test_pointwise_bodies_beyond_scalar_flux(name):
             assert rel(want[t], d["pw.vl.fp_intp"][:, 0, t, :]) < TOL, t
 
 
+def test_pointwise_wrappers_gradient_source_and_1d2v_body():
+    """more of the reference's wrappers over the same primitives, restated (CPU only -- on the device they are compositions of amdg_apply_tensor with the
+    derivative point table, amdg_pointwise_expr with X / OTHER operands, amdg_hierarchize): var_coeff_gradu_Lagr_fast (coefficient times the derivative
+    transform of FastLagrIntp::eval_der_up_Lagr, source/Interplation.cpp:4159-4175), source_from_lagr_to_rhs (:4102-4123) and the body of the shipped
+    example/07_vlasov_maxwell_sparse.cpp, interp_Vlasov_1D2V with the Maxwell coefficient functions (:4435-4505) and (B3, E1, E2) broadcast by
+    DGSolution::copy_up_intp_to_f"""
+    c = Case("pw2_vm_d3_k2_n3_v3")
+    d = c.d
+    pt, u_v, u_vx, uave, anc, wt = _tables(c)
+    pt_d1 = d["Lag_pt_Alpt_1D_d1"].T.copy()
+    rels = c.relations()
+    X = O.point_coordinates(c.ord1d, d["lagr.intep_pt"], c.b)
+    u = d["ucoe_alpt.in"]
+    # (D) fp[v][t] = coe(x, t) * d/dx_t u_v: the derivative table along t, the value table elsewhere
+    for v in range(c.vecnum):
+        for t in range(c.dim):
+            der = O.apply_tensor(u[:, v, :], c.a, c.b, [pt_d1 if s == t else pt for s in range(c.dim)], ["vol"] * c.dim, rels, c.lev, c.ord1d)
+            fp = O.position_coefficient(X, t) * der
+            assert rel(fp, d["pw2.gradu.fp_intp"][:, v, t, :]) < TOL
+            if v == 0:
+                assert rel(O.hierarchize(fp, c.b, c.lev, c.sup, c.ord1d, anc, wt), d["pw2.gradu.fucoe_intp"][:, v, t, :]) < TOL
+    # (E) rhs[v] += (u_v x ... x u_v) hierarchise(src(x, v)), coefficients untouched
+    for v in range(c.vecnum):
+        src = (1.0 + 0.5 * v) * np.prod([np.cos(2.0 * np.pi * (X[..., t] - 0.05 * (t + 1))) for t in range(c.dim)], axis=0)
+        proj = O.apply_tensor(O.hierarchize(src, c.b, c.lev, c.sup, c.ord1d, anc, wt), c.b, c.a, [u_v] * c.dim, ["vol"] * c.dim, rels, c.lev, c.ord1d)
+        assert rel(proj, d["pw2.source.rhs"][:, v, :]) < TOL
+    assert np.array_equal(d["pw2.source.ucoe_after"], u)
+    # (F) f_t + v2 f_x2 + (E1 + v2 B3) f_v1 + (E2 - v1 B3) f_v2 = 0, pos = (x2, v1, v2), fields = (B3, E1, E2) on the elements with velocity level 0
+    le, se = d["pw2.vm.BE.level"], d["pw2.vm.BE.suppt"]
+    orde = np.array([[O.order_elem(int(n), int(j)) for n, j in zip(l, s)] for l, s in zip(le, se)])
+    rels_e = {"vol": [O.relations(le, se, t, "vol") for t in range(3)]}
+    F = [O.apply_tensor(d["pw2.vm.BE.ucoe_alpt"][:, v, :], c.a, c.b, [pt] * 3, ["vol"] * 3, rels_e, le, orde) for v in range(3)]
+    rows = O.field_rows_of(c.lev, c.sup, le, se, (1, 2))
+    f = O.apply_tensor(u[:, 0, :], c.a, c.b, [pt] * 3, ["vol"] * 3, rels, c.lev, c.ord1d)
+    assert rel(f, d["pw2.vm.up_intp"][:, 0, :]) < TOL
+    B3, E1, E2 = F[0][rows], F[1][rows], F[2][rows]
+    v1, v2 = X[..., 1], X[..., 2]
+    want = [v2 * f, (E1 + v2 * B3) * f, (E2 - v1 * B3) * f]
+    for t in range(3):
+        assert rel(want[t], d["pw2.vm.fp_intp"][:, 0, t, :]) < TOL, t
+        assert rel(O.hierarchize(want[t], c.b, c.lev, c.sup, c.ord1d, anc, wt), d["pw2.vm.fucoe_intp"][:, 0, t, :]) < TOL, t
+
+
 def test_vlasov_ampere_2d2v_step_restated():
     """one RK3SSP step of the coupled 2D2V Vlasov-Ampere system, stage by stage (example/07_vlasov_ampere_02_2D2V_accuracy.cpp:255-318 without its
     manufactured source): f through interp_Vlasov_2D2V (field broadcast by copy_up_intp_to_f), HyperbolicLagrRHS vol + flx, penalty; E_t = -J through
