@@ -226,3 +226,18 @@ def test_plan_summary_cfg5():
     # second destinations move the same blocks from the epilogues of their producers; u@V serves the interpolation as well (one scatter of u less)
     assert p8.push_bytes == vol - 64
     assert sum(1 for o in p8.ops if o[0] == "scatter") == 1 and sum(1 for o in S.StagePlan(6, 2, 3, 6, part=part, dual_store=False).ops if o[0] == "scatter") == 29
+
+
+def test_rk_coefficients_of_the_fused_plan_match_every_scheme():
+    """stage.rk_coefficients (the a, b, c of u_new = a u_tn + b u + c rhs that the fused plan folds into the sweep epilogues) against the oracle's
+    ExplicitRK::step_stage restatement for every scheme and stage (source/ODESolver.cpp:209-330)"""
+    rng = np.random.default_rng(11)
+    u_tn, u, rhs = rng.standard_normal((3, 50))
+    dt = 0.0137
+    for scheme, name, stages in ((A.RK_EULER, "euler", 1), (A.RK_RK2SSP, "rk2ssp", 2), (A.RK_RK2MID, "rk2mid", 2), (A.RK_RK3SSP, "rk3ssp", 3), (A.RK_RK3HEUN, "rk3heun", 3)):
+        for stage in range(stages):
+            a, b, c = S.rk_coefficients(scheme, stage, dt)
+            uu = u_tn if (stage == 0) else u                      # at stage 0 the current state is u_tn in every scheme
+            want = O.rk_stage(name, stage, u_tn, uu, rhs, dt)
+            got = a * u_tn + b * uu + c * rhs
+            assert np.allclose(got, want, rtol=1e-14, atol=1e-15), (name, stage)
