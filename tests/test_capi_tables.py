@@ -31,6 +31,28 @@ def test_no_cpu_compute_path(amdg):
     ctx.close()
 
 
+def test_new_entry_points_refuse_to_run_without_a_device(amdg):
+    """the entry points added in round 2 keep the contract of the header: a context created without a device builds tables only, every compute call
+    fails with AMDG_ENODEVICE and a message (no CPU path exists), table generation works"""
+    import ctypes
+    ctx = amdg.Context(2, 3, 2, 3, device=-1)
+    lev, sup = amdg.sparse_grid(2, 3)
+    ctx.grid_set(lev, sup)
+    op = ctx.op_generate_points(amdg.BASIS_LAGRANGE, 3)
+    assert ctx.op_blocks(op, 3, 4).shape[1:] == (3, 4)
+    null = ctypes.c_void_p(0)
+    one = (ctypes.c_void_p * 1)(ctypes.c_void_p(8))
+    ops = (ctypes.c_int * 2)(op, op); rels = (ctypes.c_int * 2)(0, 0)
+    assert amdg.lib.amdg_apply_tensor_coarse(ctx._h, ops, rels, ctypes.c_void_p(8), ctypes.c_void_p(16), 1, 1.0, 0, 2) == -2
+    assert b"no CPU compute path" in amdg.lib.amdg_last_error()
+    assert amdg.lib.amdg_indicator_norm(ctx._h, 1, one, ctypes.c_void_p(16)) == -2
+    sizes = (ctypes.c_int * 2)(3, 3)
+    assert amdg.lib.amdg_sweep1d_batch_dual(ctx._h, op, 0, 2, 0, sizes, one, one, None, None, None, None, None, None, 1) == -2
+    info = (ctypes.c_int * 5)()
+    assert amdg.lib.amdg_ctx_info(ctx._h, info) == 0 and list(info) == [2, 3, 2, 3, -1]
+    ctx.close()
+
+
 def test_invalid_arguments(amdg):
     with pytest.raises(amdg.AmdgError):
         amdg.Context(0, 3, 2, 3, device=-1)
