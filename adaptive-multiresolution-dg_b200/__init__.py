@@ -50,6 +50,7 @@ SYMBOLS = {
     "amdg_hash_key": (_i, [_i, _ip, _ip]),
     "amdg_order_elem": (_i, [_i, _i]),
     "amdg_sparse_grid": (_i64, [_i, _i, _i, _ip, _ip]),
+    "amdg_aux_grid": (_i64, [_i, _i, _i, _ip, _ip]),
     "amdg_grid_set": (_i, [_p, _i64, _ip, _ip]),
     "amdg_grid_size": (_i64, [_p]),
     "amdg_grid_keys": (_i, [_p, _ip, _ip]),
@@ -146,6 +147,16 @@ def sparse_grid(dim, level_init, sparse=True):
     lev = np.zeros((n, dim), dtype=np.int32)
     sup = np.zeros((n, dim), dtype=np.int32)
     _check(lib.amdg_sparse_grid(dim, level_init, int(sparse), lev.ctypes.data_as(_ip), sup.ctypes.data_as(_ip)))
+    return lev, sup
+
+
+def aux_grid(dim, level_init, aux_dim):
+    """Grid of a field solution with auxiliary dimensions (reference source/DGSolution.cpp:59-116): full grid in the first dim - aux_dim dimensions,
+    level 0 in the rest."""
+    n = _check(lib.amdg_aux_grid(dim, level_init, aux_dim, None, None))
+    lev = np.zeros((n, dim), dtype=np.int32)
+    sup = np.zeros((n, dim), dtype=np.int32)
+    _check(lib.amdg_aux_grid(dim, level_init, aux_dim, lev.ctypes.data_as(_ip), sup.ctypes.data_as(_ip)))
     return lev, sup
 
 

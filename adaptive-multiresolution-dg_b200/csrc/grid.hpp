@@ -390,4 +390,29 @@ inline int64_t sparse_grid(int dim, int level_init, bool sparse, std::vector<int
     return count;
 }
 
+// ---- DGSolution with auxiliary dimensions (source/DGSolution.cpp:59-116): full grid of level `level_init` in the first dim - aux_dim dimensions,
+// level 0 in the remaining ones -- the grid of a field (E, B) that lives with f in one phase space (example/07_vlasov_*.cpp) ------------------------
+inline int64_t aux_grid(int dim, int level_init, int aux_dim, std::vector<int> * level, std::vector<int> * suppt)
+{
+    const int real_dim = dim - aux_dim;
+    int64_t count = 0;
+    std::vector<int> n(dim, 0), j(dim, 0), jmax(dim, 1);
+    while (true)
+    {
+        for (int t = 0; t < dim; ++t) { jmax[t] = n[t] == 0 ? 1 : (1 << (n[t] - 1)); j[t] = 0; }
+        while (true)
+        {
+            if (level) for (int t = 0; t < dim; ++t) { level->push_back(n[t]); suppt->push_back(2 * j[t] + 1); }
+            ++count;
+            int t = dim - 1;
+            while (t >= 0 && ++j[t] == jmax[t]) { j[t] = 0; --t; }
+            if (t < 0) break;
+        }
+        int t = real_dim - 1;                       // the auxiliary dimensions stay at level 0
+        while (t >= 0 && ++n[t] == level_init + 1) { n[t] = 0; --t; }
+        if (t < 0) break;
+    }
+    return count;
+}
+
 }  // namespace amdg

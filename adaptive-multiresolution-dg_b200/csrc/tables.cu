@@ -110,4 +110,15 @@ int amdg_points_generate(amdg_ctx * c, int basis, int pmax, int msh_case, double
     return AMDG_OK;
 }
 
+// the grid of a field solution with auxiliary dimensions (grid.hpp: aux_grid); level == NULL returns the count
+int64_t amdg_aux_grid(int dim, int level_init, int aux_dim, int * level, int * suppt)
+{
+    if (dim < 1 || dim > 8 || level_init < 0 || level_init > 12 || aux_dim < 0 || aux_dim >= dim) return fail(AMDG_EINVAL, "bad grid parameters");
+    if (!level) return aux_grid(dim, level_init, aux_dim, nullptr, nullptr);
+    std::vector<int> l, j;
+    const int64_t n = aux_grid(dim, level_init, aux_dim, &l, &j);
+    std::memcpy(level, l.data(), l.size() * sizeof(int)); std::memcpy(suppt, j.data(), j.size() * sizeof(int));
+    return n;
+}
+
 }  // extern "C"

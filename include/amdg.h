@@ -75,6 +75,9 @@ int amdg_order_elem(int level, int suppt);
 /* Initial grid of DGSolution (source/DGSolution.cpp:10-57): fills level/suppt ([n][dim], construction order);
  * call with level == NULL to get the count. */
 int64_t amdg_sparse_grid(int dim, int level_init, int sparse, int *level, int *suppt);
+/* The grid of a field solution with auxiliary dimensions (DGSolution's second constructor, source/DGSolution.cpp:59-116): full grid of level_init in the
+ * first dim - aux_dim dimensions, level 0 in the rest -- where E / B live next to f (example/07_vlasov_*.cpp).  Same calling convention. */
+int64_t amdg_aux_grid(int dim, int level_init, int aux_dim, int *level, int *suppt);
 
 /* ---- grid: replaces DGSolution::find_ptr_vol_alpt / find_ptr_flx_alpt (source/DGSolution.cpp:675-728) and
  * the per-adapt updates (source/DGAdapt.cpp:1073-1248).  Call after construction / refine / coarsen. ---- */

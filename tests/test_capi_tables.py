@@ -53,6 +53,20 @@ def test_new_entry_points_refuse_to_run_without_a_device(amdg):
     ctx.close()
 
 
+@pytest.mark.parametrize("name,key", [("moment_d3_k2_n4", "moment"), ("moment_d4_k1_n3", "moment"), ("vlasov_ampere_d4_k1_n3_v2", "va.E"), ("pw2_vm_d3_k2_n3_v3", "pw2.vm.BE")])
+def test_auxiliary_dimension_grid(amdg, name, key):
+    """amdg_aux_grid against the reference's DGSolution constructor with auxiliary dimensions (the grids of E / B in the Vlasov examples), joined
+    through the bit-exact hash key"""
+    d = load_golden(name)
+    dim, nmax = int(d["config"][0]), int(d["config"][1])
+    lev, sup = amdg.aux_grid(dim, nmax, 2)
+    keys = np.array([amdg.hash_key(l, s) for l, s in zip(lev, sup)])
+    o = np.argsort(keys, kind="stable")
+    assert np.array_equal(keys[o], d[key + ".hash_key"])
+    assert np.array_equal(lev[o], d[key + ".level"]) and np.array_equal(sup[o], d[key + ".suppt"])
+    assert (lev[:, dim - 2:] == 0).all() and lev[:, :dim - 2].max() == nmax
+
+
 def test_invalid_arguments(amdg):
     with pytest.raises(amdg.AmdgError):
         amdg.Context(0, 3, 2, 3, device=-1)
