@@ -357,6 +357,34 @@ def test_pointwise_wrappers_gradient_source_and_1d2v_body():
         assert rel(O.hierarchize(want[t], c.b, c.lev, c.sup, c.ord1d, anc, wt), d["pw2.vm.fucoe_intp"][:, 0, t, :]) < TOL, t
 
 
+def test_stack_programs_restated():
+    """the (operation, argument) programs of amdg_pointwise_expr interpreted by the oracle: the benchmark's own Vlasov program (bench.vlasov_program)
+    on the d = 6 fixture against the reference's fp_intp, the operand order of the binary operations, and the header's opcode numbering"""
+    import importlib
+    import os
+    import re
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    A = importlib.import_module("adaptive-multiresolution-dg_b200")
+    assert A.PW == O.PW_OPS
+    hdr = open(os.path.join(ROOT, "include", "amdg.h")).read()
+    for name, val in O.PW_OPS.items():
+        assert re.search(r"AMDG_PW_%s = %d\b" % (name, val), hdr), name
+    c = Case("cfg5_vlasov_d6_k1_n2")
+    d = c.d
+    X = O.point_coordinates(c.ord1d, d["lagr.intep_pt"], c.b)
+    up = d["up_intp"][:, 0, :]
+    prog, ptr, consts = bench.vlasov_program(A, c.dim)
+    outs = O.pointwise_expr(prog, ptr, consts, [up], X)
+    for t in range(c.dim):
+        assert rel(outs[t], d["fp_intp"][:, 0, t, :]) < 1e-14
+    P = O.PW_OPS
+    two = O.pointwise_expr([(P["VAR"], 0), (P["CONST"], 0), (P["SUB"], 0), (P["VAR"], 0), (P["CONST"], 1), (P["DIV"], 0)], [0, 3, 6], [2.0, 4.0], [up])
+    assert np.array_equal(two[0], up - 2.0) and np.array_equal(two[1], up / 4.0)
+
+
 def test_vlasov_ampere_2d2v_step_restated():
     """one RK3SSP step of the coupled 2D2V Vlasov-Ampere system, stage by stage (example/07_vlasov_ampere_02_2D2V_accuracy.cpp:255-318 without its
     manufactured source): f through interp_Vlasov_2D2V (field broadcast by copy_up_intp_to_f), HyperbolicLagrRHS vol + flx, penalty; E_t = -J through
