@@ -67,6 +67,21 @@ def test_auxiliary_dimension_grid(amdg, name, key):
     assert (lev[:, dim - 2:] == 0).all() and lev[:, :dim - 2].max() == nmax
 
 
+def test_duplicate_element_in_a_large_grid_is_rejected(amdg):
+    """the radix-sorted path of amdg_grid_set (>= 256 elements, threads from 2 048) still finds a duplicated element, and the context keeps its old grid"""
+    for nmax in (6, 9):
+        lev, sup = amdg.sparse_grid(2, nmax)
+        ctx = amdg.Context(2, nmax, 1, 2, device=-1)
+        ctx.grid_set(lev, sup)
+        n_ok = ctx.n_elem
+        bad_l, bad_s = np.vstack([lev, lev[lev.shape[0] // 2:lev.shape[0] // 2 + 1]]), np.vstack([sup, sup[sup.shape[0] // 2:sup.shape[0] // 2 + 1]])
+        with pytest.raises(amdg.AmdgError, match="duplicate"):
+            ctx.grid_set(bad_l, bad_s)
+        assert amdg.lib.amdg_grid_size(ctx._h) == n_ok
+        ctx.grid_set(lev[::-1].copy(), sup[::-1].copy())              # and it still takes a valid grid afterwards
+        ctx.close()
+
+
 def test_invalid_arguments(amdg):
     with pytest.raises(amdg.AmdgError):
         amdg.Context(0, 3, 2, 3, device=-1)
